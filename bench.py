@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- MNF-LeNet5 MC-predictive forward + KL throughput (BASELINE.json metric).
+
+A step = one pass of the hot path over one batch: `probs = model(x); kl = model.kl_div()`
+for x = 10 synthetic 28x28x1 images x 1024 posterior samples = 10240 rows per GPU
+(BASELINE.json configs[2]; weak scaling: every rank owns 10240 rows of a 10240*N-row global
+batch, Philox counters indexed by the GLOBAL row, no data-path collective).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference ...                     # reference algorithm on host cores
+
+The reference arm times the NumPy restatement of the reference's TF path (oracle/, float32,
+all BLAS threads) because TensorFlow cannot be installed here; it is a CPU
+baseline, not the target -- the roofline fraction is the figure of merit.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "MNF-LeNet MC-sample images/sec fwd+KL"
+UNIT = "images/s"
+N_IMAGES, N_SAMPLES = 10, 1024
+ROWS = N_IMAGES * N_SAMPLES
+# algorithmic bytes of the dominant kernel (conv2 paired implicit GEMM), SURVEY.md 8(d):
+# per row read x 12*12*20*4 + write y 8*8*50*4, plus mean_W + var_W once per launch
+CONV2_BYTES_PER_ROW = 12 * 12 * 20 * 4 + 8 * 8 * 50 * 4
+CONV2_WEIGHT_BYTES = 2 * 5 * 5 * 20 * 50 * 4
+CONV2_FLOP_PER_ROW = 2 * 2 * 64 * 500 * 50
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int) -> None:
+        self.device, self.rows, self.proc = device, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_step_factory(flow: str, rows: int):
+    """Reference algorithm on host cores: NumPy float32 restatement (oracle/), noise drawn
+    inside the step like tf.random.normal does in the reference."""
+    from oracle import mnf_oracle as O
+
+    Ps = O.make_lenet_params(seed=0, flow=flow, std_init=10.0, dtype=np.float32)
+    rng = np.random.RandomState(0)
+    imgs = rng.uniform(size=(N_IMAGES, 28, 28, 1)).astype(np.float32)
+    reps = -(-rows // N_IMAGES)
+    x = np.repeat(imgs, reps, axis=0)[:rows]
+    Ds = [20, 50, 800, 500]
+    outs = [(rows, 24, 24, 20), (rows, 8, 8, 50), (rows, 500), (rows, 10)]
+    kl_shapes = [(25,), (500,), (500,), (10,)]
+    f32 = np.float32
+
+    def step():
+        noise, bern, kln, klb = [], [], [], []
+        for D, o in zip(Ds, outs):
+            noise.append((rng.standard_normal((rows, D)).astype(f32), rng.standard_normal(o).astype(f32)))
+            bern.append([(rng.uniform(size=(rows, D)) <= 0.5).astype(f32) for _ in range(2)] if flow == "rnvp" else None)
+        for i, (D, ks) in enumerate(zip(Ds, kl_shapes)):
+            ez, ea = rng.standard_normal((1, D)).astype(f32), rng.standard_normal(ks).astype(f32)
+            kln.append((ez, ea, f32(rng.standard_normal())) if i < 2 else (ez, ea))
+            b = [(rng.uniform(size=(1, D)) <= 0.5).astype(f32) for _ in range(4)] if flow == "rnvp" else [None] * 4
+            klb.append((b[:2], b[2:]) if flow == "rnvp" else (None, None))
+        probs = O.lenet_forward(Ps, x, noise, max_std=1.0, bern=bern)
+        kl = O.lenet_kl(Ps, kln, bern=klb)
+        return probs, kl
+
+    return step
+
+
+def time_cpu(flow: str, rows: int, steps: int, warmup: int):
+    step = cpu_step_factory(flow, rows)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return float(np.mean(ts)), ts
+
+
+def blas_threads() -> int:
+    try:
+        from threadpoolctl import threadpool_info
+
+        n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(n) if n else (os.cpu_count() or 1)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank: int) -> None:
+    if rank != 0:
+        return
+    rows = args.cpu_rows
+    t, _ = time_cpu(args.flow, rows, max(args.steps, 1), max(args.warmup, 1))
+    val = rows / t
+    cores = blas_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, rows_per_step=rows),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{rows} of {ROWS} rows per step (same images, same model), NumPy float32 "
+                                   f"restatement of the reference TF path, {cores} BLAS threads of {os.cpu_count()} host cores; "
+                                   "TensorFlow not installable here"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, rows_per_step=ROWS) -> dict:
+    return {"workload": "MNF-LeNet5 MC predictive: 1024 posterior samples x 10 synthetic 28x28x1 images, "
+                        "forward of 2xMNFConv2D + 2xMNFDense (+ReLU/MaxPool/Softmax) + model.kl_div()",
+            "rows_per_gpu": rows_per_step, "flow_type": args.flow, "n_flows_q": 2, "n_flows_r": 2, "flow_h_sizes": [50],
+            "std_init": 10.0, "max_std": 1.0, "noise": "in-kernel Philox4x32-10", "l2": "flushed between timed steps "
+            "(256 MiB memset outside the per-step event pairs)", "parallelism": f"row-sharded x{args.gpus}, no collective"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
+    import torch
+
+    import tf_mnf_b200 as M
+    from tf_mnf_b200 import _lib as L
+    from tf_mnf_b200.models import MNFLeNet
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    M.runtime.set_default_device(local_rank)
+    M.set_seed(0)
+    ctx = M.default_context(local_rank)
+    lib = ctx.lib
+
+    model = MNFLeNet(max_std=1, flow_h_sizes=[50], std_init=10.0, flow_type=args.flow)
+    rng = np.random.RandomState(0)
+    imgs = rng.uniform(size=(N_IMAGES, 28, 28, 1)).astype(np.float32)
+    x_host = np.repeat(imgs, N_SAMPLES, axis=0)
+    x_dev = ctx.to_device(x_host)
+    model.set_row_offset(rank * ROWS)
+    flush = ctx.empty((64 << 20,))  # 256 MiB > 126 MB L2
+
+    def step(x):
+        probs = model(x)
+        kl = model.kl_div()
+        return probs, kl
+
+    def ev():
+        p = C.c_void_p()
+        L.check(lib.mnf_event_create(C.byref(p)))
+        return p
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev)
+    barrier()
+
+    # ---- timed: K steps, device-resident input, per-step CUDA events, L2 flushed in between
+    starts, stops = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
+    kst, ksp = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
+    launches0 = ctx.launches
+    with ClockSampler(local_rank) as clk:
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
+            L.check(lib.mnf_ctx_probe(ctx.handle, 1, 1, kst[i], ksp[i]))  # 2nd conv GEMM launch = conv2
+            L.check(lib.mnf_event_record(ctx.handle, starts[i]))
+            out = step(x_dev)
+            L.check(lib.mnf_event_record(ctx.handle, stops[i]))
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    launches = ctx.launches - launches0
+
+    def elapsed(a, b):
+        ms = C.c_float()
+        L.check(lib.mnf_event_elapsed_ms(a, b, C.byref(ms)))
+        return ms.value
+
+    step_ms = [elapsed(a, b) for a, b in zip(starts, stops)]
+    kern_ms = [elapsed(a, b) for a, b in zip(kst, ksp)]
+    my_ms = float(np.mean(step_ms))
+
+    # ---- e2e: host (pinned) input -> public API -> host result, copies inside the timed region
+    hp = C.c_void_p()
+    L.check(lib.mnf_host_alloc(x_host.nbytes, C.byref(hp)))
+    C.memmove(hp.value, x_host.ctypes.data, x_host.nbytes)
+    res_host = C.c_void_p()
+    L.check(lib.mnf_host_alloc(ROWS * 10 * 4 + 16, C.byref(res_host)))
+    x_in = ctx.empty(x_host.shape)
+
+    def e2e_step():
+        L.check(lib.mnf_memcpy_h2d(ctx.handle, C.c_void_p(x_in.ptr), hp, x_host.nbytes))
+        probs, kl = step(x_in)
+        L.check(lib.mnf_memcpy_d2h(ctx.handle, res_host, C.c_void_p(probs.ptr), probs.nbytes))
+        L.check(lib.mnf_memcpy_d2h(ctx.handle, C.c_void_p(res_host.value + probs.nbytes), C.c_void_p(kl.ptr), 4))
+        ctx.sync()
+
+    e2e_step()
+    barrier()
+    e_ms = []
+    for _ in range(args.steps):
+        L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
+        ctx.sync()
+        a, b = ev(), ev()
+        L.check(lib.mnf_event_record(ctx.handle, a))
+        e2e_step()
+        L.check(lib.mnf_event_record(ctx.handle, b))
+        e_ms.append(elapsed(a, b))
+    barrier()
+    my_e2e = float(np.mean(e_ms))
+
+    # ---- max over ranks
+    if dist is not None:
+        t = torch.tensor([my_ms, my_e2e, float(np.mean(kern_ms))], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms, k_ms = (float(v) for v in t.tolist())
+    else:
+        ms, e2e_ms, k_ms = my_ms, my_e2e, float(np.mean(kern_ms))
+
+    if rank == 0:
+        hbm, which = peaks()
+        k_bytes = CONV2_BYTES_PER_ROW * ROWS + CONV2_WEIGHT_BYTES
+        achieved = k_bytes / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": ROWS * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "e2e": {"value": ROWS * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
+                    "d2h_bytes_per_step": ROWS * 10 * 4 + 4, "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "roofline": {"bound": "hbm", "kernel": "paired_gemm_fwd<CONV,64> (conv2: 12x12x20 -> 8x8x50, 5x5)",
+                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                         "peak_source": which, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms,
+                         "algorithmic_bytes_per_launch": k_bytes,
+                         "pipe": "fp32 FFMA (parity path, <=1e-5 rel.)",
+                         "ffma_tflops": CONV2_FLOP_PER_ROW * ROWS / (k_ms * 1e-3) / 1e12},
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu:
+            rows = args.cpu_rows
+            t_cpu, _ = time_cpu(args.flow, rows, args.cpu_steps, 1)
+            cores = blas_threads()
+            line["cpu_baseline"] = {
+                "value": rows / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{args.cpu_steps} steps of {rows} of {ROWS} rows (same images/model), NumPy float32 "
+                          f"restatement of the reference TF path (oracle/), {cores} BLAS threads of {os.cpu_count()} host cores"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--flow", default="rnvp", choices=["rnvp", "iaf", "planar"])
+    ap.add_argument("--cpu-rows", type=int, default=2560, help="rows per CPU-baseline step (bounded sample)")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

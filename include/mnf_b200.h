@@ -1,0 +1,271 @@
+/*
+ * mnf_b200.h -- C ABI of libmnf_b200.so: the MNF-layer hot path of janosh/tf-mnf as
+ * hand-written CUDA for sm_100a (NVIDIA B200).
+ *
+ * The reference has no FFI of its own (it is pure Python on TensorFlow); the boundary it
+ * exposes is the Keras-style class protocol.  Each entry point below therefore cites the
+ * reference METHOD whose arithmetic it replaces (paths relative to the reference repo);
+ * the Python host package tf_mnf_b200 binds these symbols with ctypes and re-creates the
+ * tf_mnf.layers / tf_mnf.flows classes on top (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch/TF types.
+ *   - every function returns 0 on success or a negative mnf_status; the message is
+ *     available per thread from mnf_last_error().
+ *   - all tensor pointers are DEVICE pointers to compact row-major float32 unless the
+ *     parameter name starts with `h_` (host).  NULL is only legal where stated.
+ *   - work is enqueued on the context's stream; nothing synchronises unless stated.
+ *   - there is no CPU fallback: without a CUDA device mnf_ctx_create fails.
+ *
+ * Random numbers: counter-based Philox4x32-10.  A draw is addressed by
+ *   key = seed (64 bit), counter = (inner >> 2, outer, global_row, stream), lane = inner & 3
+ * so results do not depend on how rows are sharded over GPUs.  Every draw can instead be
+ * INJECTED (mnf_noise.injected != NULL) which is how parity tests feed the oracle's noise.
+ */
+#ifndef MNF_B200_H
+#define MNF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* only the functions declared here are exported from libmnf_b200.so */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define MNF_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  MNF_OK = 0,
+  MNF_ERR_INVALID = -1,     /* bad shape / null pointer / unsupported option -> ValueError */
+  MNF_ERR_CUDA = -2,        /* CUDA runtime error -> RuntimeError */
+  MNF_ERR_UNSUPPORTED = -3, /* valid in the reference, not implemented here (loud, never a fallback) */
+  MNF_ERR_NOT_CUDA = -4     /* tensor is not on a CUDA device */
+} mnf_status;
+
+typedef struct mnf_ctx mnf_ctx; /* opaque: device, stream, workspace */
+
+/* ---- runtime ------------------------------------------------------------------------ */
+int mnf_version(void);
+const char* mnf_last_error(void);
+int mnf_device_count(int* out);
+/* stream: a cudaStream_t owned by the caller, or NULL to let the context create its own. */
+int mnf_ctx_create(int device, void* stream, mnf_ctx** out);
+int mnf_ctx_destroy(mnf_ctx* ctx);
+int mnf_ctx_set_stream(mnf_ctx* ctx, void* stream);
+int mnf_ctx_get_stream(mnf_ctx* ctx, void** stream);
+int mnf_ctx_sync(mnf_ctx* ctx);
+int mnf_ctx_sm_count(mnf_ctx* ctx, int* out);
+/* kernels launched by this context since creation (bench.py reports it as gpu_launches) */
+int mnf_ctx_launch_count(mnf_ctx* ctx, int64_t* out);
+
+/* Timing probe for bench.py's roofline line: the (skip+1)-th launch of kernel family `kind`
+ * (1 conv paired GEMM, 2 dense paired GEMM, 3 flow step, 4 KL; 0 disarms) is bracketed by
+ * cudaEventRecord(ev_start/ev_stop) on the context's stream, then the probe disarms. */
+int mnf_ctx_probe(mnf_ctx* ctx, int kind, int skip, void* ev_start, void* ev_stop);
+
+int mnf_malloc(mnf_ctx* ctx, size_t bytes, void** out); /* stream-ordered pool */
+int mnf_free(mnf_ctx* ctx, void* ptr);
+int mnf_host_alloc(size_t bytes, void** out); /* pinned */
+int mnf_host_free(void* ptr);
+int mnf_memcpy_h2d(mnf_ctx* ctx, void* dst, const void* h_src, size_t bytes);
+int mnf_memcpy_d2h(mnf_ctx* ctx, void* h_dst, const void* src, size_t bytes);
+int mnf_memcpy_d2d(mnf_ctx* ctx, void* dst, const void* src, size_t bytes);
+int mnf_memset(mnf_ctx* ctx, void* dst, int value, size_t bytes);
+
+/* events for device-side timing on the context's stream */
+int mnf_event_create(void** out);
+int mnf_event_destroy(void* ev);
+int mnf_event_record(mnf_ctx* ctx, void* ev);
+int mnf_event_elapsed_ms(void* start, void* stop, float* out); /* synchronises on stop */
+
+/* CUDA-graph capture of everything enqueued between begin/end on the context's stream */
+int mnf_graph_begin(mnf_ctx* ctx);
+int mnf_graph_end(mnf_ctx* ctx, void** graph_exec_out);
+int mnf_graph_launch(mnf_ctx* ctx, void* graph_exec);
+int mnf_graph_destroy(void* graph_exec);
+
+/* ---- DLPack (zero-copy exchange with TF / any producer) ------------------------------- */
+typedef struct {
+  void* data;       /* device pointer incl. byte_offset */
+  int32_t ndim;
+  int64_t shape[6];
+  int32_t device_type; /* DLDeviceType; 2 = kDLCUDA */
+  int32_t device_id;
+  int32_t dtype_code, dtype_bits; /* 2,32 = float32 */
+  int32_t contiguous;
+} mnf_tensor_view;
+/* dl_managed_tensor: the pointer held by a "dltensor" PyCapsule (DLManagedTensor*).
+ * Borrowed view: the capsule keeps ownership. */
+int mnf_dlpack_view(void* dl_managed_tensor, mnf_tensor_view* out);
+/* Wrap device memory as a new DLManagedTensor*; when the consumer calls its deleter,
+ * release(release_arg) is invoked (may be NULL). */
+int mnf_dlpack_wrap(void* data, int32_t ndim, const int64_t* shape, int32_t device_id,
+                    void (*release)(void*), void* release_arg, void** out_dl_managed_tensor);
+/* Call the deleter of a DLManagedTensor* nobody consumed (capsule destructor path). */
+int mnf_dlpack_delete(void* dl_managed_tensor);
+
+/* ---- noise ---------------------------------------------------------------------------- */
+typedef struct {
+  uint64_t seed;         /* Philox key */
+  uint64_t row_offset;   /* global index of local row 0 (shard invariance) */
+  uint32_t stream;       /* sub-stream: distinguishes layers / draws */
+  uint32_t reserved;
+  const float* injected; /* if non-NULL: read the draw from here instead ([rows, outer, inner]) */
+} mnf_noise;
+
+/* Materialise exactly the values a kernel would draw for (seed, stream, row_offset):
+ * replaces tf.random.normal (mnf_dense.py:94,141,167; mnf_conv.py:106,156,165,194). */
+int mnf_philox_normal(mnf_ctx* ctx, uint64_t seed, uint32_t stream, uint64_t row_offset,
+                      int64_t rows, int64_t outer, int64_t inner, float* out);
+/* keras.backend.random_binomial(shape, p=0.5) (rnvp.py:36): 1.0f where uniform <= p. */
+int mnf_philox_bernoulli(mnf_ctx* ctx, uint64_t seed, uint32_t stream, uint64_t row_offset,
+                         int64_t rows, int64_t inner, float p, float* out);
+/* raw 32-bit Philox words, for the bit-exact check against the oracle's integer Philox */
+int mnf_philox_raw(mnf_ctx* ctx, uint64_t seed, uint32_t stream, uint64_t row_offset,
+                   int64_t rows, int64_t outer, int64_t inner, uint32_t* out);
+
+/* ---- flows: NormalizingFlow.forward (flows/__init__.py:22-29) --------------------------- */
+enum { MNF_FLOW_IAF = 0, MNF_FLOW_RNVP = 1, MNF_FLOW_PLANAR = 2 };
+
+/* One flow step.  D = flow dimension, H = hidden units (one hidden layer).
+ *  IAF    (maf.py:47-53, made.py:28-30,77-91): w1 [D,H], b1 [H] = first MaskedDense;
+ *         ws/wt = second MaskedDense kernel [H,2D] columns [0,D) / [D,2D) (ld2 = 2D),
+ *         bs/bt likewise halves of its bias; m1 [D,H], m2 [H,2D] optional masks (NULL = ones).
+ *  RNVP   (rnvp.py:33-47): w1,b1 = net Dense(H,tanh); ws,bs = s Dense; wt,bt = t Dense (ld2 = D);
+ *         bern = Bernoulli mask draw (injected or Philox).
+ *  PLANAR (planar.py:22-36): w1 = dense kernel w [D], b1 = dense bias [1], wt = u [D]. */
+typedef struct {
+  int32_t kind, parity, hidden, reserved;
+  const float *w1, *b1, *ws, *bs, *wt, *bt;
+  int64_t ld2;
+  const float *m1, *m2;
+  mnf_noise bern;
+} mnf_flow_step;
+
+/* sample_z + flow chain (mnf_dense.py:88-102, mnf_conv.py:100-114).
+ *  z0 != NULL: start from z0 [B,D].  Otherwise z0 = q0_mean + exp(q0_log_var/2) * eps_z.
+ *  states [T+1,B,D]: every intermediate state (the LIST the reference returns); the last
+ *  slice is z_T.  log_dets [B] = sum of per-step log-determinants (may be NULL).
+ *  saved (may be NULL) [T,B,H]: hidden activations kept for mnf_flow_backward. */
+int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, const mnf_flow_step* h_steps,
+                     const float* z0, const float* q0_mean, const float* q0_log_var,
+                     const mnf_noise* eps_z, float* states, float* log_dets, float* saved);
+
+/* Gradient of the chain (TF autodiff of the above).
+ *  d_states [T+1,B,D]: upstream grads for each state (NULL slices not supported: pass zeros),
+ *  d_log_dets [B] (NULL = zeros).  Outputs: d_z0 [B,D]; per-step parameter grads written to
+ *  the buffers in h_grad_steps (same layout as mnf_flow_step, pointers non-const via cast;
+ *  ws/wt grads honour ld2).  Grads are ACCUMULATED (+=) so the caller zeroes them. */
+int mnf_flow_backward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, const mnf_flow_step* h_steps,
+                      const float* states, const float* saved, const float* d_states,
+                      const float* d_log_dets, float* d_z0, const mnf_flow_step* h_grad_steps);
+/* d q0_mean / d q0_log_var from d_z0 (App. A-2): accumulated (+=). */
+int mnf_sample_z_backward(mnf_ctx* ctx, int64_t B, int64_t D, const float* d_z0,
+                          const float* q0_log_var, const mnf_noise* eps_z,
+                          float* d_q0_mean, float* d_q0_log_var);
+
+/* ---- layers ----------------------------------------------------------------------------- */
+/* MNFDense.call, mnf_dense.py:159-170:
+ *   y = (x*z) @ mean_W + mean_b + sqrt(x^2 @ min(exp(log_std_W),max_std)^2
+ *                                      + min(exp(log_var_b),max_std^2)) * eps
+ *  z [B,K] or NULL (use_z=False).  sd_out [B,N] (may be NULL) receives sqrt(V) for backward. */
+int mnf_dense_forward(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const float* x, const float* z,
+                      const float* mean_W, const float* log_std_W, const float* mean_b,
+                      const float* log_var_b, float max_std, const mnf_noise* eps,
+                      float* y, float* sd_out);
+/* App. A-1.  Outputs (all may be NULL to skip): dx [B,K], dz [B,K], d_mean_W, d_log_std_W [K,N],
+ * d_mean_b, d_log_var_b [N] (overwritten, not accumulated). */
+int mnf_dense_backward(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const float* x, const float* z,
+                       const float* mean_W, const float* log_std_W, const float* log_var_b,
+                       float max_std, const mnf_noise* eps, const float* sd, const float* dy,
+                       float* dx, float* dz, float* d_mean_W, float* d_log_std_W,
+                       float* d_mean_b, float* d_log_var_b);
+
+typedef struct {
+  int64_t B, H, W, C;  /* input NHWC */
+  int64_t kh, kw, F;   /* filters HWIO [kh,kw,C,F] */
+  int64_t stride;      /* same in both spatial dims */
+  int32_t same;        /* 0 = VALID, 1 = SAME (TF semantics) */
+} mnf_conv_shape;
+int mnf_conv_out_hw(const mnf_conv_shape* s, int64_t* Ho, int64_t* Wo);
+
+/* MNFConv2D.call, mnf_conv.py:182-197 (with the strides/padding the reference omits):
+ *   y = (conv(x,mean_W)+mean_b) * z[b,f] + sqrt(conv(x^2, var_W) + var_b) * eps
+ *  z [B,F] or NULL.  mean_out / sd_out [B,Ho,Wo,F] (may be NULL) saved for backward. */
+int mnf_conv2d_forward(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, const float* z,
+                       const float* mean_W, const float* log_std_W, const float* mean_b,
+                       const float* log_var_b, float max_std, const mnf_noise* eps,
+                       float* y, float* mean_out, float* sd_out);
+/* App. A-1c. */
+int mnf_conv2d_backward(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, const float* z,
+                        const float* mean_W, const float* log_std_W, const float* log_var_b,
+                        float max_std, const mnf_noise* eps, const float* mean_saved,
+                        const float* sd, const float* dy, float* dx, float* dz,
+                        float* d_mean_W, float* d_log_std_W, float* d_mean_b, float* d_log_var_b);
+
+/* ---- KL --------------------------------------------------------------------------------- */
+/* Parameters of one MNF layer as the KL needs them.  For MNFDense (mnf_dense.py:104-157):
+ * rows = n_in = D, cols = n_out, z multiplies ROWS.  For MNFConv2D (mnf_conv.py:116-180):
+ * rows = kh*kw*C, cols = F = D, z multiplies COLUMNS (conv = 1). */
+typedef struct {
+  int32_t conv;    /* 0 dense, 1 conv */
+  int32_t use_z;
+  int32_t r_all_states; /* 1: Gaussian r-term summed over all T+1 r-flow states (as written, App. B-3) */
+  int32_t n_r_states;   /* T_r + 1 */
+  int64_t rows, cols;
+  const float *mean_W, *log_std_W, *mean_b, *log_var_b;
+  const float *prior_var_r_p /*[rows]*/, *prior_var_r_p_bias /*[1]*/;
+  const float *q0_log_var, *r0_mean, *r0_log_var, *r0_apvar; /* [D] */
+  const float* z;        /* [D] final q-flow state of sample_z(1) */
+  const float* ld_q;     /* [1] */
+  const float* r_states; /* [n_r_states, D] states of flow_r.forward(z) */
+  const float* ld_r;     /* [1] */
+  mnf_noise eps_a;       /* dense: [cols]; conv: [rows] */
+  mnf_noise eps_b;       /* conv only: scalar */
+} mnf_kl_args;
+
+typedef struct { /* gradient outputs of mnf_kl_backward; all overwritten; NULL = skip */
+  float *mean_W, *log_std_W, *mean_b, *log_var_b, *prior_var_r_p, *prior_var_r_p_bias;
+  float *q0_log_var, *r0_mean, *r0_log_var, *r0_apvar;
+  float* d_z;        /* [D]  dKL/dz (direct terms; flow_r's contribution comes via d_r_states) */
+  float* d_r_states; /* [n_r_states, D] */
+} mnf_kl_grads;        /* note dKL/d(ld_q) = dKL/d(ld_r) = -scale (feed to mnf_flow_backward) */
+
+/* kl_out [1] (device).  Single pass over the weights + one finishing block. */
+int mnf_kl_forward(mnf_ctx* ctx, const mnf_kl_args* a, float* kl_out);
+/* scale = upstream dLoss/dKL (host scalar, e.g. 1/len(X_train)). */
+int mnf_kl_backward(mnf_ctx* ctx, const mnf_kl_args* a, float scale, mnf_kl_grads* g);
+
+/* ---- stock layers between MNF layers (mnf_lenet.py:23-32) ------------------ */
+/* ReLU followed by MaxPool2D(2x2, stride 2, padding SAME), NHWC.  argmax (may be NULL)
+ * receives the int8 window index (0..3) of the max for the backward pass. */
+int mnf_relu_maxpool2(mnf_ctx* ctx, int64_t B, int64_t H, int64_t W, int64_t C, const float* x,
+                      float* y, int8_t* argmax);
+int mnf_relu_maxpool2_backward(mnf_ctx* ctx, int64_t B, int64_t H, int64_t W, int64_t C,
+                               const float* x, const int8_t* argmax, const float* dy, float* dx);
+int mnf_relu(mnf_ctx* ctx, int64_t n, const float* x, float* y);
+int mnf_relu_backward(mnf_ctx* ctx, int64_t n, const float* x, const float* dy, float* dx);
+int mnf_softmax(mnf_ctx* ctx, int64_t B, int64_t N, const float* x, float* y);
+/* mean categorical cross-entropy of softmax(logits) vs one-hot labels (lenet_mnist.py:53-57);
+ * loss_out [1]; d_logits [B,N] (may be NULL) = (softmax - labels) / B_global. */
+int mnf_softmax_xent(mnf_ctx* ctx, int64_t B, int64_t N, const float* logits, const float* labels,
+                     float inv_global_batch, float* loss_out, float* d_logits);
+/* y = a*x + b (inference-mode BatchNormalization in MNFFeedForward), generic axpby helpers */
+int mnf_scale(mnf_ctx* ctx, int64_t n, float a, const float* x, float* y);
+int mnf_axpy(mnf_ctx* ctx, int64_t n, float a, const float* x, float* y); /* y += a*x */
+/* Adam update on a flat parameter buffer (lenet_mnist.py:47,115). */
+int mnf_adam_step(mnf_ctx* ctx, int64_t n, float* param, const float* grad, float* m, float* v,
+                  float lr, float beta1, float beta2, float eps, int32_t step);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* MNF_B200_H */

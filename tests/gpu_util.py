@@ -1,0 +1,119 @@
+"""Helpers for the GPU parity tests: build host layers / flows whose parameters come from a
+fixture or from the oracle's parameter dicts, and Philox in NumPy (bit-exact integer part)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def philox4x32_10(c, k):
+    """Vectorised Philox4x32-10.  c: uint32 [...,4], k: (k0,k1)."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c0, c1, c2, c3 = (c[..., i].astype(np.uint64) for i in range(4))
+    k0, k1 = np.uint64(k[0]), np.uint64(k[1])
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(M0) * c0
+        p1 = np.uint64(M1) * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + np.uint64(W0)) & mask
+        k1 = (k1 + np.uint64(W1)) & mask
+    return np.stack([c0, c1, c2, c3], -1).astype(np.uint32)
+
+
+def philox_words(seed64, stream, row_offset, rows, outer, inner):
+    """The raw words libmnf_b200 draws for a [rows, outer, inner] tensor (include/mnf_b200.h)."""
+    inner4 = (inner + 3) // 4
+    r, o, q = np.meshgrid(np.arange(rows, dtype=np.uint64), np.arange(outer, dtype=np.uint64),
+                          np.arange(inner4, dtype=np.uint64), indexing="ij")
+    grow = r + np.uint64(row_offset)
+    c3 = np.uint64(stream) ^ ((grow >> np.uint64(32)) << np.uint64(24))
+    c = np.stack([q, o, grow & np.uint64(0xFFFFFFFF), c3 & np.uint64(0xFFFFFFFF)], -1).astype(np.uint32)
+    w = philox4x32_10(c, (seed64 & 0xFFFFFFFF, (seed64 >> 32) & 0xFFFFFFFF))
+    return w.reshape(rows, outer, inner4 * 4)[:, :, :inner]
+
+
+def box_muller_f64(words):
+    """float64 restatement of csrc/common.cuh:box_muller on [..., 4k] words."""
+    w = words.reshape(*words.shape[:-1], -1, 2).astype(np.float64)
+    u = ((w[..., 0].astype(np.uint64) >> np.uint64(8)).astype(np.float64) + 0.5) / 16777216.0
+    v = ((w[..., 1].astype(np.uint64) >> np.uint64(8)).astype(np.float64) + 0.5) / 16777216.0
+    r = np.sqrt(-2 * np.log(u))
+    th = 2 * np.pi * (v - 0.5)
+    return np.stack([r * np.cos(th), r * np.sin(th)], -1).reshape(words.shape)
+
+
+def assign_flow(fl, st):
+    """Copy an oracle-layout flow step (dict of float arrays) into a host flow object."""
+    f32 = lambda a: np.asarray(a, np.float32)  # noqa: E731
+    kind = st["kind"]
+    if kind == "iaf":
+        l1, l2 = fl.net.layers
+        l1.kernel.assign(f32(st["W"][0])), l1.bias.assign(f32(st["b"][0]))
+        l2.kernel.assign(f32(st["W"][1])), l2.bias.assign(f32(st["b"][1]))
+        masks = st.get("masks")
+        if masks is not None and not all(np.all(np.asarray(m) == 1) for m in masks):
+            l1.set_mask(masks[0], l1.kernel.ctx), l2.set_mask(masks[1], l2.kernel.ctx)
+    elif kind == "rnvp":
+        fl.net_kernel.assign(f32(st["Wn"][0])), fl.net_bias.assign(f32(st["bn"][0]))
+        fl.t_kernel.assign(f32(st["Wt"])), fl.t_bias.assign(f32(st["bt"]))
+        fl.s_kernel.assign(f32(st["Ws"])), fl.s_bias.assign(f32(st["bs"]))
+    else:
+        fl.u.assign(f32(st["u"])), fl.w.assign(f32(st["w"])), fl.b.assign(f32(st["b"]))
+
+
+def make_flows(steps, D):
+    from tf_mnf_b200.flows import IAF, RNVP, PlanarFlow
+
+    out = []
+    for st in steps:
+        if st["kind"] == "iaf":
+            fl = IAF(parity=int(st["parity"]), h_sizes=(st["W"][0].shape[1],))
+        elif st["kind"] == "rnvp":
+            fl = RNVP(D, h_sizes=(st["Wn"][0].shape[1],))
+        else:
+            fl = PlanarFlow(D)
+        fl.build(D)
+        assign_flow(fl, st)
+        out.append(fl)
+    return out
+
+
+def make_layer(P, x_shape, max_std=1.0, use_z=True, r_term="all_states", stride=1, padding="VALID", **kw):
+    """Host MNFDense / MNFConv2D carrying the parameters of oracle dict P."""
+    from tf_mnf_b200.layers import MNFConv2D, MNFDense
+
+    conv = P["mean_W"].ndim == 4
+    fq, fr = P["flow_q"], P["flow_r"]
+    kind = (fq or fr or [dict(kind="iaf")])[0]["kind"]
+    h = 50
+    for st in [*fq, *fr]:
+        h = st["W"][0].shape[1] if kind == "iaf" else st["Wn"][0].shape[1] if kind == "rnvp" else 50
+    common = dict(n_flows_q=len(fq), n_flows_r=len(fr), use_z=use_z, flow_h_sizes=(h,), max_std=max_std,
+                  flow_type=kind, r_term=r_term, **kw)
+    if conv:
+        kh, kw_, _, F = P["mean_W"].shape
+        lyr = MNFConv2D(F, (kh, kw_), strides=stride, padding=padding, **common)
+    else:
+        lyr = MNFDense(P["mean_W"].shape[1], **common)
+    lyr.build(x_shape)
+    for name in ("mean_W", "log_std_W", "mean_b", "log_var_b", "q0_mean", "q0_log_var", "r0_mean", "r0_log_var",
+                 "r0_apvar", "prior_var_r_p", "prior_var_r_p_bias"):
+        if name in P and hasattr(lyr, name):
+            getattr(lyr, name).assign(np.asarray(P[name], np.float32))
+    for fl, st in zip(lyr.flow_q.flows, fq):
+        assign_flow(fl, st)
+    for fl, st in zip(lyr.flow_r.flows, fr):
+        assign_flow(fl, st)
+    return lyr
+
+
+def close(a, b, rtol=1e-5, what=""):
+    """|a-b| <= rtol * max|b| elementwise-scale bound (fp32 parity bar, north_star: 1e-5 relative)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = max(np.max(np.abs(b)), 1e-30)
+    err = np.max(np.abs(a - b)) / scale
+    assert err <= rtol, f"{what}: max err / max|ref| = {err:.3e} > {rtol:g}"
+    return err

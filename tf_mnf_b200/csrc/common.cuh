@@ -1,0 +1,176 @@
+// Shared internals of libmnf_b200: context, error plumbing, Philox, small device helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mnf_b200.h"
+
+struct mnf_ctx {
+  int device;
+  cudaStream_t stream;
+  bool owns_stream;
+  int sm_count;
+  int64_t launches;
+  void* ws;  // grow-only device workspace
+  size_t ws_bytes;
+  bool capturing;
+  // timing probe: bracket the probe_skip-th launch of kernel family probe_kind with events
+  int probe_kind;
+  int probe_skip;
+  cudaEvent_t probe_start, probe_stop;
+};
+
+enum { MNF_PROBE_NONE = 0, MNF_PROBE_CONV_GEMM = 1, MNF_PROBE_DENSE_GEMM = 2, MNF_PROBE_FLOW_STEP = 3, MNF_PROBE_KL = 4 };
+
+// returns true when this launch is the probed one (and records the start event)
+static inline bool mnf_probe_begin(mnf_ctx* ctx, int kind) {
+  if (ctx->probe_kind != kind) return false;
+  if (ctx->probe_skip-- != 0) return false;
+  cudaEventRecord(ctx->probe_start, ctx->stream);
+  return true;
+}
+static inline void mnf_probe_end(mnf_ctx* ctx, bool on) {
+  if (on) {
+    cudaEventRecord(ctx->probe_stop, ctx->stream);
+    ctx->probe_kind = MNF_PROBE_NONE;
+  }
+}
+
+void mnf_set_error(const char* fmt, ...);
+void* mnf_workspace(mnf_ctx* ctx, size_t bytes);  // nullptr on failure (error set)
+
+#define MNF_CHECK_ARG(cond, ...)      \
+  do {                                \
+    if (!(cond)) {                    \
+      mnf_set_error(__VA_ARGS__);     \
+      return MNF_ERR_INVALID;         \
+    }                                 \
+  } while (0)
+
+#define MNF_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      mnf_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return MNF_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+// after a kernel launch: count it and surface launch-configuration errors
+#define MNF_LAUNCHED(ctx)                                                           \
+  do {                                                                              \
+    (ctx)->launches++;                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      mnf_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return MNF_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------- Philox
+// Philox4x32-10 (Salmon et al. 2011).  counter = (c0,c1,c2,c3), key = (k0,k1).
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                            uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+#else
+    uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+// Device-side view of mnf_noise.
+struct NoiseDev {
+  uint32_t k0, k1;
+  uint32_t stream;
+  uint64_t row_offset;
+  const float* injected;
+};
+
+static inline NoiseDev make_noise(const mnf_noise* n) {
+  NoiseDev d;
+  if (n) {
+    d.k0 = (uint32_t)n->seed; d.k1 = (uint32_t)(n->seed >> 32);
+    d.stream = n->stream; d.row_offset = n->row_offset; d.injected = n->injected;
+  } else {
+    d.k0 = d.k1 = 0; d.stream = 0; d.row_offset = 0; d.injected = nullptr;
+  }
+  return d;
+}
+
+#ifdef __CUDACC__
+// counter layout documented in include/mnf_b200.h; rows beyond 2^32 spill into the top
+// 8 bits of the stream word.
+__device__ __forceinline__ Philox4 philox_at(const NoiseDev& n, uint64_t grow, uint32_t outer, uint32_t inner4) {
+  uint32_t c3 = n.stream ^ ((uint32_t)(grow >> 32) << 24);
+  return philox4x32_10(inner4, outer, (uint32_t)grow, c3, n.k0, n.k1);
+}
+
+__device__ __forceinline__ float u01_open(uint32_t x) {  // (0,1), 24 bits
+  return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+}
+
+// Box-Muller on two 32-bit words -> two N(0,1)
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+  float u = u01_open(a);
+  float v = u01_open(b);
+  float r = sqrtf(-2.0f * __logf(u));
+  float s, c;
+  __sincosf(6.283185307179586f * (v - 0.5f), &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+
+__device__ __forceinline__ void philox_normal4(const NoiseDev& n, uint64_t grow, uint32_t outer, uint32_t inner4,
+                                               float out[4]) {
+  Philox4 p = philox_at(n, grow, outer, inner4);
+  box_muller(p.x, p.y, out[0], out[1]);
+  box_muller(p.z, p.w, out[2], out[3]);
+}
+
+// one normal at (row, outer, inner); `stride_*` describe the injected layout [rows, outer, inner]
+__device__ __forceinline__ float noise_normal1(const NoiseDev& n, int64_t lrow, uint32_t outer, uint32_t inner,
+                                               int64_t n_outer, int64_t n_inner) {
+  if (n.injected) return n.injected[(lrow * n_outer + outer) * n_inner + inner];
+  float v[4];
+  philox_normal4(n, n.row_offset + (uint64_t)lrow, outer, inner >> 2, v);
+  return v[inner & 3];
+}
+
+__device__ __forceinline__ float noise_bern1(const NoiseDev& n, int64_t lrow, uint32_t inner, int64_t n_inner,
+                                             float p) {
+  if (n.injected) return n.injected[lrow * n_inner + inner];
+  Philox4 q = philox_at(n, n.row_offset + (uint64_t)lrow, 0u, inner >> 2);
+  uint32_t w = (inner & 3) == 0 ? q.x : (inner & 3) == 1 ? q.y : (inner & 3) == 2 ? q.z : q.w;
+  return u01_open(w) <= p ? 1.0f : 0.0f;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif

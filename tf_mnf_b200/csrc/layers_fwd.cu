@@ -1,0 +1,338 @@
+// MNFDense.call (mnf_dense.py:159-170) and MNFConv2D.call (mnf_conv.py:182-197) forward:
+// the paired mean/variance contraction with the local-reparameterisation epilogue fused in.
+//
+// fp32-exact path (<= 1e-5 rel. vs the fp64 oracle): register-blocked FFMA GEMM / implicit
+// GEMM.  One staged x tile feeds BOTH products: the loader writes a1 = x*z (dense) or x
+// (conv) and a2 = x*x into shared memory; the CTA accumulates mean and variance tiles side
+// by side and the epilogue adds the biases, applies the conv z-scale, draws eps from Philox
+// (or reads the injected draw) and writes y once.
+#include "common.cuh"
+
+#define PG_BM 128
+#define PG_BK 16
+#define PG_TM 8
+#define PG_TN 4
+#define PG_PAD 4
+
+struct PairedArgs {
+  int64_t M;  // rows of the (implicit) GEMM: B (dense) or B*Ho*Wo (conv)
+  int K, N;
+  const float* x;
+  const float* z;   // dense: [M,K]; conv: [B,N]; nullptr = ones
+  const float* Wm;  // [K,N]
+  const float* Vw;  // [K,N] clipped variance (precomputed)
+  const float* bm;  // [N]
+  const float* vb;  // [N] clipped bias variance
+  float* y;
+  float* mean_out;  // conv: pre-z mean (for dz in backward); may be nullptr
+  float* sd_out;    // sqrt(V); may be nullptr
+  NoiseDev eps;
+  // conv geometry
+  int H, W, C, kh, kw, Ho, Wo, stride, pad_t, pad_l;
+};
+
+// Vw = min(exp(Ls), max_std)^2 ; vb = min(exp(lvb), max_std^2)   (mnf_dense.py:163-165)
+__global__ void prep_var_kernel(int64_t nW, const float* __restrict__ Ls, float max_std, float* __restrict__ Vw,
+                                int N, const float* __restrict__ lvb, float* __restrict__ vb) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nW; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = fminf(expf(Ls[i]), max_std);
+    Vw[i] = s * s;
+    if (i < N) vb[i] = fminf(expf(lvb[i]), max_std * max_std);
+  }
+}
+
+template <bool CONV, int BN>
+__global__ void __launch_bounds__((PG_BM / PG_TM) * (BN / PG_TN)) paired_gemm_fwd(PairedArgs a) {
+  constexpr int NT = (PG_BM / PG_TM) * (BN / PG_TN);
+  constexpr int TXN = BN / PG_TN;
+  constexpr int A_PER = PG_BM * PG_BK / NT;  // A elements per thread per k-step
+  constexpr int B_PER = PG_BK * BN / NT;
+  constexpr int AROWS = NT / PG_BK;          // rows covered per pass of the A loader
+
+  __shared__ __align__(16) float As1[PG_BK][PG_BM + PG_PAD];
+  __shared__ __align__(16) float As2[PG_BK][PG_BM + PG_PAD];
+  __shared__ __align__(16) float Bs1[PG_BK][BN + PG_PAD];
+  __shared__ __align__(16) float Bs2[PG_BK][BN + PG_PAD];
+  __shared__ int64_t rowoff[CONV ? PG_BM : 1];
+  __shared__ short rhi[CONV ? PG_BM : 1], rwi[CONV ? PG_BM : 1];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TXN, ty = tid / TXN;
+  const int64_t m0 = (int64_t)blockIdx.x * PG_BM;
+  const int n0 = blockIdx.y * BN;
+  const int K = a.K, N = a.N;
+
+  if (CONV) {
+    for (int m = tid; m < PG_BM; m += NT) {
+      int64_t gm = m0 + m;
+      if (gm < a.M) {
+        int pix = (int)(gm % ((int64_t)a.Ho * a.Wo));
+        int64_t b = gm / ((int64_t)a.Ho * a.Wo);
+        int ho = pix / a.Wo, wo = pix - ho * a.Wo;
+        int hi0 = ho * a.stride - a.pad_t, wi0 = wo * a.stride - a.pad_l;
+        rowoff[m] = ((b * a.H + hi0) * a.W + wi0) * a.C;
+        rhi[m] = (short)hi0;
+        rwi[m] = (short)wi0;
+      } else {
+        rowoff[m] = 0;
+        rhi[m] = (short)-20000;  // forces the bounds check to fail
+        rwi[m] = 0;
+      }
+    }
+    __syncthreads();
+  }
+
+  float acc1[PG_TM][PG_TN], acc2[PG_TM][PG_TN];
+#pragma unroll
+  for (int i = 0; i < PG_TM; ++i)
+#pragma unroll
+    for (int j = 0; j < PG_TN; ++j) acc1[i][j] = acc2[i][j] = 0.f;
+
+  const int ak = tid % PG_BK;   // this thread's k within the tile
+  const int am = tid / PG_BK;   // first row it loads
+  float ra1[A_PER], ra2[A_PER], rb1[B_PER], rb2[B_PER];
+
+  auto load_tiles = [&](int k0) {
+    const int kk = k0 + ak;
+    if (CONV) {
+      int i = 0, j = 0, c = 0;
+      int64_t koff = 0;
+      const bool kok = kk < K;
+      if (kok) {
+        int kwC = a.kw * a.C;
+        i = kk / kwC;
+        int rem = kk - i * kwC;
+        j = rem / a.C;
+        c = rem - j * a.C;
+        koff = ((int64_t)i * a.W + j) * a.C + c;
+      }
+#pragma unroll
+      for (int q = 0; q < A_PER; ++q) {
+        int m = am + AROWS * q;
+        float v = 0.f;
+        int hi = rhi[m] + i, wi = rwi[m] + j;
+        if (kok && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) v = __ldg(a.x + rowoff[m] + koff);
+        ra1[q] = v;
+        ra2[q] = v * v;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < A_PER; ++q) {
+        int64_t gm = m0 + am + AROWS * q;
+        float v = 0.f, zv = 1.f;
+        if (gm < a.M && kk < K) {
+          v = __ldg(a.x + gm * K + kk);
+          if (a.z) zv = __ldg(a.z + gm * K + kk);
+        }
+        ra1[q] = v * zv;
+        ra2[q] = v * v;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < B_PER; ++q) {
+      int e = tid + NT * q;
+      int n = e % BN, k = e / BN;
+      float w = 0.f, v = 0.f;
+      if (k0 + k < K && n0 + n < N) {
+        w = __ldg(a.Wm + (int64_t)(k0 + k) * N + n0 + n);
+        v = __ldg(a.Vw + (int64_t)(k0 + k) * N + n0 + n);
+      }
+      rb1[q] = w;
+      rb2[q] = v;
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int q = 0; q < A_PER; ++q) {
+      As1[ak][am + AROWS * q] = ra1[q];
+      As2[ak][am + AROWS * q] = ra2[q];
+    }
+#pragma unroll
+    for (int q = 0; q < B_PER; ++q) {
+      int e = tid + NT * q;
+      Bs1[e / BN][e % BN] = rb1[q];
+      Bs2[e / BN][e % BN] = rb2[q];
+    }
+  };
+
+  load_tiles(0);
+  for (int k0 = 0; k0 < K; k0 += PG_BK) {
+    store_tiles();
+    __syncthreads();
+    if (k0 + PG_BK < K) load_tiles(k0 + PG_BK);
+#pragma unroll
+    for (int k = 0; k < PG_BK; ++k) {
+      float4 p0 = *reinterpret_cast<const float4*>(&As1[k][ty * PG_TM]);
+      float4 p1 = *reinterpret_cast<const float4*>(&As1[k][ty * PG_TM + 4]);
+      float4 q0 = *reinterpret_cast<const float4*>(&As2[k][ty * PG_TM]);
+      float4 q1 = *reinterpret_cast<const float4*>(&As2[k][ty * PG_TM + 4]);
+      float4 bw = *reinterpret_cast<const float4*>(&Bs1[k][tx * PG_TN]);
+      float4 bv = *reinterpret_cast<const float4*>(&Bs2[k][tx * PG_TN]);
+      float a1[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+      float a2[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      float b1[4] = {bw.x, bw.y, bw.z, bw.w};
+      float b2[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < PG_TM; ++i)
+#pragma unroll
+        for (int j = 0; j < PG_TN; ++j) {
+          acc1[i][j] = fmaf(a1[i], b1[j], acc1[i][j]);
+          acc2[i][j] = fmaf(a2[i], b2[j], acc2[i][j]);
+        }
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: bias, (conv) z-scale, sqrt(V) * eps
+  const int nb = n0 + tx * PG_TN;
+  if (nb >= N) return;
+  float bmv[PG_TN], vbv[PG_TN];
+#pragma unroll
+  for (int j = 0; j < PG_TN; ++j) {
+    bmv[j] = nb + j < N ? a.bm[nb + j] : 0.f;
+    vbv[j] = nb + j < N ? a.vb[nb + j] : 1.f;
+  }
+  const int64_t HoWo = CONV ? (int64_t)a.Ho * a.Wo : 1;
+#pragma unroll
+  for (int i = 0; i < PG_TM; ++i) {
+    const int64_t gm = m0 + ty * PG_TM + i;
+    if (gm >= a.M) continue;
+    const int64_t brow = CONV ? gm / HoWo : gm;
+    const uint32_t outer = CONV ? (uint32_t)(gm - brow * HoWo) : 0u;
+    float e[4];
+    if (a.eps.injected) {
+#pragma unroll
+      for (int j = 0; j < PG_TN; ++j) e[j] = nb + j < N ? a.eps.injected[gm * N + nb + j] : 0.f;
+    } else {
+      philox_normal4(a.eps, a.eps.row_offset + (uint64_t)brow, outer, (uint32_t)(nb >> 2), e);
+    }
+    float out[PG_TN], mo[PG_TN], so[PG_TN];
+#pragma unroll
+    for (int j = 0; j < PG_TN; ++j) {
+      float mean = acc1[i][j] + bmv[j];
+      float sd = sqrtf(acc2[i][j] + vbv[j]);
+      mo[j] = mean;
+      so[j] = sd;
+      if (CONV) {
+        float zv = (a.z && nb + j < N) ? __ldg(a.z + brow * N + nb + j) : 1.f;
+        mean *= zv;
+      }
+      out[j] = fmaf(sd, e[j], mean);
+    }
+    float* yp = a.y + gm * N + nb;
+    if ((N & 3) == 0) {
+      *reinterpret_cast<float4*>(yp) = make_float4(out[0], out[1], out[2], out[3]);
+      if (a.sd_out) *reinterpret_cast<float4*>(a.sd_out + gm * N + nb) = make_float4(so[0], so[1], so[2], so[3]);
+      if (CONV && a.mean_out)
+        *reinterpret_cast<float4*>(a.mean_out + gm * N + nb) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < PG_TN; ++j)
+        if (nb + j < N) {
+          yp[j] = out[j];
+          if (a.sd_out) a.sd_out[gm * N + nb + j] = so[j];
+          if (CONV && a.mean_out) a.mean_out[gm * N + nb + j] = mo[j];
+        }
+    }
+  }
+}
+
+template <bool CONV>
+static int launch_paired(mnf_ctx* ctx, const PairedArgs& a) {
+  dim3 grid((unsigned)cdiv(a.M, PG_BM), 1);
+  const bool probed = mnf_probe_begin(ctx, CONV ? MNF_PROBE_CONV_GEMM : MNF_PROBE_DENSE_GEMM);
+  if (a.N > 32) {
+    grid.y = (unsigned)cdiv(a.N, 64);
+    paired_gemm_fwd<CONV, 64><<<grid, (PG_BM / PG_TM) * (64 / PG_TN), 0, ctx->stream>>>(a);
+  } else if (a.N > 16) {
+    paired_gemm_fwd<CONV, 32><<<grid, (PG_BM / PG_TM) * (32 / PG_TN), 0, ctx->stream>>>(a);
+  } else {
+    paired_gemm_fwd<CONV, 16><<<grid, (PG_BM / PG_TM) * (16 / PG_TN), 0, ctx->stream>>>(a);
+  }
+  mnf_probe_end(ctx, probed);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+// workspace layout for one layer call: Vw [K*N] then vb [N]
+static int prep_var(mnf_ctx* ctx, int64_t KN, int N, const float* Ls, const float* lvb, float max_std, float** Vw,
+                    float** vb) {
+  size_t bytes = sizeof(float) * (size_t)(KN + N + 8);
+  float* ws = (float*)mnf_workspace(ctx, bytes);
+  if (!ws) return MNF_ERR_CUDA;
+  *Vw = ws;
+  *vb = ws + ((KN + 3) / 4) * 4;
+  int64_t nthr = KN > N ? KN : N;
+  int grid = (int)(cdiv(nthr, 256) < ctx->sm_count * 8 ? cdiv(nthr, 256) : ctx->sm_count * 8);
+  prep_var_kernel<<<grid, 256, 0, ctx->stream>>>(nthr, Ls, max_std, *Vw, N, lvb, *vb);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+extern "C" {
+
+int mnf_conv_out_hw(const mnf_conv_shape* s, int64_t* Ho, int64_t* Wo) {
+  MNF_CHECK_ARG(s && Ho && Wo, "mnf_conv_out_hw: NULL argument");
+  MNF_CHECK_ARG(s->stride >= 1 && s->kh >= 1 && s->kw >= 1, "mnf_conv_out_hw: bad kernel/stride");
+  if (s->same) {
+    *Ho = cdiv(s->H, s->stride);
+    *Wo = cdiv(s->W, s->stride);
+  } else {
+    MNF_CHECK_ARG(s->H >= s->kh && s->W >= s->kw, "conv VALID: input %lldx%lld smaller than kernel %lldx%lld",
+                  (long long)s->H, (long long)s->W, (long long)s->kh, (long long)s->kw);
+    *Ho = (s->H - s->kh) / s->stride + 1;
+    *Wo = (s->W - s->kw) / s->stride + 1;
+  }
+  return MNF_OK;
+}
+
+int mnf_dense_forward(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const float* x, const float* z,
+                      const float* mean_W, const float* log_std_W, const float* mean_b, const float* log_var_b,
+                      float max_std, const mnf_noise* eps, float* y, float* sd_out) {
+  MNF_CHECK_ARG(ctx && x && mean_W && log_std_W && mean_b && log_var_b && y, "mnf_dense_forward: NULL argument");
+  MNF_CHECK_ARG(B >= 0 && K >= 1 && N >= 1 && K < (1 << 30) && N < (1 << 30), "mnf_dense_forward: bad shape");
+  MNF_CHECK_ARG(eps, "mnf_dense_forward: eps noise spec is NULL");
+  if (B == 0) return MNF_OK;
+  float *Vw, *vb;
+  // note: the second rounded-up offset inside prep_var must match (K*N padded to 4)
+  int rc = prep_var(ctx, K * N, (int)N, log_std_W, log_var_b, max_std, &Vw, &vb);
+  if (rc) return rc;
+  PairedArgs a = {};
+  a.M = B; a.K = (int)K; a.N = (int)N;
+  a.x = x; a.z = z; a.Wm = mean_W; a.Vw = Vw; a.bm = mean_b; a.vb = vb;
+  a.y = y; a.mean_out = nullptr; a.sd_out = sd_out; a.eps = make_noise(eps);
+  return launch_paired<false>(ctx, a);
+}
+
+int mnf_conv2d_forward(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, const float* z, const float* mean_W,
+                       const float* log_std_W, const float* mean_b, const float* log_var_b, float max_std,
+                       const mnf_noise* eps, float* y, float* mean_out, float* sd_out) {
+  MNF_CHECK_ARG(ctx && s && x && mean_W && log_std_W && mean_b && log_var_b && y, "mnf_conv2d_forward: NULL argument");
+  MNF_CHECK_ARG(eps, "mnf_conv2d_forward: eps noise spec is NULL");
+  MNF_CHECK_ARG(s->B >= 0 && s->H >= 1 && s->W >= 1 && s->C >= 1 && s->F >= 1 && s->H < 16384 && s->W < 16384,
+                "mnf_conv2d_forward: bad input shape");
+  int64_t Ho, Wo;
+  int rc = mnf_conv_out_hw(s, &Ho, &Wo);
+  if (rc) return rc;
+  if (s->B == 0) return MNF_OK;
+  const int64_t Kc = s->kh * s->kw * s->C;
+  MNF_CHECK_ARG(Kc < (1 << 30) && s->F < (1 << 30), "mnf_conv2d_forward: filter too large");
+  float *Vw, *vb;
+  rc = prep_var(ctx, Kc * s->F, (int)s->F, log_std_W, log_var_b, max_std, &Vw, &vb);
+  if (rc) return rc;
+  PairedArgs a = {};
+  a.M = s->B * Ho * Wo; a.K = (int)Kc; a.N = (int)s->F;
+  a.x = x; a.z = z; a.Wm = mean_W; a.Vw = Vw; a.bm = mean_b; a.vb = vb;
+  a.y = y; a.mean_out = mean_out; a.sd_out = sd_out; a.eps = make_noise(eps);
+  a.H = (int)s->H; a.W = (int)s->W; a.C = (int)s->C; a.kh = (int)s->kh; a.kw = (int)s->kw;
+  a.Ho = (int)Ho; a.Wo = (int)Wo; a.stride = (int)s->stride;
+  a.pad_t = a.pad_l = 0;
+  if (s->same) {  // TF SAME: total pad = max((out-1)*stride + k - in, 0), smaller half first
+    int64_t ph = (Ho - 1) * s->stride + s->kh - s->H, pw = (Wo - 1) * s->stride + s->kw - s->W;
+    a.pad_t = (int)((ph > 0 ? ph : 0) / 2);
+    a.pad_l = (int)((pw > 0 ? pw : 0) / 2);
+  }
+  return launch_paired<true>(ctx, a);
+}
+
+}  // extern "C"

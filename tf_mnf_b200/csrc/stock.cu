@@ -1,0 +1,218 @@
+// Stock layers that sit between the MNF layers in the reference models
+// (mnf_lenet.py:23-32: ReLU, MaxPool2D(padding="SAME"), Flatten, Softmax;
+//  mnf_feed_forward.py:20: ReLU, inference-mode BatchNormalization) plus the training-step
+// closure pieces (lenet_mnist.py:53-57 cross-entropy, :47,115 Adam).  SURVEY.md 8(f)-1,3.
+#include "common.cuh"
+
+static inline int ew_grid(mnf_ctx* ctx, int64_t n, int threads = 256) {
+  int64_t g = cdiv(n, threads), cap = (int64_t)ctx->sm_count * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// ReLU then 2x2/stride-2 max-pool with TF "SAME" padding (pad only at bottom/right for odd sizes)
+__global__ void relu_maxpool2_kernel(int64_t B, int H, int W, int C, int Ho, int Wo, const float* __restrict__ x,
+                                     float* __restrict__ y, int8_t* __restrict__ argmax) {
+  const int64_t total = B * Ho * Wo * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int wo = (int)(t % Wo);
+    t /= Wo;
+    int ho = (int)(t % Ho);
+    int64_t b = t / Ho;
+    float best = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int hi = 2 * ho + (q >> 1), wi = 2 * wo + (q & 1);
+      if (hi < H && wi < W) {
+        float v = __ldg(x + ((b * H + hi) * W + wi) * C + c);
+        if (v > best) { best = v; arg = q; }
+      }
+    }
+    y[i] = fmaxf(best, 0.f);
+    if (argmax) argmax[i] = (int8_t)arg;
+  }
+}
+
+__global__ void relu_maxpool2_bwd_kernel(int64_t B, int H, int W, int C, int Ho, int Wo, const float* __restrict__ x,
+                                         const int8_t* __restrict__ argmax, const float* __restrict__ dy,
+                                         float* __restrict__ dx) {
+  const int64_t total = B * H * W * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int wi = (int)(t % W);
+    t /= W;
+    int hi = (int)(t % H);
+    int64_t b = t / H;
+    int ho = hi >> 1, wo = wi >> 1;
+    int q = ((hi & 1) << 1) | (wi & 1);
+    int64_t o = ((b * Ho + ho) * Wo + wo) * C + c;
+    float g = (argmax[o] == q && x[i] > 0.f) ? dy[o] : 0.f;
+    dx[i] = g;
+  }
+}
+
+__global__ void relu_kernel(int64_t n, const float* __restrict__ x, float* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = fmaxf(x[i], 0.f);
+}
+__global__ void relu_bwd_kernel(int64_t n, const float* __restrict__ x, const float* __restrict__ dy,
+                                float* __restrict__ dx) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] = x[i] > 0.f ? dy[i] : 0.f;
+}
+__global__ void scale_kernel(int64_t n, float a, const float* __restrict__ x, float* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = a * x[i];
+}
+__global__ void axpy_kernel(int64_t n, float a, const float* __restrict__ x, float* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = fmaf(a, x[i], y[i]);
+}
+
+// warp per row softmax (N small: class count)
+__global__ void softmax_kernel(int64_t B, int N, const float* __restrict__ x, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  float mx = -INFINITY;
+  for (int j = lane; j < N; j += 32) mx = fmaxf(mx, x[row * N + j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float s = 0.f;
+  for (int j = lane; j < N; j += 32) s += expf(x[row * N + j] - mx);
+  s = warp_sum(s);
+  for (int j = lane; j < N; j += 32) y[row * N + j] = expf(x[row * N + j] - mx) / s;
+}
+
+// loss = mean_b( -sum_j labels * log softmax ), d_logits = (softmax * sum(labels) - labels) * inv_global_batch
+__global__ void softmax_xent_kernel(int64_t B, int N, const float* __restrict__ x, const float* __restrict__ lab,
+                                    float inv_gb, float* loss_out, float* __restrict__ dlog) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  float l = 0.f;
+  if (row < B) {
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, x[row * N + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float s = 0.f, ls = 0.f;
+    for (int j = lane; j < N; j += 32) {
+      s += expf(x[row * N + j] - mx);
+      ls += lab[row * N + j];
+    }
+    s = warp_sum(s);
+    ls = warp_sum(ls);
+    float lse = mx + logf(s);
+    for (int j = lane; j < N; j += 32) {
+      float lp = x[row * N + j] - lse;
+      l -= lab[row * N + j] * lp;
+      if (dlog) dlog[row * N + j] = (expf(lp) * ls - lab[row * N + j]) * inv_gb;
+    }
+    l = warp_sum(l);
+  }
+  if (lane == 0 && row < B) atomicAdd(loss_out, l * inv_gb);
+}
+
+__global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, float lr_t, float b1, float b2, float eps) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+extern "C" {
+
+int mnf_relu_maxpool2(mnf_ctx* ctx, int64_t B, int64_t H, int64_t W, int64_t C, const float* x, float* y,
+                      int8_t* argmax) {
+  MNF_CHECK_ARG(ctx && x && y && B >= 0 && H >= 1 && W >= 1 && C >= 1, "mnf_relu_maxpool2: bad argument");
+  if (B == 0) return MNF_OK;
+  int Ho = (int)cdiv(H, 2), Wo = (int)cdiv(W, 2);
+  relu_maxpool2_kernel<<<ew_grid(ctx, B * Ho * Wo * C), 256, 0, ctx->stream>>>(B, (int)H, (int)W, (int)C, Ho, Wo, x, y,
+                                                                            argmax);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+int mnf_relu_maxpool2_backward(mnf_ctx* ctx, int64_t B, int64_t H, int64_t W, int64_t C, const float* x,
+                               const int8_t* argmax, const float* dy, float* dx) {
+  MNF_CHECK_ARG(ctx && x && argmax && dy && dx && B >= 0 && H >= 1 && W >= 1 && C >= 1,
+                "mnf_relu_maxpool2_backward: bad argument");
+  if (B == 0) return MNF_OK;
+  int Ho = (int)cdiv(H, 2), Wo = (int)cdiv(W, 2);
+  relu_maxpool2_bwd_kernel<<<ew_grid(ctx, B * H * W * C), 256, 0, ctx->stream>>>(B, (int)H, (int)W, (int)C, Ho, Wo, x,
+                                                                              argmax, dy, dx);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+int mnf_relu(mnf_ctx* ctx, int64_t n, const float* x, float* y) {
+  MNF_CHECK_ARG(ctx && (n == 0 || (x && y)) && n >= 0, "mnf_relu: bad argument");
+  if (n == 0) return MNF_OK;
+  relu_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(n, x, y);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+int mnf_relu_backward(mnf_ctx* ctx, int64_t n, const float* x, const float* dy, float* dx) {
+  MNF_CHECK_ARG(ctx && (n == 0 || (x && dy && dx)) && n >= 0, "mnf_relu_backward: bad argument");
+  if (n == 0) return MNF_OK;
+  relu_bwd_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(n, x, dy, dx);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+int mnf_softmax(mnf_ctx* ctx, int64_t B, int64_t N, const float* x, float* y) {
+  MNF_CHECK_ARG(ctx && x && y && B >= 0 && N >= 1 && N < (1 << 30), "mnf_softmax: bad argument");
+  if (B == 0) return MNF_OK;
+  softmax_kernel<<<(unsigned)cdiv(B, 8), 256, 0, ctx->stream>>>(B, (int)N, x, y);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+int mnf_softmax_xent(mnf_ctx* ctx, int64_t B, int64_t N, const float* logits, const float* labels,
+                     float inv_global_batch, float* loss_out, float* d_logits) {
+  MNF_CHECK_ARG(ctx && logits && labels && loss_out && B >= 0 && N >= 1 && N < (1 << 30), "mnf_softmax_xent: bad argument");
+  MNF_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), ctx->stream));
+  if (B == 0) return MNF_OK;
+  softmax_xent_kernel<<<(unsigned)cdiv(B, 8), 256, 0, ctx->stream>>>(B, (int)N, logits, labels, inv_global_batch,
+                                                                     loss_out, d_logits);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+int mnf_scale(mnf_ctx* ctx, int64_t n, float a, const float* x, float* y) {
+  MNF_CHECK_ARG(ctx && (n == 0 || (x && y)) && n >= 0, "mnf_scale: bad argument");
+  if (n == 0) return MNF_OK;
+  scale_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(n, a, x, y);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+int mnf_axpy(mnf_ctx* ctx, int64_t n, float a, const float* x, float* y) {
+  MNF_CHECK_ARG(ctx && (n == 0 || (x && y)) && n >= 0, "mnf_axpy: bad argument");
+  if (n == 0) return MNF_OK;
+  axpy_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(n, a, x, y);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+int mnf_adam_step(mnf_ctx* ctx, int64_t n, float* param, const float* grad, float* m, float* v, float lr, float beta1,
+                  float beta2, float eps, int32_t step) {
+  MNF_CHECK_ARG(ctx && (n == 0 || (param && grad && m && v)) && n >= 0 && step >= 1, "mnf_adam_step: bad argument");
+  if (n == 0) return MNF_OK;
+  // Keras/TF Adam: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t); update = lr_t * m / (sqrt(v) + eps)
+  double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step));
+  adam_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(n, param, grad, m, v, (float)lr_t, beta1, beta2, eps);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+}  // extern "C"

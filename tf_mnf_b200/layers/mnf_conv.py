@@ -1,0 +1,96 @@
+"""MNFConv2D on libmnf_b200 (reference: tf_mnf/layers/mnf_conv.py:11-197)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any
+
+from .. import _lib as L
+from .. import noise as nz
+from ..runtime import DeviceArray, as_device, default_context
+from .base import MNFLayerBase, _p
+
+
+def conv_out_hw(H: int, W: int, kh: int, kw: int, stride: int, padding: str) -> tuple[int, int]:
+    """TF output-size rule for VALID / SAME (host-side twin of mnf_conv_out_hw)."""
+    if padding == "SAME":
+        return -(-H // stride), -(-W // stride)
+    if H < kh or W < kw:
+        raise ValueError(f"VALID convolution: input {H}x{W} is smaller than the kernel {kh}x{kw}")
+    return (H - kh) // stride + 1, (W - kw) // stride + 1
+
+
+class MNFConv2D(MNFLayerBase):
+    """Bayesian conv2d layer, multiplicative noise on the OUTPUT filters (z scales conv+bias,
+    mnf_conv.py:193).  `strides` / `padding` are the constructor arguments the reference's
+    callers already pass (mnf_lenet.py:22,25) but its `call` forgets to use (App. B-1)."""
+
+    _conv = True
+
+    def __init__(self, n_filters: int, kernel_size, strides: int = 1, padding: str = "VALID", **kwargs: Any) -> None:
+        self.n_filters = int(n_filters)
+        self.kernel_size = [kernel_size, kernel_size] if isinstance(kernel_size, int) else list(kernel_size)
+        if len(self.kernel_size) != 2:
+            raise ValueError("kernel_size must be an int or a pair")
+        if isinstance(strides, (tuple, list)):
+            if len(set(strides)) != 1:
+                raise NotImplementedError("different strides per spatial dimension")
+            strides = strides[0]
+        self.strides = int(strides)
+        self.padding = str(padding).upper()
+        if self.padding not in ("VALID", "SAME"):
+            raise ValueError(f"padding must be 'VALID' or 'SAME', got {padding!r}")
+        self.input_dim: int | None = None
+        self.stack_size: int | None = None
+        super().__init__(**kwargs)
+
+    def _flow_dim(self) -> int:
+        return self.n_filters
+
+    def _kl_shape(self):
+        return self.input_dim, self.n_filters
+
+    def build(self, input_shape) -> None:
+        self.stack_size = int(input_shape[-1])
+        n_rows, n_cols = self.kernel_size
+        self.input_dim = n_cols * self.stack_size * n_rows
+        self._build_common((n_rows, n_cols, self.stack_size, self.n_filters), self.input_dim)
+
+    def _shape(self, x: DeviceArray) -> L.ConvShape:
+        s = L.ConvShape()
+        s.B, s.H, s.W, s.C = x.shape
+        s.kh, s.kw = self.kernel_size
+        s.F, s.stride, s.same = self.n_filters, self.strides, int(self.padding == "SAME")
+        return s
+
+    def call(self, x: Any, noise: dict | None = None) -> DeviceArray:  # noqa: A002
+        """mnf_conv.py:182-197.  noise: {eps_z [B,F], bern_q [...], eps_out [B,Ho,Wo,F]}."""
+        self.ctx = self.ctx or default_context()
+        x = as_device(x, self.ctx)
+        if x.ndim != 4:
+            raise ValueError(f"MNFConv2D expects NHWC input, got shape {x.shape}")
+        if not self.built:
+            self.build(x.shape)
+        if x.shape[3] != self.stack_size:
+            raise ValueError(f"MNFConv2D built for {self.stack_size} input channels, got {x.shape[3]}")
+        ctx, B = self.ctx, x.shape[0]
+        Ho, Wo = conv_out_hw(x.shape[1], x.shape[2], *self.kernel_size, self.strides, self.padding)
+        inj = noise or {}
+        z, _, run = self._sample_z(B, nz.CALL_Z, nz.BERN_Q_CALL, inj, self.training, self.row_offset)
+        oshape = (B, Ho, Wo, self.n_filters)
+        eo = as_device(inj["eps_out"], ctx) if inj.get("eps_out") is not None else None
+        if eo is not None and eo.shape != oshape:
+            raise ValueError(f"injected eps_out must have shape {oshape}, got {eo.shape}")
+        eps = nz.make(self.seed, self.call_index, self.uid, nz.CALL_OUT, self.row_offset, eo)
+        y = ctx.empty(oshape)
+        mean = ctx.empty(oshape) if self.training else None
+        sd = ctx.empty(oshape) if self.training else None
+        s = self._shape(x)
+        L.check(ctx.lib.mnf_conv2d_forward(ctx.handle, C.byref(s), _p(x), _p(z), _p(self.mean_W), _p(self.log_std_W),
+                                           _p(self.mean_b), _p(self.log_var_b), self.max_std, C.byref(eps),
+                                           _p(y), _p(mean), _p(sd)))
+        if self.training:
+            self._tape = dict(x=x, z=z, run=run, mean=mean, sd=sd, eps=eps, eps_keep=eo, shape=s)
+        self.call_index += 1
+        return y
+
+    __call__ = call

@@ -1,0 +1,62 @@
+"""MNFDense on libmnf_b200 (reference: tf_mnf/layers/mnf_dense.py:11-170)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any
+
+from .. import _lib as L
+from .. import noise as nz
+from ..runtime import DeviceArray, as_device, default_context
+from .base import MNFLayerBase, _p
+
+
+class MNFDense(MNFLayerBase):
+    """Bayesian dense layer with multiplicative normalizing-flow noise on the INPUT units.
+    Same constructor and methods as the reference class; tensors are DeviceArrays (DLPack /
+    __cuda_array_interface__), or NumPy arrays which are copied to the GPU first."""
+
+    _conv = False
+
+    def __init__(self, n_out: int, **kwargs: Any) -> None:
+        self.n_out = int(n_out)
+        self.n_in: int | None = None
+        super().__init__(**kwargs)
+
+    def _flow_dim(self) -> int:
+        return self.n_in
+
+    def _kl_shape(self):
+        return self.n_in, self.n_out
+
+    def build(self, input_shape) -> None:
+        self.n_in = int(input_shape[-1])
+        self._build_common((self.n_in, self.n_out), self.n_in)
+
+    def call(self, x: Any, noise: dict | None = None) -> DeviceArray:  # noqa: A002
+        """mnf_dense.py:159-170.  noise: optional injected draws {eps_z [B,n_in], bern_q [...], eps_out [B,n_out]}."""
+        self.ctx = self.ctx or default_context()
+        x = as_device(x, self.ctx)
+        if x.ndim != 2:
+            raise ValueError(f"MNFDense expects [batch, features], got shape {x.shape}")
+        if not self.built:
+            self.build(x.shape)
+        if x.shape[1] != self.n_in:
+            raise ValueError(f"MNFDense built for {self.n_in} input features, got {x.shape[1]}")
+        ctx, B = self.ctx, x.shape[0]
+        inj = noise or {}
+        z, _, run = self._sample_z(B, nz.CALL_Z, nz.BERN_Q_CALL, inj, self.training, self.row_offset)
+        eo = as_device(inj["eps_out"], ctx) if inj.get("eps_out") is not None else None
+        if eo is not None and eo.shape != (B, self.n_out):
+            raise ValueError(f"injected eps_out must have shape {(B, self.n_out)}, got {eo.shape}")
+        eps = nz.make(self.seed, self.call_index, self.uid, nz.CALL_OUT, self.row_offset, eo)
+        y = ctx.empty((B, self.n_out))
+        sd = ctx.empty((B, self.n_out)) if self.training else None
+        L.check(ctx.lib.mnf_dense_forward(ctx.handle, B, self.n_in, self.n_out, _p(x), _p(z), _p(self.mean_W),
+                                          _p(self.log_std_W), _p(self.mean_b), _p(self.log_var_b),
+                                          self.max_std, C.byref(eps), _p(y), _p(sd)))
+        if self.training:
+            self._tape = dict(x=x, z=z, run=run, sd=sd, eps=eps, eps_keep=eo)
+        self.call_index += 1
+        return y
+
+    __call__ = call

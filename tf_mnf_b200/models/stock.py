@@ -1,0 +1,145 @@
+"""The stock Keras layers the reference models put between MNF layers (mnf_lenet.py:23-32,
+mnf_feed_forward.py:20), as thin host objects over libmnf_b200's element-wise kernels, and
+a minimal Sequential container with the reference's `.layers` / `__call__` protocol."""
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+
+from .. import _lib as L
+from ..layers.base import _p
+from ..runtime import DeviceArray, as_device, default_context
+
+
+class StockLayer:
+    training = False
+
+    def backward(self, dy: DeviceArray) -> DeviceArray:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+
+class ReLU(StockLayer):
+    def __call__(self, x: DeviceArray) -> DeviceArray:
+        y = x.ctx.empty(x.shape)
+        L.check(x.ctx.lib.mnf_relu(x.ctx.handle, x.size, _p(x), _p(y)))
+        if self.training:
+            self._x = x
+        return y
+
+    def backward(self, dy):
+        dx = dy.ctx.empty(self._x.shape)
+        L.check(dy.ctx.lib.mnf_relu_backward(dy.ctx.handle, dx.size, _p(self._x), _p(dy), _p(dx)))
+        return dx
+
+
+class MaxPool2D(StockLayer):
+    """2x2 / stride 2 (Keras defaults).  padding="SAME" as in mnf_lenet.py:24,27."""
+
+    def __init__(self, pool_size=2, strides=None, padding: str = "VALID") -> None:
+        ps = pool_size if isinstance(pool_size, int) else pool_size[0]
+        st = ps if strides is None else (strides if isinstance(strides, int) else strides[0])
+        if ps != 2 or st != 2:
+            raise NotImplementedError("only the 2x2 / stride-2 pool of MNFLeNet is implemented")
+        self.padding = padding.upper()
+        self.fuse_relu = False
+
+    def _pool(self, x: DeviceArray, argmax) -> DeviceArray:
+        B, H, W, Cc = x.shape
+        if self.padding == "VALID" and (H % 2 or W % 2):
+            raise NotImplementedError("VALID max-pool on odd sizes")
+        y = x.ctx.empty((B, -(-H // 2), -(-W // 2), Cc))
+        L.check(x.ctx.lib.mnf_relu_maxpool2(x.ctx.handle, B, H, W, Cc, _p(x), _p(y), _p(argmax)))
+        return y
+
+
+class ReLUMaxPool2D(MaxPool2D):
+    """ReLU + MaxPool2D fused into one pass (relu(max) == max(relu))."""
+
+    def __call__(self, x: DeviceArray) -> DeviceArray:
+        am = None
+        if self.training:
+            B, H, W, Cc = x.shape
+            am = x.ctx.empty((B, -(-H // 2), -(-W // 2), Cc), "i1")
+            self._x, self._am = x, am
+        return self._pool(x, am)
+
+    def backward(self, dy):
+        x = self._x
+        dx = x.ctx.empty(x.shape)
+        L.check(x.ctx.lib.mnf_relu_maxpool2_backward(x.ctx.handle, *x.shape, _p(x), _p(self._am), _p(dy), _p(dx)))
+        return dx
+
+
+class Flatten(StockLayer):
+    def __call__(self, x: DeviceArray) -> DeviceArray:
+        self._shape = x.shape
+        return x.reshape(x.shape[0], -1)
+
+    def backward(self, dy):
+        return dy.reshape(self._shape)
+
+
+class Softmax(StockLayer):
+    def __call__(self, x: DeviceArray) -> DeviceArray:
+        y = x.ctx.empty(x.shape)
+        L.check(x.ctx.lib.mnf_softmax(x.ctx.handle, x.shape[0], x.shape[1], _p(x), _p(y)))
+        return y
+
+
+class BatchNormalization(StockLayer):
+    """Inference mode (what `model(x)` evaluates in the reference's loops): moving mean 0,
+    variance 1, epsilon 1e-3, gamma 1, beta 0  ->  y = x / sqrt(1 + 1e-3)."""
+
+    scale = float(1.0 / np.sqrt(1.0 + 1e-3))
+
+    def __call__(self, x: DeviceArray) -> DeviceArray:
+        y = x.ctx.empty(x.shape)
+        L.check(x.ctx.lib.mnf_scale(x.ctx.handle, x.size, self.scale, _p(x), _p(y)))
+        return y
+
+    def backward(self, dy):
+        dx = dy.ctx.empty(dy.shape)
+        L.check(dy.ctx.lib.mnf_scale(dy.ctx.handle, dy.size, self.scale, _p(dy), _p(dx)))
+        return dx
+
+
+class Sequential:
+    def __init__(self, layers=None) -> None:
+        self.layers = list(layers or [])
+
+    def __call__(self, x: Any, noise: list | None = None) -> DeviceArray:  # noqa: A002
+        """noise: optional list with one injected-draw dict per MNF layer (program order)."""
+        x = as_device(x, default_context())
+        it = iter(noise or [])
+        for lyr in self.layers:
+            if hasattr(lyr, "kl_div"):
+                x = lyr(x, noise=next(it, None))
+            else:
+                x = lyr(x)
+        return x
+
+    def kl_div(self, noise: list | None = None) -> DeviceArray:  # noqa: A002
+        """Sum of the layers' KL terms (mnf_lenet.py:35-39, mnf_feed_forward.py:23-28)."""
+        it = iter(noise or [])
+        total = None
+        for lyr in self.layers:
+            if hasattr(lyr, "kl_div"):
+                kl = lyr.kl_div(noise=next(it, None))
+                if total is None:
+                    total = kl
+                else:
+                    L.check(kl.ctx.lib.mnf_axpy(kl.ctx.handle, 1, 1.0, _p(kl), _p(total)))
+        return total
+
+    @property
+    def mnf_layers(self) -> list:
+        return [l for l in self.layers if hasattr(l, "kl_div")]
+
+    def set_training(self, flag: bool) -> None:
+        for lyr in self.layers:
+            lyr.training = flag
+
+    def set_row_offset(self, off: int) -> None:
+        for lyr in self.mnf_layers:
+            lyr.row_offset = int(off)

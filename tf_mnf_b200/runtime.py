@@ -1,0 +1,322 @@
+"""Device context and the DeviceArray handle the host classes pass around.
+
+DeviceArray is deliberately thin: a device pointer, a shape and an owner.  It speaks DLPack
+(`__dlpack__`) and `__cuda_array_interface__`, so TF (`tf.experimental.dlpack.from_dlpack`),
+PyTorch (`torch.from_dlpack` / `torch.as_tensor`) or CuPy consume it zero-copy, and
+`as_device()` accepts any of those producers zero-copy in the other direction.
+NumPy inputs are copied host->device explicitly (what Keras does for the reference when
+it is handed a NumPy batch, notebooks/lenet_mnist.py:84); compute never runs on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Any, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+_DT = {"f4": np.float32, "i1": np.int8, "u4": np.uint32}
+
+
+class Context:
+    """One (device, stream, workspace).  Not thread-safe: use one context per thread."""
+
+    def __init__(self, device: int = 0, stream: int | None = None) -> None:
+        self.lib = L.load()
+        h = C.c_void_p()
+        L.check(self.lib.mnf_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.handle = h
+        self.device = device
+
+    # -- memory
+    def empty(self, shape: Sequence[int], dtype: str = "f4") -> "DeviceArray":
+        shape = tuple(int(s) for s in shape)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(_DT[dtype]).itemsize
+        p = C.c_void_p()
+        L.check(self.lib.mnf_malloc(self.handle, nbytes, C.byref(p)))
+        return DeviceArray(self, p.value, shape, dtype, owner=_Owned(self, p.value))
+
+    def zeros(self, shape: Sequence[int], dtype: str = "f4") -> "DeviceArray":
+        a = self.empty(shape, dtype)
+        L.check(self.lib.mnf_memset(self.handle, a.ptr, 0, a.nbytes))
+        return a
+
+    def to_device(self, arr: Any, dtype: str = "f4") -> "DeviceArray":
+        h = np.ascontiguousarray(arr, dtype=_DT[dtype])
+        a = self.empty(h.shape, dtype)
+        L.check(self.lib.mnf_memcpy_h2d(self.handle, a.ptr, h.ctypes.data, h.nbytes))
+        self.sync()  # h may be a temporary
+        return a
+
+    def sync(self) -> None:
+        L.check(self.lib.mnf_ctx_sync(self.handle))
+
+    def set_stream(self, stream: int) -> None:
+        L.check(self.lib.mnf_ctx_set_stream(self.handle, C.c_void_p(stream)))
+
+    @property
+    def stream(self) -> int:
+        p = C.c_void_p()
+        L.check(self.lib.mnf_ctx_get_stream(self.handle, C.byref(p)))
+        return p.value or 0
+
+    @property
+    def sm_count(self) -> int:
+        n = C.c_int()
+        L.check(self.lib.mnf_ctx_sm_count(self.handle, C.byref(n)))
+        return n.value
+
+    @property
+    def launches(self) -> int:
+        n = C.c_int64()
+        L.check(self.lib.mnf_ctx_launch_count(self.handle, C.byref(n)))
+        return n.value
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.lib.mnf_ctx_destroy(self.handle)
+            self.handle = None
+
+
+class _Owned:
+    """Frees a stream-ordered allocation when the last view dies."""
+
+    def __init__(self, ctx: Context, ptr: int) -> None:
+        self.ctx, self.ptr = ctx, ptr
+
+    def __del__(self) -> None:
+        try:
+            if self.ctx.handle:
+                self.ctx.lib.mnf_free(self.ctx.handle, C.c_void_p(self.ptr))
+        except Exception:  # interpreter shutdown
+            pass
+
+
+_tls = threading.local()
+
+
+def default_context(device: int | None = None) -> Context:
+    """Per-thread, per-device default context (created on first use; fails without a GPU)."""
+    ctxs = getattr(_tls, "ctxs", None)
+    if ctxs is None:
+        ctxs = _tls.ctxs = {}
+    if device is None:
+        device = getattr(_tls, "device", 0)
+    if device not in ctxs:
+        ctxs[device] = Context(device)
+    return ctxs[device]
+
+
+def set_default_device(device: int) -> None:
+    _tls.device = device
+
+
+class DeviceArray:
+    __slots__ = ("ctx", "ptr", "shape", "dtype", "owner", "__weakref__")
+
+    def __init__(self, ctx: Context, ptr: int, shape, dtype: str = "f4", owner: Any = None) -> None:
+        self.ctx, self.ptr, self.shape, self.dtype, self.owner = ctx, int(ptr or 0), tuple(shape), dtype, owner
+
+    # -- basic properties
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape, dtype=np.int64))
+
+    @property
+    def itemsize(self) -> int:
+        return np.dtype(_DT[self.dtype]).itemsize
+
+    @property
+    def nbytes(self) -> int:
+        return self.size * self.itemsize
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+    def __len__(self) -> int:
+        return self.shape[0]
+
+    def __repr__(self) -> str:
+        return f"DeviceArray(shape={self.shape}, dtype={self.dtype}, ptr=0x{self.ptr:x}, device={self.ctx.device})"
+
+    # -- views
+    def reshape(self, *shape) -> "DeviceArray":
+        if len(shape) == 1 and not isinstance(shape[0], (int, np.integer)):
+            shape = tuple(shape[0])
+        shape = list(shape)
+        if -1 in shape:
+            i = shape.index(-1)
+            rest = int(np.prod([s for s in shape if s != -1], dtype=np.int64))
+            shape[i] = self.size // max(rest, 1)
+        if int(np.prod(shape, dtype=np.int64)) != self.size:
+            raise ValueError(f"cannot reshape {self.shape} to {tuple(shape)}")
+        return DeviceArray(self.ctx, self.ptr, shape, self.dtype, self.owner)
+
+    def __getitem__(self, idx) -> "DeviceArray":
+        """Leading-axis integer index or contiguous slice (a view)."""
+        inner = int(np.prod(self.shape[1:], dtype=np.int64)) * self.itemsize
+        if isinstance(idx, (int, np.integer)):
+            i = int(idx) % self.shape[0] if self.shape[0] else 0
+            return DeviceArray(self.ctx, self.ptr + i * inner, self.shape[1:], self.dtype, self.owner)
+        if isinstance(idx, slice):
+            start, stop, step = idx.indices(self.shape[0])
+            if step != 1:
+                raise ValueError("only contiguous slices are views")
+            n = max(stop - start, 0)
+            return DeviceArray(self.ctx, self.ptr + start * inner, (n, *self.shape[1:]), self.dtype, self.owner)
+        raise TypeError("DeviceArray supports leading-axis int / slice indexing only")
+
+    # -- host transfer
+    def numpy(self) -> np.ndarray:
+        out = np.empty(self.shape, _DT[self.dtype])
+        if self.nbytes:
+            L.check(self.ctx.lib.mnf_memcpy_d2h(self.ctx.handle, out.ctypes.data, C.c_void_p(self.ptr), self.nbytes))
+            self.ctx.sync()
+        return out
+
+    def copy_from_host(self, arr) -> "DeviceArray":
+        h = np.ascontiguousarray(arr, dtype=_DT[self.dtype])
+        if h.shape != self.shape:
+            raise ValueError(f"shape mismatch: {h.shape} vs {self.shape}")
+        L.check(self.ctx.lib.mnf_memcpy_h2d(self.ctx.handle, C.c_void_p(self.ptr), h.ctypes.data, h.nbytes))
+        self.ctx.sync()
+        return self
+
+    def copy(self) -> "DeviceArray":
+        out = self.ctx.empty(self.shape, self.dtype)
+        L.check(self.ctx.lib.mnf_memcpy_d2d(self.ctx.handle, C.c_void_p(out.ptr), C.c_void_p(self.ptr), self.nbytes))
+        return out
+
+    def assign(self, value) -> "DeviceArray":
+        """tf.Variable.assign look-alike (host array or device array)."""
+        if isinstance(value, DeviceArray):
+            if value.shape != self.shape:
+                raise ValueError(f"shape mismatch: {value.shape} vs {self.shape}")
+            L.check(self.ctx.lib.mnf_memcpy_d2d(self.ctx.handle, C.c_void_p(self.ptr), C.c_void_p(value.ptr), self.nbytes))
+            return self
+        return self.copy_from_host(value)
+
+    # -- zero-copy export
+    @property
+    def __cuda_array_interface__(self) -> dict:
+        typestr = {"f4": "<f4", "i1": "|i1", "u4": "<u4"}[self.dtype]
+        return {"shape": self.shape, "typestr": typestr, "data": (self.ptr, False), "version": 3,
+                "strides": None, "stream": self.ctx.stream or None}
+
+    def __dlpack_device__(self):
+        return (2, self.ctx.device)  # kDLCUDA
+
+    def __dlpack__(self, stream=None, **_):
+        if self.dtype != "f4":
+            raise TypeError("DLPack export is float32 only")
+        self.ctx.sync()  # old-style capsules carry no stream: hand over finished data
+        keep = _KEEP.pin(self)
+        shape = (C.c_int64 * max(self.ndim, 1))(*self.shape)
+        out = C.c_void_p()
+        L.check(self.ctx.lib.mnf_dlpack_wrap(C.c_void_p(self.ptr), self.ndim, shape, self.ctx.device,
+                                             _RELEASE, C.c_void_p(keep), C.byref(out)))
+        return _capsule_new(out.value)
+
+
+class _KeepAlive:
+    """Keeps exported arrays alive until the DLPack consumer calls the deleter."""
+
+    def __init__(self) -> None:
+        self.live: dict[int, Any] = {}
+        self.n = 0
+        self.lock = threading.Lock()
+
+    def pin(self, obj) -> int:
+        with self.lock:
+            self.n += 1
+            self.live[self.n] = obj
+            return self.n
+
+    def release(self, key) -> None:
+        with self.lock:
+            self.live.pop(int(key or 0), None)
+
+
+_KEEP = _KeepAlive()
+_RELEASE = L.RELEASE_FN(lambda key: _KEEP.release(key))
+
+_PyCapsule_New = C.pythonapi.PyCapsule_New
+_PyCapsule_New.restype = C.py_object
+_PyCapsule_New.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+_PyCapsule_GetPointer = C.pythonapi.PyCapsule_GetPointer
+_PyCapsule_GetPointer.restype = C.c_void_p
+_PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+_PyCapsule_IsValid = C.pythonapi.PyCapsule_IsValid
+_PyCapsule_IsValid.restype = C.c_int
+_PyCapsule_IsValid.argtypes = [C.py_object, C.c_char_p]
+
+
+_IsValid_raw = C.PYFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p)(("PyCapsule_IsValid", C.pythonapi))
+_GetPointer_raw = C.PYFUNCTYPE(C.c_void_p, C.c_void_p, C.c_char_p)(("PyCapsule_GetPointer", C.pythonapi))
+
+
+@C.PYFUNCTYPE(None, C.c_void_p)
+def _capsule_destructor(cap_ptr):
+    # a consumer renames the capsule to "used_dltensor"; if it is still "dltensor" nobody took it
+    if _IsValid_raw(cap_ptr, b"dltensor"):
+        L.load().mnf_dlpack_delete(C.c_void_p(_GetPointer_raw(cap_ptr, b"dltensor")))
+
+
+def _capsule_new(ptr: int):
+    return _PyCapsule_New(ptr, b"dltensor", C.cast(_capsule_destructor, C.c_void_p))
+
+
+def dlpack_view(capsule) -> L.TensorView:
+    """Borrowed view of a "dltensor" capsule (the capsule keeps ownership)."""
+    if not _PyCapsule_IsValid(capsule, b"dltensor"):
+        raise ValueError("expected an unconsumed 'dltensor' PyCapsule")
+    p = _PyCapsule_GetPointer(capsule, b"dltensor")
+    tv = L.TensorView()
+    L.check(L.load().mnf_dlpack_view(C.c_void_p(p), C.byref(tv)))
+    return tv
+
+
+def as_device(x: Any, ctx: Context | None = None) -> DeviceArray:
+    """Zero-copy view of a device tensor from any framework, or an explicit H2D copy of a
+    NumPy array.  float32 and C-contiguous only; anything else is an error (no silent casts
+    on device tensors)."""
+    if isinstance(x, DeviceArray):
+        return x
+    ctx = ctx or default_context()
+    cai = getattr(x, "__cuda_array_interface__", None)
+    if cai is not None:
+        if cai["typestr"] not in ("<f4", "=f4"):
+            raise ValueError(f"expected float32 device tensor, got {cai['typestr']}")
+        if cai.get("strides") is not None:
+            exp, ok = 4, True
+            for s, st in zip(reversed(cai["shape"]), reversed(cai["strides"])):
+                ok &= s == 1 or st == exp
+                exp *= s
+            if not ok:
+                raise ValueError("device tensor must be C-contiguous")
+        return DeviceArray(ctx, cai["data"][0], cai["shape"], "f4", owner=x)
+    if isinstance(x, np.ndarray) or isinstance(x, (list, tuple, float, int)):
+        return ctx.to_device(np.asarray(x, dtype=np.float32))
+    if hasattr(x, "__dlpack__"):
+        dev = x.__dlpack_device__() if hasattr(x, "__dlpack_device__") else (2, ctx.device)
+        if int(dev[0]) not in (2, 13):
+            raise ValueError(f"tensor is on DLPack device type {int(dev[0])}, not CUDA: tf_mnf_b200 has no CPU path")
+        cap = x.__dlpack__()
+        tv = dlpack_view(cap)
+        if (tv.dtype_code, tv.dtype_bits) != (2, 32) or not tv.contiguous:
+            raise ValueError("expected a C-contiguous float32 tensor")
+        shape = tuple(tv.shape[i] for i in range(tv.ndim))
+        return DeviceArray(ctx, tv.data, shape, "f4", owner=(cap, x))
+    raise TypeError(f"cannot interpret {type(x).__name__} as a device tensor")
+
+
+def from_dlpack_capsule(capsule, ctx: Context | None = None) -> DeviceArray:
+    """For TF 2.1-style `tf.experimental.dlpack.to_dlpack(t)` capsules."""
+    ctx = ctx or default_context()
+    tv = dlpack_view(capsule)
+    if (tv.dtype_code, tv.dtype_bits) != (2, 32) or not tv.contiguous:
+        raise ValueError("expected a C-contiguous float32 tensor")
+    return DeviceArray(ctx, tv.data, tuple(tv.shape[i] for i in range(tv.ndim)), "f4", owner=capsule)
