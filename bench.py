@@ -224,6 +224,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
             torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
+        L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
         step(x_dev)
     barrier()
 
@@ -251,6 +252,8 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     step_ms = [elapsed(a, b) for a, b in zip(starts, stops)]
     kern_ms = [elapsed(a, b) for a, b in zip(kst, ksp)]
     my_ms = float(np.mean(step_ms))
+    print(f"[rank {rank}] step_ms={np.round(step_ms, 3).tolist()} conv2_ms={np.round(kern_ms, 3).tolist()} "
+          f"wall_per_step_ms={t_wall / args.steps * 1e3:.3f}", file=sys.stderr, flush=True)
 
     # ---- e2e: host (pinned) input -> public API -> host result, copies inside the timed region
     hp = C.c_void_p()

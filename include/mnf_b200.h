@@ -157,12 +157,14 @@ int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, const mnf_fl
                      const mnf_noise* eps_z, float* states, float* log_dets, float* saved);
 
 /* Gradient of the chain (TF autodiff of the above).
- *  d_states [T+1,B,D]: upstream grads for each state (NULL slices not supported: pass zeros),
- *  d_log_dets [B] (NULL = zeros).  Outputs: d_z0 [B,D]; per-step parameter grads written to
- *  the buffers in h_grad_steps (same layout as mnf_flow_step, pointers non-const via cast;
- *  ws/wt grads honour ld2).  Grads are ACCUMULATED (+=) so the caller zeroes them. */
+ *  states [T+1,B,D], saved: what mnf_flow_forward wrote (saved must not be NULL).
+ *  d_states [T+1,B,D] or NULL: upstream grads for every state; d_zT [B,D] or NULL: an
+ *  additional upstream grad for the last state only; d_log_dets [B] (NULL = zeros).
+ *  Outputs: d_z0 [B,D]; per-step parameter grads are ACCUMULATED (+=) into the buffers named
+ *  by h_grad_steps (same slots as mnf_flow_step: w1,b1,ws,bs,wt,bt with ld2; planar: w1=dw,
+ *  b1=db, wt=du), so the caller zeroes them.  IAF masks are applied to the kernel grads. */
 int mnf_flow_backward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, const mnf_flow_step* h_steps,
-                      const float* states, const float* saved, const float* d_states,
+                      const float* states, const float* saved, const float* d_states, const float* d_zT,
                       const float* d_log_dets, float* d_z0, const mnf_flow_step* h_grad_steps);
 /* d q0_mean / d q0_log_var from d_z0 (App. A-2): accumulated (+=). */
 int mnf_sample_z_backward(mnf_ctx* ctx, int64_t B, int64_t D, const float* d_z0,

@@ -92,6 +92,8 @@ def test_flow_chain_oracle(ctx, kind, D, B, masks):
             if k.startswith("b"):
                 for b in v if isinstance(v, list) else [v]:
                     b[...] = 0.1 * rng.standard_normal(b.shape)
+        if kind == "iaf":  # keep exp(s) of three chained un-masked steps inside the fp32 range
+            st["W"][1] *= 0.25
     z = rng.standard_normal((B, D))
     bern = [(rng.uniform(size=(B, D)) <= 0.5).astype(np.float64) for _ in range(3)]
     ref_states, ref_ld, _ = O.flow_forward(z, steps, bern)

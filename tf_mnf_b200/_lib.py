@@ -91,7 +91,7 @@ SIGNATURES = {
     "mnf_philox_bernoulli": [vp, _u64, _u32, _u64, _i64, _i64, _f, vp],
     "mnf_philox_raw": [vp, _u64, _u32, _u64, _i64, _i64, _i64, vp],
     "mnf_flow_forward": [vp, _i64, _i64, _i32, C.POINTER(FlowStep), vp, vp, vp, C.POINTER(Noise), vp, vp, vp],
-    "mnf_flow_backward": [vp, _i64, _i64, _i32, C.POINTER(FlowStep), vp, vp, vp, vp, vp, C.POINTER(FlowStep)],
+    "mnf_flow_backward": [vp, _i64, _i64, _i32, C.POINTER(FlowStep), vp, vp, vp, vp, vp, vp, C.POINTER(FlowStep)],
     "mnf_sample_z_backward": [vp, _i64, _i64, vp, vp, C.POINTER(Noise), vp, vp],
     "mnf_dense_forward": [vp, _i64, _i64, _i64, vp, vp, vp, vp, vp, vp, _f, C.POINTER(Noise), vp, vp],
     "mnf_dense_backward": [vp, _i64, _i64, _i64, vp, vp, vp, vp, vp, _f, C.POINTER(Noise), vp, vp,

@@ -24,7 +24,9 @@ struct KlDev {
   float* part_vw;
   float* mw;        // [L]  (conv: written directly)
   float* vw;
-  float* aux;       // [L + 8]: a_j, then abar, mu_b, var_b, sd_b_eps
+  float* aux;       // [L + 8]: a_j, then abar, mu_b, var_b
+  float* dmw;       // [L] backward: dKL/d mean_w
+  float* dvw;       // [L] backward: dKL/d var_w
   unsigned int* counter;
   int nchunk;
   float* kl_out;
@@ -248,6 +250,8 @@ static int kl_plan(mnf_ctx* ctx, const mnf_kl_args* a, float* kl_out, KlPlan* ou
   size_t o_mw = take(sizeof(float) * L);
   size_t o_vw = take(sizeof(float) * L);
   size_t o_aux = take(sizeof(float) * (L + 8));
+  size_t o_dmw = take(sizeof(float) * L);
+  size_t o_dvw = take(sizeof(float) * L);
   size_t o_cnt = take(sizeof(unsigned int) * 4);
   char* ws = (char*)mnf_workspace(ctx, off);
   if (!ws) return MNF_ERR_CUDA;
@@ -257,6 +261,8 @@ static int kl_plan(mnf_ctx* ctx, const mnf_kl_args* a, float* kl_out, KlPlan* ou
   k.mw = (float*)(ws + o_mw);
   k.vw = (float*)(ws + o_vw);
   k.aux = (float*)(ws + o_aux);
+  k.dmw = (float*)(ws + o_dmw);
+  k.dvw = (float*)(ws + o_dvw);
   k.counter = (unsigned int*)(ws + o_cnt);
   return MNF_OK;
 }
@@ -267,6 +273,158 @@ extern "C" int mnf_kl_forward(mnf_ctx* ctx, const mnf_kl_args* a, float* kl_out)
   if (rc) return rc;
   MNF_CUDA(cudaMemsetAsync(p.k.counter, 0, sizeof(unsigned int) * 4, ctx->stream));
   kl_fwd_kernel<<<p.grid, KL_THREADS, 0, ctx->stream>>>(p.k);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+// ------------------------------------------------------------------------------ backward
+struct KlGradDev {
+  float *Wm, *Ls, *bm, *lvb, *p, *pb, *q0lv, *r0m, *r0lv, *cap, *dz, *drst;
+};
+
+// scalar tail of the backward pass: one CTA (App. A-4 / A-5 derivatives)
+__global__ void __launch_bounds__(KL_THREADS) kl_bwd_scalar(KlDev k, float scale, KlGradDev g) {
+  __shared__ double sh[32];
+  const int tid = threadIdx.x;
+  const int L = k.conv ? k.rows : k.cols;
+  const double pb = k.pb[0], epb = exp(pb);
+  // prior_var_r_p_bias (learn_p)
+  if (g.pb) {
+    double s = 0;
+    for (int j = tid; j < k.cols; j += blockDim.x) {
+      double b = k.bm[j];
+      if (k.conv && k.use_z) b *= k.z[j];
+      s += 1.0 - (exp((double)k.lvb[j]) + b * b) / epb;
+    }
+    s = block_sum_d(s, sh);
+    if (tid == 0) g.pb[0] = (float)(scale * 0.5 * s);
+  }
+  if (!k.use_z) {
+    for (int j = tid; j < k.cols; j += blockDim.x) {
+      if (g.bm) g.bm[j] = (float)(scale * k.bm[j] / epb);
+      if (g.lvb) g.lvb[j] = (float)(scale * 0.5 * (-1.0 + exp((double)k.lvb[j]) / epb));
+    }
+    return;
+  }
+  const double abar = k.aux[L], var_b = k.aux[L + 2];
+  // Gaussian r-term
+  double dab = 0;
+  const int s0 = k.r_all ? 0 : k.n_states - 1;
+  for (int d = tid; d < k.D; d += blockDim.x) {
+    double mr = abar * k.r0m[d], lv = abar * k.r0lv[d], e = exp(lv);
+    double s1 = 0, s2 = 0;
+    for (int st = 0; st < k.n_states; ++st) {
+      double diff = (double)k.rst[(size_t)st * k.D + d] - mr;
+      bool in = st >= s0;
+      if (in) { s1 += e * diff; s2 += -e * diff * diff + 1.0; }
+      if (g.drst) g.drst[(size_t)st * k.D + d] = in ? (float)(scale * e * diff) : 0.f;
+    }
+    double dmr = -scale * s1, dlv = -scale * 0.5 * s2;
+    if (g.r0m) g.r0m[d] = (float)(dmr * abar);
+    if (g.r0lv) g.r0lv[d] = (float)(dlv * abar);
+    if (g.q0lv) g.q0lv[d] = -0.5f * scale;
+    dab += dmr * k.r0m[d] + dlv * k.r0lv[d];
+  }
+  const double dabar = block_sum_d(dab, sh);
+  const double da = dabar / (double)L;
+  for (int j = tid; j < L; j += blockDim.x) {
+    float ea = noise_normal1(k.eps_a, 0, 0u, (uint32_t)j, 1, L);
+    double dpre = da;
+    if (!k.conv) {
+      double a = k.aux[j];
+      dpre = da * (1.0 - a * a);
+    }
+    k.dmw[j] = (float)dpre;
+    k.dvw[j] = (float)(dpre * ea / (2.0 * sqrt((double)k.vw[j])));
+  }
+  if (!k.conv) {
+    for (int j = tid; j < k.cols; j += blockDim.x) {
+      if (g.bm) g.bm[j] = (float)(scale * k.bm[j] / epb);
+      if (g.lvb) g.lvb[j] = (float)(scale * 0.5 * (-1.0 + exp((double)k.lvb[j]) / epb));
+    }
+  } else {
+    float eb = noise_normal1(k.eps_b, 0, 0u, 0u, 1, 1);
+    const double dmu_b = dabar, dvar_b = dabar * eb / (2.0 * sqrt(var_b));
+    for (int f = tid; f < k.cols; f += blockDim.x) {
+      double c = k.cap[f], zf = k.z[f], bmf = k.bm[f], bt = bmf * zf, elv = exp((double)k.lvb[f]);
+      double dbt = scale * bt / epb + dmu_b * c;
+      if (g.lvb) g.lvb[f] = (float)(scale * 0.5 * (-1.0 + elv / epb) + dvar_b * elv * c * c);
+      if (g.bm) g.bm[f] = (float)(dbt * zf);
+      if (g.dz) g.dz[f] = (float)(dbt * bmf);
+      if (g.cap) g.cap[f] = (float)(dmu_b * bt + dvar_b * 2.0 * c * elv);
+    }
+  }
+}
+
+// element-wise pass over the weights: warp per row
+__global__ void __launch_bounds__(KL_THREADS) kl_bwd_weights(KlDev k, float scale, KlGradDev g) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int i = blockIdx.x * (KL_THREADS / 32) + wid;
+  if (i >= k.rows) return;
+  const float pi = k.p[i], Pi = expf(pi);
+  float rs_dz = 0.f, rs_dc = 0.f, rs_dp = 0.f;
+  const float zi = (!k.conv && k.use_z) ? k.z[i] : 1.f;
+  const float ci = (!k.conv && k.use_z) ? k.cap[i] : 0.f;
+  const float dmw_i = (k.conv && k.use_z) ? k.dmw[i] : 0.f, dvw_i = (k.conv && k.use_z) ? k.dvw[i] : 0.f;
+  for (int j = lane; j < k.cols; j += 32) {
+    const size_t o = (size_t)i * k.cols + j;
+    float ls = __ldg(k.Ls + o), wm = __ldg(k.Wm + o);
+    float e = expf(ls), vt = e * e;
+    float gw, gl;
+    if (!k.conv) {
+      float mt = zi * wm;
+      float dmw = k.use_z ? k.dmw[j] : 0.f, dvw = k.use_z ? k.dvw[j] : 0.f;
+      gw = scale * mt * zi / Pi + zi * ci * dmw;
+      gl = scale * (-1.f + vt / Pi) + 2.f * vt * ci * ci * dvw;
+      rs_dz += scale * mt * wm / Pi + wm * dmw * ci;
+      rs_dc += mt * dmw + 2.f * ci * vt * dvw;
+      rs_dp += 1.f - (vt + mt * mt) / Pi;
+    } else {
+      float zf = k.use_z ? k.z[j] : 1.f, cf = k.use_z ? k.cap[j] : 0.f;
+      float mt = zf * wm;
+      gw = scale * mt * zf / Pi + dmw_i * zf * cf;
+      gl = scale * (-0.5f + vt / Pi) + 2.f * vt * dvw_i * cf * cf;
+      rs_dp += 1.f - (vt + mt * mt) / Pi;
+      if (k.use_z) {
+        if (g.dz) atomicAdd(g.dz + j, scale * mt * wm / Pi + wm * dmw_i * cf);
+        if (g.cap) atomicAdd(g.cap + j, mt * dmw_i + 2.f * cf * vt * dvw_i);
+      }
+    }
+    if (g.Wm) g.Wm[o] = gw;
+    if (g.Ls) g.Ls[o] = gl;
+  }
+  rs_dp = warp_sum(rs_dp);
+  if (!k.conv) {
+    rs_dz = warp_sum(rs_dz);
+    rs_dc = warp_sum(rs_dc);
+  }
+  if (lane == 0) {
+    if (g.p) g.p[i] = scale * 0.5f * rs_dp;
+    if (!k.conv && k.use_z) {
+      if (g.dz) g.dz[i] = rs_dz;
+      if (g.cap) g.cap[i] = rs_dc;
+    }
+  }
+}
+
+extern "C" int mnf_kl_backward(mnf_ctx* ctx, const mnf_kl_args* a, float scale, mnf_kl_grads* gr) {
+  MNF_CHECK_ARG(gr, "mnf_kl_backward: grads is NULL");
+  KlPlan p;
+  // the forward pass is re-run for its side outputs (mean_w, var_w, a, abar); its scalar
+  // result lands in a scratch slot of the workspace
+  float dummy_slot;
+  (void)dummy_slot;
+  int rc = kl_plan(ctx, a, (float*)1, &p);
+  if (rc) return rc;
+  p.k.kl_out = p.k.aux + ((a->conv ? a->rows : a->cols) + 4);
+  MNF_CUDA(cudaMemsetAsync(p.k.counter, 0, sizeof(unsigned int) * 4, ctx->stream));
+  kl_fwd_kernel<<<p.grid, KL_THREADS, 0, ctx->stream>>>(p.k);
+  MNF_LAUNCHED(ctx);
+  KlGradDev g = {gr->mean_W, gr->log_std_W, gr->mean_b, gr->log_var_b, gr->prior_var_r_p, gr->prior_var_r_p_bias,
+                 gr->q0_log_var, gr->r0_mean, gr->r0_log_var, gr->r0_apvar, gr->d_z, gr->d_r_states};
+  kl_bwd_scalar<<<1, KL_THREADS, 0, ctx->stream>>>(p.k, scale, g);
+  MNF_LAUNCHED(ctx);
+  kl_bwd_weights<<<(unsigned)cdiv(p.k.rows, KL_THREADS / 32), KL_THREADS, 0, ctx->stream>>>(p.k, scale, g);
   MNF_LAUNCHED(ctx);
   return MNF_OK;
 }

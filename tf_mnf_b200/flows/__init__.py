@@ -32,6 +32,33 @@ class NormalizingFlow:
         self.last_run = run
         return states, ld
 
+    def backward(self, d_states: Any = None, d_zT: Any = None, d_log_dets: Any = None):
+        """Gradient of the last `forward(z, record=True)`.  d_states [T+1,B,D] (grads for every
+        returned state), d_zT [B,D] (extra grad for the last state), d_log_dets [B].
+        Returns (d_z0, [ {name: grad} per flow ]) -- what tape.gradient gives in the reference."""
+        import ctypes as C
+
+        from .. import _lib as L
+        from ..runtime import as_device
+
+        run = self.last_run
+        if run is None or (run.saved is None and any(f.kind != L.MNF_FLOW_PLANAR for f in self.flows)):
+            raise RuntimeError("call forward(z, record=True) before backward()")
+        ctx = run.states.ctx
+        p = lambda a: C.c_void_p(a.ptr) if a is not None else None  # noqa: E731
+        ds = as_device(d_states, ctx) if d_states is not None else None
+        dz = as_device(d_zT, ctx) if d_zT is not None else None
+        dl = as_device(d_log_dets, ctx) if d_log_dets is not None else None
+        grads = [{n: ctx.zeros(v.shape) for n, v in fl.variables().items()} for fl in self.flows]
+        gsteps = (L.FlowStep * max(len(self.flows), 1))()
+        for k, fl in enumerate(self.flows):
+            by_id = {id(v): grads[k][n] for n, v in fl.variables().items()}
+            fl.fill_step(gsteps[k], ptr_of=lambda a, m=by_id: m[id(a)].ptr)
+        d_z0 = ctx.empty((run.B, run.D))
+        L.check(ctx.lib.mnf_flow_backward(ctx.handle, run.B, run.D, len(self.flows), run.steps, p(run.states),
+                                          p(run.saved), p(ds), p(dz), p(dl), p(d_z0), gsteps))
+        return d_z0, grads
+
     def inverse(self, x: Any):
         raise NotImplementedError("NormalizingFlow.inverse is never called by the MNF layers (SURVEY.md 8f-4)")
 

@@ -197,3 +197,76 @@ class MNFLayerBase:
             self._kl_tape = dict(args=a, qrun=qrun, rrun=rrun, keep=keep, z=z, ldq=ldq)
         self.call_index += 1
         return out
+
+    # ------------------------------------------------------------------- backward
+    def zero_grads(self) -> dict[str, DeviceArray]:
+        """(Re)create zeroed gradient buffers, one per variable (same keys as variables())."""
+        ctx = self.ctx
+        for name, v in self.variables().items():
+            g = self.grads.get(name)
+            if g is None or g.shape != v.shape:
+                self.grads[name] = ctx.zeros(v.shape)
+            else:
+                L.check(ctx.lib.mnf_memset(ctx.handle, _p(g), 0, g.nbytes))
+        return self.grads
+
+    def _grad_steps(self, tag: str, nf: NormalizingFlow):
+        """mnf_flow_step array whose pointer slots name the GRADIENT buffers of flow `tag`."""
+        steps = (L.FlowStep * max(len(nf.flows), 1))()
+        for k, fl in enumerate(nf.flows):
+            by_id = {id(v): self.grads[f"{tag}/{k}/{n}"] for n, v in fl.variables().items()}
+            fl.fill_step(steps[k], ptr_of=lambda a, m=by_id: m[id(a)].ptr)
+        return steps
+
+    def _flow_backward(self, tag: str, nf: NormalizingFlow, run: ChainRun, d_states, d_zT, d_ld) -> DeviceArray:
+        ctx = self.ctx
+        B, D, T = run.B, run.D, len(nf.flows)
+        d_z0 = ctx.empty((B, D))
+        gsteps = self._grad_steps(tag, nf)
+        L.check(ctx.lib.mnf_flow_backward(ctx.handle, B, D, T, run.steps, _p(run.states), _p(run.saved),
+                                          _p(d_states), _p(d_zT), _p(d_ld), _p(d_z0), gsteps))
+        return d_z0
+
+    def _sample_z_backward(self, run: ChainRun, dz: DeviceArray, d_ld: DeviceArray | None) -> None:
+        """Through flow_q back to q0_mean / q0_log_var; accumulates."""
+        ctx = self.ctx
+        d_z0 = self._flow_backward("flow_q", self.flow_q, run, None, dz, d_ld)
+        L.check(ctx.lib.mnf_sample_z_backward(ctx.handle, run.B, run.D, _p(d_z0), _p(self.q0_log_var),
+                                              C.byref(run.eps), _p(self.grads["q0_mean"]), _p(self.grads["q0_log_var"])))
+
+    def _add_grad(self, name: str, src: DeviceArray) -> None:
+        dst = self.grads[name]
+        L.check(self.ctx.lib.mnf_axpy(self.ctx.handle, dst.size, 1.0, _p(src), _p(dst)))
+
+    def kl_backward(self, scale: float = 1.0) -> None:
+        """Gradient of scale * kl_div() (the most recent kl_div() call made with
+        `training=True`) accumulated into self.grads."""
+        t = self._kl_tape
+        if not t:
+            raise RuntimeError(f"{self.name}: call kl_div() with layer.training = True before kl_backward()")
+        if not self.grads:
+            self.zero_grads()
+        ctx, D = self.ctx, self._flow_dim()
+        a: L.KlArgs = t["args"]
+        g = L.KlGrads()
+        names = ["mean_W", "log_std_W", "mean_b", "log_var_b"]
+        if self.learn_p:
+            names += ["prior_var_r_p", "prior_var_r_p_bias"]
+        if self.use_z:
+            names += ["q0_log_var", "r0_mean", "r0_log_var", "r0_apvar"]
+        scratch = {n: ctx.empty(getattr(self, n).shape) for n in names}
+        for n, buf in scratch.items():
+            setattr(g, n, buf.ptr)
+        d_z = d_rst = None
+        if self.use_z:
+            d_z = ctx.empty((1, D))
+            d_rst = ctx.empty((a.n_r_states, 1, D))
+            g.d_z, g.d_r_states = d_z.ptr, d_rst.ptr
+        L.check(ctx.lib.mnf_kl_backward(ctx.handle, C.byref(a), float(scale), C.byref(g)))
+        for n, buf in scratch.items():
+            self._add_grad(n, buf)
+        if self.use_z:
+            d_ld = ctx.to_device(np.array([-float(scale)], np.float32))  # dKL/d(ld_q) = dKL/d(ld_r) = -scale
+            dz_r = self._flow_backward("flow_r", self.flow_r, t["rrun"], d_rst, None, d_ld)
+            L.check(ctx.lib.mnf_axpy(ctx.handle, D, 1.0, _p(dz_r), _p(d_z)))
+            self._sample_z_backward(t["qrun"], d_z, d_ld)

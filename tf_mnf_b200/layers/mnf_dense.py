@@ -60,3 +60,30 @@ class MNFDense(MNFLayerBase):
         return y
 
     __call__ = call
+
+    def backward(self, dy: Any) -> DeviceArray:
+        """Gradient of the most recent call() (made with `training=True`) given dL/dy:
+        returns dL/dx and ACCUMULATES parameter gradients into self.grads (App. A-1, A-2)."""
+        t = self._tape
+        if not t:
+            raise RuntimeError(f"{self.name}: call the layer with layer.training = True before backward()")
+        if not self.grads:
+            self.zero_grads()
+        ctx = self.ctx
+        dy = as_device(dy, ctx)
+        x, z = t["x"], t["z"]
+        B = x.shape[0]
+        if dy.shape != (B, self.n_out):
+            raise ValueError(f"dy must have shape {(B, self.n_out)}, got {dy.shape}")
+        dx = ctx.empty(x.shape)
+        dz = ctx.empty(x.shape) if self.use_z else None
+        tmp = {n: ctx.empty(getattr(self, n).shape) for n in ("mean_W", "log_std_W", "mean_b", "log_var_b")}
+        L.check(ctx.lib.mnf_dense_backward(ctx.handle, B, self.n_in, self.n_out, _p(x), _p(z), _p(self.mean_W),
+                                           _p(self.log_std_W), _p(self.log_var_b), self.max_std, C.byref(t["eps"]),
+                                           _p(t["sd"]), _p(dy), _p(dx), _p(dz), _p(tmp["mean_W"]),
+                                           _p(tmp["log_std_W"]), _p(tmp["mean_b"]), _p(tmp["log_var_b"])))
+        for n, buf in tmp.items():
+            self._add_grad(n, buf)
+        if self.use_z:
+            self._sample_z_backward(t["run"], dz, None)
+        return dx
