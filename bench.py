@@ -62,7 +62,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.device)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -72,7 +72,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc:
@@ -80,10 +80,13 @@ class ClockSampler:
             self.proc.terminate()
             self.t.join(timeout=2)
 
-    def summary(self) -> dict:
+    def summary(self, t0: float = 0.0, t1: float = float("inf")) -> dict:
+        """Only samples that arrived inside [t0, t1] (the timed region) are used."""
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if not (t0 <= ts <= t1 + 0.03):
+                continue
             try:
                 sm.append(float(r[0])), mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -223,25 +226,28 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
             dist.barrier()
             torch.cuda.synchronize()
 
+    clk = ClockSampler(local_rank).__enter__()  # started early: nvidia-smi's NVML init stalls the GPU briefly
     for _ in range(max(args.warmup, 3)):
         L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
         step(x_dev)
     barrier()
+    time.sleep(0.3)
 
     # ---- timed: K steps, device-resident input, per-step CUDA events, L2 flushed in between
     starts, stops = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
     kst, ksp = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
     launches0 = ctx.launches
-    with ClockSampler(local_rank) as clk:
-        t_wall0 = time.perf_counter()
-        for i in range(args.steps):
-            L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
-            L.check(lib.mnf_ctx_probe(ctx.handle, 1, 1, kst[i], ksp[i]))  # 2nd conv GEMM launch = conv2
-            L.check(lib.mnf_event_record(ctx.handle, starts[i]))
-            out = step(x_dev)
-            L.check(lib.mnf_event_record(ctx.handle, stops[i]))
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
+        L.check(lib.mnf_ctx_probe(ctx.handle, 1, 1, kst[i], ksp[i]))  # 2nd conv GEMM launch = conv2
+        L.check(lib.mnf_event_record(ctx.handle, starts[i]))
+        out = step(x_dev)
+        L.check(lib.mnf_event_record(ctx.handle, stops[i]))
+    barrier()
+    t_wall1 = time.perf_counter()
+    t_wall = t_wall1 - t_wall0
+    clk.__exit__()
     launches = ctx.launches - launches0
 
     def elapsed(a, b):
@@ -304,7 +310,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
             "e2e": {"value": ROWS * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
                     "d2h_bytes_per_step": ROWS * 10 * 4 + 4, "ms_per_step": e2e_ms},
             "gpu_launches": int(launches),
-            "clocks": clk.summary(),
+            "clocks": clk.summary(t_wall0, t_wall1),
             "roofline": {"bound": "hbm", "kernel": "paired_gemm_fwd<CONV,64> (conv2: 12x12x20 -> 8x8x50, 5x5)",
                          "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
                          "peak_source": which, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms,
@@ -330,8 +336,8 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--flow", default="rnvp", choices=["rnvp", "iaf", "planar"])
     ap.add_argument("--cpu-rows", type=int, default=2560, help="rows per CPU-baseline step (bounded sample)")

@@ -4,16 +4,11 @@
 //   RNVP  : rnvp.py:33-47
 //   planar: planar.py:22-36
 //   chain : flows/__init__.py:22-29;  z0 sampling: mnf_dense.py:93-96 / mnf_conv.py:105-108
-// One launch per flow step.  A CTA owns FT_ROWS rows; the D->H->2D coupling MLP runs out of
-// shared memory (weights streamed in 32-wide chunks), the per-row log-det is reduced with
-// warp shuffles and never touches global memory until the final [B] store.
+// One launch per flow step (flows_tile.cuh); kl_div's single-row chains run as ONE launch
+// (flow_chain_row1).  The D->H->2D coupling MLP runs out of shared memory (weights streamed
+// in 32-wide chunks); the per-row log-det is reduced with warp shuffles.
 #include "common.cuh"
 
-#define FT_ROWS 32
-#define FT_THREADS 256
-#define FT_DC 32    // reduction / column chunk
-#define FT_HMAX 64  // hidden units supported by the fused kernel (static smem budget)
-#define FT_JMAX (FT_HMAX / 8)
 
 struct FlowStepArgs {
   int64_t B;
@@ -39,133 +34,7 @@ __device__ __forceinline__ float load_zin(const FlowStepArgs& a, int64_t row, in
   return a.q0_mean[d] + expf(0.5f * a.q0_log_var[d]) * e;
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(FT_THREADS) flow_mlp_step_fwd(FlowStepArgs a) {
-  __shared__ float zs[FT_ROWS][FT_DC + 1];
-  __shared__ float wsm[2][FT_DC > FT_HMAX ? FT_DC : FT_HMAX][FT_DC + 1];  // weight chunks
-  __shared__ float hs[FT_ROWS][FT_HMAX + 1];
-
-  const int tid = threadIdx.x;
-  const int r = tid >> 3, g = tid & 7;
-  const int64_t row0 = (int64_t)blockIdx.x * FT_ROWS;
-  const int64_t row = row0 + r;
-  const bool row_ok = row < a.B;
-  const int D = a.D, H = a.H;
-
-  // ---- stage 1: h = act(in @ W1 + b1), in = z (IAF) or m*z (RNVP)
-  float acc[FT_JMAX];
-#pragma unroll
-  for (int j = 0; j < FT_JMAX; ++j) acc[j] = 0.f;
-
-  for (int d0 = 0; d0 < D; d0 += FT_DC) {
-    // z chunk [32 rows][32 d]: thread loads 4 elements
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      int e = tid + FT_THREADS * q;
-      int rr = e >> 5, dd = e & 31;
-      int64_t grow = row0 + rr;
-      int d = d0 + dd;
-      float v = 0.f;
-      if (grow < a.B && d < D) {
-        v = load_zin(a, grow, d);
-        if (a.z0_out && !a.zin) a.z0_out[grow * D + d] = v;
-        if (KIND == MNF_FLOW_RNVP) v *= noise_bern1(a.bern, grow, (uint32_t)d, D, 0.5f);
-      }
-      zs[rr][dd] = v;
-    }
-    // W1 chunk [32 d][H] -> wsm[0][h][dd] (transposed so stage-1 reads are conflict-free)
-    for (int e = tid; e < FT_DC * H; e += FT_THREADS) {
-      int dd = e / H, h = e - dd * H;
-      int d = d0 + dd;
-      float w = 0.f;
-      if (d < D) {
-        w = a.w1[(int64_t)d * H + h];
-        if (a.m1) w *= a.m1[(int64_t)d * H + h];
-      }
-      wsm[0][h][dd] = w;
-    }
-    __syncthreads();
-#pragma unroll 4
-    for (int dd = 0; dd < FT_DC; ++dd) {
-      float zv = zs[r][dd];
-#pragma unroll
-      for (int j = 0; j < FT_JMAX; ++j) {
-        int h = g + 8 * j;
-        if (h < H) acc[j] = fmaf(zv, wsm[0][h][dd], acc[j]);
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int j = 0; j < FT_JMAX; ++j) {
-    int h = g + 8 * j;
-    if (h < H) {
-      float pre = acc[j] + a.b1[h];
-      float hv = (KIND == MNF_FLOW_IAF) ? fmaxf(pre, 0.f) : tanhf(pre);
-      hs[r][h] = hv;
-      if (a.hid_save && row_ok) a.hid_save[row * H + h] = hv;
-    }
-  }
-  __syncthreads();
-
-  // ---- stage 2: (s,t) = h @ [Ws|Wt] + [bs|bt], combine, per-row log-det
-  float ld = 0.f;
-  for (int c0 = 0; c0 < D; c0 += FT_DC) {
-    for (int e = tid; e < H * FT_DC; e += FT_THREADS) {
-      int h = e >> 5, cc = e & 31;
-      int c = c0 + cc;
-      float vs = 0.f, vt = 0.f;
-      if (c < D) {
-        vs = a.ws[(int64_t)h * a.ld2 + c];
-        vt = a.wt[(int64_t)h * a.ld2 + c];
-        if (a.m2) {  // IAF: m2 [H,2D]; scale half at column c, shift half at D + c
-          vs *= a.m2[(int64_t)h * a.ld2 + c];
-          vt *= a.m2[(int64_t)h * a.ld2 + D + c];
-        }
-      }
-      wsm[0][h][cc] = vs;
-      wsm[1][h][cc] = vt;
-    }
-    __syncthreads();
-    float s[4] = {0.f, 0.f, 0.f, 0.f}, t[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int h = 0; h < H; ++h) {
-      float hv = hs[r][h];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        s[q] = fmaf(hv, wsm[0][h][g + 8 * q], s[q]);
-        t[q] = fmaf(hv, wsm[1][h][g + 8 * q], t[q]);
-      }
-    }
-    if (row_ok) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        int c = c0 + g + 8 * q;
-        if (c < D) {
-          float sv = s[q] + a.bs[c], tv = t[q] + a.bt[c];
-          float zv = a.zin ? a.zin[row * D + c] : load_zin(a, row, c);
-          if (KIND == MNF_FLOW_IAF) {
-            float y = fmaf(zv, expf(sv), tv);
-            a.zout[row * D + (a.parity ? D - 1 - c : c)] = y;
-            ld += sv;
-          } else {
-            float m = noise_bern1(a.bern, row, (uint32_t)c, D, 0.5f);
-            float gate = 1.f / (1.f + expf(-sv));
-            // log(sigmoid(sv)) = -softplus(-sv), stable form
-            float lg = sv >= 0.f ? -log1pf(expf(-sv)) : sv - log1pf(expf(sv));
-            float x = ((1.f - m) * zv * gate + (1.f - gate) * tv) + m * zv;
-            a.zout[row * D + c] = x;
-            ld += (1.f - m) * lg;
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-  ld += __shfl_xor_sync(0xffffffffu, ld, 1);
-  ld += __shfl_xor_sync(0xffffffffu, ld, 2);
-  ld += __shfl_xor_sync(0xffffffffu, ld, 4);
-  if (g == 0 && row_ok && a.ld_out) a.ld_out[row] = (a.ld_in ? a.ld_in[row] : 0.f) + ld;
-}
+#include "flows_tile.cuh"
 
 // ------------------------------------------------------------------------------ planar
 // scal[0] = k = (softplus(u.w) - 1 - u.w) / |w|^2 ; scal[1] = w . u_hat   (planar.py:23-26,33-34)
@@ -266,6 +135,123 @@ __global__ void sample_z0_kernel(int64_t B, int D, const float* zin, const float
   }
 }
 
+// ------------------------------------------------------------- single-row chain (kl_div)
+// kl_div calls sample_z(1) and flow_r.forward on ONE row (mnf_dense.py:105,135): the row-tile
+// kernel would run a single CTA through 2*D/32 barrier-separated chunks.  Here one 1024-thread
+// CTA runs the WHOLE chain: stage 1 splits the D-reduction over 16 thread slices, stage 2
+// gives every thread output columns; z ping-pongs in shared memory between steps.
+#define C1_THREADS 1024
+#define C1_DMAX 4096
+#define C1_TMAX 8
+
+struct Chain1Step {
+  int kind, parity, H;
+  const float *w1, *b1, *ws, *bs, *wt, *bt, *m1, *m2;
+  int64_t ld2;
+  NoiseDev bern;
+};
+struct Chain1Args {
+  int D, T;
+  const float* zin;
+  const float* q0_mean;
+  const float* q0_log_var;
+  NoiseDev eps;
+  float* states;    // [T+1, D]
+  float* ld_out;    // [1] or nullptr
+  float* hid_save;  // packed [sum H] or nullptr
+  Chain1Step st[C1_TMAX];
+};
+
+__global__ void __launch_bounds__(C1_THREADS) flow_chain_row1(Chain1Args a) {
+  __shared__ float zbuf[2][C1_DMAX];
+  __shared__ float part[16][FT_HMAX + 1];
+  __shared__ float hs[FT_HMAX];
+  __shared__ float red[32];
+  const int tid = threadIdx.x, D = a.D;
+  for (int d = tid; d < D; d += C1_THREADS) {
+    float v = a.zin ? a.zin[d]
+                    : a.q0_mean[d] + expf(0.5f * a.q0_log_var[d]) * noise_normal1(a.eps, 0, 0u, (uint32_t)d, 1, D);
+    zbuf[0][d] = v;
+    a.states[d] = v;
+  }
+  __syncthreads();
+  float ld_tot = 0.f;
+  int hoff = 0;
+  for (int k = 0; k < a.T; ++k) {
+    const Chain1Step& s = a.st[k];
+    const float* zc = zbuf[k & 1];
+    float* zn = zbuf[(k + 1) & 1];
+    const int H = s.H;
+    // stage 1
+    {
+      const int j = tid & 63, sl = tid >> 6;
+      float acc = 0.f;
+      if (j < H) {
+        const int per = (D + 15) / 16;
+        const int d0 = sl * per, d1 = min(D, d0 + per);
+        for (int d = d0; d < d1; ++d) {
+          float w = __ldg(s.w1 + (int64_t)d * H + j);
+          if (s.m1) w *= __ldg(s.m1 + (int64_t)d * H + j);
+          float zv = zc[d];
+          if (s.kind == MNF_FLOW_RNVP) zv *= noise_bern1(s.bern, 0, (uint32_t)d, D, 0.5f);
+          acc = fmaf(zv, w, acc);
+        }
+        part[sl][j] = acc;
+      }
+    }
+    __syncthreads();
+    if (tid < H) {
+      float pre = s.b1[tid];
+      for (int q = 0; q < 16; ++q) pre += part[q][tid];
+      float hv = (s.kind == MNF_FLOW_IAF) ? fmaxf(pre, 0.f) : tanhf(pre);
+      hs[tid] = hv;
+      if (a.hid_save) a.hid_save[hoff + tid] = hv;
+    }
+    __syncthreads();
+    // stage 2
+    float ld = 0.f;
+    for (int c = tid; c < D; c += C1_THREADS) {
+      float sv = s.bs[c], tv = s.bt[c];
+      for (int h = 0; h < H; ++h) {
+        float ws = __ldg(s.ws + (int64_t)h * s.ld2 + c), wt = __ldg(s.wt + (int64_t)h * s.ld2 + c);
+        if (s.m2) {
+          ws *= __ldg(s.m2 + (int64_t)h * s.ld2 + c);
+          wt *= __ldg(s.m2 + (int64_t)h * s.ld2 + D + c);
+        }
+        sv = fmaf(hs[h], ws, sv);
+        tv = fmaf(hs[h], wt, tv);
+      }
+      float zv = zc[c];
+      if (s.kind == MNF_FLOW_IAF) {
+        float y = fmaf(zv, expf(sv), tv);
+        int o = s.parity ? D - 1 - c : c;
+        zn[o] = y;
+        a.states[(int64_t)(k + 1) * D + o] = y;
+        ld += sv;
+      } else {
+        float m = noise_bern1(s.bern, 0, (uint32_t)c, D, 0.5f);
+        float gate = 1.f / (1.f + expf(-sv));
+        float lg = sv >= 0.f ? -log1pf(expf(-sv)) : sv - log1pf(expf(sv));
+        float x = ((1.f - m) * zv * gate + (1.f - gate) * tv) + m * zv;
+        zn[c] = x;
+        a.states[(int64_t)(k + 1) * D + c] = x;
+        ld += (1.f - m) * lg;
+      }
+    }
+    ld = warp_sum(ld);
+    if ((tid & 31) == 0) red[tid >> 5] = ld;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+      for (int q = 0; q < C1_THREADS / 32; ++q) t += red[q];
+      ld_tot += t;
+    }
+    hoff += H;
+    __syncthreads();
+  }
+  if (tid == 0 && a.ld_out) a.ld_out[0] = ld_tot;
+}
+
 extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, const mnf_flow_step* steps,
                                 const float* z0, const float* q0_mean, const float* q0_log_var,
                                 const mnf_noise* eps_z, float* states, float* log_dets, float* saved) {
@@ -283,10 +269,32 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
     MNF_LAUNCHED(ctx);
     return MNF_OK;
   }
+  bool any_planar = false, all_mlp = true;
+  for (int k = 0; k < T; ++k) {
+    any_planar |= steps[k].kind == MNF_FLOW_PLANAR;
+    all_mlp &= (steps[k].kind == MNF_FLOW_IAF || steps[k].kind == MNF_FLOW_RNVP) && steps[k].hidden >= 1 &&
+               steps[k].hidden <= FT_HMAX && steps[k].w1 && steps[k].b1 && steps[k].ws && steps[k].bs && steps[k].wt &&
+               steps[k].bt;
+  }
+  if (B == 1 && all_mlp && T <= C1_TMAX && D <= C1_DMAX) {  // kl_div path: whole chain in one CTA
+    Chain1Args a;
+    a.D = (int)D; a.T = T; a.zin = z0; a.q0_mean = q0_mean; a.q0_log_var = q0_log_var; a.eps = eps;
+    a.states = states; a.ld_out = log_dets; a.hid_save = saved;
+    for (int k = 0; k < T; ++k) {
+      Chain1Step& s = a.st[k];
+      s.kind = steps[k].kind; s.parity = steps[k].parity; s.H = steps[k].hidden;
+      s.w1 = steps[k].w1; s.b1 = steps[k].b1; s.ws = steps[k].ws; s.bs = steps[k].bs; s.wt = steps[k].wt;
+      s.bt = steps[k].bt; s.m1 = steps[k].m1; s.m2 = steps[k].m2; s.ld2 = steps[k].ld2;
+      s.bern = make_noise(&steps[k].bern);
+    }
+    const bool probed = mnf_probe_begin(ctx, MNF_PROBE_FLOW_STEP);
+    flow_chain_row1<<<1, C1_THREADS, 0, ctx->stream>>>(a);
+    mnf_probe_end(ctx, probed);
+    MNF_LAUNCHED(ctx);
+    return MNF_OK;
+  }
   // planar scalars live in the workspace: [T][2]
   float* scal = nullptr;
-  bool any_planar = false;
-  for (int k = 0; k < T; ++k) any_planar |= steps[k].kind == MNF_FLOW_PLANAR;
   if (any_planar) {
     scal = (float*)mnf_workspace(ctx, sizeof(float) * 2 * T);
     if (!scal) return MNF_ERR_CUDA;

@@ -237,6 +237,173 @@ __global__ void __launch_bounds__((PG_BM / PG_TM) * (BN / PG_TN)) paired_gemm_fw
   }
 }
 
+// ----------------------------------------------------------------------- direct small conv
+// Few-filter convolutions (LeNet conv1: 5x5x1 -> 20) have a tiny K = kh*kw*C and N = F, so the
+// implicit-GEMM tile wastes most of its lanes and the layer is bound by the 46 KB/row output
+// write and the eps draws.  Here a CTA stages whole (zero-padded) input images plus both
+// filter banks in shared memory; a thread owns TWO horizontally adjacent output pixels and all
+// NF filters (2*2*NF accumulators), so every filter word fetched (one broadcast LDS.128 per 4
+// filters) feeds 8 FMAs and x is read once per tap.
+#define DC_THREADS 256
+struct DirectArgs {
+  PairedArgs p;
+  int Hp, Wp;   // padded input tile
+  int pad_b, pad_r;
+  int IMG;      // images per CTA
+};
+
+template <int NF>
+__global__ void __launch_bounds__(DC_THREADS) conv_direct_fwd(DirectArgs d) {
+  extern __shared__ __align__(16) float dsm[];
+  const PairedArgs& a = d.p;
+  const int K = a.K, F = a.N;
+  float* wm = dsm;                       // [K][NF]
+  float* wv = wm + K * NF;               // [K][NF]
+  float* zs = wv + K * NF;               // [IMG][NF]
+  int* koff = (int*)(zs + d.IMG * NF);   // [K]
+  float* xs = (float*)(koff + ((K + 3) & ~3));  // [IMG][Hp][Wp][C]
+  const int tid = threadIdx.x;
+  const int img_sz = d.Hp * d.Wp * a.C;
+  const int64_t b0 = (int64_t)blockIdx.x * d.IMG;
+  const int64_t B = a.M / ((int64_t)a.Ho * a.Wo);
+  const int nimg = (int)((B - b0 < d.IMG) ? B - b0 : d.IMG);
+
+  for (int e = tid; e < K * NF; e += DC_THREADS) {
+    int k = e / NF, f = e - k * NF;
+    wm[e] = f < F ? __ldg(a.Wm + (int64_t)k * F + f) : 0.f;
+    wv[e] = f < F ? __ldg(a.Vw + (int64_t)k * F + f) : 0.f;
+  }
+  for (int e = tid; e < d.IMG * NF; e += DC_THREADS) {
+    int im = e / NF, f = e - im * NF;
+    zs[e] = (a.z && im < nimg && f < F) ? __ldg(a.z + (b0 + im) * F + f) : 1.f;
+  }
+  for (int k = tid; k < K; k += DC_THREADS) {
+    int kwC = a.kw * a.C;
+    int i = k / kwC, rem = k - i * kwC, j = rem / a.C, c = rem - j * a.C;
+    koff[k] = (i * d.Wp + j) * a.C + c;
+  }
+  for (int e = tid; e < d.IMG * img_sz; e += DC_THREADS) {
+    int im = e / img_sz, r = e - im * img_sz;
+    int c = r % a.C, t = r / a.C;
+    int wp = t % d.Wp, hp = t / d.Wp;
+    int hi = hp - a.pad_t, wi = wp - a.pad_l;
+    float v = 0.f;
+    if (im < nimg && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W)
+      v = __ldg(a.x + (((b0 + im) * a.H + hi) * a.W + wi) * a.C + c);
+    xs[e] = v;
+  }
+  __syncthreads();
+
+  const int Wo2 = (a.Wo + 1) >> 1;
+  const int npairs = nimg * a.Ho * Wo2;
+  float bmv[NF], vbv[NF];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+    bmv[f] = f < F ? a.bm[f] : 0.f;
+    vbv[f] = f < F ? a.vb[f] : 1.f;
+  }
+  for (int pr = tid; pr < npairs; pr += DC_THREADS) {
+    const int im = pr / (a.Ho * Wo2);
+    const int r = pr - im * a.Ho * Wo2;
+    const int ho = r / Wo2, wo0 = (r - ho * Wo2) * 2;
+    const bool two = wo0 + 1 < a.Wo;
+    const float* x0 = xs + im * img_sz + ((ho * a.stride) * d.Wp + wo0 * a.stride) * a.C;
+    const float* x1 = x0 + (two ? a.stride * a.C : 0);
+    float m0[NF], v0[NF], m1[NF], v1[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) m0[f] = v0[f] = m1[f] = v1[f] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int o = koff[k];
+      const float xa = x0[o], xb = x1[o];
+      const float xa2 = xa * xa, xb2 = xb * xb;
+      const float4* wmk = reinterpret_cast<const float4*>(wm + k * NF);
+      const float4* wvk = reinterpret_cast<const float4*>(wv + k * NF);
+#pragma unroll
+      for (int q = 0; q < NF / 4; ++q) {
+        float4 w = wmk[q], u = wvk[q];
+        m0[4 * q + 0] = fmaf(xa, w.x, m0[4 * q + 0]); m0[4 * q + 1] = fmaf(xa, w.y, m0[4 * q + 1]);
+        m0[4 * q + 2] = fmaf(xa, w.z, m0[4 * q + 2]); m0[4 * q + 3] = fmaf(xa, w.w, m0[4 * q + 3]);
+        m1[4 * q + 0] = fmaf(xb, w.x, m1[4 * q + 0]); m1[4 * q + 1] = fmaf(xb, w.y, m1[4 * q + 1]);
+        m1[4 * q + 2] = fmaf(xb, w.z, m1[4 * q + 2]); m1[4 * q + 3] = fmaf(xb, w.w, m1[4 * q + 3]);
+        v0[4 * q + 0] = fmaf(xa2, u.x, v0[4 * q + 0]); v0[4 * q + 1] = fmaf(xa2, u.y, v0[4 * q + 1]);
+        v0[4 * q + 2] = fmaf(xa2, u.z, v0[4 * q + 2]); v0[4 * q + 3] = fmaf(xa2, u.w, v0[4 * q + 3]);
+        v1[4 * q + 0] = fmaf(xb2, u.x, v1[4 * q + 0]); v1[4 * q + 1] = fmaf(xb2, u.y, v1[4 * q + 1]);
+        v1[4 * q + 2] = fmaf(xb2, u.z, v1[4 * q + 2]); v1[4 * q + 3] = fmaf(xb2, u.w, v1[4 * q + 3]);
+      }
+    }
+    // epilogue for the one or two pixels
+    const int64_t brow = b0 + im;
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      if (px == 1 && !two) break;
+      const float* mm = px ? m1 : m0;
+      const float* vv = px ? v1 : v0;
+      const uint32_t pix = (uint32_t)(ho * a.Wo + wo0 + px);
+      const int64_t gm = brow * a.Ho * a.Wo + pix;
+#pragma unroll
+      for (int q = 0; q < NF / 4; ++q) {
+        if (4 * q >= F) break;
+        float e[4];
+        if (a.eps.injected) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) e[j] = 4 * q + j < F ? a.eps.injected[gm * F + 4 * q + j] : 0.f;
+        } else {
+          philox_normal4(a.eps, a.eps.row_offset + (uint64_t)brow, pix, (uint32_t)q, e);
+        }
+        float out[4], mo[4], so[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int f = 4 * q + j;
+          float mean = mm[f] + bmv[f];
+          float sd = sqrtf(vv[f] + vbv[f]);
+          mo[j] = mean;
+          so[j] = sd;
+          out[j] = fmaf(sd, e[j], mean * zs[im * NF + f]);
+        }
+        if ((F & 3) == 0) {
+          *reinterpret_cast<float4*>(a.y + gm * F + 4 * q) = make_float4(out[0], out[1], out[2], out[3]);
+          if (a.sd_out) *reinterpret_cast<float4*>(a.sd_out + gm * F + 4 * q) = make_float4(so[0], so[1], so[2], so[3]);
+          if (a.mean_out) *reinterpret_cast<float4*>(a.mean_out + gm * F + 4 * q) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (4 * q + j < F) {
+              a.y[gm * F + 4 * q + j] = out[j];
+              if (a.sd_out) a.sd_out[gm * F + 4 * q + j] = so[j];
+              if (a.mean_out) a.mean_out[gm * F + 4 * q + j] = mo[j];
+            }
+        }
+      }
+    }
+  }
+}
+
+// returns MNF_OK and sets *used when the direct kernel applies
+static int launch_direct(mnf_ctx* ctx, const PairedArgs& a, int pad_b, int pad_r, bool* used) {
+  constexpr int NF = 20;
+  *used = false;
+  if (a.N > NF || a.K > 256) return MNF_OK;
+  DirectArgs d;
+  d.p = a;
+  d.Hp = a.H + a.pad_t + pad_b;
+  d.Wp = a.W + a.pad_l + pad_r;
+  d.pad_b = pad_b; d.pad_r = pad_r;
+  const size_t img_bytes = sizeof(float) * (size_t)d.Hp * d.Wp * a.C;
+  const size_t fixed = sizeof(float) * (2 * (size_t)a.K * NF + 8 * NF) + sizeof(int) * ((a.K + 3) & ~3);
+  if (fixed + img_bytes > 44 * 1024) return MNF_OK;
+  int img = (int)((44 * 1024 - fixed) / img_bytes);
+  if (img > 8) img = 8;
+  const int64_t B = a.M / ((int64_t)a.Ho * a.Wo);
+  d.IMG = img;
+  const size_t smem = sizeof(float) * (2 * (size_t)a.K * NF + (size_t)img * NF) + sizeof(int) * ((a.K + 3) & ~3) + img * img_bytes;
+  const bool probed = mnf_probe_begin(ctx, MNF_PROBE_CONV_GEMM);
+  conv_direct_fwd<NF><<<(unsigned)cdiv(B, img), DC_THREADS, smem, ctx->stream>>>(d);
+  mnf_probe_end(ctx, probed);
+  MNF_LAUNCHED(ctx);
+  *used = true;
+  return MNF_OK;
+}
+
 template <bool CONV>
 static int launch_paired(mnf_ctx* ctx, const PairedArgs& a) {
   dim3 grid((unsigned)cdiv(a.M, PG_BM), 1);
@@ -327,11 +494,19 @@ int mnf_conv2d_forward(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, co
   a.H = (int)s->H; a.W = (int)s->W; a.C = (int)s->C; a.kh = (int)s->kh; a.kw = (int)s->kw;
   a.Ho = (int)Ho; a.Wo = (int)Wo; a.stride = (int)s->stride;
   a.pad_t = a.pad_l = 0;
+  int pad_b = 0, pad_r = 0;
   if (s->same) {  // TF SAME: total pad = max((out-1)*stride + k - in, 0), smaller half first
     int64_t ph = (Ho - 1) * s->stride + s->kh - s->H, pw = (Wo - 1) * s->stride + s->kw - s->W;
-    a.pad_t = (int)((ph > 0 ? ph : 0) / 2);
-    a.pad_l = (int)((pw > 0 ? pw : 0) / 2);
+    ph = ph > 0 ? ph : 0;
+    pw = pw > 0 ? pw : 0;
+    a.pad_t = (int)(ph / 2);
+    a.pad_l = (int)(pw / 2);
+    pad_b = (int)(ph - ph / 2);
+    pad_r = (int)(pw - pw / 2);
   }
+  bool used = false;
+  rc = launch_direct(ctx, a, pad_b, pad_r, &used);
+  if (rc || used) return rc;
   return launch_paired<true>(ctx, a);
 }
 
