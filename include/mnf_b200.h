@@ -63,6 +63,13 @@ int mnf_ctx_sm_count(mnf_ctx* ctx, int* out);
 /* kernels launched by this context since creation (bench.py reports it as gpu_launches) */
 int mnf_ctx_launch_count(mnf_ctx* ctx, int64_t* out);
 
+/* Arithmetic of the paired mean/variance contractions (dense and conv forward):
+ *  MNF_MATH_FP32   register-blocked FFMA kernels (default)
+ *  MNF_MATH_TF32X3 tcgen05.mma kind::tf32 with hi/lo operand splitting (3 MMAs per product,
+ *                  fp32 accumulation in TMEM): fp32-level accuracy (<= 1e-5 rel.) on tensor cores */
+enum { MNF_MATH_FP32 = 0, MNF_MATH_TF32X3 = 1 };
+int mnf_ctx_set_math(mnf_ctx* ctx, int mode);
+
 /* Timing probe for bench.py's roofline line: the (skip+1)-th launch of kernel family `kind`
  * (1 conv paired GEMM, 2 dense paired GEMM, 3 flow step, 4 KL; 0 disarms) is bracketed by
  * cudaEventRecord(ev_start/ev_stop) on the context's stream, then the probe disarms. */

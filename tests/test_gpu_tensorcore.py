@@ -1,0 +1,77 @@
+"""The tcgen05 (3xTF32) tensor-core path of the paired mean/variance contraction must meet the
+same fp32 parity bar (1e-5 relative) as the FFMA path, against the float64 oracle."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+from gpu_util import close, make_layer
+
+from oracle import mnf_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+@pytest.fixture()
+def tc_ctx():
+    import tf_mnf_b200 as M
+
+    ctx = M.default_context()
+    ctx.set_math("tf32x3")
+    yield ctx
+    ctx.set_math("fp32")
+
+
+def _f32(a):
+    return np.asarray(a, np.float32)
+
+
+@pytest.mark.parametrize("K,N,B,use_z", [(800, 500, 300, True), (500, 10, 257, True), (136, 100, 64, True),
+                                         (25, 3, 1, True), (64, 64, 128, False), (130, 70, 129, True)])
+def test_dense_tensorcore(tc_ctx, K, N, B, use_z):
+    rng = np.random.RandomState(K * 3 + N)
+    P = O.make_layer_params(rng, (K, N), flow="iaf", std_init=10.0, dtype=np.float64)
+    P["q0_log_var"][...] = -3 + 0.5 * rng.standard_normal(K)
+    P["mean_b"][...] = 0.1 * rng.standard_normal(N)
+    x = rng.standard_normal((B, K))
+    eps_z, eps = rng.standard_normal((B, K)), rng.standard_normal((B, N))
+    ref, _ = O.dense_call(P, x, eps_z, eps, 1.0, use_z=use_z)
+    lyr = make_layer(P, x.shape, use_z=use_z)
+    inj = dict(eps_out=_f32(eps))
+    if use_z:
+        inj["eps_z"] = _f32(eps_z)
+    close(lyr(_f32(x), noise=inj).numpy(), ref, RTOL, "dense call (tf32x3)")
+
+
+@pytest.mark.parametrize("shape,wshape,stride,padding", [
+    ((5, 12, 12, 20), (5, 5, 20, 50), 1, "VALID"), ((3, 9, 7, 3), (3, 3, 3, 64), 1, "SAME"),
+    ((2, 11, 10, 4), (3, 2, 4, 36), 2, "SAME"), ((4, 8, 8, 8), (3, 3, 8, 24), 1, "VALID"),
+    ((37, 12, 12, 20), (5, 5, 20, 50), 1, "VALID"),
+])
+def test_conv_tensorcore(tc_ctx, shape, wshape, stride, padding):
+    rng = np.random.RandomState(sum(shape) + sum(wshape))
+    P = O.make_layer_params(rng, wshape, flow="iaf", std_init=10.0, dtype=np.float64)
+    F = wshape[-1]
+    P["q0_log_var"][...] = -3 + 0.5 * rng.standard_normal(F)
+    P["mean_b"][...] = 0.1 * rng.standard_normal(F)
+    x = rng.uniform(size=shape)
+    y0 = O.conv2d(x, P["mean_W"], stride, padding)
+    B = shape[0]
+    eps_z, eps = rng.standard_normal((B, F)), rng.standard_normal(y0.shape)
+    ref, _ = O.conv_call(P, x, eps_z, eps, 1.0, stride=stride, padding=padding)
+    lyr = make_layer(P, x.shape, stride=stride, padding=padding)
+    got = lyr(_f32(x), noise=dict(eps_z=_f32(eps_z), eps_out=_f32(eps))).numpy()
+    close(got, ref, RTOL, "conv call (tf32x3)")
+
+
+def test_tensorcore_matches_ffma_with_philox(tc_ctx):
+    """Same seed => the tensor-core and FFMA paths draw identical in-kernel noise; outputs agree to 1e-5."""
+    rng = np.random.RandomState(3)
+    P = O.make_layer_params(rng, (5, 5, 20, 50), flow="rnvp", std_init=10.0, dtype=np.float64)
+    x = _f32(rng.uniform(size=(64, 12, 12, 20)))
+    lyr = make_layer(P, x.shape)
+    y_tc = lyr(x).numpy()
+    tc_ctx.set_math("fp32")
+    lyr.call_index = 0
+    y_ff = lyr(x).numpy()
+    close(y_tc, y_ff, RTOL, "tf32x3 vs fp32 (Philox noise)")

@@ -16,6 +16,7 @@ struct mnf_ctx {
   void* ws;  // grow-only device workspace
   size_t ws_bytes;
   bool capturing;
+  int math_mode;  // MNF_MATH_FP32 (FFMA) or MNF_MATH_TF32X3 (tcgen05, 3xTF32 split)
   // timing probe: bracket the probe_skip-th launch of kernel family probe_kind with events
   int probe_kind;
   int probe_skip;
@@ -39,6 +40,11 @@ static inline void mnf_probe_end(mnf_ctx* ctx, bool on) {
 }
 
 void mnf_set_error(const char* fmt, ...);
+struct NoiseDev;
+int mnf_tc_paired_forward(mnf_ctx* ctx, int conv, int64_t M, int K, int N, const float* x, const float* z,
+                          const float* mean_W, const float* log_std_W, const float* mean_b, const float* log_var_b,
+                          float max_std, const NoiseDev& eps, float* y, float* mean_out, float* sd_out,
+                          const int* geo);
 void* mnf_workspace(mnf_ctx* ctx, size_t bytes);  // nullptr on failure (error set)
 
 #define MNF_CHECK_ARG(cond, ...)      \

@@ -460,6 +460,9 @@ int mnf_dense_forward(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const float
   MNF_CHECK_ARG(B >= 0 && K >= 1 && N >= 1 && K < (1 << 30) && N < (1 << 30), "mnf_dense_forward: bad shape");
   MNF_CHECK_ARG(eps, "mnf_dense_forward: eps noise spec is NULL");
   if (B == 0) return MNF_OK;
+  if (ctx->math_mode == MNF_MATH_TF32X3)
+    return mnf_tc_paired_forward(ctx, 0, B, (int)K, (int)N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std,
+                                 make_noise(eps), y, nullptr, sd_out, nullptr);
   float *Vw, *vb;
   // note: the second rounded-up offset inside prep_var must match (K*N padded to 4)
   int rc = prep_var(ctx, K * N, (int)N, log_std_W, log_var_b, max_std, &Vw, &vb);
@@ -507,6 +510,11 @@ int mnf_conv2d_forward(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, co
   bool used = false;
   rc = launch_direct(ctx, a, pad_b, pad_r, &used);
   if (rc || used) return rc;
+  if (ctx->math_mode == MNF_MATH_TF32X3) {
+    const int geo[10] = {a.H, a.W, a.C, a.kh, a.kw, a.Ho, a.Wo, a.stride, a.pad_t, a.pad_l};
+    return mnf_tc_paired_forward(ctx, 1, a.M, a.K, a.N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std, a.eps, y,
+                                 mean_out, sd_out, geo);
+  }
   return launch_paired<true>(ctx, a);
 }
 

@@ -128,6 +128,13 @@ int mnf_ctx_launch_count(mnf_ctx* ctx, int64_t* out) {
   return MNF_OK;
 }
 
+int mnf_ctx_set_math(mnf_ctx* ctx, int mode) {
+  MNF_CHECK_ARG(ctx, "ctx is NULL");
+  MNF_CHECK_ARG(mode == MNF_MATH_FP32 || mode == MNF_MATH_TF32X3, "mnf_ctx_set_math: unknown mode %d", mode);
+  ctx->math_mode = mode;
+  return MNF_OK;
+}
+
 int mnf_ctx_probe(mnf_ctx* ctx, int kind, int skip, void* ev_start, void* ev_stop) {
   MNF_CHECK_ARG(ctx, "ctx is NULL");
   MNF_CHECK_ARG(kind == MNF_PROBE_NONE || (ev_start && ev_stop && skip >= 0), "mnf_ctx_probe: bad arguments");

@@ -1,0 +1,508 @@
+// Tensor-core path of the paired mean/variance contraction (MNFDense.call mnf_dense.py:161-166,
+// MNFConv2D.call mnf_conv.py:190-191) for sm_100a: tcgen05.mma (kind::tf32) with TMEM
+// accumulators, warp-specialised.
+//
+// fp32 parity on tensor cores: every operand is split x = hi + lo (hi = top 19 bits, i.e. an
+// exact TF32 value) and each product is evaluated as hi*hi + lo*hi + hi*lo (3xTF32) with fp32
+// accumulation in TMEM: per-term relative error ~2^-20, inside the 1e-5 bar.
+//
+// One CTA per SM, persistent over 128-row tiles:
+//   warps 0-3  epilogue : tcgen05.ld the mean/var accumulators, bias, conv z-scale, Philox eps,
+//                         stage y in shared memory, coalesced store
+//   warp  4    MMA      : one elected thread issues 6 tcgen05.mma per 8-wide k-step
+//                         (3 split terms x {mean, var}); tcgen05.commit frees smem stages
+//   warps 5-12 producer : gather the x tile ONCE (im2col on the fly for conv), form
+//                         {x(*z), x^2} x {hi, lo} in registers and write them K-major into the
+//                         no-swizzle UMMA layout; the pre-split weight block arrives by one
+//                         cp.async.bulk (TMA, 1-D) per stage.
+#include "common.cuh"
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 16;       // floats per pipeline stage
+constexpr int KC = BK / 4;   // 16-byte k-chunks per stage
+constexpr int STAGES = 3;
+constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
+constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;  // 416
+constexpr int A_VARIANT_BYTES = KC * BM * 16;               // 8 KB
+constexpr int A_STAGE_BYTES = 4 * A_VARIANT_BYTES;          // 32 KB
+
+struct Args {
+  int64_t M;
+  int K, N;
+  int kblocks;       // ceil(K / BK)
+  int ntiles;        // ceil(N / BN)
+  const float* x;
+  const float* z;    // dense [M,K] / conv [B,N] / nullptr
+  const float* Bp;   // packed split weights: [ntile][kblock][4 variants][KC][BN][4]
+  const float* bm;   // [N]
+  const float* vb;   // [N]
+  float* y;
+  float* mean_out;
+  float* sd_out;
+  NoiseDev eps;
+  int H, W, C, kh, kw, Ho, Wo, stride, pad_t, pad_l;
+  int vec;           // 16-byte gathers legal (conv: C % 4 == 0; dense: K % 4 == 0)
+};
+
+// ----------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//  [0,14) start >> 4 | [16,30) leading byte offset >> 4 (between the two 16-byte K chunks of
+//  one MMA) | [32,46) stride byte offset >> 4 (between 8-row groups) | [46,48) version = 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+  lo = a - hi;
+}
+
+// ---------------------------------------------------------------------------------- kernel
+template <int BN, bool CONV>
+__global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
+  constexpr int B_VARIANT_BYTES = KC * BN * 16;
+  constexpr int B_STAGE_BYTES = 4 * B_VARIANT_BYTES;
+  constexpr int TMEM_COLS = 4 * BN;  // 2 buffers x {mean, var}
+  constexpr int LDY = BN + 1;
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* As = smem;                                  // [STAGES][4][KC][BM][4 floats]
+  uint8_t* Bs = As + STAGES * A_STAGE_BYTES;           // [STAGES][4][KC][BN][4 floats]
+  float* ys = (float*)(Bs + STAGES * B_STAGE_BYTES);   // [BM][LDY]
+  uint64_t* bars = (uint64_t*)(ys + BM * LDY + 3);
+  bars = (uint64_t*)(((uintptr_t)bars + 7) & ~(uintptr_t)7);
+  uint64_t* full = bars;               // [STAGES]
+  uint64_t* empty = bars + STAGES;     // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES; // [2]
+  uint64_t* tempty = tfull + 2;        // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t mtiles = (a.M + BM - 1) / BM;
+  const int64_t ntot = mtiles * a.ntiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], PROD_WARPS / 2 + 1);  // 4 warps of one producer group + the B bulk-copy arrive
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == EPI_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < EPI_WARPS) {
+    // ================================================================== epilogue warps
+    const int r = warp * 32 + lane;  // tile row == TMEM lane
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < ntot; t += gridDim.x, ++it) {
+      const int64_t mt = t / a.ntiles;
+      const int nt = (int)(t - mt * a.ntiles);
+      const int64_t m0 = mt * BM, m = m0 + r;
+      const int n0 = nt * BN;
+      const int buf = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&tfull[buf], ph);
+      tc_fence_after();
+      const bool row_ok = m < a.M;
+      const int64_t HoWo = CONV ? (int64_t)a.Ho * a.Wo : 1;
+      const int64_t brow = CONV ? m / HoWo : m;
+      const uint32_t outer = CONV ? (uint32_t)(m - brow * HoWo) : 0u;
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 2 * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        if (n0 + c0 >= a.N) break;  // warp-uniform
+        float mv[16], vv[16];
+        tmem_ld16(trow + c0, mv);
+        tmem_ld16(trow + BN + c0, vv);
+        if (row_ok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int nb = n0 + c0 + 4 * q;
+            if (nb >= a.N) break;
+            float e[4];
+            if (a.eps.injected) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) e[j] = nb + j < a.N ? a.eps.injected[m * a.N + nb + j] : 0.f;
+            } else {
+              philox_normal4(a.eps, a.eps.row_offset + (uint64_t)brow, outer, (uint32_t)(nb >> 2), e);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = nb + j;
+              if (n < a.N) {
+                float mean = mv[4 * q + j] + __ldg(a.bm + n);
+                float sd = sqrtf(vv[4 * q + j] + __ldg(a.vb + n));
+                if (a.sd_out) a.sd_out[m * a.N + n] = sd;
+                if (CONV) {
+                  if (a.mean_out) a.mean_out[m * a.N + n] = mean;
+                  if (a.z) mean *= __ldg(a.z + brow * a.N + n);
+                }
+                ys[r * LDY + c0 + 4 * q + j] = fmaf(sd, e[j], mean);
+              }
+            }
+          }
+        }
+      }
+      // accumulators consumed: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+      // coalesced copy-out of the staged tile (rows are contiguous in y when ntiles == 1)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int rows = (int)((a.M - m0 < BM) ? a.M - m0 : BM);
+      const int ncols = (a.N - n0 < BN) ? a.N - n0 : BN;
+      for (int e = threadIdx.x; e < rows * ncols; e += EPI_WARPS * 32) {
+        int rr = e / ncols, cc = e - rr * ncols;
+        a.y[(m0 + rr) * a.N + n0 + cc] = ys[rr * LDY + cc];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  } else if (warp == EPI_WARPS) {
+    // ======================================================================= MMA issuer
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
+    int it = 0, stage = 0;
+    uint32_t sph = 0;
+    for (int64_t t = blockIdx.x; t < ntot; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&tempty[buf], ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_mean = tmem_base + (uint32_t)(buf * 2 * BN), d_var = d_mean + BN;
+      for (int kb = 0; kb < a.kblocks; ++kb) {
+        mbar_wait(&full[stage], sph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t as = a_base + stage * A_STAGE_BYTES, bs = b_base + stage * B_STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / 8; ++j) {
+            const uint32_t ao = as + 2 * j * (BM * 16), bo = bs + 2 * j * (BN * 16);
+            const uint64_t xh = make_desc(ao + 0 * A_VARIANT_BYTES, BM * 16, 128);
+            const uint64_t xl = make_desc(ao + 1 * A_VARIANT_BYTES, BM * 16, 128);
+            const uint64_t qh = make_desc(ao + 2 * A_VARIANT_BYTES, BM * 16, 128);
+            const uint64_t ql = make_desc(ao + 3 * A_VARIANT_BYTES, BM * 16, 128);
+            const uint64_t wh = make_desc(bo + 0 * B_VARIANT_BYTES, BN * 16, 128);
+            const uint64_t wl = make_desc(bo + 1 * B_VARIANT_BYTES, BN * 16, 128);
+            const uint64_t vh = make_desc(bo + 2 * B_VARIANT_BYTES, BN * 16, 128);
+            const uint64_t vl = make_desc(bo + 3 * B_VARIANT_BYTES, BN * 16, 128);
+            const uint32_t first = (kb == 0 && j == 0) ? 0u : 1u;
+            umma_tf32(d_mean, xh, wh, idesc, first);
+            umma_tf32(d_mean, xl, wh, idesc, 1u);
+            umma_tf32(d_mean, xh, wl, idesc, 1u);
+            umma_tf32(d_var, qh, vh, idesc, first);
+            umma_tf32(d_var, ql, vh, idesc, 1u);
+            umma_tf32(d_var, qh, vl, idesc, 1u);
+          }
+          umma_commit(&empty[stage]);                            // smem stage free once these MMAs retire
+          if (kb == a.kblocks - 1) umma_commit(&tfull[buf]);     // accumulators ready
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; sph ^= 1; }
+      }
+    }
+  } else {
+    // ======================================================================== producers
+    // Two groups of 4 warps; group g stages the k-blocks with (global index) % 2 == g, so two
+    // pipeline stages are always being filled concurrently.  A thread owns one tile row and
+    // the 16 k of a block: its four 16-byte gathers are issued together and the NEXT block's
+    // gathers are in flight while the current block is split and written to shared memory.
+    const int pt = threadIdx.x - (EPI_WARPS + 1) * 32;  // 0..255
+    const int r = pt & (BM - 1);
+    const int grp = pt >> 7;
+    const int64_t my_tiles = (ntot > blockIdx.x) ? (ntot - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total_kb = my_tiles * a.kblocks;
+
+    struct RowCtx {
+      int64_t tile_i;   // which of this CTA's tiles the cached row info belongs to
+      int64_t m, rowoff;
+      int hi0, wi0, nt;
+      bool ok;
+    } rc;
+    rc.tile_i = -1;
+    auto set_tile = [&](int64_t ti) {
+      if (rc.tile_i == ti) return;
+      rc.tile_i = ti;
+      const int64_t t = blockIdx.x + ti * gridDim.x;
+      const int64_t mt = t / a.ntiles;
+      rc.nt = (int)(t - mt * a.ntiles);
+      rc.m = mt * BM + r;
+      rc.ok = rc.m < a.M;
+      rc.rowoff = 0;
+      rc.hi0 = rc.wi0 = 0;
+      if (CONV && rc.ok) {
+        const int64_t HoWo = (int64_t)a.Ho * a.Wo;
+        const int64_t b = rc.m / HoWo;
+        const int pix = (int)(rc.m - b * HoWo);
+        const int ho = pix / a.Wo, wo = pix - ho * a.Wo;
+        rc.hi0 = ho * a.stride - a.pad_t;
+        rc.wi0 = wo * a.stride - a.pad_l;
+        rc.rowoff = ((b * a.H + rc.hi0) * a.W + rc.wi0) * a.C;
+      }
+    };
+    // gather the 16 x values (and z for dense) of global k-block c into registers
+    auto gather = [&](int64_t c, float xv[16], float zv[16]) {
+      const int64_t ti = c / a.kblocks;
+      const int kb = (int)(c - ti * a.kblocks);
+      set_tile(ti);
+#pragma unroll
+      for (int kc = 0; kc < KC; ++kc) {
+        const int k = kb * BK + kc * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { xv[kc * 4 + e] = 0.f; zv[kc * 4 + e] = 1.f; }
+        if (!(rc.ok && k < a.K)) continue;
+        if (CONV) {
+          const int kwC = a.kw * a.C;
+          if (a.vec) {
+            const int i = k / kwC, rem = k - i * kwC, j = rem / a.C, cch = rem - j * a.C;
+            const int hi = rc.hi0 + i, wi = rc.wi0 + j;
+            if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(a.x + rc.rowoff + ((int64_t)i * a.W + j) * a.C + cch));
+              xv[kc * 4 + 0] = v.x; xv[kc * 4 + 1] = v.y; xv[kc * 4 + 2] = v.z; xv[kc * 4 + 3] = v.w;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int kk = k + e;
+              if (kk < a.K) {
+                const int i = kk / kwC, rem = kk - i * kwC, j = rem / a.C, cch = rem - j * a.C;
+                const int hi = rc.hi0 + i, wi = rc.wi0 + j;
+                if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W)
+                  xv[kc * 4 + e] = __ldg(a.x + rc.rowoff + ((int64_t)i * a.W + j) * a.C + cch);
+              }
+            }
+          }
+        } else {
+          if (a.vec) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(a.x + rc.m * a.K + k));
+            xv[kc * 4 + 0] = v.x; xv[kc * 4 + 1] = v.y; xv[kc * 4 + 2] = v.z; xv[kc * 4 + 3] = v.w;
+            if (a.z) {
+              const float4 w = __ldg(reinterpret_cast<const float4*>(a.z + rc.m * a.K + k));
+              zv[kc * 4 + 0] = w.x; zv[kc * 4 + 1] = w.y; zv[kc * 4 + 2] = w.z; zv[kc * 4 + 3] = w.w;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (k + e < a.K) {
+                xv[kc * 4 + e] = __ldg(a.x + rc.m * a.K + k + e);
+                if (a.z) zv[kc * 4 + e] = __ldg(a.z + rc.m * a.K + k + e);
+              }
+          }
+        }
+      }
+    };
+
+    float xc[16], zc[16], xn[16], zn[16];
+    if (grp < total_kb) gather(grp, xc, zc);
+    for (int64_t c = grp; c < total_kb; c += 2) {
+      const int stage = (int)(c % STAGES);
+      const uint32_t sph = (uint32_t)((c / STAGES) & 1);
+      // B block of this stage: which tile / k-block?
+      const int64_t ti = c / a.kblocks;
+      const int kb = (int)(c - ti * a.kblocks);
+      const int64_t t = blockIdx.x + ti * gridDim.x;
+      const int nt = (int)(t % a.ntiles);
+      const bool more = c + 2 < total_kb;
+      if (more) gather(c + 2, xn, zn);  // next block's loads fly while this one is processed
+      mbar_wait(&empty[stage], sph ^ 1);
+      if (r == 0) {
+        const float* bsrc = a.Bp + ((size_t)nt * a.kblocks + kb) * (size_t)(B_STAGE_BYTES / 4);
+        mbar_arrive_expect_tx(&full[stage], B_STAGE_BYTES);
+        bulk_g2s(Bs + stage * B_STAGE_BYTES, bsrc, B_STAGE_BYTES, &full[stage]);
+      }
+      uint8_t* abase = As + stage * A_STAGE_BYTES + r * 16;
+#pragma unroll
+      for (int kc = 0; kc < KC; ++kc) {
+        float h1[4], l1[4], h2[4], l2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float xv = xc[kc * 4 + e];
+          split_tf32(CONV ? xv : xv * zc[kc * 4 + e], h1[e], l1[e]);
+          split_tf32(xv * xv, h2[e], l2[e]);
+        }
+        uint8_t* dst = abase + kc * (BM * 16);
+        *reinterpret_cast<float4*>(dst + 0 * A_VARIANT_BYTES) = make_float4(h1[0], h1[1], h1[2], h1[3]);
+        *reinterpret_cast<float4*>(dst + 1 * A_VARIANT_BYTES) = make_float4(l1[0], l1[1], l1[2], l1[3]);
+        *reinterpret_cast<float4*>(dst + 2 * A_VARIANT_BYTES) = make_float4(h2[0], h2[1], h2[2], h2[3]);
+        *reinterpret_cast<float4*>(dst + 3 * A_VARIANT_BYTES) = make_float4(l2[0], l2[1], l2[2], l2[3]);
+      }
+      fence_proxy_async();  // make this thread's st.shared visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[stage]);
+      if (more) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { xc[e] = xn[e]; zc[e] = zn[e]; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------- weight packing
+// Bp[nt][kb][v][kc][n][4]: v = {W hi, W lo, Vw hi, Vw lo}, zero padded in k and n; also vb.
+template <int BN>
+__global__ void pack_weights_kernel(int K, int N, int kblocks, int ntiles, const float* __restrict__ Wm,
+                                    const float* __restrict__ Ls, float max_std, float* __restrict__ Bp,
+                                    const float* __restrict__ lvb, float* __restrict__ vb) {
+  const int64_t total = (int64_t)ntiles * kblocks * KC * BN * 4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int e = (int)(idx & 3);
+    int64_t t = idx >> 2;
+    int n = (int)(t % BN);
+    t /= BN;
+    int kc = (int)(t % KC);
+    t /= KC;
+    int kb = (int)(t % kblocks);
+    int nt = (int)(t / kblocks);
+    int k = kb * BK + kc * 4 + e, gn = nt * BN + n;
+    float w = 0.f, v = 0.f;
+    if (k < K && gn < N) {
+      w = Wm[(int64_t)k * N + gn];
+      float s = fminf(expf(Ls[(int64_t)k * N + gn]), max_std);
+      v = s * s;
+    }
+    float wh, wl, vh, vl;
+    split_tf32(w, wh, wl);
+    split_tf32(v, vh, vl);
+    const int64_t stage_f = (int64_t)4 * KC * BN * 4;
+    float* base = Bp + ((int64_t)nt * kblocks + kb) * stage_f + ((int64_t)kc * BN + n) * 4 + e;
+    const int64_t vstride = (int64_t)KC * BN * 4;
+    base[0 * vstride] = wh;
+    base[1 * vstride] = wl;
+    base[2 * vstride] = vh;
+    base[3 * vstride] = vl;
+    if (idx < N) vb[idx] = fminf(expf(lvb[idx]), max_std * max_std);
+  }
+}
+
+template <int BN, bool CONV>
+static int launch(mnf_ctx* ctx, Args& a, const float* mean_W, const float* log_std_W, const float* log_var_b,
+                  float max_std) {
+  a.kblocks = (a.K + BK - 1) / BK;
+  a.ntiles = (a.N + BN - 1) / BN;
+  const size_t bp_floats = (size_t)a.ntiles * a.kblocks * 4 * KC * BN * 4;
+  float* ws = (float*)mnf_workspace(ctx, sizeof(float) * (bp_floats + a.N + 64));
+  if (!ws) return MNF_ERR_CUDA;
+  float* Bp = ws;
+  float* vb = ws + bp_floats;
+  const int64_t tot = (int64_t)bp_floats / 4;
+  int grid = (int)(cdiv(tot, 256) < ctx->sm_count * 8 ? cdiv(tot, 256) : ctx->sm_count * 8);
+  pack_weights_kernel<BN><<<grid, 256, 0, ctx->stream>>>(a.K, a.N, a.kblocks, a.ntiles, mean_W, log_std_W, max_std, Bp,
+                                                       log_var_b, vb);
+  MNF_LAUNCHED(ctx);
+  a.Bp = Bp;
+  a.vb = vb;
+  constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + 4 * KC * BN * 16) + sizeof(float) * (BM * (BN + 1) + 4) + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MNF_CUDA(cudaFuncSetAttribute(paired_umma_fwd<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int64_t tiles = cdiv(a.M, BM) * a.ntiles;
+  const int g = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+  const bool probed = mnf_probe_begin(ctx, CONV ? MNF_PROBE_CONV_GEMM : MNF_PROBE_DENSE_GEMM);
+  paired_umma_fwd<BN, CONV><<<g, THREADS, smem, ctx->stream>>>(a);
+  mnf_probe_end(ctx, probed);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+}  // namespace tc
+
+// Entry used by layers_fwd.cu when the context's math mode selects the tensor-core path.
+// conv != 0: geo = {H,W,C,kh,kw,Ho,Wo,stride,pad_t,pad_l}.
+int mnf_tc_paired_forward(mnf_ctx* ctx, int conv, int64_t M, int K, int N, const float* x, const float* z,
+                          const float* mean_W, const float* log_std_W, const float* mean_b, const float* log_var_b,
+                          float max_std, const NoiseDev& eps, float* y, float* mean_out, float* sd_out,
+                          const int* geo) {
+  tc::Args a = {};
+  a.M = M; a.K = K; a.N = N;
+  a.x = x; a.z = z; a.bm = mean_b; a.y = y; a.mean_out = mean_out; a.sd_out = sd_out; a.eps = eps;
+  if (conv) {
+    a.H = geo[0]; a.W = geo[1]; a.C = geo[2]; a.kh = geo[3]; a.kw = geo[4]; a.Ho = geo[5]; a.Wo = geo[6];
+    a.stride = geo[7]; a.pad_t = geo[8]; a.pad_l = geo[9];
+    a.vec = (a.C % 4 == 0) && (((uintptr_t)x & 15) == 0);
+    return tc::launch<64, true>(ctx, a, mean_W, log_std_W, log_var_b, max_std);
+  }
+  a.vec = (K % 4 == 0) && (((uintptr_t)x & 15) == 0) && (!z || ((uintptr_t)z & 15) == 0);
+  return tc::launch<64, false>(ctx, a, mean_W, log_std_W, log_var_b, max_std);
+}

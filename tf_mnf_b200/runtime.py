@@ -53,6 +53,15 @@ class Context:
     def sync(self) -> None:
         L.check(self.lib.mnf_ctx_sync(self.handle))
 
+    def set_math(self, mode: str) -> None:
+        """"fp32": FFMA kernels; "tf32x3": tcgen05 tensor cores with hi/lo operand splitting
+        (fp32-level accuracy).  Applies to the dense / conv forward contractions."""
+        codes = {"fp32": 0, "tf32x3": 1}
+        if mode not in codes:
+            raise ValueError(f"math mode must be one of {sorted(codes)}, got {mode!r}")
+        L.check(self.lib.mnf_ctx_set_math(self.handle, codes[mode]))
+        self.math = mode
+
     def set_stream(self, stream: int) -> None:
         L.check(self.lib.mnf_ctx_set_stream(self.handle, C.c_void_p(stream)))
 
