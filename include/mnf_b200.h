@@ -264,6 +264,10 @@ int mnf_softmax(mnf_ctx* ctx, int64_t B, int64_t N, const float* x, float* y);
  * loss_out [1]; d_logits [B,N] (may be NULL) = (softmax - labels) / B_global. */
 int mnf_softmax_xent(mnf_ctx* ctx, int64_t B, int64_t N, const float* logits, const float* labels,
                      float inv_global_batch, float* loss_out, float* d_logits);
+/* loss_out [1] = mean squared error over the GLOBAL batch (inv_global_n = 1 / global element
+ * count; bandgap_regression.py:57-69); dy (may be NULL) = 2 (y - target) * inv_global_n. */
+int mnf_mse_loss(mnf_ctx* ctx, int64_t n, const float* y, const float* target, float inv_global_n,
+                 float* loss_out, float* dy);
 /* y = a*x + b (inference-mode BatchNormalization in MNFFeedForward), generic axpby helpers */
 int mnf_scale(mnf_ctx* ctx, int64_t n, float a, const float* x, float* y);
 int mnf_axpy(mnf_ctx* ctx, int64_t n, float a, const float* x, float* y); /* y += a*x */

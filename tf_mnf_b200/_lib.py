@@ -109,6 +109,7 @@ SIGNATURES = {
     "mnf_relu_backward": [vp, _i64, vp, vp, vp],
     "mnf_softmax": [vp, _i64, _i64, vp, vp],
     "mnf_softmax_xent": [vp, _i64, _i64, vp, vp, _f, vp, vp],
+    "mnf_mse_loss": [vp, _i64, vp, vp, _f, vp, vp],
     "mnf_scale": [vp, _i64, _f, vp, vp],
     "mnf_axpy": [vp, _i64, _f, vp, vp],
     "mnf_adam_step": [vp, _i64, vp, vp, vp, vp, _f, _f, _f, _f, _i32],

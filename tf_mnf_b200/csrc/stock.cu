@@ -116,6 +116,20 @@ __global__ void softmax_xent_kernel(int64_t B, int N, const float* __restrict__ 
   if (lane == 0 && row < B) atomicAdd(loss_out, l * inv_gb);
 }
 
+// loss = mean((y - t)^2) over all n elements of the GLOBAL batch (bandgap_regression.py:57-69);
+// dy = 2 (y - t) * inv_n
+__global__ void mse_kernel(int64_t n, const float* __restrict__ y, const float* __restrict__ t, float inv_n,
+                           float* loss_out, float* __restrict__ dy) {
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float d = y[i] - t[i];
+    acc = fmaf(d, d, acc);
+    if (dy) dy[i] = 2.f * d * inv_n;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(loss_out, acc * inv_n);
+}
+
 __global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, float lr_t, float b1, float b2, float eps) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -184,6 +198,16 @@ int mnf_softmax_xent(mnf_ctx* ctx, int64_t B, int64_t N, const float* logits, co
   if (B == 0) return MNF_OK;
   softmax_xent_kernel<<<(unsigned)cdiv(B, 8), 256, 0, ctx->stream>>>(B, (int)N, logits, labels, inv_global_batch,
                                                                      loss_out, d_logits);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+int mnf_mse_loss(mnf_ctx* ctx, int64_t n, const float* y, const float* target, float inv_global_n, float* loss_out,
+                 float* dy) {
+  MNF_CHECK_ARG(ctx && y && target && loss_out && n >= 0, "mnf_mse_loss: bad argument");
+  MNF_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), ctx->stream));
+  if (n == 0) return MNF_OK;
+  mse_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(n, y, target, inv_global_n, loss_out, dy);
   MNF_LAUNCHED(ctx);
   return MNF_OK;
 }

@@ -136,6 +136,8 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
   uint64_t* tfull = bars + 2 * STAGES; // [2]
   uint64_t* tempty = tfull + 2;        // [2]
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  float* bias_s = (float*)(tmem_slot + 2);   // [2][BN]: mean_b, var_b of the current n-tile (ntiles == 1 only)
+  int* ktab = (int*)(bias_s + 2 * BN);       // conv gather table, one entry per k-chunk (vec) or per k
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t mtiles = (a.M + BM - 1) / BM;
@@ -162,6 +164,29 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // im2col table: offset of k (or of the 4-channel chunk starting at k) relative to the row's
+  // patch origin, tap (i,j) in the high bits; -1 = beyond K (zero fill)
+  if (CONV) {
+    const int gran = a.vec ? 4 : 1;
+    const int nent = a.kblocks * BK / gran;
+    const int kwC = a.kw * a.C;
+    for (int q = threadIdx.x; q < nent; q += THREADS) {
+      const int k = q * gran;
+      int v = -1;
+      if (k < a.K) {
+        const int i = k / kwC, rem = k - i * kwC, j = rem / a.C, cch = rem - j * a.C;
+        v = (i * a.W + j) * a.C + cch;
+        ktab[nent + q] = (i << 16) | j;
+      }
+      ktab[q] = v;
+    }
+  }
+  if (a.ntiles == 1)
+    for (int n = threadIdx.x; n < BN; n += THREADS) {
+      bias_s[n] = n < a.N ? a.bm[n] : 0.f;
+      bias_s[BN + n] = n < a.N ? a.vb[n] : 1.f;
+    }
+  __syncthreads();
 
   if (warp < EPI_WARPS) {
     // ================================================================== epilogue warps
@@ -177,6 +202,8 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
       mbar_wait(&tfull[buf], ph);
       tc_fence_after();
       const bool row_ok = m < a.M;
+      const int ncols = (a.N - n0 < BN) ? a.N - n0 : BN;
+      const int ldy = (a.ntiles == 1) ? a.N : LDY;
       const int64_t HoWo = CONV ? (int64_t)a.Ho * a.Wo : 1;
       const int64_t brow = CONV ? m / HoWo : m;
       const uint32_t outer = CONV ? (uint32_t)(m - brow * HoWo) : 0u;
@@ -203,14 +230,16 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
             for (int j = 0; j < 4; ++j) {
               const int n = nb + j;
               if (n < a.N) {
-                float mean = mv[4 * q + j] + __ldg(a.bm + n);
-                float sd = sqrtf(vv[4 * q + j] + __ldg(a.vb + n));
+                const float bmn = (a.ntiles == 1) ? bias_s[n] : __ldg(a.bm + n);
+                const float vbn = (a.ntiles == 1) ? bias_s[BN + n] : __ldg(a.vb + n);
+                float mean = mv[4 * q + j] + bmn;
+                float sd = sqrtf(vv[4 * q + j] + vbn);
                 if (a.sd_out) a.sd_out[m * a.N + n] = sd;
                 if (CONV) {
                   if (a.mean_out) a.mean_out[m * a.N + n] = mean;
                   if (a.z) mean *= __ldg(a.z + brow * a.N + n);
                 }
-                ys[r * LDY + c0 + 4 * q + j] = fmaf(sd, e[j], mean);
+                ys[r * ldy + c0 + 4 * q + j] = fmaf(sd, e[j], mean);
               }
             }
           }
@@ -223,10 +252,14 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
       // coalesced copy-out of the staged tile (rows are contiguous in y when ntiles == 1)
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int rows = (int)((a.M - m0 < BM) ? a.M - m0 : BM);
-      const int ncols = (a.N - n0 < BN) ? a.N - n0 : BN;
-      for (int e = threadIdx.x; e < rows * ncols; e += EPI_WARPS * 32) {
-        int rr = e / ncols, cc = e - rr * ncols;
-        a.y[(m0 + rr) * a.N + n0 + cc] = ys[rr * LDY + cc];
+      if (a.ntiles == 1) {  // the tile is one contiguous block of y and is staged densely
+        float* dst = a.y + m0 * a.N;
+        for (int e = threadIdx.x; e < rows * a.N; e += EPI_WARPS * 32) dst[e] = ys[e];
+      } else {
+        for (int e = threadIdx.x; e < rows * ncols; e += EPI_WARPS * 32) {
+          int rr = e / ncols, cc = e - rr * ncols;
+          a.y[(m0 + rr) * a.N + n0 + cc] = ys[rr * LDY + cc];
+        }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
@@ -234,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
     // ======================================================================= MMA issuer
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
+    const uint64_t adesc0 = make_desc(smem_u32(As), BM * 16, 128), bdesc0 = make_desc(smem_u32(Bs), BN * 16, 128);
     int it = 0, stage = 0;
     uint32_t sph = 0;
     for (int64_t t = blockIdx.x; t < ntot; t += gridDim.x, ++it) {
@@ -247,18 +280,16 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
         mbar_wait(&full[stage], sph);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t as = a_base + stage * A_STAGE_BYTES, bs = b_base + stage * B_STAGE_BYTES;
+          // descriptors differ only in their 14-bit start-address field: add offsets to a base
+          const uint64_t ad = adesc0 + (uint64_t)((stage * A_STAGE_BYTES) >> 4);
+          const uint64_t bd = bdesc0 + (uint64_t)((stage * B_STAGE_BYTES) >> 4);
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
-            const uint32_t ao = as + 2 * j * (BM * 16), bo = bs + 2 * j * (BN * 16);
-            const uint64_t xh = make_desc(ao + 0 * A_VARIANT_BYTES, BM * 16, 128);
-            const uint64_t xl = make_desc(ao + 1 * A_VARIANT_BYTES, BM * 16, 128);
-            const uint64_t qh = make_desc(ao + 2 * A_VARIANT_BYTES, BM * 16, 128);
-            const uint64_t ql = make_desc(ao + 3 * A_VARIANT_BYTES, BM * 16, 128);
-            const uint64_t wh = make_desc(bo + 0 * B_VARIANT_BYTES, BN * 16, 128);
-            const uint64_t wl = make_desc(bo + 1 * B_VARIANT_BYTES, BN * 16, 128);
-            const uint64_t vh = make_desc(bo + 2 * B_VARIANT_BYTES, BN * 16, 128);
-            const uint64_t vl = make_desc(bo + 3 * B_VARIANT_BYTES, BN * 16, 128);
+            const uint64_t ao = ad + (uint64_t)((2 * j * BM * 16) >> 4), bo = bd + (uint64_t)((2 * j * BN * 16) >> 4);
+            const uint64_t xh = ao, xl = ao + (A_VARIANT_BYTES >> 4), qh = ao + (2 * A_VARIANT_BYTES >> 4),
+                           ql = ao + (3 * A_VARIANT_BYTES >> 4);
+            const uint64_t wh = bo, wl = bo + (B_VARIANT_BYTES >> 4), vh = bo + (2 * B_VARIANT_BYTES >> 4),
+                           vl = bo + (3 * B_VARIANT_BYTES >> 4);
             const uint32_t first = (kb == 0 && j == 0) ? 0u : 1u;
             umma_tf32(d_mean, xh, wh, idesc, first);
             umma_tf32(d_mean, xl, wh, idesc, 1u);
@@ -283,103 +314,122 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
     const int pt = threadIdx.x - (EPI_WARPS + 1) * 32;  // 0..255
     const int r = pt & (BM - 1);
     const int grp = pt >> 7;
-    const int64_t my_tiles = (ntot > blockIdx.x) ? (ntot - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total_kb = my_tiles * a.kblocks;
-
     struct RowCtx {
-      int64_t tile_i;   // which of this CTA's tiles the cached row info belongs to
-      int64_t m, rowoff;
+      int tile_i;       // which of this CTA's tiles the cached row info belongs to
+      int64_t m;
+      const float* xrow;  // conv: x + rowoff ; dense: x + m*K
+      const float* zrow;  // dense: z + m*K
       int hi0, wi0, nt;
       bool ok;
     } rc;
     rc.tile_i = -1;
-    auto set_tile = [&](int64_t ti) {
+    auto set_tile = [&](int ti) {
       if (rc.tile_i == ti) return;
       rc.tile_i = ti;
-      const int64_t t = blockIdx.x + ti * gridDim.x;
+      const int64_t t = blockIdx.x + (int64_t)ti * gridDim.x;
       const int64_t mt = t / a.ntiles;
       rc.nt = (int)(t - mt * a.ntiles);
       rc.m = mt * BM + r;
       rc.ok = rc.m < a.M;
-      rc.rowoff = 0;
+      if (!rc.ok) rc.m = a.M - 1;  // gather from a valid row; the epilogue never stores it
       rc.hi0 = rc.wi0 = 0;
-      if (CONV && rc.ok) {
-        const int64_t HoWo = (int64_t)a.Ho * a.Wo;
-        const int64_t b = rc.m / HoWo;
-        const int pix = (int)(rc.m - b * HoWo);
-        const int ho = pix / a.Wo, wo = pix - ho * a.Wo;
-        rc.hi0 = ho * a.stride - a.pad_t;
-        rc.wi0 = wo * a.stride - a.pad_l;
-        rc.rowoff = ((b * a.H + rc.hi0) * a.W + rc.wi0) * a.C;
+      rc.xrow = a.x;
+      rc.zrow = a.z;
+      {
+        if (CONV) {
+          const int64_t HoWo = (int64_t)a.Ho * a.Wo;
+          const int64_t b = rc.m / HoWo;
+          const int pix = (int)(rc.m - b * HoWo);
+          const int ho = pix / a.Wo, wo = pix - ho * a.Wo;
+          rc.hi0 = ho * a.stride - a.pad_t;
+          rc.wi0 = wo * a.stride - a.pad_l;
+          rc.xrow = a.x + ((b * a.H + rc.hi0) * a.W + rc.wi0) * a.C;
+        } else {
+          rc.xrow = a.x + rc.m * a.K;
+          if (a.z) rc.zrow = a.z + rc.m * a.K;
+        }
       }
     };
-    // gather the 16 x values (and z for dense) of global k-block c into registers
-    auto gather = [&](int64_t c, float xv[16], float zv[16]) {
-      const int64_t ti = c / a.kblocks;
-      const int kb = (int)(c - ti * a.kblocks);
+    const bool padded = CONV && (a.pad_t != 0 || a.pad_l != 0 || (a.Ho - 1) * a.stride + a.kh > a.H ||
+                                 (a.Wo - 1) * a.stride + a.kw > a.W);
+    const int nent = CONV ? a.kblocks * BK / (a.vec ? 4 : 1) : 0;
+    // gather the 16 x values (and z for dense) of k-block kb of this CTA's tile ti into registers.
+    // Rows beyond M read a valid row (their results are never stored), so the fast paths carry no
+    // row predicate; conv offsets come from the shared-memory table.
+    auto gather = [&](int ti, int kb, float xv[16], float zv[16]) {
       set_tile(ti);
+      const int k0 = kb * BK;
 #pragma unroll
       for (int kc = 0; kc < KC; ++kc) {
-        const int k = kb * BK + kc * 4;
+        const int k = k0 + kc * 4;
 #pragma unroll
         for (int e = 0; e < 4; ++e) { xv[kc * 4 + e] = 0.f; zv[kc * 4 + e] = 1.f; }
-        if (!(rc.ok && k < a.K)) continue;
         if (CONV) {
-          const int kwC = a.kw * a.C;
           if (a.vec) {
-            const int i = k / kwC, rem = k - i * kwC, j = rem / a.C, cch = rem - j * a.C;
-            const int hi = rc.hi0 + i, wi = rc.wi0 + j;
-            if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(a.x + rc.rowoff + ((int64_t)i * a.W + j) * a.C + cch));
+            const int off = ktab[(k0 >> 2) + kc];
+            bool ok = off >= 0;
+            if (padded && ok) {
+              const int ij = ktab[nent + (k0 >> 2) + kc];
+              const int hi = rc.hi0 + (ij >> 16), wi = rc.wi0 + (ij & 0xFFFF);
+              ok = hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
+            }
+            if (ok) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(rc.xrow + off));
               xv[kc * 4 + 0] = v.x; xv[kc * 4 + 1] = v.y; xv[kc * 4 + 2] = v.z; xv[kc * 4 + 3] = v.w;
             }
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int kk = k + e;
-              if (kk < a.K) {
-                const int i = kk / kwC, rem = kk - i * kwC, j = rem / a.C, cch = rem - j * a.C;
-                const int hi = rc.hi0 + i, wi = rc.wi0 + j;
-                if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W)
-                  xv[kc * 4 + e] = __ldg(a.x + rc.rowoff + ((int64_t)i * a.W + j) * a.C + cch);
+              const int off = ktab[k + e];
+              bool ok = off >= 0;
+              if (padded && ok) {
+                const int ij = ktab[nent + k + e];
+                const int hi = rc.hi0 + (ij >> 16), wi = rc.wi0 + (ij & 0xFFFF);
+                ok = hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
               }
+              if (ok) xv[kc * 4 + e] = __ldg(rc.xrow + off);
             }
           }
-        } else {
+        } else if (k < a.K) {
           if (a.vec) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(a.x + rc.m * a.K + k));
+            const float4 v = __ldg(reinterpret_cast<const float4*>(rc.xrow + k));
             xv[kc * 4 + 0] = v.x; xv[kc * 4 + 1] = v.y; xv[kc * 4 + 2] = v.z; xv[kc * 4 + 3] = v.w;
             if (a.z) {
-              const float4 w = __ldg(reinterpret_cast<const float4*>(a.z + rc.m * a.K + k));
+              const float4 w = __ldg(reinterpret_cast<const float4*>(rc.zrow + k));
               zv[kc * 4 + 0] = w.x; zv[kc * 4 + 1] = w.y; zv[kc * 4 + 2] = w.z; zv[kc * 4 + 3] = w.w;
             }
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               if (k + e < a.K) {
-                xv[kc * 4 + e] = __ldg(a.x + rc.m * a.K + k + e);
-                if (a.z) zv[kc * 4 + e] = __ldg(a.z + rc.m * a.K + k + e);
+                xv[kc * 4 + e] = __ldg(rc.xrow + k + e);
+                if (a.z) zv[kc * 4 + e] = __ldg(rc.zrow + k + e);
               }
           }
         }
       }
     };
 
+    // group g walks the k-blocks c = g, g+2, ... of this CTA's (tile, k-block) sequence
+    const int my_tiles = (int)((ntot > blockIdx.x) ? (ntot - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+    int ti = 0, kb = grp, stage = grp;
+    uint32_t sph = 0;
+    while (kb >= a.kblocks) { kb -= a.kblocks; ++ti; }
+    int nti = ti, nkb = kb;
+    auto advance2 = [&](int& t_, int& k_) {
+      k_ += 2;
+      while (k_ >= a.kblocks) { k_ -= a.kblocks; ++t_; }
+    };
     float xc[16], zc[16], xn[16], zn[16];
-    if (grp < total_kb) gather(grp, xc, zc);
-    for (int64_t c = grp; c < total_kb; c += 2) {
-      const int stage = (int)(c % STAGES);
-      const uint32_t sph = (uint32_t)((c / STAGES) & 1);
-      // B block of this stage: which tile / k-block?
-      const int64_t ti = c / a.kblocks;
-      const int kb = (int)(c - ti * a.kblocks);
-      const int64_t t = blockIdx.x + ti * gridDim.x;
-      const int nt = (int)(t % a.ntiles);
-      const bool more = c + 2 < total_kb;
-      if (more) gather(c + 2, xn, zn);  // next block's loads fly while this one is processed
+    if (ti < my_tiles) gather(ti, kb, xc, zc);
+    while (ti < my_tiles) {
+      advance2(nti, nkb);
+      const bool more = nti < my_tiles;
+      const int cur_nt = rc.nt;          // n-tile of the CURRENT block (rc may move on in gather below)
+      if (more) gather(nti, nkb, xn, zn);  // next block's loads fly while this one is processed
       mbar_wait(&empty[stage], sph ^ 1);
       if (r == 0) {
-        const float* bsrc = a.Bp + ((size_t)nt * a.kblocks + kb) * (size_t)(B_STAGE_BYTES / 4);
+        const float* bsrc = a.Bp + ((size_t)cur_nt * a.kblocks + kb) * (size_t)(B_STAGE_BYTES / 4);
         mbar_arrive_expect_tx(&full[stage], B_STAGE_BYTES);
         bulk_g2s(Bs + stage * B_STAGE_BYTES, bsrc, B_STAGE_BYTES, &full[stage]);
       }
@@ -406,6 +456,9 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) { xc[e] = xn[e]; zc[e] = zn[e]; }
       }
+      ti = nti; kb = nkb;
+      stage += 2;
+      if (stage >= STAGES) { stage -= STAGES; sph ^= 1; }
     }
   }
 
@@ -471,11 +524,14 @@ static int launch(mnf_ctx* ctx, Args& a, const float* mean_W, const float* log_s
   MNF_LAUNCHED(ctx);
   a.Bp = Bp;
   a.vb = vb;
-  constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + 4 * KC * BN * 16) + sizeof(float) * (BM * (BN + 1) + 4) + 256;
-  static bool attr_done = false;
-  if (!attr_done) {
+  const size_t tab_bytes = CONV ? sizeof(int) * 2 * (size_t)a.kblocks * BK / (a.vec ? 4 : 1) : 0;
+  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + 4 * KC * BN * 16) + sizeof(float) * (BM * (BN + 1) + 4) + 256 +
+                      sizeof(float) * 2 * BN + tab_bytes;
+  MNF_CHECK_ARG(smem <= 227 * 1024, "tensor-core conv path: K = %d is too large for the im2col table", a.K);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
     MNF_CUDA(cudaFuncSetAttribute(paired_umma_fwd<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_smem = smem;
   }
   const int64_t tiles = cdiv(a.M, BM) * a.ntiles;
   const int g = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
