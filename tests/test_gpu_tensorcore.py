@@ -75,3 +75,37 @@ def test_tensorcore_matches_ffma_with_philox(tc_ctx):
     lyr.call_index = 0
     y_ff = lyr(x).numpy()
     close(y_tc, y_ff, RTOL, "tf32x3 vs fp32 (Philox noise)")
+
+
+@pytest.mark.parametrize("kind", ["iaf", "rnvp"])
+@pytest.mark.parametrize("D,B,masks", [(20, 37, "ones"), (50, 300, "autoregressive"), (800, 130, "ones"),
+                                       (136, 64, "autoregressive"), (10, 129, "ones"), (500, 257, "ones")])
+def test_flow_chain_tensorcore(tc_ctx, kind, D, B, masks):
+    """IAF / RNVP steps on tcgen05 (flows_umma.cu) vs the float64 oracle, incl. saved activations."""
+    from gpu_util import make_flows
+
+    from tf_mnf_b200.flows import NormalizingFlow
+
+    if kind != "iaf" and masks == "autoregressive":
+        pytest.skip("masks only apply to IAF")
+    rng = np.random.RandomState(D + B)
+    steps = O.make_flow(rng, kind, D, 3, (50,), masks, np.float64)
+    for st in steps:
+        for k, v in st.items():
+            if k.startswith("b"):
+                for b in v if isinstance(v, list) else [v]:
+                    b[...] = 0.1 * rng.standard_normal(b.shape)
+        if kind == "iaf":
+            st["W"][1] *= 0.25
+    z = rng.standard_normal((B, D))
+    bern = [(rng.uniform(size=(B, D)) <= 0.5).astype(np.float64) for _ in range(3)]
+    ref_states, ref_ld, caches = O.flow_forward(z, steps, bern)
+    nf = NormalizingFlow(make_flows(steps, D))
+    states, ld = nf.forward(_f32(z), bern=[_f32(b) for b in bern] if kind == "rnvp" else None, record=True)
+    for k, (a, b) in enumerate(zip(states, ref_states)):
+        close(a.numpy(), b, RTOL, f"state {k}")
+    close(ld.numpy(), ref_ld, RTOL, "log_dets")
+    # hidden activations saved for backward: first step's h
+    h_ref = caches[0]["acts"][1] if kind == "iaf" else caches[0]["hs"][0]
+    h_got = nf.last_run.saved.numpy()[: B * 50].reshape(B, 50)
+    close(h_got, h_ref, RTOL, "saved hidden")

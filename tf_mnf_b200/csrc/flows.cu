@@ -294,10 +294,19 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
     return MNF_OK;
   }
   // planar scalars live in the workspace: [T][2]
+  // workspace: planar scalars [T][2] (padded to 256 B), then the packed split weights of one
+  // tensor-core flow step (re-used step after step: launches are ordered on the stream)
   float* scal = nullptr;
-  if (any_planar) {
-    scal = (float*)mnf_workspace(ctx, sizeof(float) * 2 * T);
-    if (!scal) return MNF_ERR_CUDA;
+  float* pack_ws = nullptr;
+  const bool use_tc = ctx->math_mode == MNF_MATH_TF32X3 && B >= 32;
+  {
+    const size_t scal_floats = ((size_t)2 * T + 63) & ~(size_t)63;
+    const size_t pack_floats = use_tc ? mnf_flow_umma_pack_floats((int)D) : 0;
+    if (any_planar || use_tc) {
+      scal = (float*)mnf_workspace(ctx, sizeof(float) * (scal_floats + pack_floats));
+      if (!scal) return MNF_ERR_CUDA;
+      pack_ws = scal + scal_floats;
+    }
   }
   int64_t saved_off = 0;  // saved is packed: step k starts after sum_{j<k} B*hidden_j
   for (int k = 0; k < T; ++k) {
@@ -320,6 +329,12 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
       a.w1 = st.w1; a.b1 = st.b1; a.ws = st.ws; a.bs = st.bs; a.wt = st.wt; a.bt = st.bt;
       a.m1 = st.m1; a.m2 = st.m2; a.ld2 = st.ld2;
       a.bern = make_noise(&st.bern);
+      if (use_tc && (z0_out || zin)) {  // tcgen05 path (3xTF32): same arithmetic contract, fp32 parity
+        int rc = mnf_flow_umma_step(ctx, B, (int)D, st.hidden, st.kind, st.parity, zin, q0_mean, q0_log_var, eps, z0_out,
+                                    zout, a.ld_in, a.ld_out, a.hid_save, st, a.bern, pack_ws);
+        if (rc) return rc;
+        continue;
+      }
       int grid = (int)cdiv(B, FT_ROWS);
       if (st.kind == MNF_FLOW_IAF)
         flow_mlp_step_fwd<MNF_FLOW_IAF><<<grid, FT_THREADS, 0, ctx->stream>>>(a);

@@ -1,0 +1,552 @@
+// IAF / RNVP flow step on the 5th-gen tensor cores (sm_100a): the whole coupling MLP of one
+// step for a 128-row tile in ONE CTA, both layers as 3xTF32 tcgen05.mma with TMEM accumulators,
+// the hidden activations never leaving the SM.
+//   reference: IAF.forward = MAF.inverse maf.py:47-53,63 (MADE made.py:77-91, MaskedDense :28-30),
+//              RNVP.forward rnvp.py:33-47, z0 sampling mnf_dense.py:93-96
+//
+//   stage 1   acc_h[128 x 64]  = in[128 x D] @ W1[D x H]      (in = z, or m*z for RNVP)
+//             producers (warps 5-12) load/sample z, apply the Bernoulli mask, split hi/lo and
+//             write K-major UMMA tiles; W1 arrives pre-split by cp.async.bulk; MMA warp 4.
+//   stage 1e  epilogue warps 0-3: tcgen05.ld acc_h, + b1, ReLU/tanh, split hi/lo and write it
+//             back to shared memory AS THE A OPERAND of stage 2 (never to HBM unless saved).
+//   stage 2   per 32-column chunk: acc[128 x 64] = h @ [Ws chunk | Wt chunk]  (K = 64), weights
+//             streamed by cp.async.bulk (warp 12), accumulators double-buffered in TMEM.
+//   stage 2e  warps 0-3 and 8-11: (s,t) -> y = z*exp(s)+t (IAF, with reversal) or the gated
+//             RNVP update; per-row log-det accumulated in registers, reduced through smem.
+#include "common.cuh"
+
+namespace fu {
+
+constexpr int BM = 128;
+constexpr int HP = 64;         // hidden units padded to 64
+constexpr int BK = 16, KC = 4; // stage-1 k-block (floats) and its 16-byte chunks
+constexpr int S1 = 3;          // stage-1 ring depth
+constexpr int CN = 32;         // stage-2 columns per chunk (s and t: N = 64 per MMA)
+constexpr int S2 = 3;          // stage-2 weight ring depth
+constexpr int THREADS = 13 * 32;
+constexpr int A1_VAR = KC * BM * 16;        // 8 KB: one variant (hi or lo) of a stage-1 A block
+constexpr int A1_STAGE = 2 * A1_VAR;        // 16 KB
+constexpr int B1_VAR = KC * HP * 16;        // 4 KB
+constexpr int B1_STAGE = 2 * B1_VAR;        // 8 KB
+constexpr int H_VAR = (HP / 4) * BM * 16;   // 32 KB: h hi (or lo) as a K = 64 A operand
+constexpr int B2_VAR = (HP / 4) * 64 * 16;  // 16 KB: [K = 64][N = 64] weights, one variant
+constexpr int B2_STAGE = 2 * B2_VAR;        // 32 KB
+constexpr int TMEM_COLS = 256;              // acc_h: 64, stage-2 accumulators: 2 x 64
+
+struct Args {
+  int64_t B;
+  int D, H, parity, kind;
+  int kblocks;   // ceil(D / 16)
+  int chunks;    // ceil(D / 32)
+  const float* zin;
+  const float* q0_mean;
+  const float* q0_log_var;
+  NoiseDev eps;
+  float* z0_out;
+  float* zout;
+  const float* ld_in;
+  float* ld_out;
+  float* hid_save;
+  const float* b1;
+  const float* bs;
+  const float* bt;
+  const float* B1p;  // [kblocks][2][KC][HP][4]
+  const float* B2p;  // [chunks][2][HP/4][64][4]
+  NoiseDev bern;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// K-major SWIZZLE_NONE descriptor (see tc_gemm.cu): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// x = hi + lo with BOTH parts rounded to nearest TF32 (cvt.rna): truncation would bias every
+// term the same way and the error of a K-term sum would grow like K instead of sqrt(K)
+__device__ __forceinline__ float tf32_rna(float a) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
+  hi = tf32_rna(a);
+  lo = tf32_rna(a - hi);
+}
+
+// z (or the sampled z0) for elements [4*g4, 4*g4+4) of one row
+__device__ __forceinline__ void load_z4(const Args& a, int64_t row, int g4, float out[4]) {
+  const int D = a.D, d = g4 * 4;
+  if (a.zin) {
+    const float* p = a.zin + row * D + d;
+    if (d + 3 < D && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+      out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) out[e] = d + e < D ? __ldg(p + e) : 0.f;
+    }
+    return;
+  }
+  float nrm[4];
+  if (a.eps.injected) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) nrm[e] = d + e < D ? a.eps.injected[row * D + d + e] : 0.f;
+  } else {
+    philox_normal4(a.eps, a.eps.row_offset + (uint64_t)row, 0u, (uint32_t)g4, nrm);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) out[e] = d + e < D ? a.q0_mean[d + e] + expf(0.5f * a.q0_log_var[d + e]) * nrm[e] : 0.f;
+}
+__device__ __forceinline__ void bern4(const NoiseDev& n, int64_t lrow, uint32_t g4, int n_inner, float out[4]) {
+  if (n.injected) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d = (int)(g4 * 4 + e);
+      out[e] = d < n_inner ? n.injected[lrow * n_inner + d] : 0.f;
+    }
+    return;
+  }
+  const Philox4 q = philox_at(n, n.row_offset + (uint64_t)lrow, 0u, g4);
+  out[0] = u01_open(q.x) <= 0.5f ? 1.f : 0.f;
+  out[1] = u01_open(q.y) <= 0.5f ? 1.f : 0.f;
+  out[2] = u01_open(q.z) <= 0.5f ? 1.f : 0.f;
+  out[3] = u01_open(q.w) <= 0.5f ? 1.f : 0.f;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // region R: stage-1 rings, later re-used as the stage-2 weight ring
+  uint8_t* A1 = smem;                         // [S1][2][KC][BM][16B]        48 KB
+  uint8_t* B1 = A1 + S1 * A1_STAGE;           // [S1][2][KC][HP][16B]        24 KB
+  uint8_t* B2 = smem;                         // [S2][2][16][64][16B]        96 KB (aliases A1/B1)
+  uint8_t* Hs = smem + S2 * B2_STAGE;         // [2][16][BM][16B]            64 KB
+  float* ldp = (float*)(Hs + 2 * H_VAR);      // [2][BM] log-det partials
+  uint64_t* bars = (uint64_t*)(ldp + 2 * BM);
+  uint64_t* full1 = bars;            // [S1]
+  uint64_t* empty1 = full1 + S1;     // [S1]
+  uint64_t* acc1_full = empty1 + S1; // [1]
+  uint64_t* h_ready = acc1_full + 1; // [1]
+  uint64_t* full2 = h_ready + 1;     // [S2]
+  uint64_t* empty2 = full2 + S2;     // [S2]
+  uint64_t* afull = empty2 + S2;     // [2]
+  uint64_t* aempty = afull + 2;      // [2]
+  uint32_t* tmem_slot = (uint32_t*)(aempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * BM;
+  const int D = a.D;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S1; ++s) { mbar_init(&full1[s], 4 + 1); mbar_init(&empty1[s], 1); }
+    mbar_init(acc1_full, 1);
+    mbar_init(h_ready, 4);
+    for (int s = 0; s < S2; ++s) { mbar_init(&full2[s], 1); mbar_init(&empty2[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&afull[b], 1); mbar_init(&aempty[b], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_acc1 = tmem_base, t_acc2 = tmem_base + 64;  // acc2 buffers at +64, +128
+
+  // instruction descriptor: D = F32, A = B = TF32, K-major, M = 128, N = 64
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  if (warp >= 5) {
+    // =========================================================== stage-1 producers (warps 5-12)
+    const int pt = threadIdx.x - 5 * 32;   // 0..255
+    const int r = pt & (BM - 1), grp = pt >> 7;
+    int64_t row = row0 + r;
+    const bool row_ok = row < a.B;
+    if (!row_ok) row = a.B - 1;
+    float cur[16], nxt[16];
+    auto gather = [&](int kb, float v[16]) {
+#pragma unroll
+      for (int kc = 0; kc < KC; ++kc) {
+        const int g4 = kb * KC + kc;
+        if (g4 * 4 < D) {
+          load_z4(a, row, g4, &v[kc * 4]);
+          if (a.z0_out && !a.zin && row_ok) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (g4 * 4 + e < D) a.z0_out[row * D + g4 * 4 + e] = v[kc * 4 + e];
+          }
+          if (a.kind == MNF_FLOW_RNVP) {
+            float m[4];
+            bern4(a.bern, row, (uint32_t)g4, D, m);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[kc * 4 + e] *= m[e];
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[kc * 4 + e] = 0.f;
+        }
+      }
+    };
+    int stage = grp;
+    uint32_t sph = 0;
+    if (grp < a.kblocks) gather(grp, cur);
+    for (int kb = grp; kb < a.kblocks; kb += 2) {
+      const bool more = kb + 2 < a.kblocks;
+      if (more) gather(kb + 2, nxt);
+      mbar_wait(&empty1[stage], sph ^ 1);
+      if (r == 0) {
+        mbar_arrive_expect_tx(&full1[stage], B1_STAGE);
+        bulk_g2s(B1 + stage * B1_STAGE, a.B1p + (size_t)kb * (B1_STAGE / 4), B1_STAGE, &full1[stage]);
+      }
+      uint8_t* dst0 = A1 + stage * A1_STAGE + r * 16;
+#pragma unroll
+      for (int kc = 0; kc < KC; ++kc) {
+        float h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_tf32(cur[kc * 4 + e], h[e], l[e]);
+        *reinterpret_cast<float4*>(dst0 + kc * (BM * 16)) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(dst0 + A1_VAR + kc * (BM * 16)) = make_float4(l[0], l[1], l[2], l[3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full1[stage]);
+      if (more) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) cur[e] = nxt[e];
+      }
+      stage += 2;
+      if (stage >= S1) { stage -= S1; sph ^= 1; }
+    }
+    // ---- warp 12: stage-2 weight loader (the ring re-uses the stage-1 buffers, so wait until
+    //      stage 1 has fully drained: acc1_full fires after the last stage-1 MMA retired)
+    if (warp == 12) {
+      mbar_wait(acc1_full, 0);
+      if (lane == 0) {
+        int s2 = 0;
+        uint32_t p2 = 0;
+        for (int c = 0; c < a.chunks; ++c) {
+          mbar_wait(&empty2[s2], p2 ^ 1);
+          mbar_arrive_expect_tx(&full2[s2], B2_STAGE);
+          bulk_g2s(B2 + s2 * B2_STAGE, a.B2p + (size_t)c * (B2_STAGE / 4), B2_STAGE, &full2[s2]);
+          if (++s2 == S2) { s2 = 0; p2 ^= 1; }
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 4) {
+    // ================================================================================ MMA warp
+    const uint64_t a1d = make_desc(smem_u32(A1), BM * 16, 128), b1d = make_desc(smem_u32(B1), HP * 16, 128);
+    int stage = 0;
+    uint32_t sph = 0;
+    for (int kb = 0; kb < a.kblocks; ++kb) {
+      mbar_wait(&full1[stage], sph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t ad = a1d + (uint64_t)((stage * A1_STAGE) >> 4), bd = b1d + (uint64_t)((stage * B1_STAGE) >> 4);
+#pragma unroll
+        for (int j = 0; j < BK / 8; ++j) {
+          const uint64_t ah = ad + (uint64_t)((2 * j * BM * 16) >> 4), al = ah + (A1_VAR >> 4);
+          const uint64_t bh = bd + (uint64_t)((2 * j * HP * 16) >> 4), bl = bh + (B1_VAR >> 4);
+          umma_tf32(t_acc1, ah, bh, idesc, (kb == 0 && j == 0) ? 0u : 1u);
+          umma_tf32(t_acc1, al, bh, idesc, 1u);
+          umma_tf32(t_acc1, ah, bl, idesc, 1u);
+        }
+        umma_commit(&empty1[stage]);
+        if (kb == a.kblocks - 1) umma_commit(acc1_full);
+      }
+      __syncwarp();
+      if (++stage == S1) { stage = 0; sph ^= 1; }
+    }
+    // stage 2: h (hi/lo in Hs) @ weight chunks
+    mbar_wait(h_ready, 0);
+    tc_fence_after();
+    const uint64_t hd = make_desc(smem_u32(Hs), BM * 16, 128), b2d = make_desc(smem_u32(B2), 64 * 16, 128);
+    int s2 = 0;
+    uint32_t p2 = 0;
+    for (int c = 0; c < a.chunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(&aempty[buf], ((c >> 1) & 1) ^ 1);
+      mbar_wait(&full2[s2], p2);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t bd = b2d + (uint64_t)((s2 * B2_STAGE) >> 4);
+        const uint32_t dacc = t_acc2 + buf * 64;
+#pragma unroll
+        for (int j = 0; j < HP / 8; ++j) {
+          const uint64_t ah = hd + (uint64_t)((2 * j * BM * 16) >> 4), al = ah + (H_VAR >> 4);
+          const uint64_t bh = bd + (uint64_t)((2 * j * 64 * 16) >> 4), bl = bh + (B2_VAR >> 4);
+          umma_tf32(dacc, ah, bh, idesc, j == 0 ? 0u : 1u);
+          umma_tf32(dacc, al, bh, idesc, 1u);
+          umma_tf32(dacc, ah, bl, idesc, 1u);
+        }
+        umma_commit(&empty2[s2]);
+        umma_commit(&afull[buf]);
+      }
+      __syncwarp();
+      if (++s2 == S2) { s2 = 0; p2 ^= 1; }
+    }
+  } else {
+    // ======================================================= stage-1 epilogue (warps 0-3): h -> Hs
+    const int r = warp * 32 + lane;
+    const int64_t row = row0 + r;
+    mbar_wait(acc1_full, 0);
+    tc_fence_after();
+    const uint32_t trow = t_acc1 + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < HP; c0 += 16) {
+      float v[16];
+      tmem_ld16(trow + c0, v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float h4[4], l4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int h = c0 + 4 * q + e;
+          float hv = 0.f;
+          if (h < a.H) {
+            const float pre = v[4 * q + e] + __ldg(a.b1 + h);
+            hv = (a.kind == MNF_FLOW_IAF) ? fmaxf(pre, 0.f) : tanhf(pre);
+            if (a.hid_save && row < a.B) a.hid_save[row * a.H + h] = hv;
+          }
+          split_tf32(hv, h4[e], l4[e]);
+        }
+        const int kc = (c0 >> 2) + q;  // 16-byte chunk index along K = hidden
+        *reinterpret_cast<float4*>(Hs + kc * (BM * 16) + r * 16) = make_float4(h4[0], h4[1], h4[2], h4[3]);
+        *reinterpret_cast<float4*>(Hs + H_VAR + kc * (BM * 16) + r * 16) = make_float4(l4[0], l4[1], l4[2], l4[3]);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(h_ready);
+  }
+
+  // ============================================ stage-2 epilogue: warps 0-3 (cols 0-15) and 8-11 (cols 16-31)
+  if (warp < 4 || (warp >= 8 && warp < 12)) {
+    const int g = warp & 3, half = warp >= 8 ? 1 : 0;
+    const int r = g * 32 + lane;
+    const int64_t row = row0 + r;
+    const bool row_ok = row < a.B;
+    float ld = 0.f;
+    for (int c = 0; c < a.chunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(&afull[buf], (c >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tb = t_acc2 + buf * 64 + ((uint32_t)(g * 32) << 16) + half * 16;
+      float sv[16], tv[16];
+      tmem_ld16(tb, sv);
+      tmem_ld16(tb + 32, tv);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&aempty[buf]);
+      const int cb = c * CN + half * 16;
+      if (row_ok && cb < D) {
+        const float* zsrc = a.zin ? a.zin : a.z0_out;  // the sampled z0 was stored by the producers
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c4 = cb + 4 * q;
+          if (c4 >= D) break;
+          float z4[4], m4[4] = {0.f, 0.f, 0.f, 0.f};
+          const float* zp = zsrc + row * D + c4;
+          if (c4 + 3 < D && ((reinterpret_cast<uintptr_t>(zp) & 15) == 0)) {
+            const float4 v = *reinterpret_cast<const float4*>(zp);
+            z4[0] = v.x; z4[1] = v.y; z4[2] = v.z; z4[3] = v.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) z4[e] = c4 + e < D ? zp[e] : 0.f;
+          }
+          if (a.kind == MNF_FLOW_RNVP) bern4(a.bern, row, (uint32_t)(c4 >> 2), D, m4);
+          float out[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = c4 + e;
+            if (col < D) {
+              const float s = sv[4 * q + e] + __ldg(a.bs + col), t = tv[4 * q + e] + __ldg(a.bt + col);
+              if (a.kind == MNF_FLOW_IAF) {
+                out[e] = fmaf(z4[e], expf(s), t);
+                ld += s;
+              } else {
+                const float m = m4[e];
+                const float gate = 1.f / (1.f + expf(-s));
+                const float lg = s >= 0.f ? -log1pf(expf(-s)) : s - log1pf(expf(s));
+                out[e] = ((1.f - m) * z4[e] * gate + (1.f - gate) * t) + m * z4[e];
+                ld += (1.f - m) * lg;
+              }
+            }
+          }
+          if (a.kind == MNF_FLOW_IAF && a.parity) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (c4 + e < D) a.zout[row * D + (D - 1 - c4 - e)] = out[e];
+          } else {
+            float* op = a.zout + row * D + c4;
+            if (c4 + 3 < D && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+              *reinterpret_cast<float4*>(op) = make_float4(out[0], out[1], out[2], out[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (c4 + e < D) op[e] = out[e];
+            }
+          }
+        }
+      }
+    }
+    ldp[half * BM + r] = ld;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < BM) {
+    const int64_t row = row0 + threadIdx.x;
+    if (row < a.B && a.ld_out)
+      a.ld_out[row] = (a.ld_in ? a.ld_in[row] : 0.f) + ldp[threadIdx.x] + ldp[BM + threadIdx.x];
+  }
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// W1 [D,H] (masked) -> B1p[kb][v][kc][n = hidden][4 k];  [Ws|Wt] -> B2p[chunk][v][kc (hidden/4)][n][4 hidden]
+__global__ void pack_flow_weights(int D, int H, int kblocks, int chunks, const float* __restrict__ w1,
+                                  const float* __restrict__ m1, const float* __restrict__ ws,
+                                  const float* __restrict__ wt, const float* __restrict__ m2, int64_t ld2,
+                                  float* __restrict__ B1p, float* __restrict__ B2p) {
+  const int64_t n1 = (int64_t)kblocks * KC * HP * 4;
+  const int64_t n2 = (int64_t)chunks * (HP / 4) * 64 * 4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n1 + n2; idx += (int64_t)gridDim.x * blockDim.x) {
+    float w = 0.f;
+    float* dst;
+    int64_t vstride;
+    if (idx < n1) {
+      const int e = (int)(idx & 3);
+      int64_t t = idx >> 2;
+      const int n = (int)(t % HP);
+      t /= HP;
+      const int kc = (int)(t % KC);
+      const int kb = (int)(t / KC);
+      const int k = kb * BK + kc * 4 + e;
+      if (k < D && n < H) {
+        w = w1[(int64_t)k * H + n];
+        if (m1) w *= m1[(int64_t)k * H + n];
+      }
+      dst = B1p + (int64_t)kb * (B1_STAGE / 4) + ((int64_t)kc * HP + n) * 4 + e;
+      vstride = B1_VAR / 4;
+    } else {
+      const int64_t i2 = idx - n1;
+      const int e = (int)(i2 & 3);
+      int64_t t = i2 >> 2;
+      const int n = (int)(t % 64);
+      t /= 64;
+      const int kc = (int)(t % (HP / 4));
+      const int c = (int)(t / (HP / 4));
+      const int h = kc * 4 + e, col = c * CN + (n & 31);
+      if (h < H && col < D) {
+        const int64_t o = (int64_t)h * ld2 + col;
+        w = n < 32 ? ws[o] : wt[o];
+        if (m2) w *= n < 32 ? m2[o] : m2[o + D];
+      }
+      dst = B2p + (int64_t)c * (B2_STAGE / 4) + ((int64_t)kc * 64 + n) * 4 + e;
+      vstride = B2_VAR / 4;
+    }
+    float hi, lo;
+    split_tf32(w, hi, lo);
+    dst[0] = hi;
+    dst[vstride] = lo;
+  }
+}
+
+}  // namespace fu
+
+// One IAF/RNVP step on tensor cores; ws_off: byte offset into the context workspace to use.
+int mnf_flow_umma_step(mnf_ctx* ctx, int64_t B, int D, int H, int kind, int parity, const float* zin,
+                       const float* q0_mean, const float* q0_log_var, const NoiseDev& eps, float* z0_out, float* zout,
+                       const float* ld_in, float* ld_out, float* hid_save, const mnf_flow_step& st,
+                       const NoiseDev& bern, float* pack_ws) {
+  using namespace fu;
+  Args a = {};
+  a.B = B; a.D = D; a.H = H; a.parity = parity; a.kind = kind;
+  a.kblocks = (D + BK - 1) / BK;
+  a.chunks = (D + CN - 1) / CN;
+  a.zin = zin; a.q0_mean = q0_mean; a.q0_log_var = q0_log_var; a.eps = eps; a.z0_out = z0_out; a.zout = zout;
+  a.ld_in = ld_in; a.ld_out = ld_out; a.hid_save = hid_save;
+  a.b1 = st.b1; a.bs = st.bs; a.bt = st.bt; a.bern = bern;
+  float* B1p = pack_ws;
+  float* B2p = pack_ws + (size_t)a.kblocks * (B1_STAGE / 4);
+  a.B1p = B1p; a.B2p = B2p;
+  const int64_t tot = (int64_t)a.kblocks * KC * HP * 4 + (int64_t)a.chunks * (HP / 4) * 64 * 4;
+  int grid = (int)(cdiv(tot, 256) < ctx->sm_count * 4 ? cdiv(tot, 256) : ctx->sm_count * 4);
+  pack_flow_weights<<<grid, 256, 0, ctx->stream>>>(D, H, a.kblocks, a.chunks, st.w1, st.m1, st.ws, st.wt, st.m2, st.ld2,
+                                                  B1p, B2p);
+  MNF_LAUNCHED(ctx);
+  constexpr size_t smem = (size_t)S2 * B2_STAGE + 2 * H_VAR + sizeof(float) * 2 * BM + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MNF_CUDA(cudaFuncSetAttribute(flow_umma_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const bool probed = mnf_probe_begin(ctx, MNF_PROBE_FLOW_STEP);
+  flow_umma_step<<<(unsigned)cdiv(B, BM), THREADS, smem, ctx->stream>>>(a);
+  mnf_probe_end(ctx, probed);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+size_t mnf_flow_umma_pack_floats(int D) {
+  using namespace fu;
+  const size_t kblocks = (D + BK - 1) / BK, chunks = (D + CN - 1) / CN;
+  return kblocks * (B1_STAGE / 4) + chunks * (B2_STAGE / 4) + 64;
+}

@@ -2,8 +2,8 @@
 // MNFConv2D.call mnf_conv.py:190-191) for sm_100a: tcgen05.mma (kind::tf32) with TMEM
 // accumulators, warp-specialised.
 //
-// fp32 parity on tensor cores: every operand is split x = hi + lo (hi = top 19 bits, i.e. an
-// exact TF32 value) and each product is evaluated as hi*hi + lo*hi + hi*lo (3xTF32) with fp32
+// fp32 parity on tensor cores: every operand is split x = hi + lo (both rounded to nearest
+// TF32 values) and each product is evaluated as hi*hi + lo*hi + hi*lo (3xTF32) with fp32
 // accumulation in TMEM: per-term relative error ~2^-20, inside the 1e-5 bar.
 //
 // One CTA per SM, persistent over 128-row tiles:
@@ -111,9 +111,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// x = hi + lo with BOTH parts rounded to nearest TF32 (cvt.rna): truncation would bias every
+// term the same way and the error of a K-term sum would grow like K instead of sqrt(K)
+__device__ __forceinline__ float tf32_rna(float a) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
-  lo = a - hi;
+  hi = tf32_rna(a);
+  lo = tf32_rna(a - hi);
 }
 
 // ---------------------------------------------------------------------------------- kernel
