@@ -20,7 +20,7 @@ namespace fu {
 constexpr int BM = 128;
 constexpr int HP = 64;         // hidden units padded to 64
 constexpr int BK = 16, KC = 4; // stage-1 k-block (floats) and its 16-byte chunks
-constexpr int S1 = 3;          // stage-1 ring depth
+constexpr int S1 = 4;          // stage-1 ring depth (S1 * 24 KB == S2 * 32 KB: the two rings alias)
 constexpr int CN = 32;         // stage-2 columns per chunk (s and t: N = 64 per MMA)
 constexpr int S2 = 3;          // stage-2 weight ring depth
 constexpr int THREADS = 13 * 32;
@@ -167,8 +167,8 @@ __device__ __forceinline__ void bern4(const NoiseDev& n, int64_t lrow, uint32_t 
 __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // region R: stage-1 rings, later re-used as the stage-2 weight ring
-  uint8_t* A1 = smem;                         // [S1][2][KC][BM][16B]        48 KB
-  uint8_t* B1 = A1 + S1 * A1_STAGE;           // [S1][2][KC][HP][16B]        24 KB
+  uint8_t* A1 = smem;                         // [S1][2][KC][BM][16B]        64 KB
+  uint8_t* B1 = A1 + S1 * A1_STAGE;           // [S1][2][KC][HP][16B]        32 KB
   uint8_t* B2 = smem;                         // [S2][2][16][64][16B]        96 KB (aliases A1/B1)
   uint8_t* Hs = smem + S2 * B2_STAGE;         // [2][16][BM][16B]            64 KB
   float* ldp = (float*)(Hs + 2 * H_VAR);      // [2][BM] log-det partials
@@ -182,6 +182,8 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
   uint64_t* afull = empty2 + S2;     // [2]
   uint64_t* aempty = afull + 2;      // [2]
   uint32_t* tmem_slot = (uint32_t*)(aempty + 2);
+  float* bias_s = (float*)(tmem_slot + 2);                       // [2][chunks*32]: bs | bt
+  uint16_t* mbits = (uint16_t*)(bias_s + 2 * a.chunks * CN);     // [BM][kblocks] RNVP mask bits of each 16-col block
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row0 = (int64_t)blockIdx.x * BM;
@@ -206,6 +208,11 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t t_acc1 = tmem_base, t_acc2 = tmem_base + 64;  // acc2 buffers at +64, +128
+  for (int c = threadIdx.x; c < a.chunks * CN; c += THREADS) {
+    bias_s[c] = c < a.D ? a.bs[c] : 0.f;
+    bias_s[a.chunks * CN + c] = c < a.D ? a.bt[c] : 0.f;
+  }
+  __syncthreads();
 
   // instruction descriptor: D = F32, A = B = TF32, K-major, M = 128, N = 64
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -219,6 +226,7 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
     if (!row_ok) row = a.B - 1;
     float cur[16], nxt[16];
     auto gather = [&](int kb, float v[16]) {
+      uint32_t bits = 0;
 #pragma unroll
       for (int kc = 0; kc < KC; ++kc) {
         const int g4 = kb * KC + kc;
@@ -233,20 +241,22 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
             float m[4];
             bern4(a.bern, row, (uint32_t)g4, D, m);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[kc * 4 + e] *= m[e];
+            for (int e = 0; e < 4; ++e) {
+              v[kc * 4 + e] *= m[e];
+              bits |= (m[e] != 0.f ? 1u : 0u) << (kc * 4 + e);
+            }
           }
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[kc * 4 + e] = 0.f;
         }
       }
+      if (a.kind == MNF_FLOW_RNVP) mbits[r * a.kblocks + kb] = (uint16_t)bits;  // re-used by the stage-2 epilogue
     };
-    int stage = grp;
-    uint32_t sph = 0;
-    if (grp < a.kblocks) gather(grp, cur);
-    for (int kb = grp; kb < a.kblocks; kb += 2) {
-      const bool more = kb + 2 < a.kblocks;
-      if (more) gather(kb + 2, nxt);
+    // split one k-block (16 values of this row) into the UMMA A tiles of its ring stage
+    auto publish = [&](int kb, const float v[16]) {
+      const int stage = kb % S1;
+      const uint32_t sph = (uint32_t)((kb / S1) & 1);
       mbar_wait(&empty1[stage], sph ^ 1);
       if (r == 0) {
         mbar_arrive_expect_tx(&full1[stage], B1_STAGE);
@@ -257,19 +267,78 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
       for (int kc = 0; kc < KC; ++kc) {
         float h[4], l[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) split_tf32(cur[kc * 4 + e], h[e], l[e]);
+        for (int e = 0; e < 4; ++e) split_tf32(v[kc * 4 + e], h[e], l[e]);
         *reinterpret_cast<float4*>(dst0 + kc * (BM * 16)) = make_float4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<float4*>(dst0 + A1_VAR + kc * (BM * 16)) = make_float4(l[0], l[1], l[2], l[3]);
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full1[stage]);
-      if (more) {
+    };
+    const bool use_async = a.zin && (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.zin) & 15) == 0);
+    if (use_async) {
+      // deep prefetch: this thread's 64 bytes of each k-block travel global -> shared by cp.async
+      // into a raw ring (8 blocks in flight per CTA; the ring borrows the h buffers, which are
+      // not written before stage 1 has drained).  A thread only ever reads back its own bytes.
+      constexpr int RAW = 8, PF = RAW / 2;
+      const float* zrow = a.zin + row * D;
+      const int sw = (r >> 1) & 3;
+      auto issue = [&](int kb) {
+        const uint32_t dst = smem_u32(Hs + (kb % RAW) * (BM * 64) + r * 64);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) cur[e] = nxt[e];
+        for (int kc = 0; kc < KC; ++kc) {
+          const int d = (kb * KC + kc) * 4;
+          if (d < D)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + ((kc ^ sw) << 4)), "l"(zrow + d) : "memory");
+        }
+      };
+#pragma unroll
+      for (int i = 0; i < PF; ++i) {
+        if (grp + 2 * i < a.kblocks) issue(grp + 2 * i);
+        asm volatile("cp.async.commit_group;" ::: "memory");
       }
-      stage += 2;
-      if (stage >= S1) { stage -= S1; sph ^= 1; }
+      for (int kb = grp; kb < a.kblocks; kb += 2) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");
+        const uint8_t* src = Hs + (kb % RAW) * (BM * 64) + r * 64;
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if ((kb * KC + kc) * 4 < D) v = *reinterpret_cast<const float4*>(src + ((kc ^ sw) << 4));
+          cur[kc * 4 + 0] = v.x; cur[kc * 4 + 1] = v.y; cur[kc * 4 + 2] = v.z; cur[kc * 4 + 3] = v.w;
+        }
+        if (kb + RAW < a.kblocks) issue(kb + RAW);  // same slot, already copied to registers
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (a.kind == MNF_FLOW_RNVP) {
+          uint32_t bits = 0;
+#pragma unroll
+          for (int kc = 0; kc < KC; ++kc) {
+            const int g4 = kb * KC + kc;
+            if (g4 * 4 < D) {
+              float m[4];
+              bern4(a.bern, row, (uint32_t)g4, D, m);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                cur[kc * 4 + e] *= m[e];
+                bits |= (m[e] != 0.f ? 1u : 0u) << (kc * 4 + e);
+              }
+            }
+          }
+          mbits[r * a.kblocks + kb] = (uint16_t)bits;
+        }
+        publish(kb, cur);
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    } else {
+      if (grp < a.kblocks) gather(grp, cur);
+      for (int kb = grp; kb < a.kblocks; kb += 2) {
+        const bool more = kb + 2 < a.kblocks;
+        if (more) gather(kb + 2, nxt);
+        publish(kb, cur);
+        if (more) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) cur[e] = nxt[e];
+        }
+      }
     }
     // ---- warp 12: stage-2 weight loader (the ring re-uses the stage-1 buffers, so wait until
     //      stage 1 has fully drained: acc1_full fires after the last stage-1 MMA retired)
@@ -376,14 +445,39 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
   }
 
   // ============================================ stage-2 epilogue: warps 0-3 (cols 0-15) and 8-11 (cols 16-31)
+  // Fast-math note: exp / log / reciprocal use the MUFU approximations (__expf, __logf,
+  // __fdividef): relative error ~1e-6 for the |s| this path sees, inside the 1e-5 parity bar
+  // (tests/test_gpu_tensorcore.py); the FFMA kernels keep the IEEE-accurate versions.
   if (warp < 4 || (warp >= 8 && warp < 12)) {
     const int g = warp & 3, half = warp >= 8 ? 1 : 0;
     const int r = g * 32 + lane;
     const int64_t row = row0 + r;
     const bool row_ok = row < a.B;
+    const float* zsrc = a.zin ? a.zin : a.z0_out;  // the sampled z0 was stored by the producers
+    const float* zrow = zsrc + (row_ok ? row : 0) * D;
+    const bool vec_ok = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(zsrc) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(a.zout) & 15) == 0);
+    const float* bs_s = bias_s;
+    const float* bt_s = bias_s + a.chunks * CN;
     float ld = 0.f;
     for (int c = 0; c < a.chunks; ++c) {
       const int buf = c & 1;
+      const int cb = c * CN + half * 16;
+      // z of this thread's 16 columns: issued before the accumulator wait so the latency overlaps
+      float z16[16];
+      if (a.zin) {  // (a sampled z0 only becomes visible after the barrier chain below)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c4 = cb + 4 * q;
+          if (row_ok && vec_ok && c4 + 3 < D) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(zrow + c4));
+            z16[4 * q + 0] = v.x; z16[4 * q + 1] = v.y; z16[4 * q + 2] = v.z; z16[4 * q + 3] = v.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) z16[4 * q + e] = (row_ok && c4 + e < D) ? __ldg(zrow + c4 + e) : 0.f;
+          }
+        }
+      }
       mbar_wait(&afull[buf], (c >> 1) & 1);
       tc_fence_after();
       const uint32_t tb = t_acc2 + buf * 64 + ((uint32_t)(g * 32) << 16) + half * 16;
@@ -393,53 +487,43 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&aempty[buf]);
-      const int cb = c * CN + half * 16;
+      if (!a.zin) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) z16[e] = (row_ok && cb + e < D) ? zrow[cb + e] : 0.f;
+      }
       if (row_ok && cb < D) {
-        const float* zsrc = a.zin ? a.zin : a.z0_out;  // the sampled z0 was stored by the producers
+        const uint32_t mb = (a.kind == MNF_FLOW_RNVP) ? (uint32_t)mbits[r * a.kblocks + (cb >> 4)] : 0u;
+        float out[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c4 = cb + 4 * q;
-          if (c4 >= D) break;
-          float z4[4], m4[4] = {0.f, 0.f, 0.f, 0.f};
-          const float* zp = zsrc + row * D + c4;
-          if (c4 + 3 < D && ((reinterpret_cast<uintptr_t>(zp) & 15) == 0)) {
-            const float4 v = *reinterpret_cast<const float4*>(zp);
-            z4[0] = v.x; z4[1] = v.y; z4[2] = v.z; z4[3] = v.w;
+        for (int e = 0; e < 16; ++e) {
+          const float s = sv[e] + bs_s[cb + e], t = tv[e] + bt_s[cb + e], zv = z16[e];
+          if (a.kind == MNF_FLOW_IAF) {
+            out[e] = fmaf(zv, __expf(s), t);
+            if (cb + e < D) ld += s;
           } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) z4[e] = c4 + e < D ? zp[e] : 0.f;
+            const float m = (mb >> e) & 1u ? 1.f : 0.f;
+            const float u = __expf(-fabsf(s));           // in (0, 1]
+            const float rcp = __fdividef(1.f, 1.f + u);
+            const float gate = s >= 0.f ? rcp : u * rcp;  // sigmoid(s)
+            const float lg = fminf(s, 0.f) - __logf(1.f + u);  // log(sigmoid(s))
+            out[e] = ((1.f - m) * zv * gate + (1.f - gate) * t) + m * zv;
+            if (cb + e < D) ld += (1.f - m) * lg;
           }
-          if (a.kind == MNF_FLOW_RNVP) bern4(a.bern, row, (uint32_t)(c4 >> 2), D, m4);
-          float out[4];
+        }
+        if (a.kind == MNF_FLOW_IAF && a.parity) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = c4 + e;
-            if (col < D) {
-              const float s = sv[4 * q + e] + __ldg(a.bs + col), t = tv[4 * q + e] + __ldg(a.bt + col);
-              if (a.kind == MNF_FLOW_IAF) {
-                out[e] = fmaf(z4[e], expf(s), t);
-                ld += s;
-              } else {
-                const float m = m4[e];
-                const float gate = 1.f / (1.f + expf(-s));
-                const float lg = s >= 0.f ? -log1pf(expf(-s)) : s - log1pf(expf(s));
-                out[e] = ((1.f - m) * z4[e] * gate + (1.f - gate) * t) + m * z4[e];
-                ld += (1.f - m) * lg;
-              }
-            }
-          }
-          if (a.kind == MNF_FLOW_IAF && a.parity) {
+          for (int e = 0; e < 16; ++e)
+            if (cb + e < D) a.zout[row * D + (D - 1 - cb - e)] = out[e];
+        } else {
+          float* op = a.zout + row * D + cb;
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (c4 + e < D) a.zout[row * D + (D - 1 - c4 - e)] = out[e];
-          } else {
-            float* op = a.zout + row * D + c4;
-            if (c4 + 3 < D && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-              *reinterpret_cast<float4*>(op) = make_float4(out[0], out[1], out[2], out[3]);
+          for (int q = 0; q < 4; ++q) {
+            if (vec_ok && cb + 4 * q + 3 < D) {
+              *reinterpret_cast<float4*>(op + 4 * q) = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                if (c4 + e < D) op[e] = out[e];
+                if (cb + 4 * q + e < D) op[4 * q + e] = out[4 * q + e];
             }
           }
         }
@@ -532,11 +616,12 @@ int mnf_flow_umma_step(mnf_ctx* ctx, int64_t B, int D, int H, int kind, int pari
   pack_flow_weights<<<grid, 256, 0, ctx->stream>>>(D, H, a.kblocks, a.chunks, st.w1, st.m1, st.ws, st.wt, st.m2, st.ld2,
                                                   B1p, B2p);
   MNF_LAUNCHED(ctx);
-  constexpr size_t smem = (size_t)S2 * B2_STAGE + 2 * H_VAR + sizeof(float) * 2 * BM + 256;
-  static bool attr_done = false;
-  if (!attr_done) {
+  const size_t smem = (size_t)S2 * B2_STAGE + 2 * H_VAR + sizeof(float) * 2 * BM + 256 +
+                      sizeof(float) * 2 * (size_t)a.chunks * CN + sizeof(uint16_t) * (size_t)BM * a.kblocks + 16;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
     MNF_CUDA(cudaFuncSetAttribute(flow_umma_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_smem = smem;
   }
   const bool probed = mnf_probe_begin(ctx, MNF_PROBE_FLOW_STEP);
   flow_umma_step<<<(unsigned)cdiv(B, BM), THREADS, smem, ctx->stream>>>(a);
