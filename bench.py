@@ -210,9 +210,12 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     model.set_row_offset(rank * ROWS)
     flush = ctx.empty((64 << 20,))  # 256 MiB > 126 MB L2
 
+    kl_ctx = ctx.fork()  # kl_div() does not depend on x: it runs on a sibling stream beside the forward
+
     def step(x):
         probs = model(x)
-        kl = model.kl_div()
+        kl = model.kl_div(ctx=kl_ctx)
+        ctx.wait(kl_ctx)  # join: the step (and its stop event) completes only when the KL has
         return probs, kl
 
     def ev():
@@ -222,6 +225,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
 
     def barrier():
         ctx.sync()
+        kl_ctx.sync()
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
@@ -232,6 +236,41 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
         L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
         step(x_dev)
     barrier()
+    if args.breakdown and rank == 0:  # per-call device times of one (warm) step, for DESIGN.md / profiles
+        marks = []
+
+        def mark(name):
+            e = ev()
+            L.check(lib.mnf_event_record(ctx.handle, e))
+            marks.append((name, e))
+
+        for rep in range(3):
+            marks.clear()
+            L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
+            mark("start")
+            h = x_dev
+            for lyr in model.layers:
+                h = lyr(h)
+                mark(type(lyr).__name__)
+            for lyr in model.mnf_layers:
+                lyr.kl_div()
+                mark("kl_div:" + type(lyr).__name__)
+            ctx.sync()
+        parts = []
+        for (n0, e0), (n1, e1) in zip(marks, marks[1:]):
+            ms_ = C.c_float()
+            L.check(lib.mnf_event_elapsed_ms(e0, e1, C.byref(ms_)))
+            parts.append((n1, round(ms_.value * 1e3, 1)))
+        print("[breakdown us] " + ", ".join(f"{n}={v}" for n, v in parts) + f"  total={sum(v for _, v in parts):.0f}",
+              file=sys.stderr, flush=True)
+        ctx.sync()
+        t0 = time.perf_counter()
+        model(x_dev)
+        t1 = time.perf_counter()
+        model.kl_div()
+        t2 = time.perf_counter()
+        ctx.sync()
+        print(f"[host enqueue us] forward={(t1 - t0) * 1e6:.0f} kl_div={(t2 - t1) * 1e6:.0f}", file=sys.stderr, flush=True)
     t_dead = time.perf_counter() + 8.0  # nvidia-smi has finished initialising once it prints samples
     while clk.proc is not None and len(clk.rows) < 3 and time.perf_counter() < t_dead:
         time.sleep(0.05)
@@ -243,7 +282,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     # ---- timed: K steps, device-resident input, per-step CUDA events, L2 flushed in between
     starts, stops = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
     kst, ksp = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
-    launches0 = ctx.launches
+    launches0 = ctx.launches + kl_ctx.launches
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
@@ -255,7 +294,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     t_wall1 = time.perf_counter()
     t_wall = t_wall1 - t_wall0
     clk.__exit__()
-    launches = ctx.launches - launches0
+    launches = ctx.launches + kl_ctx.launches - launches0
 
     def elapsed(a, b):
         ms = C.c_float()
@@ -282,6 +321,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
         L.check(lib.mnf_memcpy_d2h(ctx.handle, res_host, C.c_void_p(probs.ptr), probs.nbytes))
         L.check(lib.mnf_memcpy_d2h(ctx.handle, C.c_void_p(res_host.value + probs.nbytes), C.c_void_p(kl.ptr), 4))
         ctx.sync()
+        kl_ctx.sync()
 
     e2e_step()
     barrier()
@@ -355,6 +395,7 @@ def main() -> None:
     ap.add_argument("--cpu-rows", type=int, default=2560, help="rows per CPU-baseline step (bounded sample)")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print per-layer device times of one step (stderr)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

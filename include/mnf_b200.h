@@ -59,6 +59,9 @@ int mnf_ctx_destroy(mnf_ctx* ctx);
 int mnf_ctx_set_stream(mnf_ctx* ctx, void* stream);
 int mnf_ctx_get_stream(mnf_ctx* ctx, void** stream);
 int mnf_ctx_sync(mnf_ctx* ctx);
+/* Make all FUTURE work on ctx's stream wait for everything enqueued so far on other's stream
+ * (event fork/join; lets kl_div(), which does not depend on x, run on a second context). */
+int mnf_ctx_wait(mnf_ctx* ctx, mnf_ctx* other);
 int mnf_ctx_sm_count(mnf_ctx* ctx, int* out);
 /* kernels launched by this context since creation (bench.py reports it as gpu_launches) */
 int mnf_ctx_launch_count(mnf_ctx* ctx, int64_t* out);

@@ -65,6 +65,7 @@ SIGNATURES = {
     "mnf_ctx_set_stream": [vp, vp],
     "mnf_ctx_get_stream": [vp, C.POINTER(vp)],
     "mnf_ctx_sync": [vp],
+    "mnf_ctx_wait": [vp, vp],
     "mnf_ctx_sm_count": [vp, C.POINTER(C.c_int)],
     "mnf_ctx_launch_count": [vp, C.POINTER(_i64)],
     "mnf_ctx_set_math": [vp, C.c_int],

@@ -252,6 +252,151 @@ __global__ void __launch_bounds__(C1_THREADS) flow_chain_row1(Chain1Args a) {
   if (tid == 0 && a.ld_out) a.ld_out[0] = ld_tot;
 }
 
+// -------------------------------------------------- single-row chain on a thread-block cluster
+// The one-CTA kernel above pulls every step's ~(6*D*H) weight words through a single SM and is
+// latency bound (65 us per step at D = 800).  Here a cluster of CL_N CTAs splits each step:
+// stage 1 reduces a D-slice per CTA (partials exchanged through a tiny global scratch + a cluster
+// barrier), stage 2 gives each CTA a column slice; the new state goes to `states` (which the
+// reference returns anyway) and is re-read after the next cluster barrier.
+#define CL_N 8
+#define CL_THREADS 256
+
+struct ChainClArgs {
+  Chain1Args c;
+  float* part_h;   // [CL_N][FT_HMAX] stage-1 partial sums (re-used every step)
+  float* part_ld;  // [CL_N]
+};
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+__global__ void __cluster_dims__(CL_N, 1, 1) __launch_bounds__(CL_THREADS) flow_chain_row1_cluster(ChainClArgs ca) {
+  const Chain1Args& a = ca.c;
+  __shared__ float part[4][FT_HMAX + 1];
+  __shared__ float hs[FT_HMAX];
+  __shared__ float red[CL_THREADS / 32];
+  const int tid = threadIdx.x, D = a.D;
+  const int rank = (int)cluster_rank();
+  // column / reduction slice of this CTA (multiples of 4 so one Philox call serves 4 draws)
+  const int per = ((D + CL_N - 1) / CL_N + 3) & ~3;
+  const int lo = min(D, rank * per), hi = min(D, lo + per);
+  // states[0]
+  for (int d = lo + tid; d < hi; d += CL_THREADS)
+    a.states[d] = a.zin ? a.zin[d]
+                        : a.q0_mean[d] + expf(0.5f * a.q0_log_var[d]) * noise_normal1(a.eps, 0, 0u, (uint32_t)d, 1, D);
+  __threadfence();
+  cluster_sync_all();
+  float ld_tot = 0.f;
+  int hoff = 0;
+  for (int k = 0; k < a.T; ++k) {
+    const Chain1Step& s = a.st[k];
+    const float* zc = a.states + (int64_t)k * D;
+    float* zn = a.states + (int64_t)(k + 1) * D;
+    const int H = s.H;
+    // ---- stage 1: partial h over d in [lo, hi); thread = (hidden j, one of 4 d-sub-slices)
+    {
+      const int j = tid & 63, sl = tid >> 6;
+      float acc = 0.f;
+      if (j < H) {
+        const int n = hi - lo, sub = ((n + 3) / 4 + 3) & ~3;
+        const int d0 = lo + sl * sub, d1 = min(hi, d0 + sub);
+        for (int dq = d0; dq < d1; dq += 4) {
+          float m4[4] = {1.f, 1.f, 1.f, 1.f};
+          if (s.kind == MNF_FLOW_RNVP) noise_bern4(s.bern, 0, (uint32_t)(dq >> 2), D, 0.5f, m4);
+          float w[4], zv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int d = dq + e;
+            const bool ok = d < d1;
+            w[e] = ok ? __ldg(s.w1 + (int64_t)d * H + j) : 0.f;
+            if (ok && s.m1) w[e] *= __ldg(s.m1 + (int64_t)d * H + j);
+            zv[e] = ok ? zc[d] : 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc = fmaf(zv[e] * m4[e], w[e], acc);
+        }
+        part[sl][j] = acc;
+      }
+    }
+    __syncthreads();
+    if (tid < FT_HMAX) ca.part_h[rank * FT_HMAX + tid] = tid < H ? part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid] : 0.f;
+    __threadfence();
+    cluster_sync_all();
+    if (tid < H) {
+      float pre = s.b1[tid];
+#pragma unroll
+      for (int q = 0; q < CL_N; ++q) pre += __ldcg(ca.part_h + q * FT_HMAX + tid);
+      const float hv = (s.kind == MNF_FLOW_IAF) ? fmaxf(pre, 0.f) : tanhf(pre);
+      hs[tid] = hv;
+      if (a.hid_save && rank == 0) a.hid_save[hoff + tid] = hv;
+    }
+    __syncthreads();
+    // ---- stage 2: this CTA's columns
+    float ld = 0.f;
+    for (int c = lo + tid; c < hi; c += CL_THREADS) {
+      float sv = s.bs[c], tv = s.bt[c];
+      for (int h0 = 0; h0 < H; h0 += 10) {
+        float ws[10], wt[10];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) {
+          const int h = h0 + q;
+          ws[q] = wt[q] = 0.f;
+          if (h < H) {
+            ws[q] = __ldg(s.ws + (int64_t)h * s.ld2 + c);
+            wt[q] = __ldg(s.wt + (int64_t)h * s.ld2 + c);
+            if (s.m2) {
+              ws[q] *= __ldg(s.m2 + (int64_t)h * s.ld2 + c);
+              wt[q] *= __ldg(s.m2 + (int64_t)h * s.ld2 + D + c);
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 10; ++q)
+          if (h0 + q < H) {
+            sv = fmaf(hs[h0 + q], ws[q], sv);
+            tv = fmaf(hs[h0 + q], wt[q], tv);
+          }
+      }
+      const float zv = zc[c];
+      if (s.kind == MNF_FLOW_IAF) {
+        zn[s.parity ? D - 1 - c : c] = fmaf(zv, expf(sv), tv);
+        ld += sv;
+      } else {
+        const float m = noise_bern1(s.bern, 0, (uint32_t)c, D, 0.5f);
+        const float gate = 1.f / (1.f + expf(-sv));
+        const float lg = sv >= 0.f ? -log1pf(expf(-sv)) : sv - log1pf(expf(sv));
+        zn[c] = ((1.f - m) * zv * gate + (1.f - gate) * tv) + m * zv;
+        ld += (1.f - m) * lg;
+      }
+    }
+    ld = warp_sum(ld);
+    if ((tid & 31) == 0) red[tid >> 5] = ld;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+      for (int q = 0; q < CL_THREADS / 32; ++q) t += red[q];
+      ld_tot += t;
+    }
+    hoff += H;
+    __threadfence();
+    cluster_sync_all();  // new state visible to every CTA; part_h / hs / red free for the next step
+  }
+  if (tid == 0) ca.part_ld[rank] = ld_tot;
+  __threadfence();
+  cluster_sync_all();
+  if (rank == 0 && tid == 0 && a.ld_out) {
+    float t = 0.f;
+    for (int q = 0; q < CL_N; ++q) t += __ldcg(ca.part_ld + q);
+    a.ld_out[0] = t;
+  }
+}
+
 extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, const mnf_flow_step* steps,
                                 const float* z0, const float* q0_mean, const float* q0_log_var,
                                 const mnf_noise* eps_z, float* states, float* log_dets, float* saved) {
@@ -288,7 +433,17 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
       s.bern = make_noise(&steps[k].bern);
     }
     const bool probed = mnf_probe_begin(ctx, MNF_PROBE_FLOW_STEP);
-    flow_chain_row1<<<1, C1_THREADS, 0, ctx->stream>>>(a);
+    if (D >= 16) {  // split the chain over a cluster of CL_N CTAs (scratch: [CL_N][64] + [CL_N] floats)
+      ChainClArgs ca;
+      ca.c = a;
+      float* scratch = (float*)mnf_workspace(ctx, sizeof(float) * (CL_N * FT_HMAX + CL_N + 64));
+      if (!scratch) return MNF_ERR_CUDA;
+      ca.part_h = scratch;
+      ca.part_ld = scratch + CL_N * FT_HMAX;
+      flow_chain_row1_cluster<<<CL_N, CL_THREADS, 0, ctx->stream>>>(ca);
+    } else {
+      flow_chain_row1<<<1, C1_THREADS, 0, ctx->stream>>>(a);
+    }
     mnf_probe_end(ctx, probed);
     MNF_LAUNCHED(ctx);
     return MNF_OK;

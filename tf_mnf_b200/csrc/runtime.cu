@@ -116,6 +116,21 @@ int mnf_ctx_sync(mnf_ctx* ctx) {
   return MNF_OK;
 }
 
+int mnf_ctx_wait(mnf_ctx* ctx, mnf_ctx* other) {
+  MNF_CHECK_ARG(ctx && other, "mnf_ctx_wait: NULL context");
+  if (ctx == other || ctx->stream == other->stream) return MNF_OK;
+  cudaEvent_t ev;
+  MNF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaError_t e = cudaEventRecord(ev, other->stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev, 0);
+  cudaEventDestroy(ev);  // released once the recorded work completes
+  if (e != cudaSuccess) {
+    mnf_set_error("mnf_ctx_wait failed: %s", cudaGetErrorString(e));
+    return MNF_ERR_CUDA;
+  }
+  return MNF_OK;
+}
+
 int mnf_ctx_sm_count(mnf_ctx* ctx, int* out) {
   MNF_CHECK_ARG(ctx && out, "ctx/out is NULL");
   *out = ctx->sm_count;

@@ -121,9 +121,9 @@ class MNFLayerBase:
 
     # ------------------------------------------------------------------- sample_z
     def _sample_z(self, batch_size: int, z_draw: int, bern_draw: int, inject: dict | None, record: bool,
-                  row_offset: int):
+                  row_offset: int, ctx: Context | None = None):
         """mnf_dense.py:88-102 / mnf_conv.py:100-114 -> (z, log_dets, ChainRun | None)."""
-        ctx, D = self.ctx, self._flow_dim()
+        ctx, D = ctx or self.ctx, self._flow_dim()
         B = int(batch_size)
         if not self.use_z:
             return None, ctx.zeros((B,)), None
@@ -157,16 +157,17 @@ class MNFLayerBase:
     def _kl_shape(self) -> tuple[int, int]:  # pragma: no cover - abstract
         raise NotImplementedError
 
-    def kl_div(self, noise: dict | None = None) -> DeviceArray:  # noqa: A002
+    def kl_div(self, noise: dict | None = None, ctx: Context | None = None) -> DeviceArray:  # noqa: A002
         """MNFDense.kl_div mnf_dense.py:104-157 / MNFConv2D.kl_div mnf_conv.py:116-180.
-        Returns a 1-element device array (float(kl) copies it to the host)."""
+        Returns a 1-element device array (float(kl) copies it to the host).  `ctx`: run on
+        another context/stream (kl_div does not depend on x); join with `main.wait(ctx)`."""
 
 
         self._require_built()
-        ctx, D = self.ctx, self._flow_dim()
+        ctx, D = ctx or self.ctx, self._flow_dim()
         inj = noise or {}
         rows, cols = self._kl_shape()
-        z, ldq, qrun = self._sample_z(1, nz.KL_Z, nz.BERN_Q_KL, inj, self.training, 0)
+        z, ldq, qrun = self._sample_z(1, nz.KL_Z, nz.BERN_Q_KL, inj, self.training, 0, ctx)
         a = L.KlArgs()
         a.conv, a.use_z = int(self._conv), int(self.use_z)
         a.r_all_states = int(self.r_term == "all_states")

@@ -119,13 +119,14 @@ class Sequential:
                 x = lyr(x)
         return x
 
-    def kl_div(self, noise: list | None = None) -> DeviceArray:  # noqa: A002
-        """Sum of the layers' KL terms (mnf_lenet.py:35-39, mnf_feed_forward.py:23-28)."""
+    def kl_div(self, noise: list | None = None, ctx: Any = None) -> DeviceArray:  # noqa: A002
+        """Sum of the layers' KL terms (mnf_lenet.py:35-39, mnf_feed_forward.py:23-28).
+        `ctx`: optional sibling context (Context.fork()) so the KL runs beside a forward pass."""
         it = iter(noise or [])
         total = None
         for lyr in self.layers:
             if hasattr(lyr, "kl_div"):
-                kl = lyr.kl_div(noise=next(it, None))
+                kl = lyr.kl_div(noise=next(it, None), ctx=ctx)
                 if total is None:
                     total = kl
                 else:

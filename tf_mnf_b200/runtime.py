@@ -53,6 +53,18 @@ class Context:
     def sync(self) -> None:
         L.check(self.lib.mnf_ctx_sync(self.handle))
 
+    def fork(self) -> "Context":
+        """A sibling context on the same device with its own stream and workspace (e.g. to run
+        kl_div(), which does not depend on x, concurrently with a forward pass)."""
+        c = Context(self.device)
+        if getattr(self, "math", None):
+            c.set_math(self.math)
+        return c
+
+    def wait(self, other: "Context") -> None:
+        """Order this context's future work after everything enqueued so far on `other`."""
+        L.check(self.lib.mnf_ctx_wait(self.handle, other.handle))
+
     def set_math(self, mode: str) -> None:
         """"fp32": FFMA kernels; "tf32x3": tcgen05 tensor cores with hi/lo operand splitting
         (fp32-level accuracy).  Applies to the dense / conv forward contractions."""
