@@ -203,8 +203,13 @@ typedef struct {
   int64_t kh, kw, F;   /* filters HWIO [kh,kw,C,F] */
   int64_t stride;      /* same in both spatial dims */
   int32_t same;        /* 0 = VALID, 1 = SAME (TF semantics) */
+  int32_t fuse_relu_pool; /* forward only: apply ReLU + MaxPool2D(2x2, stride 2) in the epilogue
+                             (mnf_lenet.py:23-24,26-27); y is then [B, Ho/2, Wo/2, F] */
 } mnf_conv_shape;
 int mnf_conv_out_hw(const mnf_conv_shape* s, int64_t* Ho, int64_t* Wo);
+/* *ok = 1 when mnf_conv2d_forward can honour fuse_relu_pool for this shape under the context's
+ * math mode (even Ho/Wo, filter count within one tile); otherwise call mnf_relu_maxpool2. */
+int mnf_conv2d_can_fuse_pool(mnf_ctx* ctx, const mnf_conv_shape* s, int32_t* ok);
 
 /* MNFConv2D.call, mnf_conv.py:182-197 (with the strides/padding the reference omits):
  *   y = (conv(x,mean_W)+mean_b) * z[b,f] + sqrt(conv(x^2, var_W) + var_b) * eps

@@ -109,3 +109,27 @@ def test_flow_chain_tensorcore(tc_ctx, kind, D, B, masks):
     h_ref = caches[0]["acts"][1] if kind == "iaf" else caches[0]["hs"][0]
     h_got = nf.last_run.saved.numpy()[: B * 50].reshape(B, 50)
     close(h_got, h_ref, RTOL, "saved hidden")
+
+
+@pytest.mark.parametrize("math", ["tf32x3", "fp32"])
+@pytest.mark.parametrize("shape,wshape", [((6, 28, 28, 1), (5, 5, 1, 20)), ((5, 12, 12, 20), (5, 5, 20, 50)),
+                                          ((3, 10, 12, 4), (3, 3, 4, 8))])
+def test_conv_fused_relu_pool_equals_unfused(tc_ctx, math, shape, wshape):
+    """ReLU + MaxPool folded into the conv epilogue == conv, then mnf_relu_maxpool2 (bit-exact:
+    same arithmetic and the same Philox draws)."""
+    from tf_mnf_b200.models import ReLUMaxPool2D
+
+    tc_ctx.set_math(math)
+    rng = np.random.RandomState(11)
+    P = O.make_layer_params(rng, wshape, flow="rnvp", std_init=10.0, dtype=np.float64)
+    x = _f32(rng.uniform(size=shape))
+    lyr = make_layer(P, x.shape)
+    y_fused = lyr.call(x, fuse_relu_pool=True)
+    fused = lyr.last_fused
+    lyr.call_index = 0
+    y_ref = ReLUMaxPool2D(padding="SAME")(lyr.call(x))
+    if fused:
+        assert y_fused.shape == y_ref.shape
+        np.testing.assert_array_equal(y_fused.numpy(), y_ref.numpy())
+    else:  # FFMA path with F > 20 has no fused epilogue: the call must have stayed unfused
+        assert math == "fp32" and wshape[-1] > 20 and y_fused.shape[1] == shape[1] - wshape[0] + 1

@@ -26,7 +26,7 @@ class FlowStep(C.Structure):
 class ConvShape(C.Structure):
     _fields_ = [("B", C.c_int64), ("H", C.c_int64), ("W", C.c_int64), ("C", C.c_int64),
                 ("kh", C.c_int64), ("kw", C.c_int64), ("F", C.c_int64), ("stride", C.c_int64),
-                ("same", C.c_int32)]
+                ("same", C.c_int32), ("fuse_relu_pool", C.c_int32)]
 
 
 class KlArgs(C.Structure):
@@ -99,6 +99,7 @@ SIGNATURES = {
     "mnf_dense_backward": [vp, _i64, _i64, _i64, vp, vp, vp, vp, vp, _f, C.POINTER(Noise), vp, vp,
                            vp, vp, vp, vp, vp, vp],
     "mnf_conv_out_hw": [C.POINTER(ConvShape), C.POINTER(_i64), C.POINTER(_i64)],
+    "mnf_conv2d_can_fuse_pool": [vp, C.POINTER(ConvShape), C.POINTER(_i32)],
     "mnf_conv2d_forward": [vp, C.POINTER(ConvShape), vp, vp, vp, vp, vp, vp, _f, C.POINTER(Noise), vp, vp, vp],
     "mnf_conv2d_backward": [vp, C.POINTER(ConvShape), vp, vp, vp, vp, vp, _f, C.POINTER(Noise), vp, vp, vp,
                             vp, vp, vp, vp, vp, vp],

@@ -49,7 +49,7 @@ size_t mnf_flow_umma_pack_floats(int D);
 int mnf_tc_paired_forward(mnf_ctx* ctx, int conv, int64_t M, int K, int N, const float* x, const float* z,
                           const float* mean_W, const float* log_std_W, const float* mean_b, const float* log_var_b,
                           float max_std, const NoiseDev& eps, float* y, float* mean_out, float* sd_out,
-                          const int* geo);
+                          const int* geo);  // conv geo: H,W,C,kh,kw,Ho,Wo,stride,pad_t,pad_l,pool
 void* mnf_workspace(mnf_ctx* ctx, size_t bytes);  // nullptr on failure (error set)
 
 #define MNF_CHECK_ARG(cond, ...)      \

@@ -29,6 +29,7 @@ struct PairedArgs {
   NoiseDev eps;
   // conv geometry
   int H, W, C, kh, kw, Ho, Wo, stride, pad_t, pad_l;
+  int pool;  // conv only: fuse ReLU + 2x2/stride-2 max-pool into the epilogue (y is [B,Ho/2,Wo/2,F])
 };
 
 // Vw = min(exp(Ls), max_std)^2 ; vb = min(exp(lvb), max_std^2)   (mnf_dense.py:163-165)
@@ -252,7 +253,7 @@ struct DirectArgs {
   int IMG;      // images per CTA
 };
 
-template <int NF>
+template <int NF, bool POOL>
 __global__ void __launch_bounds__(DC_THREADS) conv_direct_fwd(DirectArgs d) {
   extern __shared__ __align__(16) float dsm[];
   const PairedArgs& a = d.p;
@@ -302,10 +303,26 @@ __global__ void __launch_bounds__(DC_THREADS) conv_direct_fwd(DirectArgs d) {
     bmv[f] = f < F ? a.bm[f] : 0.f;
     vbv[f] = f < F ? a.vb[f] : 1.f;
   }
-  for (int pr = tid; pr < npairs; pr += DC_THREADS) {
-    const int im = pr / (a.Ho * Wo2);
-    const int r = pr - im * a.Ho * Wo2;
-    const int ho = r / Wo2, wo0 = (r - ho * Wo2) * 2;
+  for (int pbase = 0; pbase < npairs; pbase += DC_THREADS) {
+    const int pr0 = pbase + tid;
+    const bool valid = pr0 < npairs;
+    const int pr = valid ? pr0 : 0;
+    int im, ho, wo0;
+    if (POOL) {  // lanes l and l^1 own the two rows of one pooling window (Ho, Wo even)
+      const int hpar = pr & 1;
+      int q = pr >> 1;
+      const int wp = q % Wo2;
+      q /= Wo2;
+      const int ho2 = q % (a.Ho >> 1);
+      im = q / (a.Ho >> 1);
+      ho = 2 * ho2 + hpar;
+      wo0 = 2 * wp;
+    } else {
+      im = pr / (a.Ho * Wo2);
+      const int r = pr - im * a.Ho * Wo2;
+      ho = r / Wo2;
+      wo0 = (r - ho * Wo2) * 2;
+    }
     const bool two = wo0 + 1 < a.Wo;
     const float* x0 = xs + im * img_sz + ((ho * a.stride) * d.Wp + wo0 * a.stride) * a.C;
     const float* x1 = x0 + (two ? a.stride * a.C : 0);
@@ -333,6 +350,48 @@ __global__ void __launch_bounds__(DC_THREADS) conv_direct_fwd(DirectArgs d) {
     }
     // epilogue for the one or two pixels
     const int64_t brow = b0 + im;
+    if (POOL) {
+      const uint32_t pix0 = (uint32_t)(ho * a.Wo + wo0);
+#pragma unroll
+      for (int q = 0; q < NF / 4; ++q) {
+        if (4 * q >= F) break;
+        float e0[4], e1[4];
+        if (a.eps.injected) {
+          const int64_t gm = brow * a.Ho * a.Wo + pix0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            e0[j] = 4 * q + j < F ? a.eps.injected[gm * F + 4 * q + j] : 0.f;
+            e1[j] = 4 * q + j < F ? a.eps.injected[(gm + 1) * F + 4 * q + j] : 0.f;
+          }
+        } else {
+          philox_normal4(a.eps, a.eps.row_offset + (uint64_t)brow, pix0, (uint32_t)q, e0);
+          philox_normal4(a.eps, a.eps.row_offset + (uint64_t)brow, pix0 + 1, (uint32_t)q, e1);
+        }
+        float out[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int f = 4 * q + j;
+          const float zf = zs[im * NF + f];
+          const float y0 = fmaf(sqrtf(v0[f] + vbv[f]), e0[j], (m0[f] + bmv[f]) * zf);
+          const float y1 = fmaf(sqrtf(v1[f] + vbv[f]), e1[j], (m1[f] + bmv[f]) * zf);
+          float v = fmaxf(y0, y1);
+          v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));  // the other row of the window
+          out[j] = fmaxf(v, 0.f);                            // ReLU
+        }
+        if (valid && (ho & 1) == 0) {
+          const int64_t gp = ((brow * (a.Ho >> 1) + (ho >> 1)) * (a.Wo >> 1) + (wo0 >> 1)) * F + 4 * q;
+          if ((F & 3) == 0) {
+            *reinterpret_cast<float4*>(a.y + gp) = make_float4(out[0], out[1], out[2], out[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (4 * q + j < F) a.y[gp + j] = out[j];
+          }
+        }
+      }
+      continue;
+    }
+    if (!valid) continue;
 #pragma unroll
     for (int px = 0; px < 2; ++px) {
       if (px == 1 && !two) break;
@@ -397,7 +456,10 @@ static int launch_direct(mnf_ctx* ctx, const PairedArgs& a, int pad_b, int pad_r
   d.IMG = img;
   const size_t smem = sizeof(float) * (2 * (size_t)a.K * NF + (size_t)img * NF) + sizeof(int) * ((a.K + 3) & ~3) + img * img_bytes;
   const bool probed = mnf_probe_begin(ctx, MNF_PROBE_CONV_GEMM);
-  conv_direct_fwd<NF><<<(unsigned)cdiv(B, img), DC_THREADS, smem, ctx->stream>>>(d);
+  if (a.pool)
+    conv_direct_fwd<NF, true><<<(unsigned)cdiv(B, img), DC_THREADS, smem, ctx->stream>>>(d);
+  else
+    conv_direct_fwd<NF, false><<<(unsigned)cdiv(B, img), DC_THREADS, smem, ctx->stream>>>(d);
   mnf_probe_end(ctx, probed);
   MNF_LAUNCHED(ctx);
   *used = true;
@@ -450,6 +512,33 @@ int mnf_conv_out_hw(const mnf_conv_shape* s, int64_t* Ho, int64_t* Wo) {
     *Ho = (s->H - s->kh) / s->stride + 1;
     *Wo = (s->W - s->kw) / s->stride + 1;
   }
+  return MNF_OK;
+}
+
+int mnf_conv2d_can_fuse_pool(mnf_ctx* ctx, const mnf_conv_shape* s, int32_t* ok) {
+  MNF_CHECK_ARG(ctx && s && ok, "mnf_conv2d_can_fuse_pool: NULL argument");
+  *ok = 0;
+  int64_t Ho, Wo;
+  int rc = mnf_conv_out_hw(s, &Ho, &Wo);
+  if (rc) return rc;
+  if ((Ho & 1) || (Wo & 1)) return MNF_OK;
+  const int64_t Kc = s->kh * s->kw * s->C;
+  if (s->F <= 20 && Kc <= 256) {  // direct small-filter kernel (same smem test as launch_direct)
+    int64_t ph = 0, pw = 0;
+    if (s->same) {
+      ph = (Ho - 1) * s->stride + s->kh - s->H;
+      pw = (Wo - 1) * s->stride + s->kw - s->W;
+      ph = ph > 0 ? ph : 0;
+      pw = pw > 0 ? pw : 0;
+    }
+    const size_t img_bytes = sizeof(float) * (size_t)((s->H + ph) * (s->W + pw) * s->C);
+    const size_t fixed = sizeof(float) * (2 * (size_t)Kc * 20 + 8 * 20) + sizeof(int) * ((Kc + 3) & ~3);
+    if (fixed + img_bytes <= 44 * 1024) {
+      *ok = 1;
+      return MNF_OK;
+    }
+  }
+  if (ctx->math_mode == MNF_MATH_TF32X3 && s->F <= 64 && s->F > 20 && 128 % (2 * Wo) == 0) *ok = 1;
   return MNF_OK;
 }
 
@@ -507,11 +596,21 @@ int mnf_conv2d_forward(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, co
     pad_b = (int)(ph - ph / 2);
     pad_r = (int)(pw - pw / 2);
   }
+  a.pool = s->fuse_relu_pool ? 1 : 0;
+  if (a.pool) {
+    int32_t ok = 0;
+    rc = mnf_conv2d_can_fuse_pool(ctx, s, &ok);
+    if (rc) return rc;
+    if (!ok || mean_out || sd_out) {
+      mnf_set_error("mnf_conv2d_forward: fuse_relu_pool is not available for this shape / math mode / training call");
+      return MNF_ERR_UNSUPPORTED;
+    }
+  }
   bool used = false;
   rc = launch_direct(ctx, a, pad_b, pad_r, &used);
   if (rc || used) return rc;
   if (ctx->math_mode == MNF_MATH_TF32X3) {
-    const int geo[10] = {a.H, a.W, a.C, a.kh, a.kw, a.Ho, a.Wo, a.stride, a.pad_t, a.pad_l};
+    const int geo[11] = {a.H, a.W, a.C, a.kh, a.kw, a.Ho, a.Wo, a.stride, a.pad_t, a.pad_l, a.pool};
     return mnf_tc_paired_forward(ctx, 1, a.M, a.K, a.N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std, a.eps, y,
                                  mean_out, sd_out, geo);
   }

@@ -44,6 +44,7 @@ struct Args {
   NoiseDev eps;
   int H, W, C, kh, kw, Ho, Wo, stride, pad_t, pad_l;
   int vec;           // 16-byte gathers legal (conv: C % 4 == 0; dense: K % 4 == 0)
+  int pool;          // conv: ReLU + 2x2 max-pool fused into the copy-out (ntiles == 1, BM % (2 Wo) == 0)
 };
 
 // ----------------------------------------------------------------------------- PTX helpers
@@ -259,7 +260,19 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
       // coalesced copy-out of the staged tile (rows are contiguous in y when ntiles == 1)
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int rows = (int)((a.M - m0 < BM) ? a.M - m0 : BM);
-      if (a.ntiles == 1) {  // the tile is one contiguous block of y and is staged densely
+      if (a.pool) {
+        // rows of the tile are consecutive output pixels and the tile starts on an even output
+        // row, so its BM/4 pooled pixels are one contiguous block of the pooled tensor
+        const int Wp = a.Wo >> 1, np = rows >> 2;
+        float* dst = a.y + (m0 >> 2) * a.N;
+        for (int e = threadIdx.x; e < np * a.N; e += EPI_WARPS * 32) {
+          const int pp = e / a.N, c = e - pp * a.N;
+          const int hp = pp / Wp, wp = pp - hp * Wp;
+          const float* s0 = ys + ((2 * hp) * a.Wo + 2 * wp) * ldy + c;
+          float v = fmaxf(fmaxf(s0[0], s0[ldy]), fmaxf(s0[a.Wo * ldy], s0[(a.Wo + 1) * ldy]));
+          dst[e] = fmaxf(v, 0.f);
+        }
+      } else if (a.ntiles == 1) {  // the tile is one contiguous block of y and is staged densely
         float* dst = a.y + m0 * a.N;
         for (int e = threadIdx.x; e < rows * a.N; e += EPI_WARPS * 32) dst[e] = ys[e];
       } else {
@@ -558,6 +571,7 @@ int mnf_tc_paired_forward(mnf_ctx* ctx, int conv, int64_t M, int K, int N, const
                           float max_std, const NoiseDev& eps, float* y, float* mean_out, float* sd_out,
                           const int* geo) {
   tc::Args a = {};
+  a.pool = (conv && geo[10]) ? 1 : 0;
   a.M = M; a.K = K; a.N = N;
   a.x = x; a.z = z; a.bm = mean_b; a.y = y; a.mean_out = mean_out; a.sd_out = sd_out; a.eps = eps;
   if (conv) {

@@ -62,8 +62,11 @@ class MNFConv2D(MNFLayerBase):
         s.F, s.stride, s.same = self.n_filters, self.strides, int(self.padding == "SAME")
         return s
 
-    def call(self, x: Any, noise: dict | None = None) -> DeviceArray:  # noqa: A002
-        """mnf_conv.py:182-197.  noise: {eps_z [B,F], bern_q [...], eps_out [B,Ho,Wo,F]}."""
+    def call(self, x: Any, noise: dict | None = None, fuse_relu_pool: bool = False) -> DeviceArray:  # noqa: A002
+        """mnf_conv.py:182-197.  noise: {eps_z [B,F], bern_q [...], eps_out [B,Ho,Wo,F]}.
+        fuse_relu_pool: ask the kernel to also apply the ReLU + MaxPool2D(2x2) that follows the
+        layer in MNFLeNet (mnf_lenet.py:23-24); `self.last_fused` tells whether it did (it does
+        not when training, or for shapes the fused epilogue does not cover)."""
         self.ctx = self.ctx or default_context()
         x = as_device(x, self.ctx)
         if x.ndim != 4:
@@ -81,10 +84,17 @@ class MNFConv2D(MNFLayerBase):
         if eo is not None and eo.shape != oshape:
             raise ValueError(f"injected eps_out must have shape {oshape}, got {eo.shape}")
         eps = nz.make(self.seed, self.call_index, self.uid, nz.CALL_OUT, self.row_offset, eo)
-        y = ctx.empty(oshape)
+        s = self._shape(x)
+        self.last_fused = False
+        if fuse_relu_pool and not self.training:
+            ok = C.c_int32(0)
+            L.check(ctx.lib.mnf_conv2d_can_fuse_pool(ctx.handle, C.byref(s), C.byref(ok)))
+            if ok.value:
+                s.fuse_relu_pool = 1
+                self.last_fused = True
+        y = ctx.empty((B, Ho // 2, Wo // 2, self.n_filters) if self.last_fused else oshape)
         mean = ctx.empty(oshape) if self.training else None
         sd = ctx.empty(oshape) if self.training else None
-        s = self._shape(x)
         L.check(ctx.lib.mnf_conv2d_forward(ctx.handle, C.byref(s), _p(x), _p(z), _p(self.mean_W), _p(self.log_std_W),
                                            _p(self.mean_b), _p(self.log_var_b), self.max_std, C.byref(eps),
                                            _p(y), _p(mean), _p(sd)))

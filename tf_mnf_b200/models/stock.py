@@ -112,9 +112,18 @@ class Sequential:
         """noise: optional list with one injected-draw dict per MNF layer (program order)."""
         x = as_device(x, default_context())
         it = iter(noise or [])
-        for lyr in self.layers:
+        skip = False
+        for i, lyr in enumerate(self.layers):
+            if skip:  # this ReLU+MaxPool was folded into the preceding conv's epilogue
+                skip = False
+                continue
             if hasattr(lyr, "kl_div"):
-                x = lyr(x, noise=next(it, None))
+                nxt = self.layers[i + 1] if i + 1 < len(self.layers) else None
+                if isinstance(nxt, ReLUMaxPool2D) and hasattr(lyr, "n_filters") and not lyr.training:
+                    x = lyr.call(x, noise=next(it, None), fuse_relu_pool=True)
+                    skip = lyr.last_fused
+                else:
+                    x = lyr(x, noise=next(it, None))
             else:
                 x = lyr(x)
         return x
