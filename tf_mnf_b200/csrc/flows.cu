@@ -122,16 +122,31 @@ __global__ void __launch_bounds__(256) planar_step_fwd(PlanarArgs a) {
   }
 }
 
-// T == 0: states[0] = z0 (sampled or copied), log_dets = 0
+// T == 0: states[0] = z0 (sampled or copied), log_dets = 0.  One thread per 4 consecutive
+// elements of a row: one Philox call yields the four normals.
 __global__ void sample_z0_kernel(int64_t B, int D, const float* zin, const float* q0_mean, const float* q0_log_var,
                                  NoiseDev eps, float* zout, float* ld_out) {
-  int64_t total = B * D;
+  const int D4 = (D + 3) >> 2;
+  const int64_t total = B * D4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / D;
-    int d = (int)(i - r * D);
-    float v = zin ? zin[i] : q0_mean[d] + expf(0.5f * q0_log_var[d]) * noise_normal1(eps, r, 0u, (uint32_t)d, 1, D);
-    zout[i] = v;
-    if (ld_out && d == 0) ld_out[r] = 0.f;
+    const int64_t r = i / D4;
+    const int g4 = (int)(i - r * D4), d0 = g4 * 4;
+    float nrm[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!zin && !eps.injected) philox_normal4(eps, eps.row_offset + (uint64_t)r, 0u, (uint32_t)g4, nrm);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d = d0 + e;
+      if (d < D) {
+        float v;
+        if (zin) v = zin[r * D + d];
+        else {
+          const float n = eps.injected ? eps.injected[r * D + d] : nrm[e];
+          v = q0_mean[d] + expf(0.5f * q0_log_var[d]) * n;
+        }
+        zout[r * D + d] = v;
+      }
+    }
+    if (ld_out && g4 == 0) ld_out[r] = 0.f;
   }
 }
 
@@ -485,7 +500,19 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
       a.m1 = st.m1; a.m2 = st.m2; a.ld2 = st.ld2;
       a.bern = make_noise(&st.bern);
       if (use_tc && (z0_out || zin)) {  // tcgen05 path (3xTF32): same arithmetic contract, fp32 parity
-        int rc = mnf_flow_umma_step(ctx, B, (int)D, st.hidden, st.kind, st.parity, zin, q0_mean, q0_log_var, eps, z0_out,
+        const float* zin_tc = zin;
+        float* z0_tc = z0_out;
+        if (!zin) {
+          // sample z0 for ALL rows with a full-chip elementwise kernel (same Philox counters) instead
+          // of inside the 80 row-tile CTAs' producer warps, where it sits on the critical path
+          const int64_t n4 = B * ((D + 3) / 4);
+          int g0 = (int)(cdiv(n4, 256) < ctx->sm_count * 8 ? cdiv(n4, 256) : ctx->sm_count * 8);
+          sample_z0_kernel<<<g0, 256, 0, ctx->stream>>>(B, (int)D, nullptr, q0_mean, q0_log_var, eps, states, nullptr);
+          MNF_LAUNCHED(ctx);
+          zin_tc = states;
+          z0_tc = nullptr;
+        }
+        int rc = mnf_flow_umma_step(ctx, B, (int)D, st.hidden, st.kind, st.parity, zin_tc, q0_mean, q0_log_var, eps, z0_tc,
                                     zout, a.ld_in, a.ld_out, a.hid_save, st, a.bern, pack_ws);
         if (rc) return rc;
         continue;

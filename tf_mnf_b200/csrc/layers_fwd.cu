@@ -254,7 +254,7 @@ struct DirectArgs {
 };
 
 template <int NF, bool POOL>
-__global__ void __launch_bounds__(DC_THREADS) conv_direct_fwd(DirectArgs d) {
+__global__ void __launch_bounds__(DC_THREADS, 2) conv_direct_fwd(DirectArgs d) {
   extern __shared__ __align__(16) float dsm[];
   const PairedArgs& a = d.p;
   const int K = a.K, F = a.N;
