@@ -46,6 +46,10 @@ int mnf_flow_umma_step(mnf_ctx* ctx, int64_t B, int D, int H, int kind, int pari
                        const float* ld_in, float* ld_out, float* hid_save, const mnf_flow_step& st,
                        const NoiseDev& bern, float* pack_ws);
 size_t mnf_flow_umma_pack_floats(int D);
+int mnf_conv_raw_umma_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, const float* x, const float* z,
+                              const float* mean_W, const float* log_std_W, const float* mean_b,
+                              const float* log_var_b, float max_std, const NoiseDev& eps, float* y, float* mean_out,
+                              float* sd_out, bool* used);
 int mnf_tc_paired_forward(mnf_ctx* ctx, int conv, int64_t M, int K, int N, const float* x, const float* z,
                           const float* mean_W, const float* log_std_W, const float* mean_b, const float* log_var_b,
                           float max_std, const NoiseDev& eps, float* y, float* mean_out, float* sd_out,
