@@ -18,9 +18,10 @@
 // the gather in tc_gemm.cu.  The mean and the variance products run as two phases per tile so
 // the planes of one phase are refilled while the tensor core works on the other.
 //
-//   warps 0-3  epilogue (TMEM -> bias, z-scale, Philox eps, optional ReLU+2x2 max-pool, store)
-//   warp  4    MMA issue (3 tcgen05.mma.kind::tf32 per step and phase), tcgen05.commit
-//   warps 5-11 plane producers;  warp 12 lane 0: weight-block loader (cp.async.bulk ring)
+//   warps 0-3, 8-11  epilogue, columns [0,32) resp. [32,64) of a row (TMEM -> bias, z-scale,
+//                    Philox eps, optional ReLU+2x2 max-pool, staged coalesced store)
+//   warp  4          MMA issue (3 tcgen05.mma.kind::tf32 per step and phase), tcgen05.commit
+//   warps 5-7        plane producers;  warp 12 lane 0: weight-block loader (cp.async.bulk ring)
 #include <utility>
 #include <vector>
 
@@ -31,12 +32,12 @@ using namespace um;
 
 constexpr int BM = 128, BN = 64;
 constexpr int G = 6;                 // k8-steps per weight stage
-constexpr int STEP_B = 2 * 2 * BN * 16;  // bytes of one step's weights for one phase: [hi|lo][2 kc][64 n][16 B] = 4 KB
+constexpr int STEP_B = 2 * 2 * BN * 16;  // bytes of one step's weights for one phase: [2 kc][hi 64 n | lo 64 n][16 B] = 4 KB
 constexpr int B_STAGE = G * STEP_B;  // 24 KB
 constexpr int SB = 3;                // weight ring depth
 constexpr int THREADS = 13 * 32;
-constexpr int PROD_WARPS = 7;
-constexpr int TMEM_COLS = 256;
+constexpr int PROD_WARPS = 3;      // warps 5-7 fill the planes; warps 8-11 are the second epilogue group
+constexpr int TMEM_COLS = 512;  // [2 buffers][2 phases][hi-product 64 | lo-product 64]
 
 struct Args {
   int64_t B;         // images
@@ -67,7 +68,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_umma(Args a) {
   float* ys = (float*)(Bs + SB * B_STAGE);    // [BM][N] dense staging
   int* stab = (int*)(ys + BM * BN);           // [steps][2]
   float* bias_s = (float*)(stab + 2 * a.steps);  // [2][BN]
-  uint64_t* bars = (uint64_t*)(((uintptr_t)(bias_s + 2 * BN) + 7) & ~(uintptr_t)7);
+  float* zs = bias_s + 2 * BN;                   // [I][BN] z rows of the tile being written out
+  uint64_t* bars = (uint64_t*)(((uintptr_t)(zs + 16 * BN) + 7) & ~(uintptr_t)7);
   uint64_t* pfull = bars;        // [2] planes of phase ready
   uint64_t* pempty = pfull + 2;  // [2]
   uint64_t* bfull = pempty + 2;  // [SB]
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_umma(Args a) {
   if (threadIdx.x == 0) {
     for (int p = 0; p < 2; ++p) { mbar_init(&pfull[p], PROD_WARPS); mbar_init(&pempty[p], 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -103,27 +105,45 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_umma(Args a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 4 || (warp >= 8 && warp < 12)) {
     // ================================================================== epilogue warps
-    const int r = warp * 32 + lane;             // TMEM lane = tile row (ho, img, wo)
+    const int quad = warp & 3, chalf = warp >= 8 ? 1 : 0;
+    const int et = chalf * 128 + quad * 32 + lane;   // 0..255 among the epilogue threads
+    const int r = quad * 32 + lane;             // TMEM lane = tile row (ho, img, wo)
     const int wo = r & 7, g = r >> 3, img = g % a.I, ho = g / a.I;
     const int rl = img * HoWo + ho * 8 + wo;    // row inside the tile's block of y
     int it = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int64_t b0 = t * a.I, brow = b0 + img;
       const int buf = it & 1;
+      // this tile's z rows -> shared memory (the previous tile's readers passed the closing barrier)
+      for (int e = et; e < a.I * BN; e += 256) {
+        const int im = e / BN, n = e - im * BN;
+        zs[e] = (a.z && b0 + im < a.B && n < a.N) ? __ldg(a.z + (b0 + im) * a.N + n) : 1.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull[buf], (it >> 1) & 1);
       tc_fence_after();
       const bool row_ok = brow < a.B;
       const uint32_t outer = (uint32_t)(ho * 8 + wo);
       const int64_t m = brow * HoWo + outer;
-      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 2 * BN);
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 4 * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      for (int c0 = chalf * 32; c0 < chalf * 32 + 32; c0 += 16) {
         if (c0 >= a.N) break;
         float mv[16], vv[16];
-        tmem_ld16(trow + c0, mv);
-        tmem_ld16(trow + BN + c0, vv);
+        {
+          float m2[16], v2[16];
+          tmem_ld16(trow + c0, mv);
+          tmem_ld16(trow + BN + c0, m2);
+          tmem_ld16(trow + 2 * BN + c0, vv);
+          tmem_ld16(trow + 3 * BN + c0, v2);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            mv[j] += m2[j];
+            vv[j] += v2[j];
+          }
+        }
         if (row_ok) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -144,7 +164,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_umma(Args a) {
                 const float sd = sqrtf(vv[4 * q + j] + bias_s[BN + n]);
                 if (a.sd_out) a.sd_out[m * a.N + n] = sd;
                 if (a.mean_out) a.mean_out[m * a.N + n] = mean;
-                if (a.z) mean *= __ldg(a.z + brow * a.N + n);
+                if (a.z) mean *= zs[img * BN + n];
                 ys[rl * a.N + n] = fmaf(sd, e[j], mean);
               }
             }
@@ -154,13 +174,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_umma(Args a) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const int64_t nimg = (a.B - b0 < a.I) ? a.B - b0 : a.I;
       const int rows = (int)nimg * HoWo;
       if (a.pool) {
         const int np = rows >> 2;
         float* dst = a.y + (b0 * HoWo >> 2) * a.N;
-        for (int e = threadIdx.x; e < np * a.N; e += 128) {
+        for (int e = et; e < np * a.N; e += 256) {
           const int pp = e / a.N, c = e - pp * a.N;
           const int hp = pp >> 2, wp = pp & 3;  // Wo / 2 == 4 pooled columns
           const float* s0 = ys + ((2 * hp) * 8 + 2 * wp) * a.N + c;
@@ -169,15 +189,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_umma(Args a) {
         }
       } else {
         float* dst = a.y + b0 * HoWo * a.N;
-        for (int e = threadIdx.x; e < rows * a.N; e += 128) dst[e] = ys[e];
+        for (int e = et; e < rows * a.N; e += 256) dst[e] = ys[e];
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
   } else if (warp == 4) {
     // ======================================================================= MMA issuer
+    // x_hi * [W_hi | W_lo] is ONE N=128 instruction (the A tile is read from shared memory once for
+    // both products: at N=64 the operand fetch, not the tensor pipe, sets the pace); x_lo * W_hi
+    // is an N=64 instruction into the first 64 columns.  The epilogue adds the two column halves.
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     const uint32_t sbo = (uint32_t)(a.Wi * 16);
-    const uint64_t bdesc0 = make_desc(smem_u32(Bs), BN * 16, 128);
+    const uint64_t bdesc0 = make_desc(smem_u32(Bs), 2 * BN * 16, 128);
     const uint32_t plane0 = smem_u32(planes);
     int it = 0, st = 0;
     uint32_t bph = 0;
@@ -187,10 +211,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_umma(Args a) {
       for (int ph = 0; ph < 2; ++ph) {
         mbar_wait(&pfull[ph], it & 1);
         tc_fence_after();
-        const uint32_t dacc = tmem_base + (uint32_t)(buf * 2 * BN + ph * BN);
+        const uint32_t dacc = tmem_base + (uint32_t)(buf * 4 * BN + ph * 2 * BN);
         const uint32_t pa_hi = plane0 + (uint32_t)((2 * ph) * PLANE), pa_lo = pa_hi + (uint32_t)PLANE;
         for (int sg = 0; sg < nstages; ++sg) {
-          mbar_wait(&bfull[st], bph);
+            mbar_wait(&bfull[st], bph);
           tc_fence_after();
           if (lane == 0) {
             const int s1 = min(a.steps, (sg + 1) * G);
@@ -198,10 +222,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_umma(Args a) {
               const uint32_t aoff = (uint32_t)stab[2 * s], lbo = (uint32_t)stab[2 * s + 1];
               const uint64_t ah = make_desc(pa_hi + aoff, lbo, sbo), al = make_desc(pa_lo + aoff, lbo, sbo);
               const uint64_t bh = bdesc0 + (uint64_t)((st * B_STAGE + (s - sg * G) * STEP_B) >> 4);
-              const uint64_t bl = bh + (uint64_t)((STEP_B / 2) >> 4);
-              umma_tf32(dacc, ah, bh, idesc, s == 0 ? 0u : 1u);
+              umma_tf32(dacc, ah, bh, idesc2, s == 0 ? 0u : 1u);
               umma_tf32(dacc, al, bh, idesc, 1u);
-              umma_tf32(dacc, ah, bl, idesc, 1u);
             }
             umma_commit(&bempty[st]);
             if (sg == nstages - 1) {
@@ -235,38 +257,56 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_umma(Args a) {
     __syncwarp();
   } else {
     // ================================================================== plane producers
-    const int pt = threadIdx.x - 5 * 32;  // 0 .. 223
-    constexpr int NP = PROD_WARPS * 32;
-    const int nchunks = a.cpt * pix;       // 16-byte chunks per variant
-    const int img_f = a.H * a.W * a.C;     // floats per input image
-    int it = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      const int64_t b0 = t * a.I;
-      for (int ph = 0; ph < 2; ++ph) {
-        mbar_wait(&pempty[ph], (it & 1) ^ 1);
-        uint8_t* dst_hi = planes + (2 * ph) * PLANE;
-        uint8_t* dst_lo = dst_hi + PLANE;
-        for (int q = pt; q < nchunks; q += NP) {
-          // q enumerates (hi, img, wi, cc) with cc fastest so that a warp reads consecutive floats
-          const int cc = q % a.cpt;
-          int p = q / a.cpt;
-          const int wi = p % a.Wi;
-          p /= a.Wi;
-          const int im = p % a.I, hi = p / a.I;
-          int64_t b = b0 + im;
-          if (b >= a.B) b = a.B - 1;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (hi < a.H && wi < a.W) v = __ldg(reinterpret_cast<const float4*>(a.x + b * img_f + (hi * a.W + wi) * a.C + cc * 4));
-          float in[4] = {v.x, v.y, v.z, v.w}, h[4], l[4];
+    if (warp < 8) {
+      const int pt = threadIdx.x - 5 * 32;  // 0 .. 95
+      constexpr int NP = PROD_WARPS * 32;
+      const int nchunks = a.cpt * pix;       // 16-byte chunks per variant
+      const int img_f = a.H * a.W * a.C;     // floats per input image
+      int it = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int64_t b0 = t * a.I;
+        for (int ph = 0; ph < 2; ++ph) {
+          mbar_wait(&pempty[ph], (it & 1) ^ 1);
+          uint8_t* dst_hi = planes + (2 * ph) * PLANE;
+          uint8_t* dst_lo = dst_hi + PLANE;
+          for (int q0 = pt; q0 < nchunks; q0 += 4 * NP) {
+            // four independent 16-byte loads in flight per thread, then split + store
+            float4 v[4];
+            int o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) split_tf32(ph == 0 ? in[e] : in[e] * in[e], h[e], l[e]);
-          const int o = cc * CCS + ((hi * a.I + im) * a.Wi + wi) * 16;
-          *reinterpret_cast<float4*>(dst_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<float4*>(dst_lo + o) = make_float4(l[0], l[1], l[2], l[3]);
+            for (int u = 0; u < 4; ++u) {
+              const int q = q0 + u * NP;
+              v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              o[u] = -1;
+              if (q < nchunks) {
+                // q enumerates (hi, img, wi, cc), cc fastest: a warp reads consecutive floats
+                const int cc = q % a.cpt;
+                int p = q / a.cpt;
+                const int wi = p % a.Wi;
+                p /= a.Wi;
+                const int im = p % a.I, hi = p / a.I;
+                int64_t b = b0 + im;
+                if (b >= a.B) b = a.B - 1;
+                if (hi < a.H && wi < a.W)
+                  v[u] = __ldg(reinterpret_cast<const float4*>(a.x + b * img_f + (hi * a.W + wi) * a.C + cc * 4));
+                o[u] = cc * CCS + ((hi * a.I + im) * a.Wi + wi) * 16;
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (o[u] < 0) continue;
+              const float in[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+              float h[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) split_tf32(ph == 0 ? in[e] : in[e] * in[e], h[e], l[e]);
+              *reinterpret_cast<float4*>(dst_hi + o[u]) = make_float4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<float4*>(dst_lo + o[u]) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&pfull[ph]);
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&pfull[ph]);
       }
     }
   }
@@ -279,7 +319,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_umma(Args a) {
   }
 }
 
-// weights -> Bp[phase][step][hi|lo][kc 2][n 64][4 k]; kmap[step][8] = global k index or -1
+// weights -> Bp[phase][step][kc 2][hi n 64 | lo n 64][4 k]; kmap[step][8] = global k index or -1
 __global__ void pack_raw_weights(int N, int steps, const int* __restrict__ kmap, const float* __restrict__ Wm,
                                  const float* __restrict__ Ls, float max_std, float* __restrict__ Bp,
                                  const float* __restrict__ lvb, float* __restrict__ vb) {
@@ -303,9 +343,9 @@ __global__ void pack_raw_weights(int N, int steps, const int* __restrict__ kmap,
     }
     float hi, lo;
     split_tf32(w, hi, lo);
-    float* base = Bp + ((int64_t)ph * steps + s) * (STEP_B / 4) + ((int64_t)kc * BN + n) * 4 + e;
+    float* base = Bp + ((int64_t)ph * steps + s) * (STEP_B / 4) + ((int64_t)kc * 2 * BN + n) * 4 + e;
     base[0] = hi;
-    base[STEP_B / 8] = lo;  // lo variant follows the hi variant inside the step block
+    base[BN * 4] = lo;  // the lo rows follow the 64 hi rows of the same K chunk
     if (idx < N) vb[idx] = fminf(expf(lvb[idx]), max_std * max_std);
   }
 }
@@ -367,7 +407,7 @@ int mnf_conv_raw_umma_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, co
   a.steps = (int)tab.size() / 2;
   const size_t plane_bytes = (size_t)4 * a.cpt * CCS;
   const size_t smem = plane_bytes + (size_t)SB * B_STAGE + sizeof(float) * BM * BN + sizeof(int) * 2 * a.steps +
-                      sizeof(float) * 2 * BN + 256;
+                      sizeof(float) * (2 + 16) * BN + 256;
   if (smem > 227 * 1024) return MNF_OK;
   // ---- workspace: Bp | vb | steptab | kmap
   const size_t bp_floats = (size_t)2 * a.steps * (STEP_B / 4);

@@ -6,6 +6,7 @@
 // (conv) and a2 = x*x into shared memory; the CTA accumulates mean and variance tiles side
 // by side and the epilogue adds the biases, applies the conv z-scale, draws eps from Philox
 // (or reads the injected draw) and writes y once.
+#include <cstdlib>
 #include "common.cuh"
 
 #define PG_BM 128
