@@ -271,6 +271,16 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
         t2 = time.perf_counter()
         ctx.sync()
         print(f"[host enqueue us] forward={(t1 - t0) * 1e6:.0f} kl_div={(t2 - t1) * 1e6:.0f}", file=sys.stderr, flush=True)
+    if args.hostprof and rank == 0:  # where the host time of one step goes (stderr)
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(20):
+            step(x_dev)
+        pr.disable()
+        barrier()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime").print_stats(28)
     t_dead = time.perf_counter() + 8.0  # nvidia-smi has finished initialising once it prints samples
     while clk.proc is not None and len(clk.rows) < 3 and time.perf_counter() < t_dead:
         time.sleep(0.05)
@@ -395,6 +405,7 @@ def main() -> None:
     ap.add_argument("--cpu-rows", type=int, default=2560, help="rows per CPU-baseline step (bounded sample)")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--hostprof", action="store_true", help="cProfile of 20 steps' host-side enqueue (stderr)")
     ap.add_argument("--breakdown", action="store_true", help="print per-layer device times of one step (stderr)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -1,0 +1,72 @@
+"""Stream-level concurrency must not change results: z drawn ahead of call() on a side
+context (Sequential.presample_z), and kl_div() on a forked context, are bit-identical to the
+in-line path (same Philox counters, same kernels)."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _lenet(seed=3, **kw):
+    import tf_mnf_b200 as M
+    from tf_mnf_b200.models import MNFLeNet
+
+    M.set_seed(seed)
+    return MNFLeNet(6, 12, 40, 10, max_std=1, flow_h_sizes=[16], std_init=1.0, **kw)
+
+
+@pytest.mark.parametrize("flow_type", ["rnvp", "iaf"])
+@pytest.mark.parametrize("math", ["fp32", "tf32x3"])
+def test_presampled_z_is_bit_identical(flow_type, math):
+    import tf_mnf_b200 as M
+
+    ctx = M.default_context()
+    ctx.set_math(math)
+    try:
+        x = np.random.RandomState(0).uniform(size=(96, 28, 28, 1)).astype(np.float32)
+        outs = []
+        for pre in (False, True):
+            model = _lenet(flow_type=flow_type)
+            model.presample_z = pre
+            ys = [model(x).numpy() for _ in range(3)]  # call 0 builds the layers; 1 and 2 use the side stream
+            outs.append(ys)
+            if pre:
+                assert model._side is not None
+        for a, b in zip(*outs):
+            np.testing.assert_array_equal(a, b)
+        assert not np.array_equal(outs[0][1], outs[0][2])  # fresh noise per call
+    finally:
+        ctx.set_math("fp32")
+
+
+def test_presample_survives_changed_batch_and_training_flag():
+    model = _lenet()
+    rng = np.random.RandomState(1)
+    xa = rng.uniform(size=(32, 28, 28, 1)).astype(np.float32)
+    xb = rng.uniform(size=(48, 28, 28, 1)).astype(np.float32)
+    model(xa)
+    lyr = model.mnf_layers[2]
+    side = lyr.ctx.fork()
+    lyr.presample(32, side)          # stale: the next call has 48 rows
+    y1 = model(xb).numpy()
+    ref = _lenet()
+    ref.presample_z = False
+    ref(xa)
+    y2 = ref(xb).numpy()
+    np.testing.assert_array_equal(y1, y2)
+
+
+def test_kl_on_forked_context_matches_inline():
+    x = np.random.RandomState(2).uniform(size=(8, 28, 28, 1)).astype(np.float32)
+    m1 = _lenet()
+    m1(x)  # variables are created on the first call, from counters set_seed() resets
+    m2 = _lenet()
+    m2(x)
+    side = m1.mnf_layers[0].ctx.fork()
+    k1 = m1.kl_div(ctx=side)
+    m1.mnf_layers[0].ctx.wait(side)
+    side.sync()
+    k2 = m2.kl_div()
+    assert float(k1.numpy()[0]) == float(k2.numpy()[0])

@@ -79,7 +79,11 @@ class ChainRun:
     def forward(self, z: Any = None, q0_mean: DeviceArray | None = None, q0_log_var: DeviceArray | None = None,
                 B: int | None = None, eps: L.Noise | None = None, bern: Sequence[Any] | None = None,
                 seed: int = 0, call_index: int = 0, layer_id: int = 0, bern_draw: int = noise.FLOW_BERN,
-                row_offset: int = 0, record: bool = False, ctx: Context | None = None):
+                row_offset: int = 0, record: bool = False, ctx: Context | None = None,
+                alloc: Context | None = None):
+        """`alloc`: context whose stream owns the output buffers when the chain itself runs on
+        another (`ctx`); the caller orders `ctx` after `alloc` before and `alloc` after `ctx`
+        behind this call (MNFLayerBase.presample)."""
         if z is not None:
             z = as_device(z, ctx)
             ctx = z.ctx
@@ -91,11 +95,14 @@ class ChainRun:
             D = q0_mean.shape[0]
         T = len(self.flows)
         steps = self._marshal(ctx, D, seed, call_index, layer_id, bern_draw, row_offset, bern)
-        states = ctx.empty((T + 1, B, D))
-        ld = ctx.empty((B,))
+        actx = alloc or ctx
+        states = actx.empty((T + 1, B, D))
+        ld = actx.empty((B,))
         saved = None
         if record and T:
-            saved = ctx.empty((sum(B * max(f.hidden, 1) for f in self.flows),))
+            saved = actx.empty((sum(B * max(f.hidden, 1) for f in self.flows),))
+        if alloc is not None and alloc is not ctx:
+            ctx.wait(alloc)  # the buffers exist on ctx's stream only behind alloc's allocation point
         L.check(ctx.lib.mnf_flow_forward(
             ctx.handle, B, D, T, steps,
             C.c_void_p(z.ptr) if z is not None else None,

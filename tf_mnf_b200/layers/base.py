@@ -58,6 +58,7 @@ class MNFLayerBase:
         self.grads: dict[str, Any] = {}
         self._tape: dict[str, Any] = {}
         self._kl_tape: dict[str, Any] = {}
+        self._pre: dict[str, Any] | None = None  # z sampled ahead of call() on a side context
 
     # ------------------------------------------------------------------ variables
     def _flow_dim(self) -> int:  # pragma: no cover - abstract
@@ -121,13 +122,18 @@ class MNFLayerBase:
 
     # ------------------------------------------------------------------- sample_z
     def _sample_z(self, batch_size: int, z_draw: int, bern_draw: int, inject: dict | None, record: bool,
-                  row_offset: int, ctx: Context | None = None):
+                  row_offset: int, ctx: Context | None = None, alloc: Context | None = None):
         """mnf_dense.py:88-102 / mnf_conv.py:100-114 -> (z, log_dets, ChainRun | None)."""
         ctx, D = ctx or self.ctx, self._flow_dim()
         B = int(batch_size)
         if not self.use_z:
             return None, ctx.zeros((B,)), None
         inject = inject or {}
+        pre, self._pre = (self._pre, None) if z_draw == nz.CALL_Z else (None, self._pre)
+        if pre is not None:
+            ctx.wait(pre["side"])  # also orders the buffers' (stream-ordered) release after the side work
+            if (not inject and pre["key"] == (B, self.call_index, row_offset, bool(record)) and ctx is self.ctx):
+                return pre["z"], pre["ld"], pre["run"]
         eps_inj = as_device(inject["eps_z"], ctx) if inject.get("eps_z") is not None else None
         if eps_inj is not None and eps_inj.shape != (B, D):
             raise ValueError(f"injected eps_z must have shape {(B, D)}, got {eps_inj.shape}")
@@ -136,10 +142,25 @@ class MNFLayerBase:
         states, ld = run.forward(q0_mean=self.q0_mean, q0_log_var=self.q0_log_var, B=B, eps=eps,
                                  bern=inject.get("bern_q"), seed=self.seed, call_index=self.call_index,
                                  layer_id=self.uid, bern_draw=bern_draw, row_offset=row_offset, record=record,
-                                 ctx=ctx)
+                                 ctx=ctx, alloc=alloc)
         run.eps = eps
         run._eps_keep = eps_inj
         return states[-1], ld, run
+
+    def presample(self, batch_size: int, side: Context) -> None:
+        """Enqueue the z draw of the NEXT call() on `side` (a Context.fork() of this layer's
+        context): z does not depend on x, so it can be computed beside the layers in front of
+        this one.  Same Philox counters as the in-line draw -> bit-identical z.  The buffers
+        belong to the layer's own context; call() joins the two streams."""
+        self._require_built()
+        if not self.use_z or side is self.ctx:
+            return
+        if self._pre is not None:
+            self.ctx.wait(self._pre["side"])
+        self._pre = None
+        B = int(batch_size)
+        z, ld, run = self._sample_z(B, nz.CALL_Z, nz.BERN_Q_CALL, None, self.training, self.row_offset, side, self.ctx)
+        self._pre = dict(key=(B, self.call_index, self.row_offset, bool(self.training)), z=z, ld=ld, run=run, side=side)
 
     def sample_z(self, batch_size: int, noise: dict | None = None):  # noqa: A002 - mirrors reference name
         self._require_built()

@@ -107,12 +107,21 @@ class BatchNormalization(StockLayer):
 class Sequential:
     def __init__(self, layers=None) -> None:
         self.layers = list(layers or [])
+        self.presample_z = True   # draw the later layers' z on a side stream beside the first layers
+        self._side = None
 
     def __call__(self, x: Any, noise: list | None = None) -> DeviceArray:  # noqa: A002
         """noise: optional list with one injected-draw dict per MNF layer (program order)."""
         x = as_device(x, default_context())
         it = iter(noise or [])
         skip = False
+        if self.presample_z and not noise:
+            later = [l for l in self.mnf_layers[1:] if l.built and l.use_z and l.ctx is x.ctx]
+            if later:
+                if self._side is None or self._side.device != x.ctx.device:
+                    self._side = x.ctx.fork()
+                for lyr in later:
+                    lyr.presample(x.shape[0], self._side)
         for i, lyr in enumerate(self.layers):
             if skip:  # this ReLU+MaxPool was folded into the preceding conv's epilogue
                 skip = False

@@ -10,6 +10,7 @@ it is handed a NumPy batch, notebooks/lenet_mnist.py:84); compute never runs on 
 from __future__ import annotations
 
 import ctypes as C
+import math
 import threading
 from typing import Any, Sequence
 
@@ -18,6 +19,7 @@ import numpy as np
 from . import _lib as L
 
 _DT = {"f4": np.float32, "i1": np.int8, "u4": np.uint32}
+_ITEMSIZE = {k: np.dtype(v).itemsize for k, v in _DT.items()}
 
 
 class Context:
@@ -33,7 +35,7 @@ class Context:
     # -- memory
     def empty(self, shape: Sequence[int], dtype: str = "f4") -> "DeviceArray":
         shape = tuple(int(s) for s in shape)
-        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(_DT[dtype]).itemsize
+        nbytes = math.prod(shape) * _ITEMSIZE[dtype]
         p = C.c_void_p()
         L.check(self.lib.mnf_malloc(self.handle, nbytes, C.byref(p)))
         return DeviceArray(self, p.value, shape, dtype, owner=_Owned(self, p.value))
@@ -143,11 +145,11 @@ class DeviceArray:
     # -- basic properties
     @property
     def size(self) -> int:
-        return int(np.prod(self.shape, dtype=np.int64))
+        return math.prod(self.shape)
 
     @property
     def itemsize(self) -> int:
-        return np.dtype(_DT[self.dtype]).itemsize
+        return _ITEMSIZE[self.dtype]
 
     @property
     def nbytes(self) -> int:
@@ -170,15 +172,15 @@ class DeviceArray:
         shape = list(shape)
         if -1 in shape:
             i = shape.index(-1)
-            rest = int(np.prod([s for s in shape if s != -1], dtype=np.int64))
+            rest = math.prod(int(s) for s in shape if s != -1)
             shape[i] = self.size // max(rest, 1)
-        if int(np.prod(shape, dtype=np.int64)) != self.size:
+        if math.prod(int(s) for s in shape) != self.size:
             raise ValueError(f"cannot reshape {self.shape} to {tuple(shape)}")
         return DeviceArray(self.ctx, self.ptr, shape, self.dtype, self.owner)
 
     def __getitem__(self, idx) -> "DeviceArray":
         """Leading-axis integer index or contiguous slice (a view)."""
-        inner = int(np.prod(self.shape[1:], dtype=np.int64)) * self.itemsize
+        inner = math.prod(self.shape[1:]) * self.itemsize
         if isinstance(idx, (int, np.integer)):
             i = int(idx) % self.shape[0] if self.shape[0] else 0
             return DeviceArray(self.ctx, self.ptr + i * inner, self.shape[1:], self.dtype, self.owner)
