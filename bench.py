@@ -210,13 +210,23 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     model.set_row_offset(rank * ROWS)
     flush = ctx.empty((64 << 20,))  # 256 MiB > 126 MB L2
 
-    kl_ctx = ctx.fork()  # kl_div() does not depend on x: it runs on a sibling stream beside the forward
+    # kl_div() does not depend on x: the four layers' terms run on sibling streams beside the
+    # forward.  They are forked from the step's stream at its start and joined at its end, so all
+    # of a step's work lies between its start and stop events.
+    kl_lanes = [ctx.fork() for _ in range(4)]
+    kl_ctx = kl_lanes[0]
+    model(x_dev)  # variables are created on the first call (Keras build protocol)
 
     def step(x):
+        for c in kl_lanes:
+            c.wait(ctx)
+        kl = model.kl_div(ctx=kl_lanes)
         probs = model(x)
-        kl = model.kl_div(ctx=kl_ctx)
-        ctx.wait(kl_ctx)  # join: the step (and its stop event) completes only when the KL has
+        ctx.wait(kl_ctx)
         return probs, kl
+
+    def side_launches():  # the model's own side context (z of the later layers, drawn ahead)
+        return model._side.launches if getattr(model, "_side", None) is not None else 0
 
     def ev():
         p = C.c_void_p()
@@ -225,7 +235,8 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
 
     def barrier():
         ctx.sync()
-        kl_ctx.sync()
+        for c in kl_lanes:
+            c.sync()
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
@@ -292,7 +303,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     # ---- timed: K steps, device-resident input, per-step CUDA events, L2 flushed in between
     starts, stops = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
     kst, ksp = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
-    launches0 = ctx.launches + kl_ctx.launches
+    launches0 = ctx.launches + sum(c.launches for c in kl_lanes) + side_launches()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
@@ -304,7 +315,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     t_wall1 = time.perf_counter()
     t_wall = t_wall1 - t_wall0
     clk.__exit__()
-    launches = ctx.launches + kl_ctx.launches - launches0
+    launches = ctx.launches + sum(c.launches for c in kl_lanes) + side_launches() - launches0
 
     def elapsed(a, b):
         ms = C.c_float()

@@ -139,16 +139,25 @@ class Sequential:
 
     def kl_div(self, noise: list | None = None, ctx: Any = None) -> DeviceArray:  # noqa: A002
         """Sum of the layers' KL terms (mnf_lenet.py:35-39, mnf_feed_forward.py:23-28).
-        `ctx`: optional sibling context (Context.fork()) so the KL runs beside a forward pass."""
+        `ctx`: optional sibling context (Context.fork()), or a list of them, so the KL runs beside
+        a forward pass: layer i uses ctx[i % len(ctx)], the sum is formed on ctx[0] (join the
+        caller's context with `main.wait(ctx[0])`)."""
         it = iter(noise or [])
-        total = None
-        for lyr in self.layers:
-            if hasattr(lyr, "kl_div"):
-                kl = lyr.kl_div(noise=next(it, None), ctx=ctx)
-                if total is None:
-                    total = kl
-                else:
-                    L.check(kl.ctx.lib.mnf_axpy(kl.ctx.handle, 1, 1.0, _p(kl), _p(total)))
+        lanes = list(ctx) if isinstance(ctx, (list, tuple)) else [ctx]
+        total, parts = None, []
+        for i, lyr in enumerate(self.mnf_layers):
+            lane = lanes[i % len(lanes)]
+            kl = lyr.kl_div(noise=next(it, None), ctx=lane)
+            if total is None:
+                total = kl
+            else:
+                parts.append(kl)
+        for kl in parts:
+            if kl.ctx is not total.ctx:
+                total.ctx.wait(kl.ctx)
+            L.check(total.ctx.lib.mnf_axpy(total.ctx.handle, 1, 1.0, _p(kl), _p(total)))
+        for c in {id(k.ctx): k.ctx for k in parts if k.ctx is not total.ctx}.values():
+            c.wait(total.ctx)  # the partial terms are released (stream-ordered) only behind the sum
         return total
 
     @property
