@@ -47,6 +47,9 @@ def test_dense_tensorcore(tc_ctx, K, N, B, use_z):
     ((5, 12, 12, 20), (5, 5, 20, 50), 1, "VALID"), ((3, 9, 7, 3), (3, 3, 3, 64), 1, "SAME"),
     ((2, 11, 10, 4), (3, 2, 4, 36), 2, "SAME"), ((4, 8, 8, 8), (3, 3, 8, 24), 1, "VALID"),
     ((37, 12, 12, 20), (5, 5, 20, 50), 1, "VALID"),
+    # single input channel: sliding-window kernel (conv_win_umma.cu); odd batch, kw <= 4 and kw > 4
+    ((5, 28, 28, 1), (5, 5, 1, 20), 1, "VALID"), ((4, 10, 18, 1), (3, 3, 1, 32), 1, "VALID"),
+    ((3, 15, 15, 1), (8, 8, 1, 4), 1, "VALID"), ((2, 9, 32, 1), (2, 1, 1, 12), 1, "VALID"),
 ])
 def test_conv_tensorcore(tc_ctx, shape, wshape, stride, padding):
     rng = np.random.RandomState(sum(shape) + sum(wshape))
@@ -64,11 +67,12 @@ def test_conv_tensorcore(tc_ctx, shape, wshape, stride, padding):
     close(got, ref, RTOL, "conv call (tf32x3)")
 
 
-def test_tensorcore_matches_ffma_with_philox(tc_ctx):
+@pytest.mark.parametrize("shape,wshape", [((64, 12, 12, 20), (5, 5, 20, 50)), ((301, 28, 28, 1), (5, 5, 1, 20))])
+def test_tensorcore_matches_ffma_with_philox(tc_ctx, shape, wshape):
     """Same seed => the tensor-core and FFMA paths draw identical in-kernel noise; outputs agree to 1e-5."""
     rng = np.random.RandomState(3)
-    P = O.make_layer_params(rng, (5, 5, 20, 50), flow="rnvp", std_init=10.0, dtype=np.float64)
-    x = _f32(rng.uniform(size=(64, 12, 12, 20)))
+    P = O.make_layer_params(rng, wshape, flow="rnvp", std_init=10.0, dtype=np.float64)
+    x = _f32(rng.uniform(size=shape))
     lyr = make_layer(P, x.shape)
     y_tc = lyr(x).numpy()
     tc_ctx.set_math("fp32")

@@ -50,6 +50,10 @@ int mnf_conv_raw_umma_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, co
                               const float* mean_W, const float* log_std_W, const float* mean_b,
                               const float* log_var_b, float max_std, const NoiseDev& eps, float* y, float* mean_out,
                               float* sd_out, bool* used);
+// conv_win_umma.cu: single-channel stride-1 VALID convolutions (sliding-window planes)
+int mnf_conv_win_umma_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, const float* x, const float* z,
+                              const float* mean_W, const float* log_std_W, const float* mean_b,
+                              const float* log_var_b, float max_std, const NoiseDev& eps, float* y, bool* used);
 int mnf_tc_paired_forward(mnf_ctx* ctx, int conv, int64_t M, int K, int N, const float* x, const float* z,
                           const float* mean_W, const float* log_std_W, const float* mean_b, const float* log_var_b,
                           float max_std, const NoiseDev& eps, float* y, float* mean_out, float* sd_out,
@@ -143,11 +147,18 @@ __device__ __forceinline__ float u01_open(uint32_t x) {  // (0,1), 24 bits
   return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);
 }
 
+// MUFU.SQRT (2^-23 relative error, no denormal slow path); arguments here are >= 0 and normal
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // Box-Muller on two 32-bit words -> two N(0,1)
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
   float u = u01_open(a);
   float v = u01_open(b);
-  float r = sqrtf(-2.0f * __logf(u));
+  float r = sqrt_fast(-2.0f * __logf(u));
   float s, c;
   __sincosf(6.283185307179586f * (v - 0.5f), &s, &c);
   n0 = r * c;

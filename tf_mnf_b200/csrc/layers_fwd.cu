@@ -608,10 +608,15 @@ int mnf_conv2d_forward(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, co
     }
   }
   bool used = false;
+  const int geo[11] = {a.H, a.W, a.C, a.kh, a.kw, a.Ho, a.Wo, a.stride, a.pad_t, a.pad_l, a.pool};
+  if (ctx->math_mode == MNF_MATH_TF32X3 && !pad_b && !pad_r && !mean_out && !sd_out) {
+    // single-channel input (MNF-LeNet conv1): sliding-window planes on tcgen05
+    rc = mnf_conv_win_umma_forward(ctx, s->B, geo, a.N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std, a.eps, y, &used);
+    if (rc || used) return rc;
+  }
   rc = launch_direct(ctx, a, pad_b, pad_r, &used);
   if (rc || used) return rc;
   if (ctx->math_mode == MNF_MATH_TF32X3) {
-    const int geo[11] = {a.H, a.W, a.C, a.kh, a.kw, a.Ho, a.Wo, a.stride, a.pad_t, a.pad_l, a.pool};
     if (!pad_b && !pad_r) {  // raw-tile kernel: im2col expressed by UMMA descriptors (8-wide output rows)
       rc = mnf_conv_raw_umma_forward(ctx, s->B, geo, a.N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std, a.eps, y,
                                      mean_out, sd_out, &used);
