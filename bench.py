@@ -226,7 +226,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
         return probs, kl
 
     def side_launches():  # the model's own side context (z of the later layers, drawn ahead)
-        return model._side.launches if getattr(model, "_side", None) is not None else 0
+        return sum(c.launches for c in getattr(model, "_sides", []))
 
     def ev():
         p = C.c_void_p()

@@ -107,8 +107,9 @@ class BatchNormalization(StockLayer):
 class Sequential:
     def __init__(self, layers=None) -> None:
         self.layers = list(layers or [])
-        self.presample_z = True   # draw the later layers' z on a side stream beside the first layers
-        self._side = None
+        self.presample_z = True   # draw the later layers' z on side streams beside the first layers
+        self._sides: list = []    # one forked context per later MNF layer: their flow chains
+        #                           (80-CTA kernels at 10k rows) pack the SMs side by side
 
     def __call__(self, x: Any, noise: list | None = None) -> DeviceArray:  # noqa: A002
         """noise: optional list with one injected-draw dict per MNF layer (program order)."""
@@ -118,10 +119,10 @@ class Sequential:
         if self.presample_z and not noise:
             later = [l for l in self.mnf_layers[1:] if l.built and l.use_z and l.ctx is x.ctx]
             if later:
-                if self._side is None or self._side.device != x.ctx.device:
-                    self._side = x.ctx.fork()
-                for lyr in later:
-                    lyr.presample(x.shape[0], self._side)
+                if len(self._sides) < len(later) or self._sides[0].device != x.ctx.device:
+                    self._sides = [x.ctx.fork() for _ in later]
+                for lyr, side in zip(later, self._sides):
+                    lyr.presample(x.shape[0], side)
         for i, lyr in enumerate(self.layers):
             if skip:  # this ReLU+MaxPool was folded into the preceding conv's epilogue
                 skip = False
