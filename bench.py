@@ -220,6 +220,8 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     def step(x):
         for c in kl_lanes:
             c.wait(ctx)
+        if os.environ.get("MNF_BENCH_NOKL"):  # diagnostic only: how much the KL streams cost the forward
+            return model(x), None
         kl = model.kl_div(ctx=kl_lanes)
         probs = model(x)
         ctx.wait(kl_ctx)

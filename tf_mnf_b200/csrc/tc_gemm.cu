@@ -153,7 +153,9 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], PROD_WARPS / 2 + 1);  // 4 warps of one producer group + the B bulk-copy arrive
+      // dense (vector path): all 8 producer warps fill every stage; otherwise 4 warps of one
+      // producer group; plus the B bulk-copy arrive
+      mbar_init(&full[s], ((!CONV && a.vec) ? PROD_WARPS : PROD_WARPS / 2) + 1);
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -332,6 +334,89 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
     // the 16 k of a block: its four 16-byte gathers are issued together and the NEXT block's
     // gathers are in flight while the current block is split and written to shared memory.
     const int pt = threadIdx.x - (EPI_WARPS + 1) * 32;  // 0..255
+    if (!CONV && a.vec) {
+      // ---- dense rows, K % 4 == 0: the global-load latency (L2, ~1 us under load) is the
+      // enemy.  Four lanes read the 64 contiguous bytes of one row's k-block (coalesced), every
+      // thread owns two rows x one 16-byte k-chunk, and the loads of the next PF k-blocks are
+      // kept in flight in a register ring while the current block is split and stored.
+      constexpr int PF = 4;
+      const int kc = pt & 3, rs = pt >> 2;  // rows rs and rs + 64
+      const int my_tiles = (int)((ntot > blockIdx.x) ? (ntot - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+      const int64_t nblk = (int64_t)my_tiles * a.kblocks;
+      float4 xb[PF][2], zb[PF][2];
+      // load cursor
+      int lti = 0, lkb = 0;
+      const float *lx0 = nullptr, *lx1 = nullptr, *lz0 = nullptr, *lz1 = nullptr;
+      auto load_tile = [&](int ti) {
+        const int64_t t = blockIdx.x + (int64_t)ti * gridDim.x;
+        const int64_t mt = t / a.ntiles;
+        int64_t m0 = mt * BM + rs, m1 = m0 + 64;
+        if (m0 >= a.M) m0 = a.M - 1;  // rows beyond M read a valid row; never stored
+        if (m1 >= a.M) m1 = a.M - 1;
+        lx0 = a.x + m0 * a.K + kc * 4;
+        lx1 = a.x + m1 * a.K + kc * 4;
+        if (a.z) { lz0 = a.z + m0 * a.K + kc * 4; lz1 = a.z + m1 * a.K + kc * 4; }
+      };
+      auto issue = [&](float4 (&xv)[2], float4 (&zv)[2]) {
+        if (lkb == 0) load_tile(lti);
+        const int k = lkb * BK + kc * 4;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f), one = make_float4(1.f, 1.f, 1.f, 1.f);
+        xv[0] = xv[1] = zero;
+        zv[0] = zv[1] = one;
+        if (k < a.K) {
+          xv[0] = __ldg(reinterpret_cast<const float4*>(lx0 + lkb * BK));
+          xv[1] = __ldg(reinterpret_cast<const float4*>(lx1 + lkb * BK));
+          if (a.z) {
+            zv[0] = __ldg(reinterpret_cast<const float4*>(lz0 + lkb * BK));
+            zv[1] = __ldg(reinterpret_cast<const float4*>(lz1 + lkb * BK));
+          }
+        }
+        if (++lkb == a.kblocks) { lkb = 0; ++lti; }
+      };
+#pragma unroll
+      for (int d = 0; d < PF; ++d)
+        if (d < nblk) issue(xb[d], zb[d]);
+      int sti = 0, skb = 0, stage = 0;
+      uint32_t sph = 0;
+      for (int64_t b0 = 0; b0 < nblk; b0 += PF) {
+#pragma unroll
+        for (int d = 0; d < PF; ++d) {
+          const int64_t b = b0 + d;
+          if (b < nblk) {
+            mbar_wait(&empty[stage], sph ^ 1);
+            if (pt == 0) {
+              const int64_t t = blockIdx.x + (int64_t)sti * gridDim.x;
+              const int nt = (int)(t % a.ntiles);
+              const float* bsrc = a.Bp + ((size_t)nt * a.kblocks + skb) * (size_t)(B_STAGE_BYTES / 4);
+              mbar_arrive_expect_tx(&full[stage], B_STAGE_BYTES);
+              bulk_g2s(Bs + stage * B_STAGE_BYTES, bsrc, B_STAGE_BYTES, &full[stage]);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float xs[4] = {xb[d][h].x, xb[d][h].y, xb[d][h].z, xb[d][h].w};
+              const float zs[4] = {zb[d][h].x, zb[d][h].y, zb[d][h].z, zb[d][h].w};
+              float h1[4], l1[4], h2[4], l2[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                split_tf32(xs[e] * zs[e], h1[e], l1[e]);
+                split_tf32(xs[e] * xs[e], h2[e], l2[e]);
+              }
+              uint8_t* dst = As + stage * A_STAGE_BYTES + kc * (BM * 16) + (rs + 64 * h) * 16;
+              *reinterpret_cast<float4*>(dst + 0 * A_VARIANT_BYTES) = make_float4(h1[0], h1[1], h1[2], h1[3]);
+              *reinterpret_cast<float4*>(dst + 1 * A_VARIANT_BYTES) = make_float4(l1[0], l1[1], l1[2], l1[3]);
+              *reinterpret_cast<float4*>(dst + 2 * A_VARIANT_BYTES) = make_float4(h2[0], h2[1], h2[2], h2[3]);
+              *reinterpret_cast<float4*>(dst + 3 * A_VARIANT_BYTES) = make_float4(l2[0], l2[1], l2[2], l2[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
+            if (b + PF < nblk) issue(xb[d], zb[d]);  // refill this ring slot
+            if (++skb == a.kblocks) { skb = 0; ++sti; }
+            if (++stage == STAGES) { stage = 0; sph ^= 1; }
+          }
+        }
+      }
+    } else {
     const int r = pt & (BM - 1);
     const int grp = pt >> 7;
     struct RowCtx {
@@ -479,6 +564,7 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
       ti = nti; kb = nkb;
       stage += 2;
       if (stage >= STAGES) { stage -= STAGES; sph ^= 1; }
+    }
     }
   }
 
