@@ -67,6 +67,34 @@ def test_conv_tensorcore(tc_ctx, shape, wshape, stride, padding):
     close(got, ref, RTOL, "conv call (tf32x3)")
 
 
+@pytest.mark.parametrize("wshape,shape", [((5, 5, 20, 50), (7, 12, 12, 20)), ((3, 3, 8, 40), (9, 10, 10, 8)),
+                                          ((5, 5, 12, 64), (4, 12, 12, 12))])
+def test_conv_f16_split_dynamic_range(tc_ctx, wshape, shape):
+    """conv_raw_f16.cu scales every image and every weight column by a power of two before the
+    fp16 hi/lo split: images whose magnitudes differ by 1e8, zero images and weight columns of
+    very different size must each meet the parity bar relative to THEIR OWN output scale."""
+    rng = np.random.RandomState(5)
+    P = O.make_layer_params(rng, wshape, flow="iaf", std_init=10.0, dtype=np.float64)
+    F = wshape[-1]
+    P["mean_W"] *= np.exp(rng.uniform(-8, 8, size=F))            # column scales over 7 decades
+    P["mean_b"][...] = 0.0
+    P["log_var_b"][...] = -60.0                                  # bias variance ~ 0: sd comes from x^2 * sigma^2
+    x = rng.standard_normal(shape)
+    x *= np.array([1e-4, 1.0, 300.0, 1e4, 0.0, 3e-3, 7.0, 1e2, 1e-2][: shape[0]]).reshape(-1, 1, 1, 1)
+    B = shape[0]
+    y0 = O.conv2d(x, P["mean_W"], 1, "VALID")
+    eps_z, eps = rng.standard_normal((B, F)), rng.standard_normal(y0.shape)
+    ref, _ = O.conv_call(P, x, eps_z, eps, 1.0, stride=1, padding="VALID")
+    lyr = make_layer(P, x.shape)
+    got = lyr(_f32(x), noise=dict(eps_z=_f32(eps_z), eps_out=_f32(eps))).numpy()
+    for b in range(B):
+        for n in range(0, F, 7):
+            r = ref[b, ..., n]
+            if np.max(np.abs(r)) > 1e-30:
+                close(got[b, ..., n], r, 2e-5, f"image {b} filter {n}")
+    close(got, ref, RTOL, "whole tensor")
+
+
 @pytest.mark.parametrize("shape,wshape", [((64, 12, 12, 20), (5, 5, 20, 50)), ((301, 28, 28, 1), (5, 5, 1, 20))])
 def test_tensorcore_matches_ffma_with_philox(tc_ctx, shape, wshape):
     """Same seed => the tensor-core and FFMA paths draw identical in-kernel noise; outputs agree to 1e-5."""

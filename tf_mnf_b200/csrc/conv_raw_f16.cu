@@ -1,0 +1,550 @@
+// MNFConv2D.call (mnf_conv.py:182-197) on tcgen05 kind::f16 with split operands -- the raw-tile
+// kernel of conv_raw_f16.cu (im2col expressed by per-MMA UMMA descriptors over the staged input
+// tile) with HALF the bytes per K element.
+//
+// conv_raw_f16.cu is bound by the L2 -> SM stream of its weights (every 128-row tile re-reads
+// all K x 64 x {hi, lo} x {mean, var} TF32 weights: 2.6 GB per MNF-LeNet conv2 launch) and by
+// the shared-memory operand fetch of its K=8 MMAs.  fp16 carries the same 11 significant bits as
+// TF32 in 2 bytes, so the same hi/lo split (x = hi + lo, x*w ~ hi*hi + lo*hi + hi*lo, fp32
+// accumulate) needs half the weight bytes and half the MMAs (K = 16 per instruction).  What
+// fp16 lacks is range, so every operand gets an exact power-of-two scale:
+//   weights: per output column n, 2^e so that max_k |w[k,n]| * 2^e lies in [2^13, 2^14)
+//            (mean and variance weights separately), found by a column-max pre-pass;
+//   inputs:  per image of the tile, 2^e so that max |x| * 2^e lies in [2^6, 2^7), hence
+//            (x * 2^e)^2 < 2^14; found by the producer warps while the previous tile computes.
+// The epilogue multiplies the fp32 accumulators by the inverse scales (exact).  Elements far
+// below their column / image maximum lose RELATIVE precision in the lo part (fp16 subnormals,
+// quantum 2^-24 of the scaled value) but their absolute error stays below 2^-38 of the maximum,
+// far inside the 1e-5 parity bar, which is relative to the output scale.
+//
+//   planes[v][cc][hi][img][wi] of 16-byte chunks (8 channels, zero padded), v in {x hi, x lo,
+//   x^2 hi, x^2 lo};  step table, phases, warp roles and the N=128 [W_hi | W_lo] instruction as
+//   in conv_raw_f16.cu.
+#include <cuda_fp16.h>
+
+#include <utility>
+#include <vector>
+
+#include "umma.cuh"
+
+namespace cf {
+using namespace um;
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+      : "memory");
+}
+// (a0, a1) -> packed fp16 hi pair and lo pair, a = hi + lo (+ O(2^-22 |a|)), both rounded to nearest
+__device__ __forceinline__ void split_f16x2(float a0, float a1, uint32_t& hi, uint32_t& lo) {
+  const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
+  const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
+  hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+  lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+}
+
+constexpr int BM = 128, BN = 64;
+constexpr int G = 6;                 // K=16 steps per weight stage
+constexpr int STEP_B = 2 * 2 * BN * 16;  // bytes of one K=16 step's weights for one phase: [2 kc][hi 64 n | lo 64 n][8 halves] = 4 KB
+constexpr int B_STAGE = G * STEP_B;  // 24 KB
+constexpr int SB = 3;                // weight ring depth
+constexpr int THREADS = 13 * 32;
+constexpr int PROD_WARPS = 3;      // warps 5-7 fill the planes; warps 8-11 are the second epilogue group
+constexpr int TMEM_COLS = 512;  // [2 buffers][2 phases][hi-product 64 | lo-product 64]
+
+struct Args {
+  int64_t B;         // images
+  int H, W, C, kh, kw, Ho, N, I;  // Wo == 8; I images per tile
+  int Hi, Wi;        // plane extent per image: Ho-1+kh, 8-1+kw
+  int cpt;           // 16-byte channel chunks per pixel (ceil(C / 8))
+  int steps;         // K=16 steps
+  int pool;
+  const float* x;
+  const float* z;    // [B,N] or nullptr
+  const float* bm;
+  const float* vb;
+  const int* steptab;  // [steps][2]: a_off, a_lbo (bytes)
+  const float* Bp;     // [2 phases][steps][STEP_B bytes] fp16 pairs
+  const float* wsc;    // [2][BN] inverse column scales of the mean / variance weights
+  float* y;
+  float* mean_out;
+  float* sd_out;
+  NoiseDev eps;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int pix = a.Hi * a.I * a.Wi;          // 16-byte chunks per channel-chunk plane
+  const int CCS = pix * 16;                   // bytes between channel chunks
+  const int PLANE = a.cpt * CCS;              // bytes of one variant
+  uint8_t* planes = smem;                     // [4][cpt][Hi][I][Wi][16 B]
+  uint8_t* Bs = planes + 4 * PLANE;           // [SB][B_STAGE]
+  float* ys = (float*)(Bs + SB * B_STAGE);    // [BM][N] dense staging
+  int* stab = (int*)(ys + BM * BN);           // [steps][2]
+  float* bias_s = (float*)(stab + 2 * a.steps);  // [2][BN]
+  float* zs = bias_s + 2 * BN;                   // [I][BN] z rows of the tile being written out
+  float* wsc_s = zs + 16 * BN;                   // [2][BN] inverse weight-column scales
+  float* xsc = wsc_s + 2 * BN;                   // [4][16] inverse input scale per image, ring over tiles
+  float* xsf = xsc + 64;                         // [2][16] forward input scale per image (producers)
+  unsigned* xmax = (unsigned*)(xsf + 32);        // [2][16] max |x| per image (float bits), double buffered
+  uint64_t* bars = (uint64_t*)(((uintptr_t)(xmax + 32) + 7) & ~(uintptr_t)7);
+  uint64_t* pfull = bars;        // [2] planes of phase ready
+  uint64_t* pempty = pfull + 2;  // [2]
+  uint64_t* bfull = pempty + 2;  // [SB]
+  uint64_t* bempty = bfull + SB; // [SB]
+  uint64_t* tfull = bempty + SB; // [2]
+  uint64_t* tempty = tfull + 2;  // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HoWo = a.Ho * 8;
+  const int64_t ntiles = (a.B + a.I - 1) / a.I;
+  const int nstages = (a.steps + G - 1) / G;
+
+  if (threadIdx.x == 0) {
+    for (int p = 0; p < 2; ++p) { mbar_init(&pfull[p], PROD_WARPS); mbar_init(&pempty[p], 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 2 * a.steps; i += THREADS) stab[i] = a.steptab[i];
+  for (int n = threadIdx.x; n < BN; n += THREADS) {
+    bias_s[n] = n < a.N ? a.bm[n] : 0.f;
+    bias_s[BN + n] = n < a.N ? a.vb[n] : 1.f;
+    wsc_s[n] = a.wsc[n];
+    wsc_s[BN + n] = a.wsc[BN + n];
+  }
+  if (threadIdx.x < 32) xmax[threadIdx.x] = 0u;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4 || (warp >= 8 && warp < 12)) {
+    // ================================================================== epilogue warps
+    const int quad = warp & 3, chalf = warp >= 8 ? 1 : 0;
+    const int et = chalf * 128 + quad * 32 + lane;   // 0..255 among the epilogue threads
+    const int r = quad * 32 + lane;             // TMEM lane = tile row (ho, img, wo)
+    const int wo = r & 7, g = r >> 3, img = g % a.I, ho = g / a.I;
+    const int rl = img * HoWo + ho * 8 + wo;    // row inside the tile's block of y
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int64_t b0 = t * a.I, brow = b0 + img;
+      const int buf = it & 1;
+      // this tile's z rows -> shared memory (the previous tile's readers passed the closing barrier)
+      for (int e = et; e < a.I * BN; e += 256) {
+        const int im = e / BN, n = e - im * BN;
+        zs[e] = (a.z && b0 + im < a.B && n < a.N) ? __ldg(a.z + (b0 + im) * a.N + n) : 1.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(&tfull[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const bool row_ok = brow < a.B;
+      const float sx = xsc[(it & 3) * 16 + img], sx2 = sx * sx;  // written before the planes were released
+      const uint32_t outer = (uint32_t)(ho * 8 + wo);
+      const int64_t m = brow * HoWo + outer;
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 4 * BN);
+#pragma unroll 1
+      for (int c0 = chalf * 32; c0 < chalf * 32 + 32; c0 += 16) {
+        if (c0 >= a.N) break;
+        float mv[16], vv[16];
+        {
+          float m2[16], v2[16];
+          tmem_ld16(trow + c0, mv);
+          tmem_ld16(trow + BN + c0, m2);
+          tmem_ld16(trow + 2 * BN + c0, vv);
+          tmem_ld16(trow + 3 * BN + c0, v2);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            mv[j] += m2[j];
+            vv[j] += v2[j];
+          }
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int nb = c0 + 4 * q;
+            if (nb >= a.N) break;
+            float e[4];
+            if (a.eps.injected) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) e[j] = nb + j < a.N ? a.eps.injected[m * a.N + nb + j] : 0.f;
+            } else {
+              philox_normal4(a.eps, a.eps.row_offset + (uint64_t)brow, outer, (uint32_t)(nb >> 2), e);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = nb + j;
+              if (n < a.N) {
+                float mean = mv[4 * q + j] * (sx * wsc_s[n]) + bias_s[n];
+                const float sd = sqrtf(vv[4 * q + j] * (sx2 * wsc_s[BN + n]) + bias_s[BN + n]);
+                if (a.sd_out) a.sd_out[m * a.N + n] = sd;
+                if (a.mean_out) a.mean_out[m * a.N + n] = mean;
+                if (a.z) mean *= zs[img * BN + n];
+                ys[rl * a.N + n] = fmaf(sd, e[j], mean);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int64_t nimg = (a.B - b0 < a.I) ? a.B - b0 : a.I;
+      const int rows = (int)nimg * HoWo;
+      if (a.pool) {
+        const int np = rows >> 2;
+        float* dst = a.y + (b0 * HoWo >> 2) * a.N;
+        for (int e = et; e < np * a.N; e += 256) {
+          const int pp = e / a.N, c = e - pp * a.N;
+          const int hp = pp >> 2, wp = pp & 3;  // Wo / 2 == 4 pooled columns
+          const float* s0 = ys + ((2 * hp) * 8 + 2 * wp) * a.N + c;
+          const float v = fmaxf(fmaxf(s0[0], s0[a.N]), fmaxf(s0[8 * a.N], s0[9 * a.N]));
+          dst[e] = fmaxf(v, 0.f);
+        }
+      } else {
+        float* dst = a.y + b0 * HoWo * a.N;
+        for (int e = et; e < rows * a.N; e += 256) dst[e] = ys[e];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  } else if (warp == 4) {
+    // ======================================================================= MMA issuer
+    // x_hi * [W_hi | W_lo] is ONE N=128 instruction (the A tile is read from shared memory once for
+    // both products: at N=64 the operand fetch, not the tensor pipe, sets the pace); x_lo * W_hi
+    // is an N=64 instruction into the first 64 columns.  The epilogue adds the two column halves.
+    // instruction descriptor: D = F32 (bit 4), A = B = F16 (format 0), K-major, N >> 3, M >> 4
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t sbo = (uint32_t)(a.Wi * 16);
+    const uint64_t bdesc0 = make_desc(smem_u32(Bs), 2 * BN * 16, 128);
+    const uint32_t plane0 = smem_u32(planes);
+    int it = 0, st = 0;
+    uint32_t bph = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+      for (int ph = 0; ph < 2; ++ph) {
+        mbar_wait(&pfull[ph], it & 1);
+        tc_fence_after();
+        const uint32_t dacc = tmem_base + (uint32_t)(buf * 4 * BN + ph * 2 * BN);
+        const uint32_t pa_hi = plane0 + (uint32_t)((2 * ph) * PLANE), pa_lo = pa_hi + (uint32_t)PLANE;
+        for (int sg = 0; sg < nstages; ++sg) {
+            mbar_wait(&bfull[st], bph);
+          tc_fence_after();
+          if (lane == 0) {
+            const int s1 = min(a.steps, (sg + 1) * G);
+            for (int s = sg * G; s < s1; ++s) {
+              const uint32_t aoff = (uint32_t)stab[2 * s], lbo = (uint32_t)stab[2 * s + 1];
+              const uint64_t ah = make_desc(pa_hi + aoff, lbo, sbo), al = make_desc(pa_lo + aoff, lbo, sbo);
+              const uint64_t bh = bdesc0 + (uint64_t)((st * B_STAGE + (s - sg * G) * STEP_B) >> 4);
+              umma_f16(dacc, ah, bh, idesc2, s == 0 ? 0u : 1u);
+              umma_f16(dacc, al, bh, idesc, 1u);
+            }
+            umma_commit(&bempty[st]);
+            if (sg == nstages - 1) {
+              umma_commit(&pempty[ph]);              // planes of this phase may be refilled
+              if (ph == 1) umma_commit(&tfull[buf]);  // both accumulators complete
+            }
+          }
+          __syncwarp();
+          if (++st == SB) { st = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 12) {
+    // ==================================================================== weight loader
+    if (lane == 0) {
+      int st = 0;
+      uint32_t bph = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int ph = 0; ph < 2; ++ph) {
+          const float* src0 = a.Bp + (size_t)ph * a.steps * (STEP_B / 4);
+          for (int sg = 0; sg < nstages; ++sg) {
+            const int ns = min(G, a.steps - sg * G);
+            mbar_wait(&bempty[st], bph ^ 1);
+            mbar_arrive_expect_tx(&bfull[st], (uint32_t)(ns * STEP_B));
+            bulk_g2s(Bs + st * B_STAGE, src0 + (size_t)sg * G * (STEP_B / 4), (uint32_t)(ns * STEP_B), &bfull[st]);
+            if (++st == SB) { st = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================== plane producers
+    if (warp < 8) {
+      const int pt = threadIdx.x - 5 * 32;  // 0 .. 95
+      constexpr int NP = PROD_WARPS * 32;
+      const int nchunks = a.cpt * pix;       // 16-byte chunks per variant
+      const int img_f = a.H * a.W * a.C;     // floats per input image
+      const int img4 = img_f >> 2;           // float4 per image (C % 4 == 0)
+      int it = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int64_t b0 = t * a.I;
+        // ---- pass 1: max |x| per image of this tile (the whole image is the tile's input)
+        unsigned* xm = xmax + (it & 1) * 16;
+        for (int im = 0; im < a.I; ++im) {
+          int64_t b = b0 + im;
+          if (b >= a.B) b = a.B - 1;
+          const float4* src = reinterpret_cast<const float4*>(a.x + b * img_f);
+          float m = 0.f;
+          for (int i = pt; i < img4; i += NP) {
+            const float4 v = __ldg(src + i);
+            m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          if (lane == 0) atomicMax(xm + im, __float_as_uint(m));
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(NP) : "memory");
+        const float* sc = xsf + (it & 1) * 16;  // forward scale per image
+        if (pt < a.I) {
+          const float m = __uint_as_float(xm[pt]);
+          int e = 0;
+          if (m > 0.f && m < 3.0e38f) {
+            int ex;
+            frexpf(m, &ex);          // m = f * 2^ex, f in [0.5, 1)
+            e = 7 - ex;              // m * 2^e in [2^6, 2^7)
+            e = e > 100 ? 100 : (e < -100 ? -100 : e);
+          }
+          xsf[(it & 1) * 16 + pt] = ldexpf(1.f, e);
+          xsc[(it & 3) * 16 + pt] = ldexpf(1.f, -e);
+          xm[pt] = 0u;  // ready for the tile after next (the other buffer is used next)
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(NP) : "memory");
+        for (int ph = 0; ph < 2; ++ph) {
+          mbar_wait(&pempty[ph], (it & 1) ^ 1);
+          uint8_t* dst_hi = planes + (2 * ph) * PLANE;
+          uint8_t* dst_lo = dst_hi + PLANE;
+          for (int q0 = pt; q0 < nchunks; q0 += 2 * NP) {
+            // two chunks (four 16-byte loads) in flight per thread, then scale + split + store
+            float4 v[2][2];
+            int o[2];
+            float scl[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int q = q0 + u * NP;
+              v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+              o[u] = -1;
+              scl[u] = 1.f;
+              if (q < nchunks) {
+                // q enumerates (hi, img, wi, cc), cc fastest: a warp reads consecutive floats
+                const int cc = q % a.cpt;
+                int p = q / a.cpt;
+                const int wi = p % a.Wi;
+                p /= a.Wi;
+                const int im = p % a.I, hi = p / a.I;
+                int64_t b = b0 + im;
+                if (b >= a.B) b = a.B - 1;
+                if (hi < a.H && wi < a.W) {
+                  const float* src = a.x + b * img_f + (hi * a.W + wi) * a.C + cc * 8;
+                  v[u][0] = __ldg(reinterpret_cast<const float4*>(src));
+                  if (cc * 8 + 4 < a.C) v[u][1] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                }
+                o[u] = cc * CCS + ((hi * a.I + im) * a.Wi + wi) * 16;
+                scl[u] = sc[im];
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (o[u] < 0) continue;
+              const float in[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a0 = in[2 * e] * scl[u], a1 = in[2 * e + 1] * scl[u];
+                if (ph == 1) { a0 *= a0; a1 *= a1; }
+                split_f16x2(a0, a1, hw[e], lw[e]);
+              }
+              *reinterpret_cast<uint4*>(dst_hi + o[u]) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(dst_lo + o[u]) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&pfull[ph]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// column maxima -> power-of-two scales.  esc[ph*BN + n] = e with max_k |w[k,n]| * 2^e in [2^13, 2^14);
+// wsc = 2^-e (the epilogue's inverse scale); also the clipped bias variance vb.
+__global__ void f16_colscale(int K, int N, const float* __restrict__ Wm, const float* __restrict__ Ls, float max_std,
+                             int* __restrict__ esc, float* __restrict__ wsc, const float* __restrict__ lvb,
+                             float* __restrict__ vb) {
+  const int n = blockIdx.x, ph = blockIdx.y;
+  float m = 0.f;
+  if (n < N)
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      float w;
+      if (ph == 0) w = fabsf(Wm[(int64_t)k * N + n]);
+      else {
+        const float sd = fminf(expf(Ls[(int64_t)k * N + n]), max_std);
+        w = sd * sd;
+      }
+      m = fmaxf(m, w);
+    }
+  __shared__ float red[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    int e = 0;
+    if (m > 0.f && m < 3.0e38f) {
+      int ex;
+      frexpf(m, &ex);
+      e = 14 - ex;
+      e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    }
+    esc[ph * BN + n] = e;
+    wsc[ph * BN + n] = ldexpf(1.f, -e);
+    if (ph == 0 && n < N) vb[n] = fminf(expf(lvb[n]), max_std * max_std);
+  }
+}
+
+// weights -> Bp[phase][step][kc 2][hi n 64 | lo n 64][8 k] fp16; kmap[step][16] = global k index or -1
+__global__ void pack_f16_weights(int N, int steps, const int* __restrict__ kmap, const float* __restrict__ Wm,
+                                 const float* __restrict__ Ls, float max_std, const int* __restrict__ esc,
+                                 __half* __restrict__ Bp) {
+  const int64_t total = (int64_t)2 * steps * 2 * BN * 8;  // (phase, step, kc, n, e)
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(idx & 7);
+    int64_t t = idx >> 3;
+    const int n = (int)(t % BN);
+    t /= BN;
+    const int kc = (int)(t & 1);
+    t >>= 1;
+    const int s = (int)(t % steps), ph = (int)(t / steps);
+    const int k = kmap[s * 16 + kc * 8 + e];
+    float w = 0.f;
+    if (k >= 0 && n < N) {
+      if (ph == 0) w = Wm[(int64_t)k * N + n];
+      else {
+        const float sd = fminf(expf(Ls[(int64_t)k * N + n]), max_std);
+        w = sd * sd;
+      }
+      w = ldexpf(w, esc[ph * BN + n]);
+    }
+    const __half hi = __float2half_rn(w), lo = __float2half_rn(w - __half2float(hi));
+    __half* base = Bp + ((int64_t)ph * steps + s) * (STEP_B / 2) + ((int64_t)kc * 2 * BN + n) * 8 + e;
+    base[0] = hi;
+    base[BN * 8] = lo;  // the lo rows follow the 64 hi rows of the same K chunk
+  }
+}
+
+}  // namespace cf
+
+// Returns MNF_OK with *used = false when the shape is outside this kernel's domain.
+int mnf_conv_raw_f16_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, const float* x, const float* z,
+                              const float* mean_W, const float* log_std_W, const float* mean_b,
+                              const float* log_var_b, float max_std, const NoiseDev& eps, float* y, float* mean_out,
+                              float* sd_out, bool* used) {
+  using namespace cf;
+  *used = false;
+  const int H = geo[0], W = geo[1], C = geo[2], kh = geo[3], kw = geo[4], Ho = geo[5], Wo = geo[6], stride = geo[7],
+            pad_t = geo[8], pad_l = geo[9], pool = geo[10];
+  if (stride != 1 || Wo != 8 || pad_t || pad_l || (C & 3) || N > BN || N <= 20) return MNF_OK;
+  if (Ho < 1 || Ho > 16 || (16 % Ho) != 0) return MNF_OK;
+  if (((uintptr_t)x & 15) != 0) return MNF_OK;
+  Args a = {};
+  a.B = B; a.H = H; a.W = W; a.C = C; a.kh = kh; a.kw = kw; a.Ho = Ho; a.N = N;
+  a.I = 16 / Ho;
+  a.Hi = Ho - 1 + kh; a.Wi = 8 - 1 + kw;
+  if (a.Hi > H || a.Wi > W) return MNF_OK;  // VALID geometry only
+  a.cpt = (C + 7) / 8;
+  a.pool = pool;
+  // ---- step table: chunk pairs of one tap, then the odd leftover chunks of neighbouring taps
+  const int pixn = a.Hi * a.I * a.Wi, CCS = pixn * 16;
+  std::vector<int> tab, kmap;
+  auto chunk_off = [&](int i, int j, int cc) { return cc * CCS + (i * a.I * a.Wi + j) * 16; };
+  auto push_k = [&](int i, int j, int cc) {
+    for (int e = 0; e < 8; ++e) kmap.push_back(i >= 0 && cc * 8 + e < C ? (i * kw + j) * C + cc * 8 + e : -1);
+  };
+  std::vector<std::pair<int, int>> left;
+  for (int i = 0; i < kh; ++i)
+    for (int j = 0; j < kw; ++j) {
+      for (int cc = 0; cc + 1 < a.cpt; cc += 2) {
+        tab.push_back(chunk_off(i, j, cc));
+        tab.push_back(CCS);
+        push_k(i, j, cc);
+        push_k(i, j, cc + 1);
+      }
+      if (a.cpt & 1) left.push_back({i, j});
+    }
+  for (size_t m = 0; m < left.size(); m += 2) {
+    const int cc = a.cpt - 1;
+    const int o0 = chunk_off(left[m].first, left[m].second, cc);
+    tab.push_back(o0);
+    push_k(left[m].first, left[m].second, cc);
+    if (m + 1 < left.size()) {
+      const int o1 = chunk_off(left[m + 1].first, left[m + 1].second, cc);
+      if (o1 <= o0 || (o1 - o0) >= (1 << 18)) return MNF_OK;
+      tab.push_back(o1 - o0);
+      push_k(left[m + 1].first, left[m + 1].second, cc);
+    } else {
+      tab.push_back(16);   // dummy second chunk: valid memory, zero weights
+      push_k(-1, 0, 0);
+    }
+  }
+  a.steps = (int)tab.size() / 2;
+  const size_t plane_bytes = (size_t)4 * a.cpt * CCS;
+  const size_t smem = plane_bytes + (size_t)SB * B_STAGE + sizeof(float) * BM * BN + sizeof(int) * 2 * a.steps +
+                      sizeof(float) * ((2 + 16 + 2) * BN + 64 + 32 + 32) + 256;
+  if (smem > 227 * 1024) return MNF_OK;
+  // ---- workspace: Bp | vb | wsc | esc | steptab | kmap
+  const size_t bp_floats = (size_t)2 * a.steps * (STEP_B / 4);
+  const size_t ws_bytes = sizeof(float) * (bp_floats + 64 + 2 * BN + 2 * BN) + sizeof(int) * (tab.size() + kmap.size() + 128);
+  char* ws = (char*)mnf_workspace(ctx, ws_bytes);
+  if (!ws) return MNF_ERR_CUDA;
+  float* Bp = (float*)ws;
+  float* vb = Bp + bp_floats;
+  float* wsc = vb + 64;
+  int* esc = (int*)(wsc + 2 * BN);
+  int* d_tab = esc + 2 * BN;
+  int* d_kmap = d_tab + ((tab.size() + 63) & ~(size_t)63);
+  MNF_CUDA(cudaMemcpyAsync(d_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, ctx->stream));
+  MNF_CUDA(cudaMemcpyAsync(d_kmap, kmap.data(), sizeof(int) * kmap.size(), cudaMemcpyHostToDevice, ctx->stream));
+  f16_colscale<<<dim3(BN, 2), 128, 0, ctx->stream>>>(kh * kw * C, N, mean_W, log_std_W, max_std, esc, wsc, log_var_b, vb);
+  MNF_LAUNCHED(ctx);
+  const int64_t tot = (int64_t)2 * a.steps * 2 * BN * 2;
+  int grid = (int)(cdiv(tot, 256) < ctx->sm_count * 4 ? cdiv(tot, 256) : ctx->sm_count * 4);
+  pack_f16_weights<<<grid, 256, 0, ctx->stream>>>(N, a.steps, d_kmap, mean_W, log_std_W, max_std, esc, (__half*)Bp);
+  MNF_LAUNCHED(ctx);
+  a.x = x; a.z = z; a.bm = mean_b; a.vb = vb; a.steptab = d_tab; a.Bp = Bp; a.wsc = wsc;
+  a.y = y; a.mean_out = mean_out; a.sd_out = sd_out; a.eps = eps;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    MNF_CUDA(cudaFuncSetAttribute(conv_raw_f16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  const int64_t tiles = cdiv(B, a.I);
+  const int g = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+  const bool probed = mnf_probe_begin(ctx, MNF_PROBE_CONV_GEMM);
+  conv_raw_f16<<<g, THREADS, smem, ctx->stream>>>(a);
+  mnf_probe_end(ctx, probed);
+  MNF_LAUNCHED(ctx);
+  *used = true;
+  return MNF_OK;
+}

@@ -618,6 +618,11 @@ int mnf_conv2d_forward(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, co
   if (rc || used) return rc;
   if (ctx->math_mode == MNF_MATH_TF32X3) {
     if (!pad_b && !pad_r) {  // raw-tile kernel: im2col expressed by UMMA descriptors (8-wide output rows)
+      if (!getenv("MNF_NO_F16")) {  // scaled fp16 hi/lo operands: half the weight stream and MMAs
+        rc = mnf_conv_raw_f16_forward(ctx, s->B, geo, a.N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std, a.eps, y,
+                                      mean_out, sd_out, &used);
+        if (rc || used) return rc;
+      }
       rc = mnf_conv_raw_umma_forward(ctx, s->B, geo, a.N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std, a.eps, y,
                                      mean_out, sd_out, &used);
       if (rc || used) return rc;
