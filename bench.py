@@ -179,7 +179,10 @@ def workload_config(args, rows_per_step=ROWS) -> dict:
                         "forward of 2xMNFConv2D + 2xMNFDense (+ReLU/MaxPool/Softmax) + model.kl_div()",
             "rows_per_gpu": rows_per_step, "flow_type": args.flow, "n_flows_q": 2, "n_flows_r": 2, "flow_h_sizes": [50],
             "std_init": 10.0, "max_std": 1.0, "noise": "in-kernel Philox4x32-10", "l2": "flushed between timed steps "
-            "(256 MiB memset outside the per-step event pairs)", "parallelism": f"row-sharded x{args.gpus}, no collective"}
+            "(256 MiB memset outside the per-step event pairs)",
+            "streams": "KL terms on 4 sibling streams and the z chains of layers 2-4 on 3 side streams, all forked from "
+                       "the step's stream after its start event and joined before its stop event",
+            "parallelism": f"row-sharded x{args.gpus}, no collective"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -382,13 +385,14 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
             "gpu_launches": int(launches),
             "clocks": clk.summary(t_wall0, t_wall1),
             "roofline": {"bound": "hbm",
-                         "kernel": ("tc::paired_umma_fwd<64,CONV>" if args.math == "tf32x3" else "paired_gemm_fwd<CONV,64>")
-                         + " (conv2: 12x12x20 -> 8x8x50, 5x5)",
+                         "kernel": ("cf::conv_raw_f16" if args.math == "tf32x3" else "paired_gemm_fwd<CONV,64>")
+                         + " (conv2: 12x12x20 -> 8x8x50, 5x5, + fused ReLU/2x2 max-pool)",
                          "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
                          "peak_source": which, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms,
                          "algorithmic_bytes_per_launch": k_bytes,
-                         "pipe": ("tcgen05.mma kind::tf32, 3xTF32 split (fp32 parity <=1e-5 rel.)" if args.math == "tf32x3"
-                                  else "fp32 FFMA (parity path, <=1e-5 rel.)"),
+                         "pipe": ("tcgen05.mma kind::f16, power-of-two scaled fp16 hi/lo split of both operands, fp32 "
+                                  "accumulate (fp32 parity <=1e-5 rel.); bound in practice by the L2->SM weight stream"
+                                  if args.math == "tf32x3" else "fp32 FFMA (parity path, <=1e-5 rel.)"),
                          "algorithmic_tflops": CONV2_FLOP_PER_ROW * ROWS / (k_ms * 1e-3) / 1e12},
             "wall_s_timed_region": t_wall,
         }

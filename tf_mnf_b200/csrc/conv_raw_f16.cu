@@ -50,9 +50,10 @@ constexpr int BM = 128, BN = 64;
 constexpr int G = 6;                 // K=16 steps per weight stage
 constexpr int STEP_B = 2 * 2 * BN * 16;  // bytes of one K=16 step's weights for one phase: [2 kc][hi 64 n | lo 64 n][8 halves] = 4 KB
 constexpr int B_STAGE = G * STEP_B;  // 24 KB
-constexpr int SB = 3;                // weight ring depth
-constexpr int THREADS = 13 * 32;
-constexpr int PROD_WARPS = 3;      // warps 5-7 fill the planes; warps 8-11 are the second epilogue group
+constexpr int SB = 5;                // weight ring depth
+constexpr int THREADS = 16 * 32;
+constexpr int MAXC = 6;            // plane chunks a producer thread keeps in registers
+constexpr int PROD_WARPS = 6;      // warps 5-7 and 13-15 fill the planes; warps 8-11 are the second epilogue group
 constexpr int TMEM_COLS = 512;  // [2 buffers][2 phases][hi-product 64 | lo-product 64]
 
 struct Args {
@@ -283,28 +284,58 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(Args a) {
     __syncwarp();
   } else {
     // ================================================================== plane producers
-    if (warp < 8) {
-      const int pt = threadIdx.x - 5 * 32;  // 0 .. 95
+    if (warp < 8 || warp > 12) {
+      const int pt = (warp < 8 ? warp - 5 : warp - 10) * 32 + lane;  // 0 .. 191
       constexpr int NP = PROD_WARPS * 32;
-      const int nchunks = a.cpt * pix;       // 16-byte chunks per variant
+      const int nchunks = a.cpt * pix;       // 16-byte chunks per variant (<= MAXC * NP, host-checked)
       const int img_f = a.H * a.W * a.C;     // floats per input image
-      const int img4 = img_f >> 2;           // float4 per image (C % 4 == 0)
+      // this thread's chunks: plane offset, image of the tile, float offset inside the image
+      // (-1: outside the input -> zeros), whether channels 4..7 of the chunk exist
+      int o[MAXC], gsrc[MAXC], imx[MAXC];
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        const int q = pt + c * NP;
+        o[c] = -1; gsrc[c] = -1; imx[c] = 0;
+        if (q < nchunks) {
+          // q enumerates (hi, img, wi, cc), cc fastest: a warp reads consecutive floats
+          const int cc = q % a.cpt;
+          int p = q / a.cpt;
+          const int wi = p % a.Wi;
+          p /= a.Wi;
+          const int im = p % a.I, hi = p / a.I;
+          o[c] = cc * CCS + ((hi * a.I + im) * a.Wi + wi) * 16;
+          imx[c] = im | (cc * 8 + 4 < a.C ? 256 : 0);
+          if (hi < a.H && wi < a.W) gsrc[c] = (hi * a.W + wi) * a.C + cc * 8;
+        }
+      }
       int it = 0;
       for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int64_t b0 = t * a.I;
-        // ---- pass 1: max |x| per image of this tile (the whole image is the tile's input)
+        // ---- one pass over global memory: every chunk of the tile into registers
+        float4 v[MAXC][2];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+          v[c][0] = v[c][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gsrc[c] >= 0) {
+            int64_t b = b0 + (imx[c] & 255);
+            if (b >= a.B) b = a.B - 1;
+            const float* src = a.x + b * img_f + gsrc[c];
+            v[c][0] = __ldg(reinterpret_cast<const float4*>(src));
+            if (imx[c] & 256) v[c][1] = __ldg(reinterpret_cast<const float4*>(src + 4));
+          }
+        }
+        // ---- max |x| per image -> power-of-two scales
         unsigned* xm = xmax + (it & 1) * 16;
         for (int im = 0; im < a.I; ++im) {
-          int64_t b = b0 + im;
-          if (b >= a.B) b = a.B - 1;
-          const float4* src = reinterpret_cast<const float4*>(a.x + b * img_f);
           float m = 0.f;
-          for (int i = pt; i < img4; i += NP) {
-            const float4 v = __ldg(src + i);
-            m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
-          }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          for (int c = 0; c < MAXC; ++c)
+            if (o[c] >= 0 && (imx[c] & 255) == im) {
+              m = fmaxf(m, fmaxf(fmaxf(fabsf(v[c][0].x), fabsf(v[c][0].y)), fmaxf(fabsf(v[c][0].z), fabsf(v[c][0].w))));
+              m = fmaxf(m, fmaxf(fmaxf(fabsf(v[c][1].x), fabsf(v[c][1].y)), fmaxf(fabsf(v[c][1].z), fabsf(v[c][1].w))));
+            }
+#pragma unroll
+          for (int sh = 16; sh > 0; sh >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sh));
           if (lane == 0) atomicMax(xm + im, __float_as_uint(m));
         }
         asm volatile("bar.sync 2, %0;" ::"n"(NP) : "memory");
@@ -323,53 +354,29 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(Args a) {
           xm[pt] = 0u;  // ready for the tile after next (the other buffer is used next)
         }
         asm volatile("bar.sync 2, %0;" ::"n"(NP) : "memory");
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {  // scale in place (exact)
+          const float f = sc[imx[c] & 255];
+          v[c][0].x *= f; v[c][0].y *= f; v[c][0].z *= f; v[c][0].w *= f;
+          v[c][1].x *= f; v[c][1].y *= f; v[c][1].z *= f; v[c][1].w *= f;
+        }
         for (int ph = 0; ph < 2; ++ph) {
           mbar_wait(&pempty[ph], (it & 1) ^ 1);
           uint8_t* dst_hi = planes + (2 * ph) * PLANE;
           uint8_t* dst_lo = dst_hi + PLANE;
-          for (int q0 = pt; q0 < nchunks; q0 += 2 * NP) {
-            // two chunks (four 16-byte loads) in flight per thread, then scale + split + store
-            float4 v[2][2];
-            int o[2];
-            float scl[2];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int q = q0 + u * NP;
-              v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-              o[u] = -1;
-              scl[u] = 1.f;
-              if (q < nchunks) {
-                // q enumerates (hi, img, wi, cc), cc fastest: a warp reads consecutive floats
-                const int cc = q % a.cpt;
-                int p = q / a.cpt;
-                const int wi = p % a.Wi;
-                p /= a.Wi;
-                const int im = p % a.I, hi = p / a.I;
-                int64_t b = b0 + im;
-                if (b >= a.B) b = a.B - 1;
-                if (hi < a.H && wi < a.W) {
-                  const float* src = a.x + b * img_f + (hi * a.W + wi) * a.C + cc * 8;
-                  v[u][0] = __ldg(reinterpret_cast<const float4*>(src));
-                  if (cc * 8 + 4 < a.C) v[u][1] = __ldg(reinterpret_cast<const float4*>(src + 4));
-                }
-                o[u] = cc * CCS + ((hi * a.I + im) * a.Wi + wi) * 16;
-                scl[u] = sc[im];
-              }
+          for (int c = 0; c < MAXC; ++c) {
+            if (o[c] < 0) continue;
+            const float in[8] = {v[c][0].x, v[c][0].y, v[c][0].z, v[c][0].w, v[c][1].x, v[c][1].y, v[c][1].z, v[c][1].w};
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a0 = in[2 * e], a1 = in[2 * e + 1];
+              if (ph == 1) { a0 *= a0; a1 *= a1; }
+              split_f16x2(a0, a1, hw[e], lw[e]);
             }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              if (o[u] < 0) continue;
-              const float in[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
-              uint32_t hw[4], lw[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float a0 = in[2 * e] * scl[u], a1 = in[2 * e + 1] * scl[u];
-                if (ph == 1) { a0 *= a0; a1 *= a1; }
-                split_f16x2(a0, a1, hw[e], lw[e]);
-              }
-              *reinterpret_cast<uint4*>(dst_hi + o[u]) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              *reinterpret_cast<uint4*>(dst_lo + o[u]) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            }
+            *reinterpret_cast<uint4*>(dst_hi + o[c]) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(dst_lo + o[c]) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
           fence_proxy_async();
           __syncwarp();
@@ -509,6 +516,7 @@ int mnf_conv_raw_f16_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, con
     }
   }
   a.steps = (int)tab.size() / 2;
+  if (a.cpt * pixn > MAXC * PROD_WARPS * 32) return MNF_OK;  // the producers hold a whole tile in registers
   const size_t plane_bytes = (size_t)4 * a.cpt * CCS;
   const size_t smem = plane_bytes + (size_t)SB * B_STAGE + sizeof(float) * BM * BN + sizeof(int) * 2 * a.steps +
                       sizeof(float) * ((2 + 16 + 2) * BN + 64 + 32 + 32) + 256;
