@@ -21,6 +21,7 @@
 //   x^2 hi, x^2 lo};  step table, phases, warp roles and the N=128 [W_hi | W_lo] instruction as
 //   in conv_raw_f16.cu.
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include <utility>
 #include <vector>
@@ -35,9 +36,8 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
-      : "memory");
-}
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u));  // no "memory" clobber: volatile orders it against
+}                                                              // the (volatile) barrier waits and commits
 // (a0, a1) -> packed fp16 hi pair and lo pair, a = hi + lo (+ O(2^-22 |a|)), both rounded to nearest
 __device__ __forceinline__ void split_f16x2(float a0, float a1, uint32_t& hi, uint32_t& lo) {
   const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
@@ -50,11 +50,13 @@ constexpr int BM = 128, BN = 64;
 constexpr int G = 6;                 // K=16 steps per weight stage
 constexpr int STEP_B = 2 * 2 * BN * 16;  // bytes of one K=16 step's weights for one phase: [2 kc][hi 64 n | lo 64 n][8 halves] = 4 KB
 constexpr int B_STAGE = G * STEP_B;  // 24 KB
-constexpr int SB = 5;                // weight ring depth
+constexpr int SB = 3;                // weight ring depth
 constexpr int THREADS = 16 * 32;
+constexpr int MAXSTEPS = 64;
+constexpr int TT = 2;              // tiles per pass over the weights (halves the L2 -> SM weight stream)
 constexpr int MAXC = 6;            // plane chunks a producer thread keeps in registers
 constexpr int PROD_WARPS = 6;      // warps 5-7 and 13-15 fill the planes; warps 8-11 are the second epilogue group
-constexpr int TMEM_COLS = 512;  // [2 buffers][2 phases][hi-product 64 | lo-product 64]
+constexpr int TMEM_COLS = 512;  // [2 buffers][TT tiles][2 phases][64], double buffered over passes
 
 struct Args {
   int64_t B;         // images
@@ -74,41 +76,43 @@ struct Args {
   float* mean_out;
   float* sd_out;
   NoiseDev eps;
+  uint64_t dtab[MAXSTEPS];  // A descriptor of every step without the tile base: constant bank -> uniform registers
 };
 
-__global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(Args a) {
+__global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(const __grid_constant__ Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int pix = a.Hi * a.I * a.Wi;          // 16-byte chunks per channel-chunk plane
   const int CCS = pix * 16;                   // bytes between channel chunks
   const int PLANE = a.cpt * CCS;              // bytes of one variant
-  uint8_t* planes = smem;                     // [4][cpt][Hi][I][Wi][16 B]
-  uint8_t* Bs = planes + 4 * PLANE;           // [SB][B_STAGE]
+  uint8_t* planes = smem;                     // [TT][4][cpt][Hi][I][Wi][16 B]
+  uint8_t* Bs = planes + TT * 4 * PLANE;      // [SB][B_STAGE]
   float* ys = (float*)(Bs + SB * B_STAGE);    // [BM][N] dense staging
-  int* stab = (int*)(ys + BM * BN);           // [steps][2]
+  int* stab = (int*)(ys + BM * BN);              // [steps][2]
   float* bias_s = (float*)(stab + 2 * a.steps);  // [2][BN]
   float* zs = bias_s + 2 * BN;                   // [I][BN] z rows of the tile being written out
   float* wsc_s = zs + 16 * BN;                   // [2][BN] inverse weight-column scales
-  float* xsc = wsc_s + 2 * BN;                   // [4][16] inverse input scale per image, ring over tiles
-  float* xsf = xsc + 64;                         // [2][16] forward input scale per image (producers)
-  unsigned* xmax = (unsigned*)(xsf + 32);        // [2][16] max |x| per image (float bits), double buffered
+  float* xsc = wsc_s + 2 * BN;                   // [4 passes][TT][16] inverse input scale per image
+  float* xsf = xsc + 128;                        // [TT][16] forward input scale per image (producers)
+  unsigned* xmax = (unsigned*)(xsf + 32);        // [TT][16] max |x| per image (float bits)
   uint64_t* bars = (uint64_t*)(((uintptr_t)(xmax + 32) + 7) & ~(uintptr_t)7);
-  uint64_t* pfull = bars;        // [2] planes of phase ready
-  uint64_t* pempty = pfull + 2;  // [2]
-  uint64_t* bfull = pempty + 2;  // [SB]
-  uint64_t* bempty = bfull + SB; // [SB]
-  uint64_t* tfull = bempty + SB; // [2]
-  uint64_t* tempty = tfull + 2;  // [2]
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint64_t* pfull = bars;                 // [TT][2] planes of (tile, phase) ready
+  uint64_t* pempty = pfull + 2 * TT;      // [TT][2]
+  uint64_t* bfull = pempty + 2 * TT;      // [SB]
+  uint64_t* bempty = bfull + SB;          // [SB]
+  uint64_t* tfull = bempty + SB;          // [2][TT] both accumulators of a tile complete
+  uint64_t* tempty = tfull + 2 * TT;      // [2][TT]
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2 * TT);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const int HoWo = a.Ho * 8;
   const int64_t ntiles = (a.B + a.I - 1) / a.I;
+  const int64_t npass = (ntiles + TT - 1) / TT;   // a pass = TT tiles sharing one stream of the weights
   const int nstages = (a.steps + G - 1) / G;
 
   if (threadIdx.x == 0) {
-    for (int p = 0; p < 2; ++p) { mbar_init(&pfull[p], PROD_WARPS); mbar_init(&pempty[p], 1); }
+    for (int p = 0; p < 2 * TT; ++p) { mbar_init(&pfull[p], PROD_WARPS); mbar_init(&pempty[p], 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+    for (int b = 0; b < 2 * TT; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(Args a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for the compiler
 
   if (warp < 4 || (warp >= 8 && warp < 12)) {
     // ================================================================== epilogue warps
@@ -138,38 +142,30 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(Args a) {
     const int wo = r & 7, g = r >> 3, img = g % a.I, ho = g / a.I;
     const int rl = img * HoWo + ho * 8 + wo;    // row inside the tile's block of y
     int it = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    for (int64_t ps = blockIdx.x; ps < npass; ps += gridDim.x, ++it)
+    for (int tl = 0; tl < TT; ++tl) {
+      const int64_t t = ps * TT + tl;
       const int64_t b0 = t * a.I, brow = b0 + img;
-      const int buf = it & 1;
       // this tile's z rows -> shared memory (the previous tile's readers passed the closing barrier)
       for (int e = et; e < a.I * BN; e += 256) {
         const int im = e / BN, n = e - im * BN;
         zs[e] = (a.z && b0 + im < a.B && n < a.N) ? __ldg(a.z + (b0 + im) * a.N + n) : 1.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      mbar_wait(&tfull[buf], (it >> 1) & 1);
+      const int buf = it & 1;
+      mbar_wait(&tfull[buf * TT + tl], (it >> 1) & 1);
       tc_fence_after();
       const bool row_ok = brow < a.B;
-      const float sx = xsc[(it & 3) * 16 + img], sx2 = sx * sx;  // written before the planes were released
+      const float sx = xsc[((it & 3) * TT + tl) * 16 + img], sx2 = sx * sx;  // written before the planes were filled
       const uint32_t outer = (uint32_t)(ho * 8 + wo);
       const int64_t m = brow * HoWo + outer;
-      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 4 * BN);
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * TT + tl) * 2 * BN);
 #pragma unroll 1
       for (int c0 = chalf * 32; c0 < chalf * 32 + 32; c0 += 16) {
         if (c0 >= a.N) break;
         float mv[16], vv[16];
-        {
-          float m2[16], v2[16];
-          tmem_ld16(trow + c0, mv);
-          tmem_ld16(trow + BN + c0, m2);
-          tmem_ld16(trow + 2 * BN + c0, vv);
-          tmem_ld16(trow + 3 * BN + c0, v2);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            mv[j] += m2[j];
-            vv[j] += v2[j];
-          }
-        }
+        tmem_ld16(trow + c0, mv);
+        tmem_ld16(trow + BN + c0, vv);
         if (row_ok) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -199,7 +195,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(Args a) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (lane == 0) mbar_arrive(&tempty[buf * TT + tl]);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int64_t nimg = (a.B - b0 < a.I) ? a.B - b0 : a.I;
       const int rows = (int)nimg * HoWo;
@@ -232,33 +228,45 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(Args a) {
     const uint32_t plane0 = smem_u32(planes);
     int it = 0, st = 0;
     uint32_t bph = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    for (int64_t ps = blockIdx.x; ps < npass; ps += gridDim.x, ++it) {
       const int buf = it & 1;
-      mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
       for (int ph = 0; ph < 2; ++ph) {
-        mbar_wait(&pfull[ph], it & 1);
-        tc_fence_after();
-        const uint32_t dacc = tmem_base + (uint32_t)(buf * 4 * BN + ph * 2 * BN);
-        const uint32_t pa_hi = plane0 + (uint32_t)((2 * ph) * PLANE), pa_lo = pa_hi + (uint32_t)PLANE;
         for (int sg = 0; sg < nstages; ++sg) {
-            mbar_wait(&bfull[st], bph);
-          tc_fence_after();
-          if (lane == 0) {
-            const int s1 = min(a.steps, (sg + 1) * G);
-            for (int s = sg * G; s < s1; ++s) {
-              const uint32_t aoff = (uint32_t)stab[2 * s], lbo = (uint32_t)stab[2 * s + 1];
-              const uint64_t ah = make_desc(pa_hi + aoff, lbo, sbo), al = make_desc(pa_lo + aoff, lbo, sbo);
-              const uint64_t bh = bdesc0 + (uint64_t)((st * B_STAGE + (s - sg * G) * STEP_B) >> 4);
-              umma_f16(dacc, ah, bh, idesc2, s == 0 ? 0u : 1u);
-              umma_f16(dacc, al, bh, idesc, 1u);
+          mbar_wait(&bfull[st], bph);
+          for (int tl = 0; tl < TT; ++tl) {
+            if (sg == 0) {
+              if (ph == 0) mbar_wait(&tempty[buf * TT + tl], ((it >> 1) & 1) ^ 1);  // accumulators drained by the epilogue
+              mbar_wait(&pfull[tl * 2 + ph], it & 1);
             }
-            umma_commit(&bempty[st]);
-            if (sg == nstages - 1) {
-              umma_commit(&pempty[ph]);              // planes of this phase may be refilled
-              if (ph == 1) umma_commit(&tfull[buf]);  // both accumulators complete
+            tc_fence_after();
+            {
+              // warp-converged issue (umma.cuh): per MMA only an add of the (tile, phase) base to
+              // the step's pre-built descriptor, in uniform registers
+              const uint32_t dacc = tmem_base + (uint32_t)((buf * TT + tl) * 2 * BN + ph * BN);
+              const uint64_t abase = (uint64_t)((plane0 + (uint32_t)((tl * 4 + 2 * ph) * PLANE)) >> 4);
+              const uint64_t bst = bdesc0 + (uint64_t)((st * B_STAGE) >> 4);
+              const int s0 = sg * G, ns = min(G, a.steps - s0);
+#pragma unroll
+              for (int j = 0; j < G; ++j) {
+                if (j < ns) {
+                  const uint64_t ah = a.dtab[s0 + j] + abase, al = ah + (uint64_t)(PLANE >> 4);
+                  const uint64_t bh = bst + (uint64_t)((j * STEP_B) >> 4);
+                  // three N = 64 instructions into the same 64 columns (with one tile per weight pass
+                  // the [W_hi | W_lo] N = 128 form is cheaper, but it needs twice the TMEM columns
+                  // and two tiles per pass halve the L2 -> SM weight stream)
+                  umma_f16_elect(dacc, ah, bh, idesc, (s0 + j) == 0 ? 0u : 1u);
+                  umma_f16_elect(dacc, al, bh, idesc, 1u);
+                  umma_f16_elect(dacc, ah, bh + (uint64_t)((BN * 16) >> 4), idesc, 1u);
+                }
+              }
+              if (sg == nstages - 1) {
+                umma_commit_elect(&pempty[tl * 2 + ph]);       // planes of this (tile, phase) may be refilled
+                if (ph == 1) umma_commit_elect(&tfull[buf * TT + tl]);    // both accumulators of the tile complete
+              }
+              if (tl == TT - 1) umma_commit_elect(&bempty[st]);
             }
+            __syncwarp();
           }
-          __syncwarp();
           if (++st == SB) { st = 0; bph ^= 1; }
         }
       }
@@ -268,7 +276,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(Args a) {
     if (lane == 0) {
       int st = 0;
       uint32_t bph = 0;
-      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (int64_t ps = blockIdx.x; ps < npass; ps += gridDim.x) {
         for (int ph = 0; ph < 2; ++ph) {
           const float* src0 = a.Bp + (size_t)ph * a.steps * (STEP_B / 4);
           for (int sg = 0; sg < nstages; ++sg) {
@@ -309,79 +317,79 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(Args a) {
         }
       }
       int it = 0;
-      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int64_t b0 = t * a.I;
-        // ---- one pass over global memory: every chunk of the tile into registers
-        float4 v[MAXC][2];
+      for (int64_t ps = blockIdx.x; ps < npass; ps += gridDim.x, ++it) {
+        // order: (tile 0, x) (tile 1, x) (tile 0, x^2) (tile 1, x^2) -- the x planes of BOTH tiles are
+        // released half a pass before the x^2 planes, and the next pass starts with them
+        for (int ph = 0; ph < 2; ++ph)
+          for (int tl = 0; tl < TT; ++tl) {
+            const int64_t b0 = (ps * TT + tl) * a.I;
+            // ---- every chunk of the tile into registers (the second visit hits L2)
+            float4 v[MAXC][2];
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-          v[c][0] = v[c][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (gsrc[c] >= 0) {
-            int64_t b = b0 + (imx[c] & 255);
-            if (b >= a.B) b = a.B - 1;
-            const float* src = a.x + b * img_f + gsrc[c];
-            v[c][0] = __ldg(reinterpret_cast<const float4*>(src));
-            if (imx[c] & 256) v[c][1] = __ldg(reinterpret_cast<const float4*>(src + 4));
-          }
-        }
-        // ---- max |x| per image -> power-of-two scales
-        unsigned* xm = xmax + (it & 1) * 16;
-        for (int im = 0; im < a.I; ++im) {
-          float m = 0.f;
-#pragma unroll
-          for (int c = 0; c < MAXC; ++c)
-            if (o[c] >= 0 && (imx[c] & 255) == im) {
-              m = fmaxf(m, fmaxf(fmaxf(fabsf(v[c][0].x), fabsf(v[c][0].y)), fmaxf(fabsf(v[c][0].z), fabsf(v[c][0].w))));
-              m = fmaxf(m, fmaxf(fmaxf(fabsf(v[c][1].x), fabsf(v[c][1].y)), fmaxf(fabsf(v[c][1].z), fabsf(v[c][1].w))));
+            for (int c = 0; c < MAXC; ++c) {
+              v[c][0] = v[c][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (gsrc[c] >= 0) {
+                int64_t b = b0 + (imx[c] & 255);
+                if (b >= a.B) b = a.B - 1;
+                const float* src = a.x + b * img_f + gsrc[c];
+                v[c][0] = __ldg(reinterpret_cast<const float4*>(src));
+                if (imx[c] & 256) v[c][1] = __ldg(reinterpret_cast<const float4*>(src + 4));
+              }
             }
+            const float* sc = xsf + tl * 16;  // forward scale per image
+            if (ph == 0) {
+              // ---- max |x| per image -> power-of-two scales
+              unsigned* xm = xmax + tl * 16;
+              for (int im = 0; im < a.I; ++im) {
+                float m = 0.f;
 #pragma unroll
-          for (int sh = 16; sh > 0; sh >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sh));
-          if (lane == 0) atomicMax(xm + im, __float_as_uint(m));
-        }
-        asm volatile("bar.sync 2, %0;" ::"n"(NP) : "memory");
-        const float* sc = xsf + (it & 1) * 16;  // forward scale per image
-        if (pt < a.I) {
-          const float m = __uint_as_float(xm[pt]);
-          int e = 0;
-          if (m > 0.f && m < 3.0e38f) {
-            int ex;
-            frexpf(m, &ex);          // m = f * 2^ex, f in [0.5, 1)
-            e = 7 - ex;              // m * 2^e in [2^6, 2^7)
-            e = e > 100 ? 100 : (e < -100 ? -100 : e);
-          }
-          xsf[(it & 1) * 16 + pt] = ldexpf(1.f, e);
-          xsc[(it & 3) * 16 + pt] = ldexpf(1.f, -e);
-          xm[pt] = 0u;  // ready for the tile after next (the other buffer is used next)
-        }
-        asm volatile("bar.sync 2, %0;" ::"n"(NP) : "memory");
+                for (int c = 0; c < MAXC; ++c)
+                  if (o[c] >= 0 && (imx[c] & 255) == im) {
+                    m = fmaxf(m, fmaxf(fmaxf(fabsf(v[c][0].x), fabsf(v[c][0].y)), fmaxf(fabsf(v[c][0].z), fabsf(v[c][0].w))));
+                    m = fmaxf(m, fmaxf(fmaxf(fabsf(v[c][1].x), fabsf(v[c][1].y)), fmaxf(fabsf(v[c][1].z), fabsf(v[c][1].w))));
+                  }
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) {  // scale in place (exact)
-          const float f = sc[imx[c] & 255];
-          v[c][0].x *= f; v[c][0].y *= f; v[c][0].z *= f; v[c][0].w *= f;
-          v[c][1].x *= f; v[c][1].y *= f; v[c][1].z *= f; v[c][1].w *= f;
-        }
-        for (int ph = 0; ph < 2; ++ph) {
-          mbar_wait(&pempty[ph], (it & 1) ^ 1);
-          uint8_t* dst_hi = planes + (2 * ph) * PLANE;
-          uint8_t* dst_lo = dst_hi + PLANE;
-#pragma unroll
-          for (int c = 0; c < MAXC; ++c) {
-            if (o[c] < 0) continue;
-            const float in[8] = {v[c][0].x, v[c][0].y, v[c][0].z, v[c][0].w, v[c][1].x, v[c][1].y, v[c][1].z, v[c][1].w};
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float a0 = in[2 * e], a1 = in[2 * e + 1];
-              if (ph == 1) { a0 *= a0; a1 *= a1; }
-              split_f16x2(a0, a1, hw[e], lw[e]);
+                for (int sh = 16; sh > 0; sh >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sh));
+                if (lane == 0) atomicMax(xm + im, __float_as_uint(m));
+              }
+              asm volatile("bar.sync 2, %0;" ::"n"(NP) : "memory");
+              if (pt < a.I) {
+                const float m = __uint_as_float(xm[pt]);
+                int e = 0;
+                if (m > 0.f && m < 3.0e38f) {
+                  int ex;
+                  frexpf(m, &ex);          // m = f * 2^ex, f in [0.5, 1)
+                  e = 7 - ex;              // m * 2^e in [2^6, 2^7)
+                  e = e > 100 ? 100 : (e < -100 ? -100 : e);
+                }
+                xsf[tl * 16 + pt] = ldexpf(1.f, e);
+                xsc[((it & 3) * TT + tl) * 16 + pt] = ldexpf(1.f, -e);
+                xm[pt] = 0u;  // ready for the next pass
+              }
+              asm volatile("bar.sync 2, %0;" ::"n"(NP) : "memory");
             }
-            *reinterpret_cast<uint4*>(dst_hi + o[c]) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(dst_lo + o[c]) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            mbar_wait(&pempty[tl * 2 + ph], (it & 1) ^ 1);
+            uint8_t* dst_hi = planes + (tl * 4 + 2 * ph) * PLANE;
+            uint8_t* dst_lo = dst_hi + PLANE;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) {
+              if (o[c] < 0) continue;
+              const float f = sc[imx[c] & 255];
+              const float in[8] = {v[c][0].x, v[c][0].y, v[c][0].z, v[c][0].w, v[c][1].x, v[c][1].y, v[c][1].z, v[c][1].w};
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a0 = in[2 * e] * f, a1 = in[2 * e + 1] * f;
+                if (ph == 1) { a0 *= a0; a1 *= a1; }
+                split_f16x2(a0, a1, hw[e], lw[e]);
+              }
+              *reinterpret_cast<uint4*>(dst_hi + o[c]) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(dst_lo + o[c]) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pfull[tl * 2 + ph]);
           }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&pfull[ph]);
-        }
       }
     }
   }
@@ -516,10 +524,14 @@ int mnf_conv_raw_f16_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, con
     }
   }
   a.steps = (int)tab.size() / 2;
+  if (a.steps > MAXSTEPS) return MNF_OK;
+  for (int i = 0; i < a.steps; ++i)  // K-major SWIZZLE_NONE descriptor (umma.cuh:make_desc) with start = step offset
+    a.dtab[i] = (uint64_t)(((uint32_t)tab[2 * i] >> 4) & 0x3FFF) | ((uint64_t)(((uint32_t)tab[2 * i + 1] >> 4) & 0x3FFF) << 16) |
+                ((uint64_t)(((uint32_t)(a.Wi * 16) >> 4) & 0x3FFF) << 32) | (1ull << 46);
   if (a.cpt * pixn > MAXC * PROD_WARPS * 32) return MNF_OK;  // the producers hold a whole tile in registers
-  const size_t plane_bytes = (size_t)4 * a.cpt * CCS;
+  const size_t plane_bytes = (size_t)TT * 4 * a.cpt * CCS;
   const size_t smem = plane_bytes + (size_t)SB * B_STAGE + sizeof(float) * BM * BN + sizeof(int) * 2 * a.steps +
-                      sizeof(float) * ((2 + 16 + 2) * BN + 64 + 32 + 32) + 256;
+                      sizeof(float) * ((2 + 16 + 2) * BN + 128 + 32 + 32) + 256;
   if (smem > 227 * 1024) return MNF_OK;
   // ---- workspace: Bp | vb | wsc | esc | steptab | kmap
   const size_t bp_floats = (size_t)2 * a.steps * (STEP_B / 4);
@@ -547,8 +559,8 @@ int mnf_conv_raw_f16_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, con
     MNF_CUDA(cudaFuncSetAttribute(conv_raw_f16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  const int64_t tiles = cdiv(B, a.I);
-  const int g = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+  const int64_t passes = cdiv(cdiv(B, a.I), (int64_t)TT);
+  const int g = (int)(passes < ctx->sm_count ? passes : ctx->sm_count);
   const bool probed = mnf_probe_begin(ctx, MNF_PROBE_CONV_GEMM);
   conv_raw_f16<<<g, THREADS, smem, ctx->stream>>>(a);
   mnf_probe_end(ctx, probed);
