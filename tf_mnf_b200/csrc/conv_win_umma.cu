@@ -55,6 +55,7 @@ struct Args {
   const float* Bp;     // [2 phases][steps][STEP_B/4 floats]
   float* y;
   NoiseDev eps;
+  uint64_t dA[8];  // A descriptor of every step without the tile base (constant bank -> uniform registers)
 };
 
 // the destination registers are written asynchronously: nothing may touch them before tmem_ld_wait()
@@ -74,9 +75,9 @@ __device__ __forceinline__ void umma_tf32_nc(uint32_t d_tmem, uint64_t adesc, ui
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__global__ void __launch_bounds__(THREADS, 1) conv_win_umma(Args a) {
+__global__ void __launch_bounds__(THREADS, 1) conv_win_umma(const __grid_constant__ Args a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const int PV = a.H * I * a.Wp * 16;  // bytes of one plane variant
   uint8_t* planes = smem;                        // [2][4][PV]
   uint8_t* Bs = planes + 8 * PV;                 // [2 phases][steps][STEP_B]
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_win_umma(Args a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp < EPI_WARPS) {
     // ================================================================== epilogue warps
@@ -245,16 +246,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_win_umma(Args a) {
     // ======================================================================= MMA issuer
     // This warp shares its scheduler with five busy epilogue warps, so the issue loop is kept to
     // a handful of instructions per step: the per-step parts of the descriptors (offset, LBO,
-    // SBO, version) are built once and held in registers; per MMA only the tile base is added.
+    // SBO, version) come pre-built from the constant bank, the warp stays converged (elect inside
+    // the issue wrappers, umma.cuh) and per MMA only the tile base is added -- in uniform registers.
     const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    const uint32_t sbo = (uint32_t)(a.Wp * 16);
-    uint64_t dA[MAXS], dB[MAXS];
-#pragma unroll
-    for (int k = 0; k < MAXS; ++k) {
-      dA[k] = k < a.steps ? make_desc((uint32_t)stab[2 * k], (uint32_t)stab[2 * k + 1], sbo) : 0ull;
-      dB[k] = make_desc(smem_u32(Bs) + (uint32_t)(k * STEP_B), 2 * BN * 16, 128);
-    }
+    const uint64_t dB0 = make_desc(smem_u32(Bs), 2 * BN * 16, 128);
     const uint32_t plane0 = smem_u32(planes) >> 4, pv16 = (uint32_t)PV >> 4;
     const uint32_t bph = (uint32_t)(a.steps * STEP_B) >> 4;  // phase 1 weights follow phase 0
     uint32_t tcount = 0;
@@ -268,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_win_umma(Args a) {
         const int acc = tcount & (NACC - 1);
         mbar_wait(&tempty[acc], ((tcount / NACC) & 1) ^ 1);
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint32_t tbase = plane0 + (uint32_t)(buf * 4) * pv16 + (uint32_t)(hb * 8 * I * a.Wp + wg * 8);
 #pragma unroll
           for (int ph = 0; ph < 2; ++ph) {
@@ -277,15 +273,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_win_umma(Args a) {
 #pragma unroll
             for (int k = 0; k < MAXS; ++k) {
               if (k < a.steps) {
-                const uint64_t ah = dA[k] + abase, al = ah + pv16;
-                const uint64_t bh = dB[k] + (ph ? bph : 0u);
-                umma_tf32_nc(dacc, ah, bh, idesc2, k == 0 ? 0u : 1u);  // x_hi * [W_hi | W_lo]
-                umma_tf32_nc(dacc, al, bh, idesc1, 1u);                // x_lo * W_hi
+                const uint64_t ah = a.dA[k] + abase, al = ah + pv16;
+                const uint64_t bh = dB0 + (uint64_t)((k * STEP_B) >> 4) + (ph ? bph : 0u);
+                umma_tf32_elect(dacc, ah, bh, idesc2, k == 0 ? 0u : 1u);  // x_hi * [W_hi | W_lo]
+                umma_tf32_elect(dacc, al, bh, idesc1, 1u);                // x_lo * W_hi
               }
             }
           }
-          umma_commit(&tfull[acc]);
-          if (tile == ntile - 1) umma_commit(&pempty[buf]);  // this pair's planes may be refilled
+          umma_commit_elect(&tfull[acc]);
+          if (tile == ntile - 1) umma_commit_elect(&pempty[buf]);  // this pair's planes may be refilled
         }
         __syncwarp();
         if (++wg == nwg) { wg = 0; ++hb; }
@@ -424,6 +420,9 @@ int mnf_conv_win_umma_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, co
   }
   a.steps = (int)tab.size() / 2;
   if (a.steps > MAXS) return MNF_OK;
+  for (int i = 0; i < a.steps; ++i)  // K-major SWIZZLE_NONE descriptor (umma.cuh:make_desc) with start = step offset
+    a.dA[i] = (uint64_t)(((uint32_t)tab[2 * i] >> 4) & 0x3FFF) | ((uint64_t)(((uint32_t)tab[2 * i + 1] >> 4) & 0x3FFF) << 16) |
+              ((uint64_t)(((uint32_t)(a.Wp * 16) >> 4) & 0x3FFF) << 32) | (1ull << 46);
   const size_t PV = (size_t)H * I * a.Wp * 16;
   const size_t smem = 8 * PV + (size_t)2 * a.steps * STEP_B + sizeof(int) * 2 * a.steps + sizeof(float) * 2 * BN + 256;
   if (smem > 227 * 1024) return MNF_OK;

@@ -100,6 +100,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Warp-converged issue: all lanes execute, one elected lane performs the operation.  Issued from
+// `if (lane == 0)` the compiler treats every operand as a per-thread value and each tcgen05.mma
+// costs an R2UR chain inside an ELECT / BRA.U.ANY loop (~100 cycles per instruction measured);
+// from converged code with warp-uniform operands the descriptors live in uniform registers.
+__device__ __forceinline__ void umma_tf32_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u));
+}
+__device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
   uint32_t r[16];
   asm volatile(
@@ -147,7 +166,7 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
   float* bias_s = (float*)(tmem_slot + 2);   // [2][BN]: mean_b, var_b of the current n-tile (ntiles == 1 only)
   int* ktab = (int*)(bias_s + 2 * BN);       // conv gather table, one entry per k-chunk (vec) or per k
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const int64_t mtiles = (a.M + BM - 1) / BM;
   const int64_t ntot = mtiles * a.ntiles;
 
@@ -173,7 +192,7 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   // im2col table: offset of k (or of the 4-channel chunk starting at k) relative to the row's
   // patch origin, tap (i,j) in the high bits; -1 = beyond K (zero fill)
   if (CONV) {
@@ -301,7 +320,7 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
       for (int kb = 0; kb < a.kblocks; ++kb) {
         mbar_wait(&full[stage], sph);
         tc_fence_after();
-        if (lane == 0) {
+        {
           // descriptors differ only in their 14-bit start-address field: add offsets to a base
           const uint64_t ad = adesc0 + (uint64_t)((stage * A_STAGE_BYTES) >> 4);
           const uint64_t bd = bdesc0 + (uint64_t)((stage * B_STAGE_BYTES) >> 4);
@@ -313,15 +332,15 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
             const uint64_t wh = bo, wl = bo + (B_VARIANT_BYTES >> 4), vh = bo + (2 * B_VARIANT_BYTES >> 4),
                            vl = bo + (3 * B_VARIANT_BYTES >> 4);
             const uint32_t first = (kb == 0 && j == 0) ? 0u : 1u;
-            umma_tf32(d_mean, xh, wh, idesc, first);
-            umma_tf32(d_mean, xl, wh, idesc, 1u);
-            umma_tf32(d_mean, xh, wl, idesc, 1u);
-            umma_tf32(d_var, qh, vh, idesc, first);
-            umma_tf32(d_var, ql, vh, idesc, 1u);
-            umma_tf32(d_var, qh, vl, idesc, 1u);
+            umma_tf32_e(d_mean, xh, wh, idesc, first);
+            umma_tf32_e(d_mean, xl, wh, idesc, 1u);
+            umma_tf32_e(d_mean, xh, wl, idesc, 1u);
+            umma_tf32_e(d_var, qh, vh, idesc, first);
+            umma_tf32_e(d_var, ql, vh, idesc, 1u);
+            umma_tf32_e(d_var, qh, vl, idesc, 1u);
           }
-          umma_commit(&empty[stage]);                            // smem stage free once these MMAs retire
-          if (kb == a.kblocks - 1) umma_commit(&tfull[buf]);     // accumulators ready
+          umma_commit_e(&empty[stage]);                          // smem stage free once these MMAs retire
+          if (kb == a.kblocks - 1) umma_commit_e(&tfull[buf]);   // accumulators ready
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; sph ^= 1; }
