@@ -98,6 +98,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
       : "memory");
 }
+// Warp-converged issue (see umma.cuh): all lanes execute, one elected lane performs the operation,
+// so that warp-uniform descriptors stay in uniform registers instead of per-thread R2UR chains.
+__device__ __forceinline__ void umma_tf32_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u));
+}
+__device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -185,7 +202,7 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
   float* bias_s = (float*)(tmem_slot + 2);                       // [2][chunks*32]: bs | bt
   uint16_t* mbits = (uint16_t*)(bias_s + 2 * a.chunks * CN);     // [BM][kblocks] RNVP mask bits of each 16-col block
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const int64_t row0 = (int64_t)blockIdx.x * BM;
   const int D = a.D;
 
@@ -206,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t t_acc1 = tmem_base, t_acc2 = tmem_base + 64;  // acc2 buffers at +64, +128
   for (int c = threadIdx.x; c < a.chunks * CN; c += THREADS) {
     bias_s[c] = c < a.D ? a.bs[c] : 0.f;
@@ -364,18 +381,18 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
     for (int kb = 0; kb < a.kblocks; ++kb) {
       mbar_wait(&full1[stage], sph);
       tc_fence_after();
-      if (lane == 0) {
+      {
         const uint64_t ad = a1d + (uint64_t)((stage * A1_STAGE) >> 4), bd = b1d + (uint64_t)((stage * B1_STAGE) >> 4);
 #pragma unroll
         for (int j = 0; j < BK / 8; ++j) {
           const uint64_t ah = ad + (uint64_t)((2 * j * BM * 16) >> 4), al = ah + (A1_VAR >> 4);
           const uint64_t bh = bd + (uint64_t)((2 * j * HP * 16) >> 4), bl = bh + (B1_VAR >> 4);
-          umma_tf32(t_acc1, ah, bh, idesc, (kb == 0 && j == 0) ? 0u : 1u);
-          umma_tf32(t_acc1, al, bh, idesc, 1u);
-          umma_tf32(t_acc1, ah, bl, idesc, 1u);
+          umma_tf32_e(t_acc1, ah, bh, idesc, (kb == 0 && j == 0) ? 0u : 1u);
+          umma_tf32_e(t_acc1, al, bh, idesc, 1u);
+          umma_tf32_e(t_acc1, ah, bl, idesc, 1u);
         }
-        umma_commit(&empty1[stage]);
-        if (kb == a.kblocks - 1) umma_commit(acc1_full);
+        umma_commit_e(&empty1[stage]);
+        if (kb == a.kblocks - 1) umma_commit_e(acc1_full);
       }
       __syncwarp();
       if (++stage == S1) { stage = 0; sph ^= 1; }
@@ -391,19 +408,19 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
       mbar_wait(&aempty[buf], ((c >> 1) & 1) ^ 1);
       mbar_wait(&full2[s2], p2);
       tc_fence_after();
-      if (lane == 0) {
+      {
         const uint64_t bd = b2d + (uint64_t)((s2 * B2_STAGE) >> 4);
         const uint32_t dacc = t_acc2 + buf * 64;
 #pragma unroll
         for (int j = 0; j < HP / 8; ++j) {
           const uint64_t ah = hd + (uint64_t)((2 * j * BM * 16) >> 4), al = ah + (H_VAR >> 4);
           const uint64_t bh = bd + (uint64_t)((2 * j * 64 * 16) >> 4), bl = bh + (B2_VAR >> 4);
-          umma_tf32(dacc, ah, bh, idesc, j == 0 ? 0u : 1u);
-          umma_tf32(dacc, al, bh, idesc, 1u);
-          umma_tf32(dacc, ah, bl, idesc, 1u);
+          umma_tf32_e(dacc, ah, bh, idesc, j == 0 ? 0u : 1u);
+          umma_tf32_e(dacc, al, bh, idesc, 1u);
+          umma_tf32_e(dacc, ah, bl, idesc, 1u);
         }
-        umma_commit(&empty2[s2]);
-        umma_commit(&afull[buf]);
+        umma_commit_e(&empty2[s2]);
+        umma_commit_e(&afull[buf]);
       }
       __syncwarp();
       if (++s2 == S2) { s2 = 0; p2 ^= 1; }
