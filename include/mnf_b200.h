@@ -132,7 +132,10 @@ typedef struct {
  * replaces tf.random.normal (mnf_dense.py:94,141,167; mnf_conv.py:106,156,165,194). */
 int mnf_philox_normal(mnf_ctx* ctx, uint64_t seed, uint32_t stream, uint64_t row_offset,
                       int64_t rows, int64_t outer, int64_t inner, float* out);
-/* keras.backend.random_binomial(shape, p=0.5) (rnvp.py:36): 1.0f where uniform <= p. */
+/* keras.backend.random_binomial(shape, p=0.5) (rnvp.py:36).  p == 0.5 (the RNVP mask) costs one
+ * Philox BIT per element: element d of a row is bit (d & 31) of word ((d >> 5) & 3) of the block
+ * with counter (d >> 7, 0, row, stream), and the draw is 1.0f when that bit is clear.  Any other
+ * p spends one word per element: 1.0f where u01(word (d & 3) of block d >> 2) <= p. */
 int mnf_philox_bernoulli(mnf_ctx* ctx, uint64_t seed, uint32_t stream, uint64_t row_offset,
                          int64_t rows, int64_t inner, float p, float* out);
 /* raw 32-bit Philox words, for the bit-exact check against the oracle's integer Philox */

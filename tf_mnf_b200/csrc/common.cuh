@@ -186,12 +186,22 @@ __device__ __forceinline__ float noise_normal1(const NoiseDev& n, int64_t lrow, 
   return v[inner & 3];
 }
 
+// Fair coins (p == 0.5, the RNVP mask) cost one BIT each: element d of a row is bit (d & 31) of
+// word ((d >> 5) & 3) of the Philox block with inner counter d >> 7, and the draw is 1.0 when
+// the bit is clear -- 128 draws per Philox call.  Any other p spends one word per element
+// (u01(word) <= p, inner counter d >> 2).  include/mnf_b200.h documents both.
+__device__ __forceinline__ uint32_t philox_word(const Philox4& q, uint32_t i) {
+  return i == 0 ? q.x : i == 1 ? q.y : i == 2 ? q.z : q.w;
+}
+__device__ __forceinline__ float coin_of(const Philox4& q, uint32_t d) {
+  return ((philox_word(q, (d >> 5) & 3u) >> (d & 31u)) & 1u) ? 0.0f : 1.0f;
+}
 __device__ __forceinline__ float noise_bern1(const NoiseDev& n, int64_t lrow, uint32_t inner, int64_t n_inner,
                                              float p) {
   if (n.injected) return n.injected[lrow * n_inner + inner];
+  if (p == 0.5f) return coin_of(philox_at(n, n.row_offset + (uint64_t)lrow, 0u, inner >> 7), inner);
   Philox4 q = philox_at(n, n.row_offset + (uint64_t)lrow, 0u, inner >> 2);
-  uint32_t w = (inner & 3) == 0 ? q.x : (inner & 3) == 1 ? q.y : (inner & 3) == 2 ? q.z : q.w;
-  return u01_open(w) <= p ? 1.0f : 0.0f;
+  return u01_open(philox_word(q, inner & 3u)) <= p ? 1.0f : 0.0f;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

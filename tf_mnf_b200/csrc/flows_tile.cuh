@@ -23,6 +23,12 @@ __device__ __forceinline__ void noise_bern4(const NoiseDev& n, int64_t lrow, uin
     }
     return;
   }
+  if (p == 0.5f) {  // fair coins: one bit per element (common.cuh)
+    const Philox4 c = philox_at(n, n.row_offset + (uint64_t)lrow, 0u, g4 >> 5);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) out[e] = coin_of(c, g4 * 4 + e);
+    return;
+  }
   Philox4 q = philox_at(n, n.row_offset + (uint64_t)lrow, 0u, g4);
   out[0] = u01_open(q.x) <= p ? 1.f : 0.f;
   out[1] = u01_open(q.y) <= p ? 1.f : 0.f;

@@ -165,20 +165,27 @@ __device__ __forceinline__ void load_z4(const Args& a, int64_t row, int g4, floa
 #pragma unroll
   for (int e = 0; e < 4; ++e) out[e] = d + e < D ? a.q0_mean[d + e] + expf(0.5f * a.q0_log_var[d + e]) * nrm[e] : 0.f;
 }
-__device__ __forceinline__ void bern4(const NoiseDev& n, int64_t lrow, uint32_t g4, int n_inner, float out[4]) {
+// RNVP mask of the 16 elements of k-block kb of one row: bit e set = element kept.  Fair coins
+// are one bit each (common.cuh: 128 per Philox block), so a thread re-runs Philox only when its
+// k-blocks cross a 128-element boundary; `cache_blk` / `cache` carry the block between calls.
+__device__ __forceinline__ uint32_t mask16(const NoiseDev& n, int64_t lrow, int kb, int n_inner, uint32_t& cache_blk,
+                                           Philox4& cache) {
   if (n.injected) {
+    uint32_t bits = 0;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int d = (int)(g4 * 4 + e);
-      out[e] = d < n_inner ? n.injected[lrow * n_inner + d] : 0.f;
+    for (int e = 0; e < 16; ++e) {
+      const int d = kb * 16 + e;
+      if (d < n_inner && n.injected[lrow * n_inner + d] != 0.f) bits |= 1u << e;
     }
-    return;
+    return bits;
   }
-  const Philox4 q = philox_at(n, n.row_offset + (uint64_t)lrow, 0u, g4);
-  out[0] = u01_open(q.x) <= 0.5f ? 1.f : 0.f;
-  out[1] = u01_open(q.y) <= 0.5f ? 1.f : 0.f;
-  out[2] = u01_open(q.z) <= 0.5f ? 1.f : 0.f;
-  out[3] = u01_open(q.w) <= 0.5f ? 1.f : 0.f;
+  const uint32_t blk = (uint32_t)kb >> 3;
+  if (blk != cache_blk) {
+    cache = philox_at(n, n.row_offset + (uint64_t)lrow, 0u, blk);
+    cache_blk = blk;
+  }
+  const uint32_t w = philox_word(cache, ((uint32_t)kb >> 1) & 3u);
+  return ~(w >> (((uint32_t)kb & 1u) * 16u)) & 0xFFFFu;  // draw = 1 when the bit is clear
 }
 
 __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
@@ -242,6 +249,8 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
     const bool row_ok = row < a.B;
     if (!row_ok) row = a.B - 1;
     float cur[16], nxt[16];
+    uint32_t cblk = 0xFFFFFFFFu;  // fair-coin cache (mask16)
+    Philox4 cq = {0u, 0u, 0u, 0u};
     auto gather = [&](int kb, float v[16]) {
       uint32_t bits = 0;
 #pragma unroll
@@ -254,19 +263,16 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
             for (int e = 0; e < 4; ++e)
               if (g4 * 4 + e < D) a.z0_out[row * D + g4 * 4 + e] = v[kc * 4 + e];
           }
-          if (a.kind == MNF_FLOW_RNVP) {
-            float m[4];
-            bern4(a.bern, row, (uint32_t)g4, D, m);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              v[kc * 4 + e] *= m[e];
-              bits |= (m[e] != 0.f ? 1u : 0u) << (kc * 4 + e);
-            }
-          }
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[kc * 4 + e] = 0.f;
         }
+      }
+      if (a.kind == MNF_FLOW_RNVP) {
+        bits = mask16(a.bern, row, kb, D, cblk, cq);
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (!((bits >> e) & 1u)) v[e] = 0.f;
       }
       if (a.kind == MNF_FLOW_RNVP) mbits[r * a.kblocks + kb] = (uint16_t)bits;  // re-used by the stage-2 epilogue
     };
@@ -326,20 +332,10 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
         if (kb + RAW < a.kblocks) issue(kb + RAW);  // same slot, already copied to registers
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (a.kind == MNF_FLOW_RNVP) {
-          uint32_t bits = 0;
+          const uint32_t bits = mask16(a.bern, row, kb, D, cblk, cq);
 #pragma unroll
-          for (int kc = 0; kc < KC; ++kc) {
-            const int g4 = kb * KC + kc;
-            if (g4 * 4 < D) {
-              float m[4];
-              bern4(a.bern, row, (uint32_t)g4, D, m);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                cur[kc * 4 + e] *= m[e];
-                bits |= (m[e] != 0.f ? 1u : 0u) << (kc * 4 + e);
-              }
-            }
-          }
+          for (int e = 0; e < 16; ++e)
+            if (!((bits >> e) & 1u)) cur[e] = 0.f;
           mbits[r * a.kblocks + kb] = (uint16_t)bits;
         }
         publish(kb, cur);
