@@ -225,8 +225,8 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
             c.wait(ctx)
         if os.environ.get("MNF_BENCH_NOKL"):  # diagnostic only: how much the KL streams cost the forward
             return model(x), None
-        kl = model.kl_div(ctx=kl_lanes)
-        probs = model(x)
+        probs = model(x)                 # the x-dependent chain is enqueued first: it is the critical path
+        kl = model.kl_div(ctx=kl_lanes)  # lanes were forked above, so this still starts at the step's start
         ctx.wait(kl_ctx)
         return probs, kl
 
@@ -333,43 +333,70 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     print(f"[rank {rank}] step_ms={np.round(step_ms, 3).tolist()} conv2_ms={np.round(kern_ms, 3).tolist()} "
           f"wall_per_step_ms={t_wall / args.steps * 1e3:.3f}", file=sys.stderr, flush=True)
 
-    # ---- e2e: host (pinned) input -> public API -> host result, copies inside the timed region
-    hp = C.c_void_p()
-    L.check(lib.mnf_host_alloc(x_host.nbytes, C.byref(hp)))
-    C.memmove(hp.value, x_host.ctypes.data, x_host.nbytes)
+    # ---- e2e: host (pinned) input -> public API -> host result, copies inside the timed region.
+    # The call a user makes for this workload is model.mc_predict(images, n_samples): the 10
+    # distinct images cross PCIe and are repeated on the device (the reference's notebooks call the
+    # model n_samples times on one resident batch).  The same step fed with the already-repeated
+    # 10240-row batch from the host (32 MB over PCIe per step) is timed too and reported beside it.
     res_host = C.c_void_p()
     L.check(lib.mnf_host_alloc(ROWS * 10 * 4 + 16, C.byref(res_host)))
-    x_in = ctx.empty(x_host.shape)
 
-    def e2e_step():
-        L.check(lib.mnf_memcpy_h2d(ctx.handle, C.c_void_p(x_in.ptr), hp, x_host.nbytes))
-        probs, kl = step(x_in)
+    def host_buf(arr):
+        hp_ = C.c_void_p()
+        L.check(lib.mnf_host_alloc(arr.nbytes, C.byref(hp_)))
+        C.memmove(hp_.value, arr.ctypes.data, arr.nbytes)
+        return hp_
+
+    hp_img, hp_full = host_buf(imgs), host_buf(x_host)
+    img_in, x_in = ctx.empty(imgs.shape), ctx.empty(x_host.shape)
+
+    def finish(probs, kl):
         L.check(lib.mnf_memcpy_d2h(ctx.handle, res_host, C.c_void_p(probs.ptr), probs.nbytes))
         L.check(lib.mnf_memcpy_d2h(ctx.handle, C.c_void_p(res_host.value + probs.nbytes), C.c_void_p(kl.ptr), 4))
         ctx.sync()
-        kl_ctx.sync()
+        for c in kl_lanes:
+            c.sync()
 
-    e2e_step()
-    barrier()
-    e_ms = []
-    for _ in range(args.steps):
-        L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
-        ctx.sync()
-        a, b = ev(), ev()
-        L.check(lib.mnf_event_record(ctx.handle, a))
-        e2e_step()
-        L.check(lib.mnf_event_record(ctx.handle, b))
-        e_ms.append(elapsed(a, b))
-    barrier()
-    my_e2e = float(np.mean(e_ms))
+    def e2e_mc():
+        L.check(lib.mnf_memcpy_h2d(ctx.handle, C.c_void_p(img_in.ptr), hp_img, imgs.nbytes))
+        for c in kl_lanes:
+            c.wait(ctx)
+        probs = model.mc_predict(img_in, N_SAMPLES)
+        kl = model.kl_div(ctx=kl_lanes)
+        ctx.wait(kl_ctx)
+        finish(probs, kl)
+
+    def e2e_tiled():
+        L.check(lib.mnf_memcpy_h2d(ctx.handle, C.c_void_p(x_in.ptr), hp_full, x_host.nbytes))
+        probs, kl = step(x_in)
+        finish(probs, kl)
+
+    def time_e2e(fn):
+        fn()
+        barrier()
+        out_ms = []
+        for _ in range(args.steps):
+            L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
+            ctx.sync()
+            a, b = ev(), ev()
+            L.check(lib.mnf_event_record(ctx.handle, a))
+            fn()
+            L.check(lib.mnf_event_record(ctx.handle, b))
+            ctx.sync()
+            out_ms.append(elapsed(a, b))
+        barrier()
+        return float(np.mean(out_ms))
+
+    my_e2e = time_e2e(e2e_mc)
+    my_e2e_tiled = time_e2e(e2e_tiled)
 
     # ---- max over ranks
     if dist is not None:
-        t = torch.tensor([my_ms, my_e2e, float(np.mean(kern_ms))], device="cuda")
+        t = torch.tensor([my_ms, my_e2e, float(np.mean(kern_ms)), my_e2e_tiled], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, k_ms = (float(v) for v in t.tolist())
+        ms, e2e_ms, k_ms, e2e_tiled_ms = (float(v) for v in t.tolist())
     else:
-        ms, e2e_ms, k_ms = my_ms, my_e2e, float(np.mean(kern_ms))
+        ms, e2e_ms, k_ms, e2e_tiled_ms = my_ms, my_e2e, float(np.mean(kern_ms)), my_e2e_tiled
 
     if rank == 0:
         hbm, which = peaks()
@@ -380,8 +407,14 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args),
-            "e2e": {"value": ROWS * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
-                    "d2h_bytes_per_step": ROWS * 10 * 4 + 4, "ms_per_step": e2e_ms},
+            "e2e": {"value": ROWS * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(imgs.nbytes),
+                    "d2h_bytes_per_step": ROWS * 10 * 4 + 4, "ms_per_step": e2e_ms,
+                    "api": "model.kl_div() + model.mc_predict(images[10,28,28,1] from pinned host memory, 1024): the "
+                           "distinct images cross PCIe and are repeated on the device; probabilities [10240,10] and "
+                           "the KL scalar are read back every step",
+                    "host_repeated_batch": {"value": ROWS * world / (e2e_tiled_ms * 1e-3), "ms_per_step": e2e_tiled_ms,
+                                            "h2d_bytes_per_step": int(x_host.nbytes),
+                                            "note": "same step fed with the 10240-row repeated batch from the host"}},
             "gpu_launches": int(launches),
             "clocks": clk.summary(t_wall0, t_wall1),
             "roofline": {"bound": "hbm",

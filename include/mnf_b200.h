@@ -282,6 +282,10 @@ int mnf_mse_loss(mnf_ctx* ctx, int64_t n, const float* y, const float* target, f
 /* y = a*x + b (inference-mode BatchNormalization in MNFFeedForward), generic axpby helpers */
 int mnf_scale(mnf_ctx* ctx, int64_t n, float a, const float* x, float* y);
 int mnf_axpy(mnf_ctx* ctx, int64_t n, float a, const float* x, float* y); /* y += a*x */
+/* dst[(i * repeat + s) * row_elems + e] = src[i * row_elems + e]: the batch of a Monte-Carlo
+ * prediction (every input row `repeat` times, np.repeat(x, repeat, axis=0)) formed on the
+ * device, so only the distinct rows cross PCIe. */
+int mnf_tile_rows(mnf_ctx* ctx, int64_t n_rows, int64_t row_elems, int64_t repeat, const float* src, float* dst);
 /* Adam update on a flat parameter buffer (lenet_mnist.py:47,115). */
 int mnf_adam_step(mnf_ctx* ctx, int64_t n, float* param, const float* grad, float* m, float* v,
                   float lr, float beta1, float beta2, float eps, int32_t step);

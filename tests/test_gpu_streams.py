@@ -70,3 +70,30 @@ def test_kl_on_forked_context_matches_inline():
     side.sync()
     k2 = m2.kl_div()
     assert float(k1.numpy()[0]) == float(k2.numpy()[0])
+
+
+def test_tile_rows_and_mc_predict_match_host_repeat():
+    """mnf_tile_rows == np.repeat(x, n, axis=0); model.mc_predict(x, n) == model(np.repeat(x, n))
+    bit for bit (same rows -> same Philox counters)."""
+    import ctypes as C
+
+    import tf_mnf_b200 as M
+    from tf_mnf_b200 import _lib as L
+
+    ctx = M.default_context()
+    rng = np.random.RandomState(4)
+    for shape, n in (((5, 7), 3), ((3, 4, 4, 1), 6), ((2, 8), 1)):
+        x = rng.standard_normal(shape).astype(np.float32)
+        xd = ctx.to_device(x)
+        out = ctx.empty((shape[0] * n, *shape[1:]))
+        L.check(ctx.lib.mnf_tile_rows(ctx.handle, shape[0], x.size // shape[0], n, C.c_void_p(xd.ptr), C.c_void_p(out.ptr)))
+        np.testing.assert_array_equal(out.numpy(), np.repeat(x, n, axis=0))
+    imgs = rng.uniform(size=(3, 28, 28, 1)).astype(np.float32)
+    m1 = _lenet()
+    m1(imgs)
+    y1 = m1.mc_predict(imgs, 8).numpy()
+    m2 = _lenet()
+    m2(imgs)
+    y2 = m2(np.repeat(imgs, 8, axis=0)).numpy()
+    np.testing.assert_array_equal(y1, y2)
+    assert y1.shape == (24, 10) and not np.array_equal(y1[0], y1[1])  # same image, different posterior draws

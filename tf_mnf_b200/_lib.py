@@ -114,6 +114,7 @@ SIGNATURES = {
     "mnf_mse_loss": [vp, _i64, vp, vp, _f, vp, vp],
     "mnf_scale": [vp, _i64, _f, vp, vp],
     "mnf_axpy": [vp, _i64, _f, vp, vp],
+    "mnf_tile_rows": [vp, _i64, _i64, _i64, vp, vp],
     "mnf_adam_step": [vp, _i64, vp, vp, vp, vp, _f, _f, _f, _f, _i32],
 }
 NON_STATUS = {"mnf_version": ([], C.c_int), "mnf_last_error": ([], C.c_char_p)}

@@ -220,6 +220,35 @@ int mnf_scale(mnf_ctx* ctx, int64_t n, float a, const float* x, float* y) {
   return MNF_OK;
 }
 
+__global__ void tile_rows_kernel(int64_t total4, int64_t row4, int64_t repeat, const float4* __restrict__ src,
+                                 float4* __restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t orow = i / row4, e = i - orow * row4;
+    dst[i] = __ldg(src + (orow / repeat) * row4 + e);
+  }
+}
+__global__ void tile_rows_kernel1(int64_t total, int64_t row, int64_t repeat, const float* __restrict__ src,
+                                  float* __restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t orow = i / row, e = i - orow * row;
+    dst[i] = __ldg(src + (orow / repeat) * row + e);
+  }
+}
+
+int mnf_tile_rows(mnf_ctx* ctx, int64_t n_rows, int64_t row_elems, int64_t repeat, const float* src, float* dst) {
+  MNF_CHECK_ARG(ctx && n_rows >= 0 && row_elems >= 0 && repeat >= 1, "mnf_tile_rows: bad argument");
+  const int64_t total = n_rows * repeat * row_elems;
+  if (total == 0) return MNF_OK;
+  MNF_CHECK_ARG(src && dst, "mnf_tile_rows: null buffer");
+  if ((row_elems & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0)
+    tile_rows_kernel<<<ew_grid(ctx, total / 4), 256, 0, ctx->stream>>>(total / 4, row_elems / 4, repeat,
+                                                                         (const float4*)src, (float4*)dst);
+  else
+    tile_rows_kernel1<<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(total, row_elems, repeat, src, dst);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
 int mnf_axpy(mnf_ctx* ctx, int64_t n, float a, const float* x, float* y) {
   MNF_CHECK_ARG(ctx && (n == 0 || (x && y)) && n >= 0, "mnf_axpy: bad argument");
   if (n == 0) return MNF_OK;

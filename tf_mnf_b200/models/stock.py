@@ -138,6 +138,20 @@ class Sequential:
                 x = lyr(x)
         return x
 
+    def mc_predict(self, x: Any, n_samples: int) -> DeviceArray:
+        """Monte-Carlo predictive: every input row under `n_samples` independent posterior draws
+        (what the reference's notebooks do by calling the model n_samples times on one batch).
+        The repeated batch np.repeat(x, n_samples, axis=0) is formed on the device, so only the
+        distinct rows cross PCIe; returns [len(x) * n_samples, ...] in that row order."""
+        x = as_device(x, default_context())
+        n = int(n_samples)
+        if n < 1:
+            raise ValueError("n_samples must be >= 1")
+        rows = x.shape[0]
+        tiled = x.ctx.empty((rows * n, *x.shape[1:]))
+        L.check(x.ctx.lib.mnf_tile_rows(x.ctx.handle, rows, x.size // max(rows, 1), n, _p(x), _p(tiled)))
+        return self(tiled)
+
     def kl_div(self, noise: list | None = None, ctx: Any = None) -> DeviceArray:  # noqa: A002
         """Sum of the layers' KL terms (mnf_lenet.py:35-39, mnf_feed_forward.py:23-28).
         `ctx`: optional sibling context (Context.fork()), or a list of them, so the KL runs beside

@@ -31,14 +31,35 @@ class Context:
         L.check(self.lib.mnf_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
         self.handle = h
         self.device = device
+        # Host-side free list of stream-ordered allocations, by size.  A block released by Python
+        # and handed out again is only ever touched by LATER work of this context's stream, which
+        # is exactly the guarantee of cudaFreeAsync + cudaMallocAsync on one stream -- without
+        # the two library calls per temporary (a forward + KL step makes ~40 of them).
+        self._pool: dict[int, list[int]] = {}
+        self._pooled_bytes = 0
+        self.pool_limit_bytes = 2 << 30
 
     # -- memory
     def empty(self, shape: Sequence[int], dtype: str = "f4") -> "DeviceArray":
         shape = tuple(int(s) for s in shape)
-        nbytes = math.prod(shape) * _ITEMSIZE[dtype]
-        p = C.c_void_p()
-        L.check(self.lib.mnf_malloc(self.handle, nbytes, C.byref(p)))
-        return DeviceArray(self, p.value, shape, dtype, owner=_Owned(self, p.value))
+        nbytes = (math.prod(shape) * _ITEMSIZE[dtype] + 255) & ~255
+        free = self._pool.get(nbytes)
+        if free:
+            ptr = free.pop()
+            self._pooled_bytes -= nbytes
+        else:
+            p = C.c_void_p()
+            L.check(self.lib.mnf_malloc(self.handle, nbytes, C.byref(p)))
+            ptr = p.value
+        return DeviceArray(self, ptr, shape, dtype, owner=_Owned(self, ptr, nbytes))
+
+    def trim(self) -> None:
+        """Return the pooled blocks to the driver's stream-ordered pool."""
+        for free in self._pool.values():
+            for ptr in free:
+                self.lib.mnf_free(self.handle, C.c_void_p(ptr))
+        self._pool.clear()
+        self._pooled_bytes = 0
 
     def zeros(self, shape: Sequence[int], dtype: str = "f4") -> "DeviceArray":
         a = self.empty(shape, dtype)
@@ -99,6 +120,7 @@ class Context:
 
     def close(self) -> None:
         if getattr(self, "handle", None):
+            self.trim()
             self.lib.mnf_ctx_destroy(self.handle)
             self.handle = None
 
@@ -106,13 +128,21 @@ class Context:
 class _Owned:
     """Frees a stream-ordered allocation when the last view dies."""
 
-    def __init__(self, ctx: Context, ptr: int) -> None:
-        self.ctx, self.ptr = ctx, ptr
+    __slots__ = ("ctx", "ptr", "nbytes")
+
+    def __init__(self, ctx: Context, ptr: int, nbytes: int = 0) -> None:
+        self.ctx, self.ptr, self.nbytes = ctx, ptr, nbytes
 
     def __del__(self) -> None:
         try:
-            if self.ctx.handle:
-                self.ctx.lib.mnf_free(self.ctx.handle, C.c_void_p(self.ptr))
+            ctx = self.ctx
+            if ctx.handle:
+                n = self.nbytes
+                if n and ctx._pooled_bytes + n <= ctx.pool_limit_bytes:
+                    ctx._pool.setdefault(n, []).append(self.ptr)
+                    ctx._pooled_bytes += n
+                else:
+                    ctx.lib.mnf_free(ctx.handle, C.c_void_p(self.ptr))
         except Exception:  # interpreter shutdown
             pass
 
