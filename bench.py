@@ -180,6 +180,7 @@ def workload_config(args, rows_per_step=ROWS) -> dict:
             "rows_per_gpu": rows_per_step, "flow_type": args.flow, "n_flows_q": 2, "n_flows_r": 2, "flow_h_sizes": [50],
             "std_init": 10.0, "max_std": 1.0, "noise": "in-kernel Philox4x32-10", "l2": "flushed between timed steps "
             "(256 MiB memset outside the per-step event pairs)",
+            "weights": "frozen (Sequential.freeze_weights): packed / pre-split weight blocks are kept across steps",
             "streams": "KL terms on 4 sibling streams and the z chains of layers 2-4 on 3 side streams, all forked from "
                        "the step's stream after its start event and joined before its stop event",
             "parallelism": f"row-sharded x{args.gpus}, no collective"}
@@ -219,6 +220,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     kl_lanes = [ctx.fork() for _ in range(4)]
     kl_ctx = kl_lanes[0]
     model(x_dev)  # variables are created on the first call (Keras build protocol)
+    model.freeze_weights(True)  # inference: packed weight blocks are built once, not per call
 
     def step(x):
         for c in kl_lanes:

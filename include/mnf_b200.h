@@ -72,6 +72,12 @@ int mnf_ctx_launch_count(mnf_ctx* ctx, int64_t* out);
  *                  fp32 accumulation in TMEM): fp32-level accuracy (<= 1e-5 rel.) on tensor cores */
 enum { MNF_MATH_FP32 = 0, MNF_MATH_TF32X3 = 1 };
 int mnf_ctx_set_math(mnf_ctx* ctx, int mode);
+/* Inference with fixed parameters: while frozen != 0 the packed / pre-split / pre-scaled weight
+ * blocks the tensor-core kernels consume are built once per (weight pointers, shape) and kept in
+ * persistent device buffers instead of being rebuilt on every call.  The caller promises not to
+ * change the parameter buffers while frozen; unfreezing (or freezing again) drops the blocks.
+ * Results are bit-identical either way. */
+int mnf_ctx_freeze_weights(mnf_ctx* ctx, int32_t frozen);
 
 /* Timing probe for bench.py's roofline line: the (skip+1)-th launch of kernel family `kind`
  * (1 conv paired GEMM, 2 dense paired GEMM, 3 flow step, 4 KL; 0 disarms) is bracketed by

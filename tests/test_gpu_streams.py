@@ -97,3 +97,33 @@ def test_tile_rows_and_mc_predict_match_host_repeat():
     y2 = m2(np.repeat(imgs, 8, axis=0)).numpy()
     np.testing.assert_array_equal(y1, y2)
     assert y1.shape == (24, 10) and not np.array_equal(y1[0], y1[1])  # same image, different posterior draws
+
+
+@pytest.mark.parametrize("math", ["tf32x3", "fp32"])
+def test_frozen_weights_are_bit_identical_and_unfreeze_sees_updates(math):
+    """Context.freeze_weights keeps the packed weight blocks across calls: same outputs bit for
+    bit; after unfreezing, a changed parameter is picked up again."""
+    import tf_mnf_b200 as M
+
+    ctx = M.default_context()
+    ctx.set_math(math)
+    try:
+        x = np.random.RandomState(7).uniform(size=(40, 28, 28, 1)).astype(np.float32)
+        ref = _lenet()
+        ys_ref = [ref(x).numpy() for _ in range(3)]
+        mdl = _lenet()
+        mdl(x)                       # call 0 builds the variables
+        mdl.freeze_weights(True)
+        ys = [mdl(x).numpy(), mdl(x).numpy()]
+        np.testing.assert_array_equal(ys[0], ys_ref[1])
+        np.testing.assert_array_equal(ys[1], ys_ref[2])
+        mdl.freeze_weights(False)
+        w = mdl.mnf_layers[2].mean_W
+        w.assign(w.numpy() * 0.5)
+        for lyr in mdl.mnf_layers:
+            lyr.call_index = 1
+        y_new = mdl(x).numpy()
+        assert not np.array_equal(y_new, ys_ref[1])
+    finally:
+        ctx.freeze_weights(False)
+        ctx.set_math("fp32")

@@ -69,6 +69,7 @@ SIGNATURES = {
     "mnf_ctx_sm_count": [vp, C.POINTER(C.c_int)],
     "mnf_ctx_launch_count": [vp, C.POINTER(_i64)],
     "mnf_ctx_set_math": [vp, C.c_int],
+    "mnf_ctx_freeze_weights": [vp, C.c_int32],
     "mnf_ctx_probe": [vp, C.c_int, C.c_int, vp, vp],
     "mnf_malloc": [vp, _sz, C.POINTER(vp)],
     "mnf_free": [vp, vp],

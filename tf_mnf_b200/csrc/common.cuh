@@ -21,6 +21,16 @@ struct mnf_ctx {
   int probe_kind;
   int probe_skip;
   cudaEvent_t probe_start, probe_stop;
+  // frozen weights (mnf_ctx_freeze_weights): packed / pre-split weight blocks are kept in
+  // persistent device buffers keyed by the weight pointers instead of being rebuilt per call
+  bool frozen;
+  struct mnf_packed_entry* packed;
+  int packed_n, packed_cap;
+};
+struct mnf_packed_entry {
+  uint64_t key[4];
+  void* ptr;
+  size_t bytes;
 };
 
 enum { MNF_PROBE_NONE = 0, MNF_PROBE_CONV_GEMM = 1, MNF_PROBE_DENSE_GEMM = 2, MNF_PROBE_FLOW_STEP = 3, MNF_PROBE_KL = 4 };
@@ -64,6 +74,15 @@ int mnf_tc_paired_forward(mnf_ctx* ctx, int conv, int64_t M, int K, int N, const
                           float max_std, const NoiseDev& eps, float* y, float* mean_out, float* sd_out,
                           const int* geo);  // conv geo: H,W,C,kh,kw,Ho,Wo,stride,pad_t,pad_l,pool
 void* mnf_workspace(mnf_ctx* ctx, size_t bytes);  // nullptr on failure (error set)
+// Where a call's packed weights go.  Not frozen: the transient workspace, *fresh = true (pack every
+// call).  Frozen: a persistent block per key; *fresh tells whether it still has to be filled.
+void* mnf_packed(mnf_ctx* ctx, uint64_t k0, uint64_t k1, uint64_t k2, uint64_t k3, size_t bytes, bool* fresh);
+static inline uint32_t __float_as_uint_host(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+static inline uint64_t mnf_mix(uint64_t a, uint64_t b) { return (a ^ (b + 0x9E3779B97F4A7C15ull + (a << 6) + (a >> 2))); }
 
 #define MNF_CHECK_ARG(cond, ...)      \
   do {                                \

@@ -536,7 +536,11 @@ int mnf_conv_raw_f16_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, con
   // ---- workspace: Bp | vb | wsc | esc | steptab | kmap
   const size_t bp_floats = (size_t)2 * a.steps * (STEP_B / 4);
   const size_t ws_bytes = sizeof(float) * (bp_floats + 64 + 2 * BN + 2 * BN) + sizeof(int) * (tab.size() + kmap.size() + 128);
-  char* ws = (char*)mnf_workspace(ctx, ws_bytes);
+  bool fresh = true;
+  char* ws = (char*)mnf_packed(ctx, mnf_mix(0xC0F16ull, mnf_mix(((uint64_t)H << 40) | ((uint64_t)W << 20) | (uint32_t)C,
+                                                               ((uint64_t)kh << 40) | ((uint64_t)kw << 20) | (uint32_t)N)),
+                               (uint64_t)(uintptr_t)mean_W, (uint64_t)(uintptr_t)log_std_W,
+                               mnf_mix((uint64_t)(uintptr_t)log_var_b, (uint64_t)__float_as_uint_host(max_std)), ws_bytes, &fresh);
   if (!ws) return MNF_ERR_CUDA;
   float* Bp = (float*)ws;
   float* vb = Bp + bp_floats;
@@ -544,14 +548,16 @@ int mnf_conv_raw_f16_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, con
   int* esc = (int*)(wsc + 2 * BN);
   int* d_tab = esc + 2 * BN;
   int* d_kmap = d_tab + ((tab.size() + 63) & ~(size_t)63);
-  MNF_CUDA(cudaMemcpyAsync(d_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, ctx->stream));
-  MNF_CUDA(cudaMemcpyAsync(d_kmap, kmap.data(), sizeof(int) * kmap.size(), cudaMemcpyHostToDevice, ctx->stream));
-  f16_colscale<<<dim3(BN, 2), 128, 0, ctx->stream>>>(kh * kw * C, N, mean_W, log_std_W, max_std, esc, wsc, log_var_b, vb);
-  MNF_LAUNCHED(ctx);
-  const int64_t tot = (int64_t)2 * a.steps * 2 * BN * 2;
-  int grid = (int)(cdiv(tot, 256) < ctx->sm_count * 4 ? cdiv(tot, 256) : ctx->sm_count * 4);
-  pack_f16_weights<<<grid, 256, 0, ctx->stream>>>(N, a.steps, d_kmap, mean_W, log_std_W, max_std, esc, (__half*)Bp);
-  MNF_LAUNCHED(ctx);
+  if (fresh) {
+    MNF_CUDA(cudaMemcpyAsync(d_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, ctx->stream));
+    MNF_CUDA(cudaMemcpyAsync(d_kmap, kmap.data(), sizeof(int) * kmap.size(), cudaMemcpyHostToDevice, ctx->stream));
+    f16_colscale<<<dim3(BN, 2), 128, 0, ctx->stream>>>(kh * kw * C, N, mean_W, log_std_W, max_std, esc, wsc, log_var_b, vb);
+    MNF_LAUNCHED(ctx);
+    const int64_t tot = (int64_t)2 * a.steps * 2 * BN * 2;
+    int grid = (int)(cdiv(tot, 256) < ctx->sm_count * 4 ? cdiv(tot, 256) : ctx->sm_count * 4);
+    pack_f16_weights<<<grid, 256, 0, ctx->stream>>>(N, a.steps, d_kmap, mean_W, log_std_W, max_std, esc, (__half*)Bp);
+    MNF_LAUNCHED(ctx);
+  }
   a.x = x; a.z = z; a.bm = mean_b; a.vb = vb; a.steptab = d_tab; a.Bp = Bp; a.wsc = wsc;
   a.y = y; a.mean_out = mean_out; a.sd_out = sd_out; a.eps = eps;
   static size_t attr_smem = 0;

@@ -429,17 +429,22 @@ int mnf_conv_win_umma_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, co
   // ---- workspace: Bp | vb | steptab | kmap
   const size_t bp_floats = (size_t)2 * a.steps * (STEP_B / 4);
   const size_t ws_bytes = sizeof(float) * (bp_floats + N + 64) + sizeof(int) * (tab.size() + kmap.size() + 128);
-  char* ws = (char*)mnf_workspace(ctx, ws_bytes);
+  bool fresh = true;
+  char* ws = (char*)mnf_packed(ctx, mnf_mix(0xC017ull, mnf_mix(((uint64_t)H << 32) | (uint32_t)W, ((uint64_t)kh << 40) | ((uint64_t)kw << 20) | (uint32_t)N)),
+                               (uint64_t)(uintptr_t)mean_W, (uint64_t)(uintptr_t)log_std_W,
+                               mnf_mix((uint64_t)(uintptr_t)log_var_b, (uint64_t)__float_as_uint_host(max_std)), ws_bytes, &fresh);
   if (!ws) return MNF_ERR_CUDA;
   float* Bp = (float*)ws;
   float* vb = Bp + bp_floats;
   int* d_tab = (int*)(vb + ((N + 63) & ~63));
   int* d_kmap = d_tab + ((tab.size() + 63) & ~(size_t)63);
-  MNF_CUDA(cudaMemcpyAsync(d_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, ctx->stream));
-  MNF_CUDA(cudaMemcpyAsync(d_kmap, kmap.data(), sizeof(int) * kmap.size(), cudaMemcpyHostToDevice, ctx->stream));
-  const int tot = 2 * a.steps * 2 * BN * 4;
-  pack_win_weights<<<cdiv(tot, 256), 256, 0, ctx->stream>>>(N, a.steps, d_kmap, mean_W, log_std_W, max_std, Bp, log_var_b, vb);
-  MNF_LAUNCHED(ctx);
+  if (fresh) {
+    MNF_CUDA(cudaMemcpyAsync(d_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, ctx->stream));
+    MNF_CUDA(cudaMemcpyAsync(d_kmap, kmap.data(), sizeof(int) * kmap.size(), cudaMemcpyHostToDevice, ctx->stream));
+    const int tot = 2 * a.steps * 2 * BN * 4;
+    pack_win_weights<<<cdiv(tot, 256), 256, 0, ctx->stream>>>(N, a.steps, d_kmap, mean_W, log_std_W, max_std, Bp, log_var_b, vb);
+    MNF_LAUNCHED(ctx);
+  }
   a.x = x; a.z = z; a.bm = mean_b; a.vb = vb; a.steptab = d_tab; a.Bp = Bp; a.y = y; a.eps = eps;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {

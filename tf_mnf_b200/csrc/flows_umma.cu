@@ -621,14 +621,24 @@ int mnf_flow_umma_step(mnf_ctx* ctx, int64_t B, int D, int H, int kind, int pari
   a.zin = zin; a.q0_mean = q0_mean; a.q0_log_var = q0_log_var; a.eps = eps; a.z0_out = z0_out; a.zout = zout;
   a.ld_in = ld_in; a.ld_out = ld_out; a.hid_save = hid_save;
   a.b1 = st.b1; a.bs = st.bs; a.bt = st.bt; a.bern = bern;
+  bool fresh = true;
+  if (ctx->frozen) {  // frozen weights: one persistent packed block per flow step
+    pack_ws = (float*)mnf_packed(ctx, mnf_mix(0xF10Full, ((uint64_t)D << 32) | (uint32_t)H), (uint64_t)(uintptr_t)st.w1,
+                                 mnf_mix((uint64_t)(uintptr_t)st.ws, (uint64_t)(uintptr_t)st.wt),
+                                 mnf_mix((uint64_t)(uintptr_t)st.m1, mnf_mix((uint64_t)(uintptr_t)st.m2, (uint64_t)st.ld2)),
+                                 sizeof(float) * mnf_flow_umma_pack_floats(D), &fresh);
+    if (!pack_ws) return MNF_ERR_CUDA;
+  }
   float* B1p = pack_ws;
   float* B2p = pack_ws + (size_t)a.kblocks * (B1_STAGE / 4);
   a.B1p = B1p; a.B2p = B2p;
-  const int64_t tot = (int64_t)a.kblocks * KC * HP * 4 + (int64_t)a.chunks * (HP / 4) * 64 * 4;
-  int grid = (int)(cdiv(tot, 256) < ctx->sm_count * 4 ? cdiv(tot, 256) : ctx->sm_count * 4);
-  pack_flow_weights<<<grid, 256, 0, ctx->stream>>>(D, H, a.kblocks, a.chunks, st.w1, st.m1, st.ws, st.wt, st.m2, st.ld2,
-                                                  B1p, B2p);
-  MNF_LAUNCHED(ctx);
+  if (fresh) {
+    const int64_t tot = (int64_t)a.kblocks * KC * HP * 4 + (int64_t)a.chunks * (HP / 4) * 64 * 4;
+    int grid = (int)(cdiv(tot, 256) < ctx->sm_count * 4 ? cdiv(tot, 256) : ctx->sm_count * 4);
+    pack_flow_weights<<<grid, 256, 0, ctx->stream>>>(D, H, a.kblocks, a.chunks, st.w1, st.m1, st.ws, st.wt, st.m2, st.ld2,
+                                                    B1p, B2p);
+    MNF_LAUNCHED(ctx);
+  }
   const size_t smem = (size_t)S2 * B2_STAGE + 2 * H_VAR + sizeof(float) * 2 * BM + 256 +
                       sizeof(float) * 2 * (size_t)a.chunks * CN + sizeof(uint16_t) * (size_t)BM * a.kblocks + 16;
   static size_t attr_smem = 0;

@@ -577,12 +577,16 @@ int mnf_conv2d_forward(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, co
   if (s->B == 0) return MNF_OK;
   const int64_t Kc = s->kh * s->kw * s->C;
   MNF_CHECK_ARG(Kc < (1 << 30) && s->F < (1 << 30), "mnf_conv2d_forward: filter too large");
-  float *Vw, *vb;
-  rc = prep_var(ctx, Kc * s->F, (int)s->F, log_std_W, log_var_b, max_std, &Vw, &vb);
-  if (rc) return rc;
   PairedArgs a = {};
   a.M = s->B * Ho * Wo; a.K = (int)Kc; a.N = (int)s->F;
-  a.x = x; a.z = z; a.Wm = mean_W; a.Vw = Vw; a.bm = mean_b; a.vb = vb;
+  a.x = x; a.z = z; a.Wm = mean_W; a.Vw = nullptr; a.bm = mean_b; a.vb = nullptr;
+  auto need_var = [&]() -> int {  // only the FFMA kernels read the clipped variances from global memory
+    if (a.Vw) return MNF_OK;
+    float *Vw, *vb;
+    const int r = prep_var(ctx, Kc * s->F, (int)s->F, log_std_W, log_var_b, max_std, &Vw, &vb);
+    a.Vw = Vw; a.vb = vb;
+    return r;
+  };
   a.y = y; a.mean_out = mean_out; a.sd_out = sd_out; a.eps = make_noise(eps);
   a.H = (int)s->H; a.W = (int)s->W; a.C = (int)s->C; a.kh = (int)s->kh; a.kw = (int)s->kw;
   a.Ho = (int)Ho; a.Wo = (int)Wo; a.stride = (int)s->stride;
@@ -614,8 +618,12 @@ int mnf_conv2d_forward(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, co
     rc = mnf_conv_win_umma_forward(ctx, s->B, geo, a.N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std, a.eps, y, &used);
     if (rc || used) return rc;
   }
-  rc = launch_direct(ctx, a, pad_b, pad_r, &used);
-  if (rc || used) return rc;
+  if (ctx->math_mode != MNF_MATH_TF32X3 || (a.N <= 20 && a.K <= 256)) {  // shapes of the direct FFMA kernel
+    rc = need_var();
+    if (rc) return rc;
+    rc = launch_direct(ctx, a, pad_b, pad_r, &used);
+    if (rc || used) return rc;
+  }
   if (ctx->math_mode == MNF_MATH_TF32X3) {
     if (!pad_b && !pad_r) {  // raw-tile kernel: im2col expressed by UMMA descriptors (8-wide output rows)
       if (!getenv("MNF_NO_F16")) {  // scaled fp16 hi/lo operands: half the weight stream and MMAs
@@ -630,6 +638,8 @@ int mnf_conv2d_forward(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, co
     return mnf_tc_paired_forward(ctx, 1, a.M, a.K, a.N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std, a.eps, y,
                                  mean_out, sd_out, geo);
   }
+  rc = need_var();
+  if (rc) return rc;
   return launch_paired<true>(ctx, a);
 }
 

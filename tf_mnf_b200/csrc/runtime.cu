@@ -41,7 +41,58 @@ void* mnf_workspace(mnf_ctx* ctx, size_t bytes) {
   return ctx->ws;
 }
 
+void* mnf_packed(mnf_ctx* ctx, uint64_t k0, uint64_t k1, uint64_t k2, uint64_t k3, size_t bytes, bool* fresh) {
+  *fresh = true;
+  if (!ctx->frozen) return mnf_workspace(ctx, bytes);
+  for (int i = 0; i < ctx->packed_n; ++i) {
+    mnf_packed_entry& e = ctx->packed[i];
+    if (e.key[0] == k0 && e.key[1] == k1 && e.key[2] == k2 && e.key[3] == k3 && e.bytes == bytes) {
+      *fresh = false;
+      return e.ptr;
+    }
+  }
+  if (ctx->capturing) {
+    mnf_set_error("packed-weight cache miss during CUDA-graph capture; run one eager step first");
+    return nullptr;
+  }
+  if (ctx->packed_n == ctx->packed_cap) {
+    const int cap = ctx->packed_cap ? ctx->packed_cap * 2 : 32;
+    mnf_packed_entry* p = (mnf_packed_entry*)realloc(ctx->packed, sizeof(mnf_packed_entry) * cap);
+    if (!p) {
+      mnf_set_error("packed-weight cache: out of host memory");
+      return nullptr;
+    }
+    ctx->packed = p;
+    ctx->packed_cap = cap;
+  }
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, bytes);
+  if (e != cudaSuccess) {
+    mnf_set_error("packed-weight cache cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  mnf_packed_entry& n = ctx->packed[ctx->packed_n++];
+  n.key[0] = k0; n.key[1] = k1; n.key[2] = k2; n.key[3] = k3;
+  n.ptr = d;
+  n.bytes = bytes;
+  return d;
+}
+
+static void mnf_packed_clear(mnf_ctx* ctx) {
+  if (ctx->packed_n) cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < ctx->packed_n; ++i) cudaFree(ctx->packed[i].ptr);
+  ctx->packed_n = 0;
+}
+
 extern "C" {
+
+int mnf_ctx_freeze_weights(mnf_ctx* ctx, int32_t frozen) {
+  MNF_CHECK_ARG(ctx, "mnf_ctx_freeze_weights: ctx is NULL");
+  MNF_CUDA(cudaSetDevice(ctx->device));
+  if (!frozen || !ctx->frozen) mnf_packed_clear(ctx);  // (re)freezing starts from the current weights
+  ctx->frozen = frozen != 0;
+  return MNF_OK;
+}
 
 int mnf_version(void) { return MNF_B200_VERSION; }
 const char* mnf_last_error(void) { return g_err; }
@@ -87,6 +138,8 @@ int mnf_ctx_destroy(mnf_ctx* ctx) {
   if (!ctx) return MNF_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  mnf_packed_clear(ctx);
+  free(ctx->packed);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   free(ctx);

@@ -638,15 +638,21 @@ static int launch(mnf_ctx* ctx, Args& a, const float* mean_W, const float* log_s
   a.kblocks = (a.K + BK - 1) / BK;
   a.ntiles = (a.N + BN - 1) / BN;
   const size_t bp_floats = (size_t)a.ntiles * a.kblocks * 4 * KC * BN * 4;
-  float* ws = (float*)mnf_workspace(ctx, sizeof(float) * (bp_floats + a.N + 64));
+  bool fresh = true;
+  float* ws = (float*)mnf_packed(ctx, mnf_mix(0x7C6Eull + BN + (CONV ? 1024 : 0), ((uint64_t)a.K << 32) | (uint32_t)a.N),
+                                 (uint64_t)(uintptr_t)mean_W, (uint64_t)(uintptr_t)log_std_W,
+                                 mnf_mix((uint64_t)(uintptr_t)log_var_b, (uint64_t)__float_as_uint_host(max_std)),
+                                 sizeof(float) * (bp_floats + a.N + 64), &fresh);
   if (!ws) return MNF_ERR_CUDA;
   float* Bp = ws;
   float* vb = ws + bp_floats;
-  const int64_t tot = (int64_t)bp_floats / 4;
-  int grid = (int)(cdiv(tot, 256) < ctx->sm_count * 8 ? cdiv(tot, 256) : ctx->sm_count * 8);
-  pack_weights_kernel<BN><<<grid, 256, 0, ctx->stream>>>(a.K, a.N, a.kblocks, a.ntiles, mean_W, log_std_W, max_std, Bp,
-                                                       log_var_b, vb);
-  MNF_LAUNCHED(ctx);
+  if (fresh) {
+    const int64_t tot = (int64_t)bp_floats / 4;
+    int grid = (int)(cdiv(tot, 256) < ctx->sm_count * 8 ? cdiv(tot, 256) : ctx->sm_count * 8);
+    pack_weights_kernel<BN><<<grid, 256, 0, ctx->stream>>>(a.K, a.N, a.kblocks, a.ntiles, mean_W, log_std_W, max_std, Bp,
+                                                         log_var_b, vb);
+    MNF_LAUNCHED(ctx);
+  }
   a.Bp = Bp;
   a.vb = vb;
   const size_t tab_bytes = CONV ? sizeof(int) * 2 * (size_t)a.kblocks * BK / (a.vec ? 4 : 1) : 0;

@@ -138,6 +138,13 @@ class Sequential:
                 x = lyr(x)
         return x
 
+    def freeze_weights(self, frozen: bool = True) -> None:
+        """Promise that no parameter changes until unfrozen: the contexts this model runs on keep
+        their packed weight blocks across calls (Context.freeze_weights).  Outputs are unchanged."""
+        ctxs = {id(l.ctx): l.ctx for l in self.mnf_layers if l.ctx is not None}
+        for c in list(ctxs.values()) + list(self._sides):
+            c.freeze_weights(frozen)
+
     def mc_predict(self, x: Any, n_samples: int) -> DeviceArray:
         """Monte-Carlo predictive: every input row under `n_samples` independent posterior draws
         (what the reference's notebooks do by calling the model n_samples times on one batch).

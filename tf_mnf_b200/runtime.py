@@ -82,7 +82,15 @@ class Context:
         c = Context(self.device)
         if getattr(self, "math", None):
             c.set_math(self.math)
+        if getattr(self, "frozen", False):
+            c.freeze_weights(True)
         return c
+
+    def freeze_weights(self, frozen: bool = True) -> None:
+        """Inference with fixed parameters: keep the packed weight blocks of the tensor-core
+        kernels across calls (mnf_ctx_freeze_weights).  Unfreeze before changing any parameter."""
+        L.check(self.lib.mnf_ctx_freeze_weights(self.handle, int(bool(frozen))))
+        self.frozen = bool(frozen)
 
     def wait(self, other: "Context") -> None:
         """Order this context's future work after everything enqueued so far on `other`."""
