@@ -422,7 +422,10 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
             "roofline": {"bound": "hbm",
                          "kernel": ("cf::conv_raw_f16" if args.math == "tf32x3" else "paired_gemm_fwd<CONV,64>")
                          + " (conv2: 12x12x20 -> 8x8x50, 5x5, + fused ReLU/2x2 max-pool)",
-                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
+                         # (profiles/r01_ncu_full_prof_conv_f16.txt); the pooled output partly stays in L2
+                         "traffic": (120418048 + 15231488) if args.math == "tf32x3" else None,
                          "peak_source": which, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms,
                          "algorithmic_bytes_per_launch": k_bytes,
                          "pipe": ("tcgen05.mma kind::f16, power-of-two scaled fp16 hi/lo split of both operands, fp32 "
