@@ -23,7 +23,8 @@ constexpr int BK = 16, KC = 4; // stage-1 k-block (floats) and its 16-byte chunk
 constexpr int S1 = 4;          // stage-1 ring depth (S1 * 24 KB == S2 * 32 KB: the two rings alias)
 constexpr int CN = 32;         // stage-2 columns per chunk (s and t: N = 64 per MMA)
 constexpr int S2 = 3;          // stage-2 weight ring depth
-constexpr int THREADS = 13 * 32;
+constexpr int THREADS = 21 * 32;  // warps 0-3 stage-1 epilogue, 4 MMA, 5-12 and 13-20 producers; stage-2 epilogue: 0-3, 8-11, 13-20
+constexpr int NG = 4;               // producer groups of 4 warps (128 rows), group g stages k-blocks g, g+NG, ...
 constexpr int A1_VAR = KC * BM * 16;        // 8 KB: one variant (hi or lo) of a stage-1 A block
 constexpr int A1_STAGE = 2 * A1_VAR;        // 16 KB
 constexpr int B1_VAR = KC * HP * 16;        // 4 KB
@@ -195,8 +196,8 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
   uint8_t* B1 = A1 + S1 * A1_STAGE;           // [S1][2][KC][HP][16B]        32 KB
   uint8_t* B2 = smem;                         // [S2][2][16][64][16B]        96 KB (aliases A1/B1)
   uint8_t* Hs = smem + S2 * B2_STAGE;         // [2][16][BM][16B]            64 KB
-  float* ldp = (float*)(Hs + 2 * H_VAR);      // [2][BM] log-det partials
-  uint64_t* bars = (uint64_t*)(ldp + 2 * BM);
+  float* ldp = (float*)(Hs + 2 * H_VAR);      // [4][BM] log-det partials
+  uint64_t* bars = (uint64_t*)(ldp + 4 * BM);
   uint64_t* full1 = bars;            // [S1]
   uint64_t* empty1 = full1 + S1;     // [S1]
   uint64_t* acc1_full = empty1 + S1; // [1]
@@ -242,8 +243,8 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
   if (warp >= 5) {
-    // =========================================================== stage-1 producers (warps 5-12)
-    const int pt = threadIdx.x - 5 * 32;   // 0..255
+    // =========================================================== stage-1 producers (warps 5-20)
+    const int pt = threadIdx.x - 5 * 32;   // 0..511: four groups of 128 rows
     const int r = pt & (BM - 1), grp = pt >> 7;
     int64_t row = row0 + r;
     const bool row_ok = row < a.B;
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
       // deep prefetch: this thread's 64 bytes of each k-block travel global -> shared by cp.async
       // into a raw ring (8 blocks in flight per CTA; the ring borrows the h buffers, which are
       // not written before stage 1 has drained).  A thread only ever reads back its own bytes.
-      constexpr int RAW = 8, PF = RAW / 2;
+      constexpr int RAW = 8, PF = RAW / NG;
       const float* zrow = a.zin + row * D;
       const int sw = (r >> 1) & 3;
       auto issue = [&](int kb) {
@@ -317,10 +318,10 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
       };
 #pragma unroll
       for (int i = 0; i < PF; ++i) {
-        if (grp + 2 * i < a.kblocks) issue(grp + 2 * i);
+        if (grp + NG * i < a.kblocks) issue(grp + NG * i);
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
-      for (int kb = grp; kb < a.kblocks; kb += 2) {
+      for (int kb = grp; kb < a.kblocks; kb += NG) {
         asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");
         const uint8_t* src = Hs + (kb % RAW) * (BM * 64) + r * 64;
 #pragma unroll
@@ -343,9 +344,9 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
       asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
       if (grp < a.kblocks) gather(grp, cur);
-      for (int kb = grp; kb < a.kblocks; kb += 2) {
-        const bool more = kb + 2 < a.kblocks;
-        if (more) gather(kb + 2, nxt);
+      for (int kb = grp; kb < a.kblocks; kb += NG) {
+        const bool more = kb + NG < a.kblocks;
+        if (more) gather(kb + NG, nxt);
         publish(kb, cur);
         if (more) {
 #pragma unroll
@@ -461,8 +462,10 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
   // Fast-math note: exp / log / reciprocal use the MUFU approximations (__expf, __logf,
   // __fdividef): relative error ~1e-6 for the |s| this path sees, inside the 1e-5 parity bar
   // (tests/test_gpu_tensorcore.py); the FFMA kernels keep the IEEE-accurate versions.
-  if (warp < 4 || (warp >= 8 && warp < 12)) {
-    const int g = warp & 3, half = warp >= 8 ? 1 : 0;
+  if (warp < 4 || (warp >= 8 && warp < 12) || warp >= 13) {
+    // 16 epilogue warps: TMEM lane quadrant g x column half x chunk parity (= accumulator buffer)
+    const int g = warp & 3;
+    const int half = (warp >= 8 && warp < 12) || warp >= 17 ? 1 : 0, par = warp >= 13 ? 1 : 0;
     const int r = g * 32 + lane;
     const int64_t row = row0 + r;
     const bool row_ok = row < a.B;
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
     const float* bs_s = bias_s;
     const float* bt_s = bias_s + a.chunks * CN;
     float ld = 0.f;
-    for (int c = 0; c < a.chunks; ++c) {
+    for (int c = par; c < a.chunks; c += 2) {
       const int buf = c & 1;
       const int cb = c * CN + half * 16;
       // z of this thread's 16 columns: issued before the accumulator wait so the latency overlaps
@@ -542,14 +545,14 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
         }
       }
     }
-    ldp[half * BM + r] = ld;
+    ldp[(half + 2 * par) * BM + r] = ld;
   }
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x < BM) {
     const int64_t row = row0 + threadIdx.x;
     if (row < a.B && a.ld_out)
-      a.ld_out[row] = (a.ld_in ? a.ld_in[row] : 0.f) + ldp[threadIdx.x] + ldp[BM + threadIdx.x];
+      a.ld_out[row] = (a.ld_in ? a.ld_in[row] : 0.f) + ((ldp[threadIdx.x] + ldp[BM + threadIdx.x]) + (ldp[2 * BM + threadIdx.x] + ldp[3 * BM + threadIdx.x]));
   }
   if (warp == 4) {
     tc_fence_after();
@@ -639,7 +642,7 @@ int mnf_flow_umma_step(mnf_ctx* ctx, int64_t B, int D, int H, int kind, int pari
                                                     B1p, B2p);
     MNF_LAUNCHED(ctx);
   }
-  const size_t smem = (size_t)S2 * B2_STAGE + 2 * H_VAR + sizeof(float) * 2 * BM + 256 +
+  const size_t smem = (size_t)S2 * B2_STAGE + 2 * H_VAR + sizeof(float) * 4 * BM + 256 +
                       sizeof(float) * 2 * (size_t)a.chunks * CN + sizeof(uint16_t) * (size_t)BM * a.kblocks + 16;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
