@@ -314,7 +314,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
-        L.check(lib.mnf_ctx_probe(ctx.handle, 1, 1, kst[i], ksp[i]))  # 2nd conv GEMM launch = conv2
+        L.check(lib.mnf_ctx_probe(ctx.handle, 1, int(os.environ.get("MNF_BENCH_PROBE_SKIP", "1")), kst[i], ksp[i]))  # 2nd conv GEMM launch = conv2
         L.check(lib.mnf_event_record(ctx.handle, starts[i]))
         out = step(x_dev)
         L.check(lib.mnf_event_record(ctx.handle, stops[i]))

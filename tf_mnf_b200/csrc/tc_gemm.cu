@@ -15,6 +15,8 @@
 //                         {x(*z), x^2} x {hi, lo} in registers and write them K-major into the
 //                         no-swizzle UMMA layout; the pre-split weight block arrives by one
 //                         cp.async.bulk (TMA, 1-D) per stage.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tc {
@@ -22,7 +24,7 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 16;       // floats per pipeline stage
 constexpr int KC = BK / 4;   // 16-byte k-chunks per stage
-constexpr int STAGES = 3;
+constexpr int stages_for(int bn) { return bn > 64 ? 2 : 3; }  // BN = 128: 64 KB per stage + 66 KB output staging
 constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
 constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;  // 416
 constexpr int A_VARIANT_BYTES = KC * BM * 16;               // 8 KB
@@ -146,6 +148,7 @@ __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
 // ---------------------------------------------------------------------------------- kernel
 template <int BN, bool CONV>
 __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
+  constexpr int STAGES = stages_for(BN);
   constexpr int B_VARIANT_BYTES = KC * BN * 16;
   constexpr int B_STAGE_BYTES = 4 * B_VARIANT_BYTES;
   constexpr int TMEM_COLS = 4 * BN;  // 2 buffers x {mean, var}
@@ -656,6 +659,7 @@ static int launch(mnf_ctx* ctx, Args& a, const float* mean_W, const float* log_s
   a.Bp = Bp;
   a.vb = vb;
   const size_t tab_bytes = CONV ? sizeof(int) * 2 * (size_t)a.kblocks * BK / (a.vec ? 4 : 1) : 0;
+  constexpr int STAGES = stages_for(BN);
   const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + 4 * KC * BN * 16) + sizeof(float) * (BM * (BN + 1) + 4) + 256 +
                       sizeof(float) * 2 * BN + tab_bytes;
   MNF_CHECK_ARG(smem <= 227 * 1024, "tensor-core conv path: K = %d is too large for the im2col table", a.K);
@@ -692,5 +696,7 @@ int mnf_tc_paired_forward(mnf_ctx* ctx, int conv, int64_t M, int K, int N, const
     return tc::launch<64, true>(ctx, a, mean_W, log_std_W, log_var_b, max_std);
   }
   a.vec = (K % 4 == 0) && (((uintptr_t)x & 15) == 0) && (!z || ((uintptr_t)z & 15) == 0);
+  // wide dense layers: 128-column tiles halve the number of times x and z are re-read from L2
+  if (N >= 256 && !getenv("MNF_TC_BN64")) return tc::launch<128, false>(ctx, a, mean_W, log_std_W, log_var_b, max_std);
   return tc::launch<64, false>(ctx, a, mean_W, log_std_W, log_var_b, max_std);
 }
