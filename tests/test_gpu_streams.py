@@ -33,7 +33,7 @@ def test_presampled_z_is_bit_identical(flow_type, math):
             ys = [model(x).numpy() for _ in range(3)]  # call 0 builds the layers; 1 and 2 use the side stream
             outs.append(ys)
             if pre:
-                assert len(model._sides) == 3
+                assert len(model._sides) == 4
         for a, b in zip(*outs):
             np.testing.assert_array_equal(a, b)
         assert not np.array_equal(outs[0][1], outs[0][2])  # fresh noise per call

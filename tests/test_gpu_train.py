@@ -24,7 +24,7 @@ def _model_and_batch(seed=0):
 
 def _reset_calls(model):
     for lyr in model.mnf_layers:
-        lyr.call_index = 0
+        lyr.call_index = lyr.kl_index = 0
 
 
 def test_model_backward_matches_finite_differences():

@@ -53,7 +53,10 @@ class MNFLayerBase:
         self.built = False
         self.ctx: Context | None = None
         self.row_offset = 0       # global index of local row 0 (set by the sharded driver)
-        self.call_index = 0       # bumps every call()/kl_div(): fresh noise per call
+        self.call_index = 0       # bumps every call() / sample_z(): fresh noise per call
+        self.kl_index = 0         # bumps every kl_div() (its draws use their own stream ids, so the two
+        #                           counters never collide; separate so that kl_div() between two
+        #                           forward calls does not invalidate a z drawn ahead of time)
         self.training = False     # record what backward needs
         self.grads: dict[str, Any] = {}
         self._tape: dict[str, Any] = {}
@@ -122,25 +125,26 @@ class MNFLayerBase:
 
     # ------------------------------------------------------------------- sample_z
     def _sample_z(self, batch_size: int, z_draw: int, bern_draw: int, inject: dict | None, record: bool,
-                  row_offset: int, ctx: Context | None = None, alloc: Context | None = None):
+                  row_offset: int, ctx: Context | None = None, alloc: Context | None = None, index: int | None = None):
         """mnf_dense.py:88-102 / mnf_conv.py:100-114 -> (z, log_dets, ChainRun | None)."""
         ctx, D = ctx or self.ctx, self._flow_dim()
         B = int(batch_size)
         if not self.use_z:
             return None, ctx.zeros((B,)), None
         inject = inject or {}
+        index = self.call_index if index is None else index
         pre, self._pre = (self._pre, None) if z_draw == nz.CALL_Z else (None, self._pre)
         if pre is not None:
             ctx.wait(pre["side"])  # also orders the buffers' (stream-ordered) release after the side work
-            if (not inject and pre["key"] == (B, self.call_index, row_offset, bool(record)) and ctx is self.ctx):
+            if (not inject and pre["key"] == (B, index, row_offset, bool(record)) and ctx is self.ctx):
                 return pre["z"], pre["ld"], pre["run"]
         eps_inj = as_device(inject["eps_z"], ctx) if inject.get("eps_z") is not None else None
         if eps_inj is not None and eps_inj.shape != (B, D):
             raise ValueError(f"injected eps_z must have shape {(B, D)}, got {eps_inj.shape}")
-        eps = nz.make(self.seed, self.call_index, self.uid, z_draw, row_offset, eps_inj)
+        eps = nz.make(self.seed, index, self.uid, z_draw, row_offset, eps_inj)
         run = ChainRun(self.flow_q.flows)
         states, ld = run.forward(q0_mean=self.q0_mean, q0_log_var=self.q0_log_var, B=B, eps=eps,
-                                 bern=inject.get("bern_q"), seed=self.seed, call_index=self.call_index,
+                                 bern=inject.get("bern_q"), seed=self.seed, call_index=index,
                                  layer_id=self.uid, bern_draw=bern_draw, row_offset=row_offset, record=record,
                                  ctx=ctx, alloc=alloc)
         run.eps = eps
@@ -188,7 +192,7 @@ class MNFLayerBase:
         ctx, D = ctx or self.ctx, self._flow_dim()
         inj = noise or {}
         rows, cols = self._kl_shape()
-        z, ldq, qrun = self._sample_z(1, nz.KL_Z, nz.BERN_Q_KL, inj, self.training, 0, ctx)
+        z, ldq, qrun = self._sample_z(1, nz.KL_Z, nz.BERN_Q_KL, inj, self.training, 0, ctx, index=self.kl_index)
         a = L.KlArgs()
         a.conv, a.use_z = int(self._conv), int(self.use_z)
         a.r_all_states = int(self.r_term == "all_states")
@@ -200,7 +204,7 @@ class MNFLayerBase:
         if self.use_z:
             rrun = ChainRun(self.flow_r.flows)
             rstates, ldr = rrun.forward(z=z.reshape(1, D), bern=inj.get("bern_r"), seed=self.seed,
-                                        call_index=self.call_index, layer_id=self.uid, bern_draw=nz.BERN_R_KL,
+                                        call_index=self.kl_index, layer_id=self.uid, bern_draw=nz.BERN_R_KL,
                                         record=self.training, ctx=ctx)
             a.n_r_states = len(rstates)
             a.q0_log_var, a.r0_mean, a.r0_log_var, a.r0_apvar = _p(self.q0_log_var), _p(self.r0_mean), _p(self.r0_log_var), _p(self.r0_apvar)
@@ -211,13 +215,13 @@ class MNFLayerBase:
                 raise ValueError(f"injected eps_a must have {L_a} elements, got shape {ea.shape}")
             eb = as_device(np.asarray(inj["eps_b"], np.float32).reshape(1), ctx) if inj.get("eps_b") is not None else None
             keep += [ea, eb, ldr]
-            a.eps_a = nz.make(self.seed, self.call_index, self.uid, nz.KL_A, 0, ea)
-            a.eps_b = nz.make(self.seed, self.call_index, self.uid, nz.KL_B, 0, eb)
+            a.eps_a = nz.make(self.seed, self.kl_index, self.uid, nz.KL_A, 0, ea)
+            a.eps_b = nz.make(self.seed, self.kl_index, self.uid, nz.KL_B, 0, eb)
         out = ctx.empty((1,))
         L.check(ctx.lib.mnf_kl_forward(ctx.handle, C.byref(a), _p(out)))
         if self.training:
             self._kl_tape = dict(args=a, qrun=qrun, rrun=rrun, keep=keep, z=z, ldq=ldq)
-        self.call_index += 1
+        self.kl_index += 1
         return out
 
     # ------------------------------------------------------------------- backward

@@ -116,13 +116,18 @@ class Sequential:
         x = as_device(x, default_context())
         it = iter(noise or [])
         skip = False
+        self._first_rows = x.shape[0]
+        first = None
         if self.presample_z and not noise:
-            later = [l for l in self.mnf_layers[1:] if l.built and l.use_z and l.ctx is x.ctx]
-            if later:
-                if len(self._sides) < len(later) or self._sides[0].device != x.ctx.device:
-                    self._sides = [x.ctx.fork() for _ in later]
-                for lyr, side in zip(later, self._sides):
-                    lyr.presample(x.shape[0], side)
+            mnf = [l for l in self.mnf_layers if l.built and l.use_z and l.ctx is x.ctx]
+            if mnf:
+                if len(self._sides) < len(mnf) or self._sides[0].device != x.ctx.device:
+                    self._sides = [x.ctx.fork() for _ in mnf]
+                for lyr, side in zip(mnf, self._sides):
+                    if lyr is self.mnf_layers[0]:
+                        first = (lyr, side)   # its z for THIS call was drawn during the previous call
+                    else:
+                        lyr.presample(x.shape[0], side)
         for i, lyr in enumerate(self.layers):
             if skip:  # this ReLU+MaxPool was folded into the preceding conv's epilogue
                 skip = False
@@ -134,8 +139,14 @@ class Sequential:
                     skip = lyr.last_fused
                 else:
                     x = lyr(x, noise=next(it, None))
+                if first is not None and lyr is first[0]:
+                    # the first layer's z has nothing in front of it to hide behind: draw the one
+                    # for the NEXT call now, beside the rest of this call (same counters as in-line)
+                    lyr.presample(self._first_rows, first[1])
             else:
                 x = lyr(x)
+        if first is not None:
+            x.ctx.wait(first[1])  # a call is complete when its stream is: include the draw made for the next one
         return x
 
     def freeze_weights(self, frozen: bool = True) -> None:
