@@ -52,6 +52,10 @@ typedef struct mnf_ctx mnf_ctx; /* opaque: device, stream, workspace */
 /* ---- runtime ------------------------------------------------------------------------ */
 int mnf_version(void);
 const char* mnf_last_error(void);
+/* Name of the kernel family that served the calling thread's last dense / conv / flow forward
+ * call ("conv_win_umma", "conv_raw_f16", "conv_raw_umma", "paired_umma", "conv_direct", "paired_gemm",
+ * "flow_umma", "flow_mlp", ...): lets tests assert which path a shape exercised. */
+const char* mnf_last_path(void);
 int mnf_device_count(int* out);
 /* stream: a cudaStream_t owned by the caller, or NULL to let the context create its own. */
 int mnf_ctx_create(int device, void* stream, mnf_ctx** out);

@@ -38,9 +38,13 @@ def test_dense_tensorcore(tc_ctx, K, N, B, use_z):
     ref, _ = O.dense_call(P, x, eps_z, eps, 1.0, use_z=use_z)
     lyr = make_layer(P, x.shape, use_z=use_z)
     inj = dict(eps_out=_f32(eps))
+    want_path = "paired_umma<128>" if N >= 256 else "paired_umma<64>"
     if use_z:
         inj["eps_z"] = _f32(eps_z)
     close(lyr(_f32(x), noise=inj).numpy(), ref, RTOL, "dense call (tf32x3)")
+    from tf_mnf_b200 import _lib as L
+
+    assert L.last_path() == want_path, L.last_path()
 
 
 @pytest.mark.parametrize("shape,wshape,stride,padding", [
@@ -50,6 +54,10 @@ def test_dense_tensorcore(tc_ctx, K, N, B, use_z):
     # single input channel: sliding-window kernel (conv_win_umma.cu); odd batch, kw <= 4 and kw > 4
     ((5, 28, 28, 1), (5, 5, 1, 20), 1, "VALID"), ((4, 10, 18, 1), (3, 3, 1, 32), 1, "VALID"),
     ((3, 15, 15, 1), (8, 8, 1, 4), 1, "VALID"), ((2, 9, 32, 1), (2, 1, 1, 12), 1, "VALID"),
+    # raw-tile kernels with other images-per-tile counts: Ho = 4 (I = 4), Ho = 16 (I = 1), Ho = 1 (I = 16),
+    # channel counts that are / are not multiples of 8, N = 64
+    ((6, 8, 12, 8), (5, 5, 8, 32), 1, "VALID"), ((3, 20, 12, 4), (5, 5, 4, 24), 1, "VALID"),
+    ((21, 5, 12, 16), (5, 5, 16, 64), 1, "VALID"), ((9, 9, 10, 12), (2, 3, 12, 40), 1, "VALID"),
 ])
 def test_conv_tensorcore(tc_ctx, shape, wshape, stride, padding):
     rng = np.random.RandomState(sum(shape) + sum(wshape))
@@ -65,6 +73,18 @@ def test_conv_tensorcore(tc_ctx, shape, wshape, stride, padding):
     lyr = make_layer(P, x.shape, stride=stride, padding=padding)
     got = lyr(_f32(x), noise=dict(eps_z=_f32(eps_z), eps_out=_f32(eps))).numpy()
     close(got, ref, RTOL, "conv call (tf32x3)")
+    # which kernel family served the shape (mnf_last_path): the parity above is about THAT kernel
+    from tf_mnf_b200 import _lib as L
+
+    C_in, Ho, Wo = shape[3], got.shape[1], got.shape[2]
+    raw_ok = padding == "VALID" and stride == 1 and Wo == 8 and C_in % 4 == 0 and 20 < F <= 64 and 16 % Ho == 0
+    chunks = -(-C_in // 8) * (Ho - 1 + wshape[0]) * (16 // max(Ho, 1)) * (7 + wshape[1]) if raw_ok else 0
+    if padding == "VALID" and stride == 1 and C_in == 1:
+        assert L.last_path() == "conv_win_umma", L.last_path()
+    elif raw_ok and chunks <= 6 * 192:  # the producers hold a whole tile in registers (MAXC chunks per thread)
+        assert L.last_path() == "conv_raw_f16", L.last_path()
+    else:
+        assert L.last_path() in ("paired_umma<64>", "conv_raw_umma", "conv_direct"), L.last_path()
 
 
 @pytest.mark.parametrize("wshape,shape", [((5, 5, 20, 50), (7, 12, 12, 20)), ((3, 3, 8, 40), (9, 10, 10, 8)),

@@ -118,7 +118,7 @@ SIGNATURES = {
     "mnf_tile_rows": [vp, _i64, _i64, _i64, vp, vp],
     "mnf_adam_step": [vp, _i64, vp, vp, vp, vp, _f, _f, _f, _f, _i32],
 }
-NON_STATUS = {"mnf_version": ([], C.c_int), "mnf_last_error": ([], C.c_char_p)}
+NON_STATUS = {"mnf_version": ([], C.c_int), "mnf_last_error": ([], C.c_char_p), "mnf_last_path": ([], C.c_char_p)}
 ALL_SYMBOLS = sorted([*SIGNATURES, *NON_STATUS])
 
 
@@ -150,6 +150,11 @@ def load() -> C.CDLL:
         fn.restype = res
     _lib = lib
     return lib
+
+
+def last_path() -> str:
+    """Kernel family that served this thread's last dense / conv / flow forward call."""
+    return load().mnf_last_path().decode()
 
 
 def check(rc: int) -> None:

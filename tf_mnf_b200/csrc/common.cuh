@@ -74,6 +74,7 @@ int mnf_tc_paired_forward(mnf_ctx* ctx, int conv, int64_t M, int K, int N, const
                           float max_std, const NoiseDev& eps, float* y, float* mean_out, float* sd_out,
                           const int* geo);  // conv geo: H,W,C,kh,kw,Ho,Wo,stride,pad_t,pad_l,pool
 void* mnf_workspace(mnf_ctx* ctx, size_t bytes);  // nullptr on failure (error set)
+void mnf_note_path(const char* name);              // which kernel family served the last forward call (mnf_last_path)
 // Where a call's packed weights go.  Not frozen: the transient workspace, *fresh = true (pack every
 // call).  Frozen: a persistent block per key; *fresh tells whether it still has to be filled.
 void* mnf_packed(mnf_ctx* ctx, uint64_t k0, uint64_t k1, uint64_t k2, uint64_t k3, size_t bytes, bool* fresh);

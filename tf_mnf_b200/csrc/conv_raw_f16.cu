@@ -568,6 +568,7 @@ int mnf_conv_raw_f16_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, con
   const int64_t passes = cdiv(cdiv(B, a.I), (int64_t)TT);
   const int g = (int)(passes < ctx->sm_count ? passes : ctx->sm_count);
   const bool probed = mnf_probe_begin(ctx, MNF_PROBE_CONV_GEMM);
+  mnf_note_path("conv_raw_f16");
   conv_raw_f16<<<g, THREADS, smem, ctx->stream>>>(a);
   mnf_probe_end(ctx, probed);
   MNF_LAUNCHED(ctx);

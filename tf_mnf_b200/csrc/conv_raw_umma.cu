@@ -434,6 +434,7 @@ int mnf_conv_raw_umma_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, co
   const int64_t tiles = cdiv(B, a.I);
   const int g = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
   const bool probed = mnf_probe_begin(ctx, MNF_PROBE_CONV_GEMM);
+  mnf_note_path("conv_raw_umma");
   conv_raw_umma<<<g, THREADS, smem, ctx->stream>>>(a);
   mnf_probe_end(ctx, probed);
   MNF_LAUNCHED(ctx);

@@ -454,6 +454,7 @@ int mnf_conv_win_umma_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, co
   const int64_t sets = cdiv(B, (int64_t)I);
   const int g = (int)(sets < ctx->sm_count ? sets : ctx->sm_count);
   const bool probed = mnf_probe_begin(ctx, MNF_PROBE_CONV_GEMM);
+  mnf_note_path("conv_win_umma");
   conv_win_umma<<<g, THREADS, smem, ctx->stream>>>(a);
   mnf_probe_end(ctx, probed);
   MNF_LAUNCHED(ctx);

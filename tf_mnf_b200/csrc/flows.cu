@@ -518,6 +518,7 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
         continue;
       }
       int grid = (int)cdiv(B, FT_ROWS);
+      mnf_note_path("flow_mlp");
       if (st.kind == MNF_FLOW_IAF)
         flow_mlp_step_fwd<MNF_FLOW_IAF><<<grid, FT_THREADS, 0, ctx->stream>>>(a);
       else

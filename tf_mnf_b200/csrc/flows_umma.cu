@@ -650,6 +650,7 @@ int mnf_flow_umma_step(mnf_ctx* ctx, int64_t B, int D, int H, int kind, int pari
     attr_smem = smem;
   }
   const bool probed = mnf_probe_begin(ctx, MNF_PROBE_FLOW_STEP);
+  mnf_note_path("flow_umma");
   flow_umma_step<<<(unsigned)cdiv(B, BM), THREADS, smem, ctx->stream>>>(a);
   mnf_probe_end(ctx, probed);
   MNF_LAUNCHED(ctx);

@@ -457,6 +457,7 @@ static int launch_direct(mnf_ctx* ctx, const PairedArgs& a, int pad_b, int pad_r
   d.IMG = img;
   const size_t smem = sizeof(float) * (2 * (size_t)a.K * NF + (size_t)img * NF) + sizeof(int) * ((a.K + 3) & ~3) + img * img_bytes;
   const bool probed = mnf_probe_begin(ctx, MNF_PROBE_CONV_GEMM);
+  mnf_note_path("conv_direct");
   if (a.pool)
     conv_direct_fwd<NF, true><<<(unsigned)cdiv(B, img), DC_THREADS, smem, ctx->stream>>>(d);
   else
@@ -471,6 +472,7 @@ template <bool CONV>
 static int launch_paired(mnf_ctx* ctx, const PairedArgs& a) {
   dim3 grid((unsigned)cdiv(a.M, PG_BM), 1);
   const bool probed = mnf_probe_begin(ctx, CONV ? MNF_PROBE_CONV_GEMM : MNF_PROBE_DENSE_GEMM);
+  mnf_note_path("paired_gemm");
   if (a.N > 32) {
     grid.y = (unsigned)cdiv(a.N, 64);
     paired_gemm_fwd<CONV, 64><<<grid, (PG_BM / PG_TM) * (64 / PG_TN), 0, ctx->stream>>>(a);

@@ -13,6 +13,9 @@ void mnf_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local const char* g_path = "";
+void mnf_note_path(const char* name) { g_path = name; }
+
 void* mnf_workspace(mnf_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->ws_bytes) return ctx->ws;
   if (ctx->capturing) {
@@ -96,6 +99,7 @@ int mnf_ctx_freeze_weights(mnf_ctx* ctx, int32_t frozen) {
 
 int mnf_version(void) { return MNF_B200_VERSION; }
 const char* mnf_last_error(void) { return g_err; }
+const char* mnf_last_path(void) { return g_path; }
 
 int mnf_device_count(int* out) {
   MNF_CHECK_ARG(out, "mnf_device_count: out is NULL");

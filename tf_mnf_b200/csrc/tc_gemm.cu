@@ -671,6 +671,7 @@ static int launch(mnf_ctx* ctx, Args& a, const float* mean_W, const float* log_s
   const int64_t tiles = cdiv(a.M, BM) * a.ntiles;
   const int g = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
   const bool probed = mnf_probe_begin(ctx, CONV ? MNF_PROBE_CONV_GEMM : MNF_PROBE_DENSE_GEMM);
+  mnf_note_path(BN == 128 ? "paired_umma<128>" : "paired_umma<64>");
   paired_umma_fwd<BN, CONV><<<g, THREADS, smem, ctx->stream>>>(a);
   mnf_probe_end(ctx, probed);
   MNF_LAUNCHED(ctx);
