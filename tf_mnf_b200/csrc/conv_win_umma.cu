@@ -19,11 +19,13 @@
 //   x_hi * [W_hi | W_lo] is one N=64 instruction, x_lo * W_hi one N=32 instruction; four TMEM
 //   accumulator buffers of 128 columns ([mean 64 | var 64]) let the MMA warp run ahead.
 //
-//   warps 0-19   epilogue (the Philox + Box-Muller noise of 128x20 outputs per tile is the long
-//                pole, so it gets 20 of the 24 warps): warp w reads TMEM lanes 32*(w%4).. and
-//                the column quads w/4, w/4+5 -> bias, z-scale, eps, optional ReLU + 2x2 max-pool
-//                by warp shuffles (the four pixels of a pool window sit in one warp), store
-//   warp  20     MMA issue;   warps 21-23: plane producers (one lane per chunk, the three
+//   warps 0-15   epilogue (the Philox + Box-Muller noise of 128x20 outputs per tile is the long
+//                pole): four groups of four warps; group g owns TMEM accumulator buffer g and
+//                the tiles t = g (mod 4), warp w of it reads lanes 32*(w%4).. and ALL column
+//                quads of its rows (the per-tile preamble is paid once per tile, not once per
+//                quad) -> bias, z-scale, eps, optional ReLU + 2x2 max-pool by warp shuffles (the
+//                four pixels of a pool window sit in one warp), store
+//   warp  16     MMA issue;   warps 17-19: plane producers (one lane per chunk, the three
 //                neighbours of a window by shuffle)
 #include <vector>
 
@@ -34,7 +36,7 @@ using namespace um;
 
 constexpr int BM = 128, BN = 32;
 constexpr int STEP_B = 2 * 2 * BN * 16;  // bytes of one step's weights for one phase: [2 kc][hi 32 n | lo 32 n][16 B]
-constexpr int EPI_E = 5;                     // epilogue warps per TMEM lane quadrant
+constexpr int EPI_E = 4;                     // epilogue groups = TMEM accumulator buffers
 constexpr int EPI_WARPS = 4 * EPI_E, MMA_WARP = EPI_WARPS, THREADS = (EPI_WARPS + 4) * 32;
 constexpr int PROD_WARPS = 3;
 constexpr int NACC = 4, ACC_COLS = 4 * BN;  // [mean: hi-product 32 | lo-product 32][var: same]
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_win_umma(const __grid_constan
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) { mbar_init(&pfull[b], PROD_WARPS); mbar_init(&pempty[b], 1); }
-    for (int b = 0; b < NACC; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], EPI_WARPS); }
+    for (int b = 0; b < NACC; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -124,122 +126,91 @@ __global__ void __launch_bounds__(THREADS, 1) conv_win_umma(const __grid_constan
 
   if (warp < EPI_WARPS) {
     // ================================================================== epilogue warps
-    // The kernel is issue-bound on this code (Philox4x32-10 + Box-Muller per 4 outputs), so
-    // everything that does not change per tile (bias, z, row keys, output base) is hoisted and
-    // the per-tile indices are advanced incrementally.
-    const int quad = warp & 3, e0 = warp >> 2;
-    const int nq = a.N >> 2;                       // column quads (N % 4 == 0, nq <= 8 < 2 * EPI_E)
+    // The kernel is issue-bound on this code (Philox4x32-10 + Box-Muller per 4 outputs).
+    const int quad = warp & 3, grp = warp >> 2;    // grp == accumulator buffer
+    const int nq = a.N >> 2;                       // column quads (N % 4 == 0)
     const int gl = lane >> 3, img = gl & 1, hl = quad * 2 + (gl >> 1), wl = lane & 7;
     const bool writer = !a.pool || (lane & 17) == 0;
     const int HoWo = a.Ho * a.Wo;
-    const bool has0 = e0 < nq, has1 = e0 + EPI_E < nq;
-    const int nb0 = 4 * e0;
-    float bm0[4], bv0[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      bm0[j] = has0 ? bias_s[nb0 + j] : 0.f;
-      bv0[j] = has0 ? bias_s[BN + nb0 + j] : 1.f;
-    }
     // element offsets of this lane's pixel inside one image's output, for tile (0,0), and the
-    // strides of the tile loops
+    // strides of the tile grid
     const int outer0 = hl * a.Wo + wl;
     const int pix0 = a.pool ? (hl >> 1) * (a.Wo >> 1) + (wl >> 1) : outer0;
     const int pix_wg = a.pool ? 4 : 8, pix_hb = a.pool ? 4 * (a.Wo >> 1) : 8 * a.Wo;
     const int64_t img_out = a.pool ? (int64_t)(a.Ho >> 1) * (a.Wo >> 1) * a.N : (int64_t)HoWo * a.N;
-    const uint32_t tquad = tmem_base + ((uint32_t)(quad * 32) << 16);
-    uint32_t tcount = 0;
-    for (int64_t s = blockIdx.x; s < nsets; s += gridDim.x) {
-      const int64_t braw = s * I + img;
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * ACC_COLS);
+    const int64_t my_sets = (nsets > blockIdx.x) ? (nsets - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total_tiles = my_sets * ntile;
+    uint32_t k = 0;  // this group's tile counter (parity of its accumulator barrier)
+    for (int64_t tc = grp; tc < total_tiles; tc += EPI_E, ++k) {
+      const int64_t si = tc / ntile;
+      const int tile = (int)(tc - si * ntile);
+      const int hb = tile / nwg, wg = tile - hb * nwg;
+      const int64_t braw = (blockIdx.x + si * gridDim.x) * I + img;
       const bool ok = braw < a.B;
       const int64_t brow = ok ? braw : a.B - 1;
       const uint64_t grow = a.eps.row_offset + (uint64_t)brow;
       const bool st = ok && writer;
-      float* const dst_img = a.y + brow * img_out;
-      const float* const inj_img = a.eps.injected ? a.eps.injected + brow * HoWo * a.N : nullptr;
-      float z0[4] = {1.f, 1.f, 1.f, 1.f};
-      if (a.z && has0) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(a.z + brow * a.N + nb0));
-        z0[0] = t.x; z0[1] = t.y; z0[2] = t.z; z0[3] = t.w;
-      }
-      for (int hb = 0; hb < nhb; ++hb) {
-        int outer = outer0 + hb * 8 * a.Wo, pix = pix0 + hb * pix_hb;
-        for (int wg = 0; wg < nwg; ++wg, ++tcount, outer += 8, pix += pix_wg) {
-          const int acc = tcount & (NACC - 1);
-          mbar_wait(&tfull[acc], (tcount / NACC) & 1);
-          tc_fence_after();
-          const uint32_t trow = tquad + (uint32_t)(acc * ACC_COLS);
-          float mh[4], ml[4], vh[4], vl[4], mh1[4], ml1[4], vh1[4], vl1[4];
-          if (has0) {
-            tmem_ld4(trow + nb0, mh);
-            tmem_ld4(trow + nb0 + BN, ml);
-            tmem_ld4(trow + nb0 + 2 * BN, vh);
-            tmem_ld4(trow + nb0 + 3 * BN, vl);
-          }
-          if (has1) {
-            tmem_ld4(trow + nb0 + 4 * EPI_E, mh1);
-            tmem_ld4(trow + nb0 + 4 * EPI_E + BN, ml1);
-            tmem_ld4(trow + nb0 + 4 * EPI_E + 2 * BN, vh1);
-            tmem_ld4(trow + nb0 + 4 * EPI_E + 3 * BN, vl1);
-          }
-          tmem_ld_wait();
+      const int outer = outer0 + hb * 8 * a.Wo + wg * 8, pix = pix0 + hb * pix_hb + wg * pix_wg;
+      float* const dst = a.y + brow * img_out + (int64_t)pix * a.N;
+      const float* const inj = a.eps.injected ? a.eps.injected + (brow * HoWo + outer) * a.N : nullptr;
+      const float* const zrow = a.z ? a.z + brow * a.N : nullptr;
+      mbar_wait(&tfull[grp], k & 1);
+      tc_fence_after();
+      float mh[4], ml[4], vh[4], vl[4];
+      tmem_ld4(trow, mh);
+      tmem_ld4(trow + BN, ml);
+      tmem_ld4(trow + 2 * BN, vh);
+      tmem_ld4(trow + 3 * BN, vl);
+#pragma unroll 1
+      for (int q = 0; q < nq; ++q) {
+        const int nb = 4 * q;
+        tmem_ld_wait();
+        float mv[4], vv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mv[j] = mh[j] + ml[j];
+          vv[j] = vh[j] + vl[j];
+        }
+        if (q + 1 < nq) {  // the next quad's accumulators travel while this one is computed
+          tmem_ld4(trow + nb + 4, mh);
+          tmem_ld4(trow + nb + 4 + BN, ml);
+          tmem_ld4(trow + nb + 4 + 2 * BN, vh);
+          tmem_ld4(trow + nb + 4 + 3 * BN, vl);
+        } else {           // everything is in registers: hand the buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);  // the accumulator is in registers now
-          if (has0) {
-            float e[4];
-            if (inj_img) {
-              const float4 t = *reinterpret_cast<const float4*>(inj_img + (int64_t)outer * a.N + nb0);
-              e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
-            } else {
-              philox_normal4(a.eps, grow, (uint32_t)outer, (uint32_t)e0, e);
-            }
-            float o[4];
+          if (lane == 0) mbar_arrive(&tempty[grp]);
+        }
+        float e[4];
+        if (inj) {
+          const float4 t = *reinterpret_cast<const float4*>(inj + nb);
+          e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+        } else {
+          philox_normal4(a.eps, grow, (uint32_t)outer, (uint32_t)q, e);
+        }
+        float4 zq = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (zrow) zq = __ldg(reinterpret_cast<const float4*>(zrow + nb));
+        const float zz[4] = {zq.x, zq.y, zq.z, zq.w};
+        const float4 bmq = *reinterpret_cast<const float4*>(bias_s + nb);
+        const float4 bvq = *reinterpret_cast<const float4*>(bias_s + BN + nb);
+        const float bm4[4] = {bmq.x, bmq.y, bmq.z, bmq.w}, bv4[4] = {bvq.x, bvq.y, bvq.z, bvq.w};
+        float o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float mean = ((mh[j] + ml[j]) + bm0[j]) * z0[j];
-              const float sd = sqrt_fast((vh[j] + vl[j]) + bv0[j]);
-              o[j] = fmaf(sd, e[j], mean);
-            }
-            if (a.pool) {
+        for (int j = 0; j < 4; ++j) {
+          const float mean = (mv[j] + bm4[j]) * zz[j];
+          const float sd = sqrt_fast(vv[j] + bv4[j]);
+          o[j] = fmaf(sd, e[j], mean);
+        }
+        if (a.pool) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float v = fmaxf(o[j], __shfl_xor_sync(0xffffffffu, o[j], 1));   // wo pair
-                v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));              // ho pair
-                o[j] = fmaxf(v, 0.f);
-              }
-            }
-            if (st) *reinterpret_cast<float4*>(dst_img + (int64_t)pix * a.N + nb0) = make_float4(o[0], o[1], o[2], o[3]);
-          }
-          if (has1) {  // N > 20: a second quad per warp; constants are fetched in place
-            const int nb1 = nb0 + 4 * EPI_E;
-            float e[4];
-            if (inj_img) {
-              const float4 t = *reinterpret_cast<const float4*>(inj_img + (int64_t)outer * a.N + nb1);
-              e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
-            } else {
-              philox_normal4(a.eps, grow, (uint32_t)outer, (uint32_t)(e0 + EPI_E), e);
-            }
-            float4 zq = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (a.z) zq = __ldg(reinterpret_cast<const float4*>(a.z + brow * a.N + nb1));
-            const float zz[4] = {zq.x, zq.y, zq.z, zq.w};
-            float o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float mean = ((mh1[j] + ml1[j]) + bias_s[nb1 + j]) * zz[j];
-              const float sd = sqrt_fast((vh1[j] + vl1[j]) + bias_s[BN + nb1 + j]);
-              o[j] = fmaf(sd, e[j], mean);
-            }
-            if (a.pool) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float v = fmaxf(o[j], __shfl_xor_sync(0xffffffffu, o[j], 1));
-                v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
-                o[j] = fmaxf(v, 0.f);
-              }
-            }
-            if (st) *reinterpret_cast<float4*>(dst_img + (int64_t)pix * a.N + nb1) = make_float4(o[0], o[1], o[2], o[3]);
+          for (int j = 0; j < 4; ++j) {
+            float v = fmaxf(o[j], __shfl_xor_sync(0xffffffffu, o[j], 1));   // wo pair
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));              // ho pair
+            o[j] = fmaxf(v, 0.f);
           }
         }
+        if (st) *reinterpret_cast<float4*>(dst + nb) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
   } else if (warp == MMA_WARP) {
