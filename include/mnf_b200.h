@@ -203,6 +203,17 @@ int mnf_dense_forward(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const float
                       const float* mean_W, const float* log_std_W, const float* mean_b,
                       const float* log_var_b, float max_std, const mnf_noise* eps,
                       float* y, float* sd_out);
+/* The same with the activation that follows the layer in the reference's models applied in the
+ * kernel's epilogue (mnf_lenet.py:29-32: MNFDense, ReLU, MNFDense, Softmax; inference only --
+ * sd_out then belongs to the pre-activation).  mnf_dense_can_fuse_act tells whether a shape /
+ * math mode supports it (ReLU: tensor-core path and N <= 16; Softmax: N <= 16); otherwise
+ * mnf_dense_forward_act returns MNF_ERR_UNSUPPORTED and the caller runs the stock layer. */
+enum { MNF_ACT_NONE = 0, MNF_ACT_RELU = 1, MNF_ACT_SOFTMAX = 2 };
+int mnf_dense_can_fuse_act(mnf_ctx* ctx, int64_t K, int64_t N, int32_t act, int32_t* ok);
+int mnf_dense_forward_act(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const float* x, const float* z,
+                          const float* mean_W, const float* log_std_W, const float* mean_b,
+                          const float* log_var_b, float max_std, const mnf_noise* eps, int32_t act,
+                          float* y, float* sd_out);
 /* App. A-1.  Outputs (all may be NULL to skip): dx [B,K], dz [B,K], d_mean_W, d_log_std_W [K,N],
  * d_mean_b, d_log_var_b [N] (overwritten, not accumulated). */
 int mnf_dense_backward(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const float* x, const float* z,

@@ -39,6 +39,8 @@ def test_dense_tensorcore(tc_ctx, K, N, B, use_z):
     lyr = make_layer(P, x.shape, use_z=use_z)
     inj = dict(eps_out=_f32(eps))
     want_path = "paired_umma<128>" if N >= 256 else "paired_umma<64>"
+    if N <= 16 and K % 4 == 0 and K * ((N + 3) // 4 * 4) <= 12288:
+        want_path = "dense_small"  # warp-per-row FFMA kernel of the classifier head
     if use_z:
         inj["eps_z"] = _f32(eps_z)
     close(lyr(_f32(x), noise=inj).numpy(), ref, RTOL, "dense call (tf32x3)")
@@ -185,3 +187,42 @@ def test_conv_fused_relu_pool_equals_unfused(tc_ctx, math, shape, wshape):
         np.testing.assert_array_equal(y_fused.numpy(), y_ref.numpy())
     else:  # FFMA path with F > 20 has no fused epilogue: the call must have stayed unfused
         assert math == "fp32" and wshape[-1] > 20 and y_fused.shape[1] == shape[1] - wshape[0] + 1
+
+
+@pytest.mark.parametrize("math", ["tf32x3", "fp32"])
+@pytest.mark.parametrize("K,N,B,act", [(500, 10, 257, "softmax"), (500, 10, 64, "relu"), (800, 500, 130, "relu"),
+                                       (64, 16, 33, "softmax"), (24, 4, 5, None)])
+def test_dense_fused_activation(tc_ctx, math, K, N, B, act):
+    """MNFDense with the following ReLU / Softmax folded into the kernel's epilogue
+    (mnf_dense_forward_act) == MNFDense, then the stock layer; the small-N kernel (N <= 16) is also
+    pinned against the float64 oracle."""
+    from tf_mnf_b200 import _lib as L
+    from tf_mnf_b200.models import ReLU, Softmax
+
+    tc_ctx.set_math(math)
+    rng = np.random.RandomState(K + N)
+    P = O.make_layer_params(rng, (K, N), flow="rnvp", std_init=10.0, dtype=np.float64)
+    P["mean_b"][...] = 0.1 * rng.standard_normal(N)
+    x = rng.standard_normal((B, K))
+    eps_z, eps = rng.standard_normal((B, K)), rng.standard_normal((B, N))
+    bern = [(rng.uniform(size=(B, K)) <= 0.5).astype(np.float64) for _ in range(2)]
+    lyr = make_layer(P, x.shape)
+    inj = dict(eps_z=_f32(eps_z), eps_out=_f32(eps), bern_q=[_f32(b) for b in bern])
+    y_plain = lyr.call(_f32(x), noise=inj)
+    if N <= 16:
+        assert L.last_path() == "dense_small", L.last_path()
+        ref, _ = O.dense_call(P, x, eps_z, eps, 1.0, bern_q=bern)
+        close(y_plain.numpy(), ref, RTOL, "small-N dense vs oracle")
+    if act is None:
+        return
+    y_fused = lyr.call(_f32(x), noise=inj, activation=act)
+    stock = ReLU() if act == "relu" else Softmax()
+    y_ref = stock(y_plain).numpy()
+    if lyr.last_fused:
+        if act == "relu":
+            np.testing.assert_array_equal(y_fused.numpy(), y_ref)
+        else:
+            np.testing.assert_allclose(y_fused.numpy(), y_ref, rtol=2e-6, atol=1e-7)
+    else:  # FFMA path for wide layers has no fused epilogue: the call stayed unfused
+        assert math == "fp32" and N > 16
+        np.testing.assert_array_equal(y_fused.numpy(), y_plain.numpy())

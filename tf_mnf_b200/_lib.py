@@ -97,6 +97,8 @@ SIGNATURES = {
     "mnf_flow_backward": [vp, _i64, _i64, _i32, C.POINTER(FlowStep), vp, vp, vp, vp, vp, vp, C.POINTER(FlowStep)],
     "mnf_sample_z_backward": [vp, _i64, _i64, vp, vp, C.POINTER(Noise), vp, vp],
     "mnf_dense_forward": [vp, _i64, _i64, _i64, vp, vp, vp, vp, vp, vp, _f, C.POINTER(Noise), vp, vp],
+    "mnf_dense_forward_act": [vp, _i64, _i64, _i64, vp, vp, vp, vp, vp, vp, _f, C.POINTER(Noise), C.c_int32, vp, vp],
+    "mnf_dense_can_fuse_act": [vp, _i64, _i64, C.c_int32, C.POINTER(C.c_int32)],
     "mnf_dense_backward": [vp, _i64, _i64, _i64, vp, vp, vp, vp, vp, _f, C.POINTER(Noise), vp, vp,
                            vp, vp, vp, vp, vp, vp],
     "mnf_conv_out_hw": [C.POINTER(ConvShape), C.POINTER(_i64), C.POINTER(_i64)],
@@ -118,6 +120,7 @@ SIGNATURES = {
     "mnf_tile_rows": [vp, _i64, _i64, _i64, vp, vp],
     "mnf_adam_step": [vp, _i64, vp, vp, vp, vp, _f, _f, _f, _f, _i32],
 }
+MNF_ACT_NONE, MNF_ACT_RELU, MNF_ACT_SOFTMAX = 0, 1, 2
 NON_STATUS = {"mnf_version": ([], C.c_int), "mnf_last_error": ([], C.c_char_p), "mnf_last_path": ([], C.c_char_p)}
 ALL_SYMBOLS = sorted([*SIGNATURES, *NON_STATUS])
 

@@ -72,7 +72,7 @@ int mnf_conv_win_umma_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, co
 int mnf_tc_paired_forward(mnf_ctx* ctx, int conv, int64_t M, int K, int N, const float* x, const float* z,
                           const float* mean_W, const float* log_std_W, const float* mean_b, const float* log_var_b,
                           float max_std, const NoiseDev& eps, float* y, float* mean_out, float* sd_out,
-                          const int* geo);  // conv geo: H,W,C,kh,kw,Ho,Wo,stride,pad_t,pad_l,pool
+                          const int* geo, int act = 0);  // conv geo: H,W,C,kh,kw,Ho,Wo,stride,pad_t,pad_l,pool; act 1 = ReLU (dense)
 void* mnf_workspace(mnf_ctx* ctx, size_t bytes);  // nullptr on failure (error set)
 void mnf_note_path(const char* name);              // which kernel family served the last forward call (mnf_last_path)
 // Where a call's packed weights go.  Not frozen: the transient workspace, *fresh = true (pack every

@@ -486,6 +486,126 @@ static int launch_paired(mnf_ctx* ctx, const PairedArgs& a) {
   return MNF_OK;
 }
 
+// ------------------------------------------------------------------ dense layers with few outputs
+// MNFDense.call (mnf_dense.py:159-170) for N <= 16 (the classifier head: 500 -> 10).  A 128-row
+// tensor-core tile would waste 5/6 of its columns; here a warp owns a row: lanes split K (float4
+// along k, weights transposed in shared memory so that the reads are conflict-free), 2N partial
+// sums per lane, butterfly reduction, lane n finishes output n: bias, Philox eps, optional ReLU or
+// Softmax (warp-wide, same formula as softmax_kernel) -- one launch instead of GEMM + activation.
+struct SmallDenseArgs {
+  int64_t B;
+  int K, N, act;  // act: 0 none, 1 ReLU, 2 Softmax
+  const float *x, *z, *Wm, *Ls, *bm, *lvb;
+  float max_std;
+  float *y, *sd_out;
+  NoiseDev eps;
+};
+constexpr int SD_NMAX = 16;
+
+// NT: N rounded up to a multiple of 4 (compile-time loop bounds; the padding weights are zero)
+template <int NT>
+__global__ void __launch_bounds__(256) dense_small_fwd(SmallDenseArgs a) {
+  extern __shared__ __align__(16) float sd_smem[];
+  const int K4 = a.K >> 2, Kp = a.K + 4;        // transposed rows padded by one float4
+  float* Wt = sd_smem;                           // [N][Kp]  mean weights
+  float* Vt = Wt + NT * Kp;                      // [NT][Kp] clipped variances
+  for (int i = threadIdx.x; i < (NT - a.N) * Kp; i += blockDim.x) {  // zero rows of the padding outputs
+    Wt[a.N * Kp + i] = 0.f;
+    Vt[a.N * Kp + i] = 0.f;
+  }
+  {
+    const int tot = a.K * a.N;
+    for (int i0 = threadIdx.x; i0 < tot; i0 += 4 * blockDim.x) {  // four independent loads in flight
+      float w[4], l[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        w[u] = i < tot ? __ldg(a.Wm + i) : 0.f;
+        l[u] = i < tot ? __ldg(a.Ls + i) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < tot) {
+          const int k = i / a.N, n = i - k * a.N;
+          Wt[n * Kp + k] = w[u];
+          const float sd = fminf(expf(l[u]), a.max_std);
+          Vt[n * Kp + k] = sd * sd;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const float bmn = lane < a.N ? a.bm[lane] : 0.f;
+  const float vbn = lane < a.N ? fminf(expf(a.lvb[lane]), a.max_std * a.max_std) : 1.f;
+  constexpr int UI = 4;  // k4 iterations whose loads are issued together (K <= 512 in one go)
+  const int64_t rstride = (int64_t)gridDim.x * wpb;
+  for (int64_t row = blockIdx.x * (int64_t)wpb + warp; row < a.B; row += rstride) {
+    float am[NT], av[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) am[n] = av[n] = 0.f;
+    const float4* xr = reinterpret_cast<const float4*>(a.x + row * a.K);
+    const float4* zr = a.z ? reinterpret_cast<const float4*>(a.z + row * a.K) : nullptr;
+    for (int kb = 0; kb < K4; kb += 32 * UI) {
+      float4 xv[UI], zv[UI];
+#pragma unroll
+      for (int u = 0; u < UI; ++u) {
+        const int k4 = kb + lane + 32 * u;
+        xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        zv[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (k4 < K4) {
+          xv[u] = __ldg(xr + k4);
+          if (zr) zv[u] = __ldg(zr + k4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UI; ++u) {
+        const int k4 = kb + lane + 32 * u;
+        if (k4 < K4) {
+          const float xz[4] = {xv[u].x * zv[u].x, xv[u].y * zv[u].y, xv[u].z * zv[u].z, xv[u].w * zv[u].w};
+          const float x2[4] = {xv[u].x * xv[u].x, xv[u].y * xv[u].y, xv[u].z * xv[u].z, xv[u].w * xv[u].w};
+          const float* wp = Wt + 4 * k4;
+          const float* vp = Vt + 4 * k4;
+#pragma unroll
+          for (int n = 0; n < NT; ++n) {
+            const float4 w = *reinterpret_cast<const float4*>(wp + n * Kp);
+            const float4 v = *reinterpret_cast<const float4*>(vp + n * Kp);
+            am[n] = fmaf(xz[0], w.x, fmaf(xz[1], w.y, fmaf(xz[2], w.z, fmaf(xz[3], w.w, am[n]))));
+            av[n] = fmaf(x2[0], v.x, fmaf(x2[1], v.y, fmaf(x2[2], v.z, fmaf(x2[3], v.w, av[n]))));
+          }
+        }
+      }
+    }
+    float mean = 0.f, var = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const float m = warp_sum(am[n]), v = warp_sum(av[n]);
+      if (n == lane) { mean = m; var = v; }
+    }
+    float out = 0.f;
+    if (lane < a.N) {
+      const float sd = sqrtf(var + vbn);
+      if (a.sd_out) a.sd_out[row * a.N + lane] = sd;
+      out = fmaf(sd, noise_normal1(a.eps, row, 0u, (uint32_t)lane, 1, a.N), mean + bmn);
+      if (a.act == 1) out = fmaxf(out, 0.f);
+    }
+    if (a.act == 2) {  // warp-wide softmax over the N outputs (stock.cu:softmax_kernel arithmetic)
+      float mx = lane < a.N ? out : -INFINITY;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float e = lane < a.N ? expf(out - mx) : 0.f;
+      const float ssum = warp_sum(e);
+      out = e / ssum;
+    }
+    if (lane < a.N) a.y[row * a.N + lane] = out;
+  }
+}
+
+static bool small_dense_ok(int64_t K, int64_t N, const float* x, const float* z) {
+  return N <= SD_NMAX && (K & 3) == 0 && K * ((N + 3) & ~3) <= 12288 && (((uintptr_t)x | (uintptr_t)z) & 15) == 0;
+}
+
 // workspace layout for one layer call: Vw [K*N] then vb [N]
 static int prep_var(mnf_ctx* ctx, int64_t KN, int N, const float* Ls, const float* lvb, float max_std, float** Vw,
                     float** vb) {
@@ -545,16 +665,64 @@ int mnf_conv2d_can_fuse_pool(mnf_ctx* ctx, const mnf_conv_shape* s, int32_t* ok)
   return MNF_OK;
 }
 
-int mnf_dense_forward(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const float* x, const float* z,
-                      const float* mean_W, const float* log_std_W, const float* mean_b, const float* log_var_b,
-                      float max_std, const mnf_noise* eps, float* y, float* sd_out) {
+// which activations the forward kernel of this shape / math mode can apply in its epilogue
+static bool dense_act_ok(const mnf_ctx* ctx, int64_t K, int64_t N, const float* x, const float* z, int act) {
+  if (act == MNF_ACT_NONE) return true;
+  if (small_dense_ok(K, N, x, z)) return act == MNF_ACT_RELU || act == MNF_ACT_SOFTMAX;
+  return act == MNF_ACT_RELU && ctx->math_mode == MNF_MATH_TF32X3;
+}
+
+int mnf_dense_can_fuse_act(mnf_ctx* ctx, int64_t K, int64_t N, int32_t act, int32_t* ok) {
+  MNF_CHECK_ARG(ctx && ok && K >= 1 && N >= 1, "mnf_dense_can_fuse_act: bad argument");
+  MNF_CHECK_ARG(act >= MNF_ACT_NONE && act <= MNF_ACT_SOFTMAX, "mnf_dense_can_fuse_act: unknown activation %d", act);
+  *ok = dense_act_ok(ctx, K, N, nullptr, nullptr, act) ? 1 : 0;  // buffers from this library are 256-byte aligned
+  return MNF_OK;
+}
+
+int mnf_dense_forward_act(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const float* x, const float* z,
+                          const float* mean_W, const float* log_std_W, const float* mean_b, const float* log_var_b,
+                          float max_std, const mnf_noise* eps, int32_t act, float* y, float* sd_out) {
   MNF_CHECK_ARG(ctx && x && mean_W && log_std_W && mean_b && log_var_b && y, "mnf_dense_forward: NULL argument");
   MNF_CHECK_ARG(B >= 0 && K >= 1 && N >= 1 && K < (1 << 30) && N < (1 << 30), "mnf_dense_forward: bad shape");
   MNF_CHECK_ARG(eps, "mnf_dense_forward: eps noise spec is NULL");
+  MNF_CHECK_ARG(act >= MNF_ACT_NONE && act <= MNF_ACT_SOFTMAX, "mnf_dense_forward: unknown activation %d", act);
+  if (!dense_act_ok(ctx, K, N, x, z, act)) {
+    mnf_set_error("mnf_dense_forward: activation %d cannot be fused for K=%lld N=%lld in this math mode", act,
+                  (long long)K, (long long)N);
+    return MNF_ERR_UNSUPPORTED;
+  }
   if (B == 0) return MNF_OK;
+  if (small_dense_ok(K, N, x, z)) {
+    SmallDenseArgs a;
+    a.B = B; a.K = (int)K; a.N = (int)N; a.act = act;
+    a.x = x; a.z = z; a.Wm = mean_W; a.Ls = log_std_W; a.bm = mean_b; a.lvb = log_var_b;
+    a.max_std = max_std; a.y = y; a.sd_out = sd_out; a.eps = make_noise(eps);
+    const int NT = ((int)N + 3) & ~3;
+    const size_t smem = sizeof(float) * 2 * (size_t)NT * (K + 4);
+    auto kern = NT == 4 ? dense_small_fwd<4> : NT == 8 ? dense_small_fwd<8> : NT == 12 ? dense_small_fwd<12> : dense_small_fwd<16>;
+    static size_t attr_smem[4] = {0, 0, 0, 0};
+    if (smem > attr_smem[NT / 4 - 1]) {
+      MNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem[NT / 4 - 1] = smem;
+    }
+    // latency-bound per warp (load -> FMAs -> shuffles -> Philox): fill the SMs with warps, as many
+    // CTAs per SM as the transposed weights in shared memory allow
+    const int64_t blocks = cdiv(B, 8);
+    int per_sm = 1;
+    MNF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    per_sm = per_sm < 1 ? 1 : per_sm;  // one wave of resident CTAs; rows are grid-strided
+    const int64_t cap = (int64_t)ctx->sm_count * per_sm;
+    const int grid = (int)(blocks < cap ? blocks : cap);
+    mnf_note_path("dense_small");
+    const bool probed = mnf_probe_begin(ctx, MNF_PROBE_DENSE_GEMM);
+    kern<<<grid, 256, smem, ctx->stream>>>(a);
+    mnf_probe_end(ctx, probed);
+    MNF_LAUNCHED(ctx);
+    return MNF_OK;
+  }
   if (ctx->math_mode == MNF_MATH_TF32X3)
     return mnf_tc_paired_forward(ctx, 0, B, (int)K, (int)N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std,
-                                 make_noise(eps), y, nullptr, sd_out, nullptr);
+                                 make_noise(eps), y, nullptr, sd_out, nullptr, act);
   float *Vw, *vb;
   // note: the second rounded-up offset inside prep_var must match (K*N padded to 4)
   int rc = prep_var(ctx, K * N, (int)N, log_std_W, log_var_b, max_std, &Vw, &vb);
@@ -564,6 +732,13 @@ int mnf_dense_forward(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const float
   a.x = x; a.z = z; a.Wm = mean_W; a.Vw = Vw; a.bm = mean_b; a.vb = vb;
   a.y = y; a.mean_out = nullptr; a.sd_out = sd_out; a.eps = make_noise(eps);
   return launch_paired<false>(ctx, a);
+}
+
+int mnf_dense_forward(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const float* x, const float* z,
+                      const float* mean_W, const float* log_std_W, const float* mean_b, const float* log_var_b,
+                      float max_std, const mnf_noise* eps, float* y, float* sd_out) {
+  return mnf_dense_forward_act(ctx, B, K, N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std, eps, MNF_ACT_NONE, y,
+                               sd_out);
 }
 
 int mnf_conv2d_forward(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, const float* z, const float* mean_W,

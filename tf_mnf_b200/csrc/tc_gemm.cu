@@ -46,6 +46,7 @@ struct Args {
   NoiseDev eps;
   int H, W, C, kh, kw, Ho, Wo, stride, pad_t, pad_l;
   int vec;           // 16-byte gathers legal (conv: C % 4 == 0; dense: K % 4 == 0)
+  int act;           // dense: 1 = ReLU fused into the epilogue
   int pool;          // conv: ReLU + 2x2 max-pool fused into the copy-out (ntiles == 1, BM % (2 Wo) == 0)
 };
 
@@ -271,7 +272,8 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
                   if (a.mean_out) a.mean_out[m * a.N + n] = mean;
                   if (a.z) mean *= __ldg(a.z + brow * a.N + n);
                 }
-                ys[r * ldy + c0 + 4 * q + j] = fmaf(sd, e[j], mean);
+                const float out = fmaf(sd, e[j], mean);
+                ys[r * ldy + c0 + 4 * q + j] = (!CONV && a.act == 1) ? fmaxf(out, 0.f) : out;
               }
             }
           }
@@ -685,9 +687,10 @@ static int launch(mnf_ctx* ctx, Args& a, const float* mean_W, const float* log_s
 int mnf_tc_paired_forward(mnf_ctx* ctx, int conv, int64_t M, int K, int N, const float* x, const float* z,
                           const float* mean_W, const float* log_std_W, const float* mean_b, const float* log_var_b,
                           float max_std, const NoiseDev& eps, float* y, float* mean_out, float* sd_out,
-                          const int* geo) {
+                          const int* geo, int act) {
   tc::Args a = {};
   a.pool = (conv && geo[10]) ? 1 : 0;
+  a.act = conv ? 0 : act;
   a.M = M; a.K = K; a.N = N;
   a.x = x; a.z = z; a.bm = mean_b; a.y = y; a.mean_out = mean_out; a.sd_out = sd_out; a.eps = eps;
   if (conv) {

@@ -32,8 +32,11 @@ class MNFDense(MNFLayerBase):
         self.n_in = int(input_shape[-1])
         self._build_common((self.n_in, self.n_out), self.n_in)
 
-    def call(self, x: Any, noise: dict | None = None) -> DeviceArray:  # noqa: A002
-        """mnf_dense.py:159-170.  noise: optional injected draws {eps_z [B,n_in], bern_q [...], eps_out [B,n_out]}."""
+    def call(self, x: Any, noise: dict | None = None, activation: str | None = None) -> DeviceArray:  # noqa: A002
+        """mnf_dense.py:159-170.  noise: optional injected draws {eps_z [B,n_in], bern_q [...], eps_out [B,n_out]}.
+        activation: "relu" / "softmax" asks the kernel to also apply the stock layer that follows in
+        MNFLeNet / MNFFeedForward (mnf_lenet.py:29-32); `self.last_fused` tells whether it did (not
+        when training, nor for shapes / math modes whose epilogue does not cover it)."""
         self.ctx = self.ctx or default_context()
         x = as_device(x, self.ctx)
         if x.ndim != 2:
@@ -51,9 +54,17 @@ class MNFDense(MNFLayerBase):
         eps = nz.make(self.seed, self.call_index, self.uid, nz.CALL_OUT, self.row_offset, eo)
         y = ctx.empty((B, self.n_out))
         sd = ctx.empty((B, self.n_out)) if self.training else None
-        L.check(ctx.lib.mnf_dense_forward(ctx.handle, B, self.n_in, self.n_out, _p(x), _p(z), _p(self.mean_W),
-                                          _p(self.log_std_W), _p(self.mean_b), _p(self.log_var_b),
-                                          self.max_std, C.byref(eps), _p(y), _p(sd)))
+        act = L.MNF_ACT_NONE
+        self.last_fused = False
+        if activation is not None and not self.training:
+            want = {"relu": L.MNF_ACT_RELU, "softmax": L.MNF_ACT_SOFTMAX}[activation]
+            ok = C.c_int32(0)
+            L.check(ctx.lib.mnf_dense_can_fuse_act(ctx.handle, self.n_in, self.n_out, want, C.byref(ok)))
+            if ok.value:
+                act, self.last_fused = want, True
+        L.check(ctx.lib.mnf_dense_forward_act(ctx.handle, B, self.n_in, self.n_out, _p(x), _p(z), _p(self.mean_W),
+                                              _p(self.log_std_W), _p(self.mean_b), _p(self.log_var_b),
+                                              self.max_std, C.byref(eps), act, _p(y), _p(sd)))
         if self.training:
             self._tape = dict(x=x, z=z, run=run, sd=sd, eps=eps, eps_keep=eo)
         self.call_index += 1

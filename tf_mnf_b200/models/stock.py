@@ -137,6 +137,9 @@ class Sequential:
                 if isinstance(nxt, ReLUMaxPool2D) and hasattr(lyr, "n_filters") and not lyr.training:
                     x = lyr.call(x, noise=next(it, None), fuse_relu_pool=True)
                     skip = lyr.last_fused
+                elif type(nxt) in (ReLU, Softmax) and hasattr(lyr, "n_out") and not lyr.training:
+                    x = lyr.call(x, noise=next(it, None), activation="relu" if type(nxt) is ReLU else "softmax")
+                    skip = lyr.last_fused
                 else:
                     x = lyr(x, noise=next(it, None))
                 if first is not None and lyr is first[0]:
