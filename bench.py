@@ -429,7 +429,8 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
                          "peak_source": which, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms,
                          "algorithmic_bytes_per_launch": k_bytes,
                          "pipe": ("tcgen05.mma kind::f16, power-of-two scaled fp16 hi/lo split of both operands, fp32 "
-                                  "accumulate (fp32 parity <=1e-5 rel.); bound in practice by the L2->SM weight stream"
+                                  "accumulate (fp32 parity <=1e-5 rel.); bound in practice by the shared-memory operand fetch of its "
+                                  "N=64 SS-mode MMAs (DESIGN.md section 4); kernel_ms is the in-situ time, side streams running"
                                   if args.math == "tf32x3" else "fp32 FFMA (parity path, <=1e-5 rel.)"),
                          "algorithmic_tflops": CONV2_FLOP_PER_ROW * ROWS / (k_ms * 1e-3) / 1e12},
             "wall_s_timed_region": t_wall,
