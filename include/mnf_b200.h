@@ -136,6 +136,8 @@ typedef struct {
   uint32_t stream;       /* sub-stream: distinguishes layers / draws */
   uint32_t reserved;
   const float* injected; /* if non-NULL: read the draw from here instead ([rows, outer, inner]) */
+  const uint32_t* call_delta; /* if non-NULL: a DEVICE counter added to the call index (high key word) when the
+                               * kernel runs -- how a captured CUDA graph draws fresh noise on every replay */
 } mnf_noise;
 
 /* Materialise exactly the values a kernel would draw for (seed, stream, row_offset):
@@ -303,6 +305,8 @@ int mnf_mse_loss(mnf_ctx* ctx, int64_t n, const float* y, const float* target, f
 /* y = a*x + b (inference-mode BatchNormalization in MNFFeedForward), generic axpby helpers */
 int mnf_scale(mnf_ctx* ctx, int64_t n, float a, const float* x, float* y);
 int mnf_axpy(mnf_ctx* ctx, int64_t n, float a, const float* x, float* y); /* y += a*x */
+/* *counter += inc on the device (the replay counter of a captured step, see mnf_noise.call_delta) */
+int mnf_u32_add(mnf_ctx* ctx, uint32_t* counter, uint32_t inc);
 /* dst[(i * repeat + s) * row_elems + e] = src[i * row_elems + e]: the batch of a Monte-Carlo
  * prediction (every input row `repeat` times, np.repeat(x, repeat, axis=0)) formed on the
  * device, so only the distinct rows cross PCIe. */

@@ -127,3 +127,52 @@ def test_frozen_weights_are_bit_identical_and_unfreeze_sees_updates(math):
     finally:
         ctx.freeze_weights(False)
         ctx.set_math("fp32")
+
+
+def test_captured_step_replays_match_eager_calls():
+    """A forward + kl_div step captured into a CUDA graph: replay i == eager call i bit for bit
+    (the device-side replay counter reproduces the eager call indices), and eager calls after the
+    graph keep drawing fresh noise."""
+    import tf_mnf_b200 as M
+    from tf_mnf_b200.graph import CapturedStep
+
+    ctx = M.default_context()
+    ctx.set_math("tf32x3")
+    try:
+        x = np.random.RandomState(9).uniform(size=(64, 28, 28, 1)).astype(np.float32)
+        ref = _lenet()
+        ref.presample_first = False
+        ref(x)  # build
+        ref.freeze_weights(True)
+        ys_ref, kls_ref = [], []
+        for _ in range(6):
+            ys_ref.append(ref(x).numpy())
+            kls_ref.append(float(ref.kl_div().numpy()[0]))
+
+        mdl = _lenet()
+        mdl(x)
+        mdl.freeze_weights(True)
+        xd = ctx.to_device(x)
+        lanes = [ctx.fork() for _ in range(2)]
+
+        def step():
+            for c in lanes:
+                c.wait(ctx)
+            y = mdl(xd)
+            kl = mdl.kl_div(ctx=lanes)
+            ctx.wait(lanes[0])
+            return y, kl
+
+        # CapturedStep runs the step twice eagerly (warm-up, pool stocking), then captures call 3
+        g = CapturedStep(ctx, step, forks=lanes + mdl._sides, layers=mdl.mnf_layers, models=[mdl])
+        for i in range(3):
+            y, kl = g.launch()
+            ctx.sync()
+            np.testing.assert_array_equal(y.numpy(), ys_ref[2 + i])
+            assert float(kl.numpy()[0]) == kls_ref[2 + i]
+        y_after = mdl(xd).numpy()  # eager call after three replays = call index 5
+        np.testing.assert_array_equal(y_after, ys_ref[5])
+        g.close()
+    finally:
+        ctx.freeze_weights(False)
+        ctx.set_math("fp32")

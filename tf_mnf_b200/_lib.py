@@ -14,7 +14,7 @@ vp = C.c_void_p
 
 class Noise(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("row_offset", C.c_uint64), ("stream", C.c_uint32),
-                ("reserved", C.c_uint32), ("injected", vp)]
+                ("reserved", C.c_uint32), ("injected", vp), ("call_delta", vp)]
 
 
 class FlowStep(C.Structure):
@@ -118,6 +118,7 @@ SIGNATURES = {
     "mnf_scale": [vp, _i64, _f, vp, vp],
     "mnf_axpy": [vp, _i64, _f, vp, vp],
     "mnf_tile_rows": [vp, _i64, _i64, _i64, vp, vp],
+    "mnf_u32_add": [vp, vp, C.c_uint32],
     "mnf_adam_step": [vp, _i64, vp, vp, vp, vp, _f, _f, _f, _f, _i32],
 }
 MNF_ACT_NONE, MNF_ACT_RELU, MNF_ACT_SOFTMAX = 0, 1, 2

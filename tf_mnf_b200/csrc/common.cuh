@@ -147,15 +147,16 @@ struct NoiseDev {
   uint32_t stream;
   uint64_t row_offset;
   const float* injected;
+  const uint32_t* delta;  // device counter added to k1 (the call index) at run time, or nullptr
 };
 
 static inline NoiseDev make_noise(const mnf_noise* n) {
   NoiseDev d;
   if (n) {
     d.k0 = (uint32_t)n->seed; d.k1 = (uint32_t)(n->seed >> 32);
-    d.stream = n->stream; d.row_offset = n->row_offset; d.injected = n->injected;
+    d.stream = n->stream; d.row_offset = n->row_offset; d.injected = n->injected; d.delta = n->call_delta;
   } else {
-    d.k0 = d.k1 = 0; d.stream = 0; d.row_offset = 0; d.injected = nullptr;
+    d.k0 = d.k1 = 0; d.stream = 0; d.row_offset = 0; d.injected = nullptr; d.delta = nullptr;
   }
   return d;
 }
@@ -165,7 +166,8 @@ static inline NoiseDev make_noise(const mnf_noise* n) {
 // 8 bits of the stream word.
 __device__ __forceinline__ Philox4 philox_at(const NoiseDev& n, uint64_t grow, uint32_t outer, uint32_t inner4) {
   uint32_t c3 = n.stream ^ ((uint32_t)(grow >> 32) << 24);
-  return philox4x32_10(inner4, outer, (uint32_t)grow, c3, n.k0, n.k1);
+  const uint32_t k1 = n.delta ? n.k1 + __ldg(n.delta) : n.k1;  // captured graphs: fresh call index per replay
+  return philox4x32_10(inner4, outer, (uint32_t)grow, c3, n.k0, k1);
 }
 
 __device__ __forceinline__ float u01_open(uint32_t x) {  // (0,1), 24 bits

@@ -235,6 +235,15 @@ __global__ void tile_rows_kernel1(int64_t total, int64_t row, int64_t repeat, co
   }
 }
 
+__global__ void u32_add_kernel(uint32_t* p, uint32_t inc) { *p += inc; }
+
+int mnf_u32_add(mnf_ctx* ctx, uint32_t* counter, uint32_t inc) {
+  MNF_CHECK_ARG(ctx && counter, "mnf_u32_add: NULL argument");
+  u32_add_kernel<<<1, 1, 0, ctx->stream>>>(counter, inc);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
 int mnf_tile_rows(mnf_ctx* ctx, int64_t n_rows, int64_t row_elems, int64_t repeat, const float* src, float* dst) {
   MNF_CHECK_ARG(ctx && n_rows >= 0 && row_elems >= 0 && repeat >= 1, "mnf_tile_rows: bad argument");
   const int64_t total = n_rows * repeat * row_elems;

@@ -108,6 +108,7 @@ class Sequential:
     def __init__(self, layers=None) -> None:
         self.layers = list(layers or [])
         self.presample_z = True   # draw the later layers' z on side streams beside the first layers
+        self.presample_first = True  # ... and the first layer's z one call ahead (off inside captured graphs)
         self._sides: list = []    # one forked context per later MNF layer: their flow chains
         #                           (80-CTA kernels at 10k rows) pack the SMs side by side
 
@@ -125,7 +126,8 @@ class Sequential:
                     self._sides = [x.ctx.fork() for _ in mnf]
                 for lyr, side in zip(mnf, self._sides):
                     if lyr is self.mnf_layers[0]:
-                        first = (lyr, side)   # its z for THIS call was drawn during the previous call
+                        if self.presample_first:
+                            first = (lyr, side)   # its z for THIS call was drawn during the previous call
                     else:
                         lyr.presample(x.shape[0], side)
         for i, lyr in enumerate(self.layers):

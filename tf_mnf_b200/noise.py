@@ -17,6 +17,11 @@ def stream_id(layer_id: int, draw: int) -> int:
     return ((layer_id & 0xFFFF) << 8) | (draw & 0xFF)
 
 
+# While a step is being captured into a CUDA graph (graph.CapturedStep) every noise plan points at
+# the graph's device-side replay counter, so each replay draws with call index + replay number.
+_capture_delta: int | None = None
+
+
 def make(seed: int, call_index: int, layer_id: int, draw: int, row_offset: int = 0, injected: Any = None) -> L.Noise:
     """seed: user seed (low 32 bits are the Philox key low word); call_index makes every
     call draw fresh noise, as tf.random.normal does."""
@@ -26,4 +31,5 @@ def make(seed: int, call_index: int, layer_id: int, draw: int, row_offset: int =
     n.stream = stream_id(layer_id, draw)
     n.reserved = 0
     n.injected = C.c_void_p(injected.ptr) if injected is not None else None
+    n.call_delta = C.c_void_p(_capture_delta) if (_capture_delta and injected is None) else None
     return n

@@ -35,6 +35,7 @@ class Context:
         # and handed out again is only ever touched by LATER work of this context's stream, which
         # is exactly the guarantee of cudaFreeAsync + cudaMallocAsync on one stream -- without
         # the two library calls per temporary (a forward + KL step makes ~40 of them).
+        self._capture_keep: list | None = None  # graph capture: owners of every buffer handed out
         self._pool: dict[int, list[int]] = {}
         self._pooled_bytes = 0
         self.pool_limit_bytes = 2 << 30
@@ -48,10 +49,16 @@ class Context:
             ptr = free.pop()
             self._pooled_bytes -= nbytes
         else:
+            if getattr(self, "_capturing", False):
+                raise RuntimeError(f"buffer pool miss ({nbytes} bytes) while capturing a CUDA graph: the step "
+                                   "allocated differently from its warm-up pass")
             p = C.c_void_p()
             L.check(self.lib.mnf_malloc(self.handle, nbytes, C.byref(p)))
             ptr = p.value
-        return DeviceArray(self, ptr, shape, dtype, owner=_Owned(self, ptr, nbytes))
+        owner = _Owned(self, ptr, nbytes)
+        if self._capture_keep is not None:
+            self._capture_keep.append(owner)
+        return DeviceArray(self, ptr, shape, dtype, owner=owner)
 
     def trim(self) -> None:
         """Return the pooled blocks to the driver's stream-ordered pool."""
