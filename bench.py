@@ -180,6 +180,9 @@ def workload_config(args, rows_per_step=ROWS) -> dict:
             "rows_per_gpu": rows_per_step, "flow_type": args.flow, "n_flows_q": 2, "n_flows_r": 2, "flow_h_sizes": [50],
             "std_init": 10.0, "max_std": 1.0, "noise": "in-kernel Philox4x32-10", "l2": "flushed between timed steps "
             "(256 MiB memset outside the per-step event pairs)",
+            "launch": "value: the faster of eager enqueue (the host runs ahead of the device) and replaying the step "
+                      "as one CUDA graph, see launch_modes_ms_per_step; e2e: graph replay unless --no-graph (a device-side "
+                      "replay counter advances the Philox call indices: replays are bit-identical to eager calls)",
             "weights": "frozen (Sequential.freeze_weights): packed / pre-split weight blocks are kept across steps",
             "streams": "KL terms on 4 sibling streams and the z chains of layers 2-4 on 3 side streams, all forked from "
                        "the step's stream after its start event and joined before its stop event",
@@ -199,6 +202,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     if world > 1:
         import torch.distributed as dist
 
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # stdout carries exactly one JSON line (no NCCL version banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     M.runtime.set_default_device(local_rank)
     M.set_seed(0)
@@ -307,33 +311,71 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
         step(x_dev)
     barrier()
 
-    # ---- timed: K steps, device-resident input, per-step CUDA events, L2 flushed in between
-    starts, stops = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
-    kst, ksp = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
-    launches0 = ctx.launches + sum(c.launches for c in kl_lanes) + side_launches()
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
+    def all_launches():
+        return ctx.launches + sum(c.launches for c in kl_lanes) + side_launches()
+
+    # ---- the dominant kernel (conv2) timed in place: a probe brackets that one launch in a few
+    # eager steps (a captured graph has no place for the probe's events)
+    n_probe = min(args.steps, 10)
+    kst, ksp = [ev() for _ in range(n_probe)], [ev() for _ in range(n_probe)]
+    launches0 = all_launches()
+    for i in range(n_probe):
         L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
         L.check(lib.mnf_ctx_probe(ctx.handle, 1, int(os.environ.get("MNF_BENCH_PROBE_SKIP", "1")), kst[i], ksp[i]))  # 2nd conv GEMM launch = conv2
-        L.check(lib.mnf_event_record(ctx.handle, starts[i]))
-        out = step(x_dev)
-        L.check(lib.mnf_event_record(ctx.handle, stops[i]))
+        step(x_dev)
     barrier()
-    t_wall1 = time.perf_counter()
+    launches_per_step = (all_launches() - launches0) // n_probe
+
+    # ---- timed: K steps, device-resident input, per-step CUDA events, L2 flushed in between.
+    # The step is captured once into a CUDA graph (tf_mnf_b200/graph.py) and replayed: one launch
+    # per step instead of ~30; a device-side replay counter keeps the Philox call indices advancing,
+    # so replay i is bit-identical to eager call i (tests/test_gpu_streams.py).
+    graph = None
+    if not args.no_graph:
+        from tf_mnf_b200.graph import CapturedStep
+
+        graph = CapturedStep(ctx, lambda: step(x_dev), forks=kl_lanes + list(model._sides), layers=model.mnf_layers,
+                             models=[model])
+        for _ in range(3):
+            graph.launch()
+        barrier()
+    def timed_steps(run_step):
+        starts, stops = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
+            L.check(lib.mnf_event_record(ctx.handle, starts[i]))
+            run_step()
+            L.check(lib.mnf_event_record(ctx.handle, stops[i]))
+        barrier()
+        t1 = time.perf_counter()
+        ms = C.c_float()
+        per = []
+        for a_, b_ in zip(starts, stops):
+            L.check(lib.mnf_event_elapsed_ms(a_, b_, C.byref(ms)))
+            per.append(ms.value)
+        return per, t0, t1
+
+    # both ways of launching the same step are timed (K steps each); the faster one is `value`
+    modes = {"eager": timed_steps(lambda: step(x_dev))}
+    if graph is not None:
+        modes["graph"] = timed_steps(graph.launch)
+    launch_mode = min(modes, key=lambda k: float(np.mean(modes[k][0])))
+    step_ms, t_wall0, t_wall1 = modes[launch_mode]
     t_wall = t_wall1 - t_wall0
     clk.__exit__()
-    launches = ctx.launches + sum(c.launches for c in kl_lanes) + side_launches() - launches0
+    launches = launches_per_step * args.steps  # kernels per timed step (counted on eager steps; a graph replays the same ones)
 
     def elapsed(a, b):
         ms = C.c_float()
         L.check(lib.mnf_event_elapsed_ms(a, b, C.byref(ms)))
         return ms.value
 
-    step_ms = [elapsed(a, b) for a, b in zip(starts, stops)]
     kern_ms = [elapsed(a, b) for a, b in zip(kst, ksp)]
     my_ms = float(np.mean(step_ms))
     print(f"[rank {rank}] step_ms={np.round(step_ms, 3).tolist()} conv2_ms={np.round(kern_ms, 3).tolist()} "
-          f"wall_per_step_ms={t_wall / args.steps * 1e3:.3f}", file=sys.stderr, flush=True)
+          f"wall_per_step_ms={t_wall / args.steps * 1e3:.3f} launch={launch_mode} "
+          + " ".join(f"{k}_ms={np.mean(v[0]):.3f}" for k, v in modes.items()), file=sys.stderr, flush=True)
 
     # ---- e2e: host (pinned) input -> public API -> host result, copies inside the timed region.
     # The call a user makes for this workload is model.mc_predict(images, n_samples): the 10
@@ -355,11 +397,8 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     def finish(probs, kl):
         L.check(lib.mnf_memcpy_d2h(ctx.handle, res_host, C.c_void_p(probs.ptr), probs.nbytes))
         L.check(lib.mnf_memcpy_d2h(ctx.handle, C.c_void_p(res_host.value + probs.nbytes), C.c_void_p(kl.ptr), 4))
-        ctx.sync()
-        for c in kl_lanes:
-            c.sync()
 
-    def e2e_mc():
+    def enqueue_mc():
         L.check(lib.mnf_memcpy_h2d(ctx.handle, C.c_void_p(img_in.ptr), hp_img, imgs.nbytes))
         for c in kl_lanes:
             c.wait(ctx)
@@ -368,12 +407,30 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
         ctx.wait(kl_ctx)
         finish(probs, kl)
 
-    def e2e_tiled():
+    def enqueue_tiled():
         L.check(lib.mnf_memcpy_h2d(ctx.handle, C.c_void_p(x_in.ptr), hp_full, x_host.nbytes))
         probs, kl = step(x_in)
         finish(probs, kl)
 
+    def synced(enqueue):
+        def run():
+            enqueue()
+            ctx.sync()
+            for c in kl_lanes:
+                c.sync()
+        run.__wrapped__ = enqueue
+        return run
+
+    e2e_mc, e2e_tiled = synced(enqueue_mc), synced(enqueue_tiled)
+
     def time_e2e(fn):
+        if not args.no_graph:  # the whole step incl. its H2D / D2H copies (pinned memory) as one graph launch
+            inner = fn.__wrapped__
+            g = CapturedStep(ctx, inner, forks=kl_lanes + list(model._sides), layers=model.mnf_layers, models=[model])
+
+            def fn():  # noqa: F811
+                g.launch()
+                ctx.sync()
         fn()
         barrier()
         out_ms = []
@@ -418,7 +475,8 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
                                             "h2d_bytes_per_step": int(x_host.nbytes),
                                             "note": "same step fed with the 10240-row repeated batch from the host"}},
             "gpu_launches": int(launches),
-            "clocks": clk.summary(t_wall0, t_wall1),
+            "clocks": clk.summary(min(v[1] for v in modes.values()), max(v[2] for v in modes.values())),
+            "launch_modes_ms_per_step": {k: float(np.mean(v[0])) for k, v in modes.items()},
             "roofline": {"bound": "hbm",
                          "kernel": ("cf::conv_raw_f16" if args.math == "tf32x3" else "paired_gemm_fwd<CONV,64>")
                          + " (conv2: 12x12x20 -> 8x8x50, 5x5, + fused ReLU/2x2 max-pool)",
@@ -462,6 +520,7 @@ def main() -> None:
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--hostprof", action="store_true", help="cProfile of 20 steps' host-side enqueue (stderr)")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--breakdown", action="store_true", help="print per-layer device times of one step (stderr)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -141,7 +141,6 @@ def test_captured_step_replays_match_eager_calls():
     try:
         x = np.random.RandomState(9).uniform(size=(64, 28, 28, 1)).astype(np.float32)
         ref = _lenet()
-        ref.presample_first = False
         ref(x)  # build
         ref.freeze_weights(True)
         ys_ref, kls_ref = [], []
@@ -163,14 +162,14 @@ def test_captured_step_replays_match_eager_calls():
             ctx.wait(lanes[0])
             return y, kl
 
-        # CapturedStep runs the step twice eagerly (warm-up, pool stocking), then captures call 3
-        g = CapturedStep(ctx, step, forks=lanes + mdl._sides, layers=mdl.mnf_layers, models=[mdl])
-        for i in range(3):
+        # CapturedStep runs the step three times eagerly (warm-up, 2 x pool stocking), then captures call 4
+        g = CapturedStep(ctx, step, forks=lanes, layers=mdl.mnf_layers, models=[mdl])
+        for i in range(2):
             y, kl = g.launch()
             ctx.sync()
-            np.testing.assert_array_equal(y.numpy(), ys_ref[2 + i])
-            assert float(kl.numpy()[0]) == kls_ref[2 + i]
-        y_after = mdl(xd).numpy()  # eager call after three replays = call index 5
+            np.testing.assert_array_equal(y.numpy(), ys_ref[3 + i])
+            assert float(kl.numpy()[0]) == kls_ref[3 + i]
+        y_after = mdl(xd).numpy()  # eager call after two replays = call index 6
         np.testing.assert_array_equal(y_after, ys_ref[5])
         g.close()
     finally:

@@ -27,13 +27,8 @@ class CapturedStep:
                  calls_per_step: int = 1, kl_per_step: int = 1, models: Sequence[Any] = ()) -> None:
         self.ctx, self.forks, self.layers = ctx, list(forks), list(layers)
         self.calls_per_step, self.kl_per_step = calls_per_step, kl_per_step
+        self.models = list(models)
         for m in models:
-            # a graph must be self-contained: no z carried over from the previous call
-            m.presample_first = False
-            for lyr in m.mnf_layers:
-                if lyr._pre is not None:
-                    lyr.ctx.wait(lyr._pre["side"])
-                    lyr._pre = None
             if not all(getattr(lyr.ctx, "frozen", False) for lyr in m.mnf_layers if lyr.ctx is not None):
                 raise RuntimeError("CapturedStep: call model.freeze_weights() first (weight packing uploads tables "
                                    "from host memory, which a graph cannot replay)")
@@ -44,6 +39,11 @@ class CapturedStep:
                 c.sync()
 
         fn()  # eager warm-up: variables, workspaces, function attributes, packed weights
+        for m in self.models:  # side contexts the models forked for themselves (created lazily)
+            for c in getattr(m, "_sides", []):
+                if all(c is not e for e in every):
+                    self.forks.append(c)
+                    every.append(c)
         sync_all()
         # A captured step re-uses no buffer (each stays reserved for the graph's lifetime), so it
         # needs more blocks than an eager step ever holds at once: one eager pass in the same
@@ -51,8 +51,9 @@ class CapturedStep:
         stock: list = []
         for c in every:
             c._capture_keep = stock
-        fn()
-        sync_all()
+        for _ in range(2):  # twice: a z drawn one call ahead outlives its pass, the capture needs a spare
+            fn()
+            sync_all()
         for c in every:
             c._capture_keep = None
         del stock
@@ -67,9 +68,21 @@ class CapturedStep:
         try:
             for c in self.forks:
                 c.wait(ctx)  # fork: the other streams join the capture
+            # z drawn one call ahead (Sequential.presample_first): the captured step reads the z the
+            # previous replay drew (buffer X, filled eagerly for replay 0 by the stocking pass above)
+            # and draws the next one into another buffer Y; Y is copied onto X at the end of the graph.
+            carried = [(lyr, lyr._pre) for m in self.models for lyr in m.mnf_layers if lyr._pre is not None]
             self.outputs = fn()
             for c in self.forks:
                 ctx.wait(c)  # join whatever fn left pending on them
+            for lyr, x_pre in carried:
+                y_pre = lyr._pre
+                if y_pre is None or y_pre is x_pre:
+                    continue
+                for src, dst in ((y_pre["run"].states, x_pre["run"].states), (y_pre["ld"], x_pre["ld"])):
+                    L.check(ctx.lib.mnf_memcpy_d2d(ctx.handle, C.c_void_p(dst.ptr), C.c_void_p(src.ptr), src.nbytes))
+                keep.append((x_pre, y_pre))
+                lyr._pre = None  # eager calls after the graph draw their z in line
             L.check(ctx.lib.mnf_u32_add(ctx.handle, C.c_void_p(self.counter.ptr), 1))
         finally:
             nz._capture_delta = None
