@@ -334,11 +334,16 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     if not args.no_graph:
         from tf_mnf_b200.graph import CapturedStep
 
-        graph = CapturedStep(ctx, lambda: step(x_dev), forks=kl_lanes + list(model._sides), layers=model.mnf_layers,
-                             models=[model])
-        for _ in range(3):
-            graph.launch()
-        barrier()
+        try:
+            graph = CapturedStep(ctx, lambda: step(x_dev), forks=kl_lanes + list(model._sides), layers=model.mnf_layers,
+                                 models=[model])
+            for _ in range(3):
+                graph.launch()
+            barrier()
+        except Exception as exc:  # never lose the measurement to the optional launch mode
+            print(f"[rank {rank}] CUDA-graph capture unavailable ({exc!r}); eager steps only", file=sys.stderr, flush=True)
+            graph, args.no_graph = None, True
+            barrier()
     def timed_steps(run_step):
         starts, stops = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
         t0 = time.perf_counter()
@@ -425,12 +430,16 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
 
     def time_e2e(fn):
         if not args.no_graph:  # the whole step incl. its H2D / D2H copies (pinned memory) as one graph launch
-            inner = fn.__wrapped__
-            g = CapturedStep(ctx, inner, forks=kl_lanes + list(model._sides), layers=model.mnf_layers, models=[model])
+            try:
+                g = CapturedStep(ctx, fn.__wrapped__, forks=kl_lanes + list(model._sides), layers=model.mnf_layers,
+                                 models=[model])
 
-            def fn():  # noqa: F811
-                g.launch()
-                ctx.sync()
+                def fn():  # noqa: F811
+                    g.launch()
+                    ctx.sync()
+            except Exception as exc:
+                print(f"[rank {rank}] e2e graph capture unavailable ({exc!r}); eager", file=sys.stderr, flush=True)
+                barrier()
         fn()
         barrier()
         out_ms = []
