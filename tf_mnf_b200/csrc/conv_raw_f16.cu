@@ -62,6 +62,7 @@ struct Args {
   int64_t B;         // images
   int H, W, C, kh, kw, Ho, N, I;  // Wo == 8; I images per tile
   int Hi, Wi;        // plane extent per image: Ho-1+kh, 8-1+kw
+  int half;          // C % 8 == 4: the last chunk of a pixel carries 4 channels of this pixel and 4 of the next
   int cpt;           // 16-byte channel chunks per pixel (ceil(C / 8))
   int steps;         // K=16 steps
   int pool;
@@ -314,6 +315,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(const __grid_constant
           o[c] = cc * CCS + ((hi * a.I + im) * a.Wi + wi) * 16;
           imx[c] = im | (cc * 8 + 4 < a.C ? 256 : 0);
           if (hi < a.H && wi < a.W) gsrc[c] = (hi * a.W + wi) * a.C + cc * 8;
+          if (a.half && cc == a.cpt - 1 && hi < a.H && wi + 1 < a.W) imx[c] |= 512;  // second half: next pixel
         }
       }
       int it = 0;
@@ -334,6 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(const __grid_constant
                 const float* src = a.x + b * img_f + gsrc[c];
                 v[c][0] = __ldg(reinterpret_cast<const float4*>(src));
                 if (imx[c] & 256) v[c][1] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                else if (imx[c] & 512) v[c][1] = __ldg(reinterpret_cast<const float4*>(src + a.C));
               }
             }
             const float* sc = xsf + tl * 16;  // forward scale per image
@@ -497,6 +500,14 @@ int mnf_conv_raw_f16_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, con
   auto push_k = [&](int i, int j, int cc) {
     for (int e = 0; e < 8; ++e) kmap.push_back(i >= 0 && cc * 8 + e < C ? (i * kw + j) * C + cc * 8 + e : -1);
   };
+  // C % 8 == 4 (MNF-LeNet conv2: C = 20): the last chunk of a pixel is only half used.  Its plane
+  // then holds [x[p][C-4..C) | x[p+1][C-4..C)] (p+1: the next pixel of the row), so ONE chunk serves
+  // the leftover channels of two horizontally adjacent taps and a filter row needs (kw+1)/2 of them.
+  a.half = ((C & 7) == 4 && (a.cpt & 1)) ? 1 : 0;
+  auto push_k_half = [&](int i, int j, int cc) {
+    for (int e = 0; e < 4; ++e) kmap.push_back((i * kw + j) * C + cc * 8 + e);
+    for (int e = 0; e < 4; ++e) kmap.push_back(j + 1 < kw ? (i * kw + j + 1) * C + cc * 8 + e : -1);
+  };
   std::vector<std::pair<int, int>> left;
   for (int i = 0; i < kh; ++i)
     for (int j = 0; j < kw; ++j) {
@@ -506,18 +517,22 @@ int mnf_conv_raw_f16_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, con
         push_k(i, j, cc);
         push_k(i, j, cc + 1);
       }
-      if (a.cpt & 1) left.push_back({i, j});
+      if ((a.cpt & 1) && (!a.half || (j & 1) == 0)) left.push_back({i, j});
     }
+  auto push_left = [&](const std::pair<int, int>& t) {
+    if (a.half) push_k_half(t.first, t.second, a.cpt - 1);
+    else push_k(t.first, t.second, a.cpt - 1);
+  };
   for (size_t m = 0; m < left.size(); m += 2) {
     const int cc = a.cpt - 1;
     const int o0 = chunk_off(left[m].first, left[m].second, cc);
     tab.push_back(o0);
-    push_k(left[m].first, left[m].second, cc);
+    push_left(left[m]);
     if (m + 1 < left.size()) {
       const int o1 = chunk_off(left[m + 1].first, left[m + 1].second, cc);
       if (o1 <= o0 || (o1 - o0) >= (1 << 18)) return MNF_OK;
       tab.push_back(o1 - o0);
-      push_k(left[m + 1].first, left[m + 1].second, cc);
+      push_left(left[m + 1]);
     } else {
       tab.push_back(16);   // dummy second chunk: valid memory, zero weights
       push_k(-1, 0, 0);
