@@ -142,6 +142,72 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(const __grid_constant
     const int r = quad * 32 + lane;             // TMEM lane = tile row (ho, img, wo)
     const int wo = r & 7, g = r >> 3, img = g % a.I, ho = g / a.I;
     const int rl = img * HoWo + ho * 8 + wo;    // row inside the tile's block of y
+    // Fast path (inference with the fused pool, I <= 2 -- MNF-LeNet conv2): the four pixels of a pool
+    // window sit in one warp (wo pair: lane ^ 1, ho pair: lane ^ 8*I), so the max is two shuffles and
+    // the pooled value is stored straight from registers: no staging tile, no block-wide barriers.
+    const bool fastpool = a.pool && a.I <= 2 && !a.sd_out && !a.mean_out && !(a.N & 1);
+    if (fastpool) {
+      const int hbit = 8 * a.I;
+      const bool writer = (lane & 1) == 0 && (lane & hbit) == 0;
+      const int Hp = a.Ho >> 1;
+      int it = 0;
+      for (int64_t ps = blockIdx.x; ps < npass; ps += gridDim.x, ++it)
+        for (int tl = 0; tl < TT; ++tl) {
+          const int64_t braw = (ps * TT + tl) * a.I + img;
+          const bool st = braw < a.B && writer;
+          const int64_t brow = braw < a.B ? braw : a.B - 1;  // shuffles need every lane: compute on a valid row
+          const int buf = it & 1;
+          const uint32_t outer = (uint32_t)(ho * 8 + wo);
+          const int64_t m = brow * HoWo + outer;
+          const uint64_t grow = a.eps.row_offset + (uint64_t)brow;
+          const float* zrow = a.z ? a.z + brow * a.N : nullptr;
+          float* dst = a.y + ((brow * Hp + (ho >> 1)) * 4 + (wo >> 1)) * a.N;
+          mbar_wait(&tfull[buf * TT + tl], (it >> 1) & 1);
+          tc_fence_after();
+          const float sx = xsc[((it & 3) * TT + tl) * 16 + img], sx2 = sx * sx;
+          const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * TT + tl) * 2 * BN);
+#pragma unroll 1
+          for (int c0 = chalf * 32; c0 < chalf * 32 + 32; c0 += 16) {
+            if (c0 >= a.N) break;
+            float mv[16], vv[16];
+            tmem_ld16(trow + c0, mv);
+            tmem_ld16(trow + BN + c0, vv);
+            if (c0 + 16 >= a.N || c0 + 16 >= chalf * 32 + 32) {  // last chunk of this warp: accumulators are in registers
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[buf * TT + tl]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int nb = c0 + 4 * q;
+              if (nb >= a.N) break;
+              float e[4];
+              if (a.eps.injected) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) e[j] = nb + j < a.N ? a.eps.injected[m * a.N + nb + j] : 0.f;
+              } else {
+                philox_normal4(a.eps, grow, outer, (uint32_t)(nb >> 2), e);
+              }
+              float o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int n = nb + j < a.N ? nb + j : a.N - 1;
+                float mean = mv[4 * q + j] * (sx * wsc_s[n]) + bias_s[n];
+                const float sd = sqrt_fast(vv[4 * q + j] * (sx2 * wsc_s[BN + n]) + bias_s[BN + n]);
+                if (zrow) mean *= __ldg(zrow + n);
+                float v = fmaf(sd, e[j], mean);
+                v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));     // wo pair
+                v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, hbit));  // ho pair
+                o[j] = fmaxf(v, 0.f);
+              }
+              if (st) {
+                *reinterpret_cast<float2*>(dst + nb) = make_float2(o[0], o[1]);
+                if (nb + 2 < a.N) *reinterpret_cast<float2*>(dst + nb + 2) = make_float2(o[2], o[3]);
+              }
+            }
+          }
+        }
+    } else {
     int it = 0;
     for (int64_t ps = blockIdx.x; ps < npass; ps += gridDim.x, ++it)
     for (int tl = 0; tl < TT; ++tl) {
@@ -184,7 +250,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(const __grid_constant
               const int n = nb + j;
               if (n < a.N) {
                 float mean = mv[4 * q + j] * (sx * wsc_s[n]) + bias_s[n];
-                const float sd = sqrtf(vv[4 * q + j] * (sx2 * wsc_s[BN + n]) + bias_s[BN + n]);
+                const float sd = sqrt_fast(vv[4 * q + j] * (sx2 * wsc_s[BN + n]) + bias_s[BN + n]);
                 if (a.sd_out) a.sd_out[m * a.N + n] = sd;
                 if (a.mean_out) a.mean_out[m * a.N + n] = mean;
                 if (a.z) mean *= zs[img * BN + n];
@@ -216,11 +282,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(const __grid_constant
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
+    }
   } else if (warp == 4) {
     // ======================================================================= MMA issuer
-    // x_hi * [W_hi | W_lo] is ONE N=128 instruction (the A tile is read from shared memory once for
-    // both products: at N=64 the operand fetch, not the tensor pipe, sets the pace); x_lo * W_hi
-    // is an N=64 instruction into the first 64 columns.  The epilogue adds the two column halves.
+    // three N = 64 instructions per step and phase (x_hi*W_hi, x_lo*W_hi, x_hi*W_lo) into the same
+    // 64 TMEM columns; see the comment at the issue site for why not the N = 128 [W_hi | W_lo] form
     // instruction descriptor: D = F32 (bit 4), A = B = F16 (format 0), K-major, N >> 3, M >> 4
     const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     const uint32_t idesc2 = (1u << 4) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
