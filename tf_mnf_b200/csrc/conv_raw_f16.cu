@@ -51,11 +51,11 @@ constexpr int G = 6;                 // K=16 steps per weight stage
 constexpr int STEP_B = 2 * 2 * BN * 16;  // bytes of one K=16 step's weights for one phase: [2 kc][hi 64 n | lo 64 n][8 halves] = 4 KB
 constexpr int B_STAGE = G * STEP_B;  // 24 KB
 constexpr int SB = 3;                // weight ring depth
-constexpr int THREADS = 16 * 32;
+constexpr int THREADS = 20 * 32;
 constexpr int MAXSTEPS = 64;
 constexpr int TT = 2;              // tiles per pass over the weights (halves the L2 -> SM weight stream)
-constexpr int MAXC = 6;            // plane chunks a producer thread keeps in registers
-constexpr int PROD_WARPS = 6;      // warps 5-7 and 13-15 fill the planes; warps 8-11 are the second epilogue group
+constexpr int MAXC = 3;            // plane chunks a producer thread keeps in registers
+constexpr int PROD_WARPS = 10;     // warps 5-7 and 13-19 fill the planes (the fills pace the MMAs); warps 8-11: second epilogue group
 constexpr int TMEM_COLS = 512;  // [2 buffers][TT tiles][2 phases][64], double buffered over passes
 
 struct Args {
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_raw_f16(const __grid_constant
   } else {
     // ================================================================== plane producers
     if (warp < 8 || warp > 12) {
-      const int pt = (warp < 8 ? warp - 5 : warp - 10) * 32 + lane;  // 0 .. 191
+      const int pt = (warp < 8 ? warp - 5 : warp - 10) * 32 + lane;  // 0 .. 319
       constexpr int NP = PROD_WARPS * 32;
       const int nchunks = a.cpt * pix;       // 16-byte chunks per variant (<= MAXC * NP, host-checked)
       const int img_f = a.H * a.W * a.C;     // floats per input image
