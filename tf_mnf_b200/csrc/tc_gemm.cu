@@ -24,7 +24,11 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 16;       // floats per pipeline stage
 constexpr int KC = BK / 4;   // 16-byte k-chunks per stage
-constexpr int stages_for(int bn) { return bn > 64 ? 2 : 3; }  // BN = 128: 64 KB per stage + 66 KB output staging
+// BN = 128 (wide dense layers): 64 KB per stage and no output staging tile (rows are stored straight
+// from registers), so that three stages fit: with two, the weight block of the next stage is still
+// on its way from L2 when the MMAs of the current one retire (62 % of the time waiting, measured)
+constexpr int stages_for(int bn) { return 3 + 0 * bn; }
+constexpr bool direct_out(int bn, bool conv) { return bn > 64 && !conv; }
 constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
 constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;  // 416
 constexpr int A_VARIANT_BYTES = KC * BM * 16;               // 8 KB
@@ -150,6 +154,7 @@ __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
 template <int BN, bool CONV>
 __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
   constexpr int STAGES = stages_for(BN);
+  constexpr bool DIRECT = direct_out(BN, CONV);
   constexpr int B_VARIANT_BYTES = KC * BN * 16;
   constexpr int B_STAGE_BYTES = 4 * B_VARIANT_BYTES;
   constexpr int TMEM_COLS = 4 * BN;  // 2 buffers x {mean, var}
@@ -160,7 +165,7 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
   uint8_t* As = smem;                                  // [STAGES][4][KC][BM][4 floats]
   uint8_t* Bs = As + STAGES * A_STAGE_BYTES;           // [STAGES][4][KC][BN][4 floats]
   float* ys = (float*)(Bs + STAGES * B_STAGE_BYTES);   // [BM][LDY]
-  uint64_t* bars = (uint64_t*)(ys + BM * LDY + 3);
+  uint64_t* bars = (uint64_t*)(ys + (DIRECT ? 0 : BM * LDY) + 3);
   bars = (uint64_t*)(((uintptr_t)bars + 7) & ~(uintptr_t)7);
   uint64_t* full = bars;               // [STAGES]
   uint64_t* empty = bars + STAGES;     // [STAGES]
@@ -259,6 +264,7 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
             } else {
               philox_normal4(a.eps, a.eps.row_offset + (uint64_t)brow, outer, (uint32_t)(nb >> 2), e);
             }
+            float o4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int n = nb + j;
@@ -273,8 +279,17 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
                   if (a.z) mean *= __ldg(a.z + brow * a.N + n);
                 }
                 const float out = fmaf(sd, e[j], mean);
-                ys[r * ldy + c0 + 4 * q + j] = (!CONV && a.act == 1) ? fmaxf(out, 0.f) : out;
+                const float outa = (!CONV && a.act == 1) ? fmaxf(out, 0.f) : out;
+                if (DIRECT) o4[j] = outa;
+                else ys[r * ldy + c0 + 4 * q + j] = outa;
               }
+            }
+            if (DIRECT) {  // 16 contiguous bytes of this thread's output row
+              float* dstp = a.y + m * a.N + nb;
+              if (nb + 3 < a.N && !(a.N & 3)) *reinterpret_cast<float4*>(dstp) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+              else
+                for (int j = 0; j < 4; ++j)
+                  if (nb + j < a.N) dstp[j] = o4[j];
             }
           }
         }
@@ -283,6 +298,7 @@ __global__ void __launch_bounds__(THREADS, 1) paired_umma_fwd(Args a) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (DIRECT) continue;  // rows already stored from registers
       // coalesced copy-out of the staged tile (rows are contiguous in y when ntiles == 1)
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int rows = (int)((a.M - m0 < BM) ? a.M - m0 : BM);
@@ -662,7 +678,8 @@ static int launch(mnf_ctx* ctx, Args& a, const float* mean_W, const float* log_s
   a.vb = vb;
   const size_t tab_bytes = CONV ? sizeof(int) * 2 * (size_t)a.kblocks * BK / (a.vec ? 4 : 1) : 0;
   constexpr int STAGES = stages_for(BN);
-  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + 4 * KC * BN * 16) + sizeof(float) * (BM * (BN + 1) + 4) + 256 +
+  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + 4 * KC * BN * 16) +
+                      sizeof(float) * ((direct_out(BN, CONV) ? 0 : BM * (BN + 1)) + 4) + 256 +
                       sizeof(float) * 2 * BN + tab_bytes;
   MNF_CHECK_ARG(smem <= 227 * 1024, "tensor-core conv path: K = %d is too large for the im2col table", a.K);
   static size_t attr_smem = 0;
