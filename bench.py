@@ -492,7 +492,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
                          "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
                          # (profiles/r01_ncu_full_prof_conv_f16.txt); the pooled output partly stays in L2
-                         "traffic": (120418048 + 15231488) if args.math == "tf32x3" else None,
+                         "traffic": (120378624 + 14185472) if args.math == "tf32x3" else None,
                          "peak_source": which, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms,
                          "algorithmic_bytes_per_launch": k_bytes,
                          "pipe": ("tcgen05.mma kind::f16, power-of-two scaled fp16 hi/lo split of both operands, fp32 "
