@@ -202,7 +202,8 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     if world > 1:
         import torch.distributed as dist
 
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # stdout carries exactly one JSON line (no NCCL version banner)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]  # these levels print a version banner to stdout; it carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     M.runtime.set_default_device(local_rank)
     M.set_seed(0)
