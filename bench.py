@@ -203,7 +203,11 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
         import torch.distributed as dist
 
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
-            del os.environ["NCCL_DEBUG"]  # these levels print a version banner to stdout; it carries exactly one JSON line
+            # these levels print a version banner on STDOUT (NCCL_DEBUG_FILE does not move it); stdout carries
+            # exactly one JSON line, so report the version on stderr instead
+            del os.environ["NCCL_DEBUG"]
+            if rank == 0:
+                print("NCCL version " + ".".join(map(str, torch.cuda.nccl.version())), file=sys.stderr, flush=True)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     M.runtime.set_default_device(local_rank)
     M.set_seed(0)
