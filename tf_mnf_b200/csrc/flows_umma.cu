@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < S1; ++s) { mbar_init(&full1[s], 4 + 1); mbar_init(&empty1[s], 1); }
     mbar_init(acc1_full, 1);
-    mbar_init(h_ready, 4);
+    mbar_init(h_ready, 16);
     for (int s = 0; s < S2; ++s) { mbar_init(&full2[s], 1); mbar_init(&empty2[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&afull[b], 1); mbar_init(&aempty[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -241,6 +241,47 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
 
   // instruction descriptor: D = F32, A = B = TF32, K-major, M = 128, N = 64
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  // ---- stage-1 epilogue: h = act(acc1 + b1) -> hi/lo A operand of stage 2 in Hs.  Sixteen warps
+  // share it (TMEM lane quadrant x 16 hidden columns): warps 0-3, and the producer warps 8-11,
+  // 13-16, 17-20 once their k-blocks are published.  tanh by __expf (MUFU): ~1e-6 relative, inside
+  // the parity bar like the stage-2 gate math.
+  auto h_epilogue = [&](int quad, int c0) {
+    const int r = quad * 32 + lane;
+    const int64_t row = row0 + r;
+    mbar_wait(acc1_full, 0);
+    tc_fence_after();
+    const uint32_t trow = t_acc1 + ((uint32_t)(quad * 32) << 16);
+    float v[16];
+    tmem_ld16(trow + c0, v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float h4[4], l4[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int h = c0 + 4 * q + e;
+        float hv = 0.f;
+        if (h < a.H) {
+          const float pre = v[4 * q + e] + __ldg(a.b1 + h);
+          if (a.kind == MNF_FLOW_IAF) hv = fmaxf(pre, 0.f);
+          else {
+            const float t = __expf(-2.f * fabsf(pre));         // in (0, 1]
+            const float th = __fdividef(1.f - t, 1.f + t);     // tanh(|pre|)
+            hv = pre < 0.f ? -th : th;
+          }
+          if (a.hid_save && row < a.B) a.hid_save[row * a.H + h] = hv;
+        }
+        split_tf32(hv, h4[e], l4[e]);
+      }
+      const int kc = (c0 >> 2) + q;  // 16-byte chunk index along K = hidden
+      *reinterpret_cast<float4*>(Hs + kc * (BM * 16) + r * 16) = make_float4(h4[0], h4[1], h4[2], h4[3]);
+      *reinterpret_cast<float4*>(Hs + H_VAR + kc * (BM * 16) + r * 16) = make_float4(l4[0], l4[1], l4[2], l4[3]);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(h_ready);
+  };
 
   if (warp >= 5) {
     // =========================================================== stage-1 producers (warps 5-20)
@@ -354,6 +395,10 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
         }
       }
     }
+    // ---- the producer warps that also serve stage 2 take their share of the stage-1 epilogue
+    if (warp >= 8 && warp < 12) h_epilogue(warp & 3, 16);
+    else if (warp >= 13 && warp < 17) h_epilogue(warp & 3, 32);
+    else if (warp >= 17) h_epilogue(warp & 3, 48);
     // ---- warp 12: stage-2 weight loader (the ring re-uses the stage-1 buffers, so wait until
     //      stage 1 has fully drained: acc1_full fires after the last stage-1 MMA retired)
     if (warp == 12) {
@@ -423,39 +468,8 @@ __global__ void __launch_bounds__(THREADS, 1) flow_umma_step(Args a) {
       if (++s2 == S2) { s2 = 0; p2 ^= 1; }
     }
   } else {
-    // ======================================================= stage-1 epilogue (warps 0-3): h -> Hs
-    const int r = warp * 32 + lane;
-    const int64_t row = row0 + r;
-    mbar_wait(acc1_full, 0);
-    tc_fence_after();
-    const uint32_t trow = t_acc1 + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-    for (int c0 = 0; c0 < HP; c0 += 16) {
-      float v[16];
-      tmem_ld16(trow + c0, v);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float h4[4], l4[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int h = c0 + 4 * q + e;
-          float hv = 0.f;
-          if (h < a.H) {
-            const float pre = v[4 * q + e] + __ldg(a.b1 + h);
-            hv = (a.kind == MNF_FLOW_IAF) ? fmaxf(pre, 0.f) : tanhf(pre);
-            if (a.hid_save && row < a.B) a.hid_save[row * a.H + h] = hv;
-          }
-          split_tf32(hv, h4[e], l4[e]);
-        }
-        const int kc = (c0 >> 2) + q;  // 16-byte chunk index along K = hidden
-        *reinterpret_cast<float4*>(Hs + kc * (BM * 16) + r * 16) = make_float4(h4[0], h4[1], h4[2], h4[3]);
-        *reinterpret_cast<float4*>(Hs + H_VAR + kc * (BM * 16) + r * 16) = make_float4(l4[0], l4[1], l4[2], l4[3]);
-      }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(h_ready);
+    // ======================================================= stage-1 epilogue, hidden columns 0-15
+    h_epilogue(warp, 0);
   }
 
   // ============================================ stage-2 epilogue: warps 0-3 (cols 0-15) and 8-11 (cols 16-31)
