@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(C1_THREADS) flow_chain_row1(Chain1Args a) {
 // reference returns anyway) and is re-read after the next cluster barrier.
 #define CL_N 8
 #define CL_THREADS 256
+#define CL_MSK 512
 
 struct ChainClArgs {
   Chain1Args c;
@@ -296,6 +297,7 @@ __global__ void __cluster_dims__(CL_N, 1, 1) __launch_bounds__(CL_THREADS) flow_
   __shared__ float part[4][FT_HMAX + 1];
   __shared__ float hs[FT_HMAX];
   __shared__ float red[CL_THREADS / 32];
+  __shared__ float msk[CL_MSK];  // RNVP mask of this CTA's columns for the current step (one Philox per thread, once)
   const int tid = threadIdx.x, D = a.D;
   const int rank = (int)cluster_rank();
   // column / reduction slice of this CTA (multiples of 4 so one Philox call serves 4 draws)
@@ -314,6 +316,11 @@ __global__ void __cluster_dims__(CL_N, 1, 1) __launch_bounds__(CL_THREADS) flow_
     const float* zc = a.states + (int64_t)k * D;
     float* zn = a.states + (int64_t)(k + 1) * D;
     const int H = s.H;
+    const bool use_msk = s.kind == MNF_FLOW_RNVP && hi - lo <= CL_MSK;
+    if (use_msk) {
+      for (int i = tid; i < hi - lo; i += CL_THREADS) msk[i] = noise_bern1(s.bern, 0, (uint32_t)(lo + i), D, 0.5f);
+      __syncthreads();
+    }
     // ---- stage 1: partial h over d in [lo, hi); thread = (hidden j, one of 4 d-sub-slices)
     {
       const int j = tid & 63, sl = tid >> 6;
@@ -323,7 +330,12 @@ __global__ void __cluster_dims__(CL_N, 1, 1) __launch_bounds__(CL_THREADS) flow_
         const int d0 = lo + sl * sub, d1 = min(hi, d0 + sub);
         for (int dq = d0; dq < d1; dq += 4) {
           float m4[4] = {1.f, 1.f, 1.f, 1.f};
-          if (s.kind == MNF_FLOW_RNVP) noise_bern4(s.bern, 0, (uint32_t)(dq >> 2), D, 0.5f, m4);
+          if (use_msk) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m4[e] = dq + e < hi ? msk[dq + e - lo] : 0.f;
+          } else if (s.kind == MNF_FLOW_RNVP) {
+            noise_bern4(s.bern, 0, (uint32_t)(dq >> 2), D, 0.5f, m4);
+          }
           float w[4], zv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -352,38 +364,51 @@ __global__ void __cluster_dims__(CL_N, 1, 1) __launch_bounds__(CL_THREADS) flow_
       if (a.hid_save && rank == 0) a.hid_save[hoff + tid] = hv;
     }
     __syncthreads();
-    // ---- stage 2: this CTA's columns
+    // ---- stage 2: this CTA's columns, two threads per column (each half of the hidden units: the
+    //      dependent batches of weight loads are the latency of this kernel), combined by a shuffle
     float ld = 0.f;
-    for (int c = lo + tid; c < hi; c += CL_THREADS) {
-      float sv = s.bs[c], tv = s.bt[c];
-      for (int h0 = 0; h0 < H; h0 += 10) {
-        float ws[10], wt[10];
+    const int hsel = tid & 1, Hh = (H + 1) >> 1;
+    const int hb0 = hsel * Hh, hb1 = min(H, hb0 + Hh);
+    const int ncol_round = (hi - lo + (CL_THREADS >> 1) - 1) / (CL_THREADS >> 1) * (CL_THREADS >> 1);  // same trip count for all
+    for (int cp = tid >> 1; cp < ncol_round; cp += CL_THREADS >> 1) {
+      const int c = lo + cp;
+      const bool cok = c < hi;  // both threads of a pair agree; idle pairs still take part in the shuffle
+      float sv = 0.f, tv = 0.f;
+      if (cok) {
+        for (int h0 = hb0; h0 < hb1; h0 += 13) {
+          float ws[13], wt[13];
 #pragma unroll
-        for (int q = 0; q < 10; ++q) {
-          const int h = h0 + q;
-          ws[q] = wt[q] = 0.f;
-          if (h < H) {
-            ws[q] = __ldg(s.ws + (int64_t)h * s.ld2 + c);
-            wt[q] = __ldg(s.wt + (int64_t)h * s.ld2 + c);
-            if (s.m2) {
-              ws[q] *= __ldg(s.m2 + (int64_t)h * s.ld2 + c);
-              wt[q] *= __ldg(s.m2 + (int64_t)h * s.ld2 + D + c);
+          for (int q = 0; q < 13; ++q) {
+            const int h = h0 + q;
+            ws[q] = wt[q] = 0.f;
+            if (h < hb1) {
+              ws[q] = __ldg(s.ws + (int64_t)h * s.ld2 + c);
+              wt[q] = __ldg(s.wt + (int64_t)h * s.ld2 + c);
+              if (s.m2) {
+                ws[q] *= __ldg(s.m2 + (int64_t)h * s.ld2 + c);
+                wt[q] *= __ldg(s.m2 + (int64_t)h * s.ld2 + D + c);
+              }
             }
           }
-        }
 #pragma unroll
-        for (int q = 0; q < 10; ++q)
-          if (h0 + q < H) {
-            sv = fmaf(hs[h0 + q], ws[q], sv);
-            tv = fmaf(hs[h0 + q], wt[q], tv);
-          }
+          for (int q = 0; q < 13; ++q)
+            if (h0 + q < hb1) {
+              sv = fmaf(hs[h0 + q], ws[q], sv);
+              tv = fmaf(hs[h0 + q], wt[q], tv);
+            }
+        }
       }
+      sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+      tv += __shfl_xor_sync(0xffffffffu, tv, 1);
+      if (!cok || hsel) continue;
+      sv += s.bs[c];
+      tv += s.bt[c];
       const float zv = zc[c];
       if (s.kind == MNF_FLOW_IAF) {
         zn[s.parity ? D - 1 - c : c] = fmaf(zv, expf(sv), tv);
         ld += sv;
       } else {
-        const float m = noise_bern1(s.bern, 0, (uint32_t)c, D, 0.5f);
+        const float m = use_msk ? msk[cp] : noise_bern1(s.bern, 0, (uint32_t)c, D, 0.5f);
         const float gate = 1.f / (1.f + expf(-sv));
         const float lg = sv >= 0.f ? -log1pf(expf(-sv)) : sv - log1pf(expf(sv));
         zn[c] = ((1.f - m) * zv * gate + (1.f - gate) * tv) + m * zv;
