@@ -73,8 +73,14 @@ int mnf_ctx_launch_count(mnf_ctx* ctx, int64_t* out);
 /* Arithmetic of the paired mean/variance contractions (dense and conv forward):
  *  MNF_MATH_FP32   register-blocked FFMA kernels (default)
  *  MNF_MATH_TF32X3 tcgen05.mma kind::tf32 with hi/lo operand splitting (3 MMAs per product,
- *                  fp32 accumulation in TMEM): fp32-level accuracy (<= 1e-5 rel.) on tensor cores */
-enum { MNF_MATH_FP32 = 0, MNF_MATH_TF32X3 = 1 };
+ *                  fp32 accumulation in TMEM): fp32-level accuracy (<= 1e-5 rel.) on tensor cores
+ *  MNF_MATH_BF16   MNFDense contractions (N > 16) with bf16 operands, one tcgen05.mma kind::f16
+ *                  per product, fp32 accumulation (BASELINE config "wide MNFDense 4096 -> 4096,
+ *                  bf16 tensor-core path"): x*z and x^2 are formed in fp32 and rounded to nearest
+ *                  bf16, as are W and sigma^2; mean and variance are then within 2^-7 relative of
+ *                  the fp32 result term by term, ~1e-3 relative in L2 norm for K >= 64.  Everything
+ *                  else (conv, flows, KL, heads with N <= 16) runs as under MNF_MATH_TF32X3. */
+enum { MNF_MATH_FP32 = 0, MNF_MATH_TF32X3 = 1, MNF_MATH_BF16 = 2 };
 int mnf_ctx_set_math(mnf_ctx* ctx, int mode);
 /* Inference with fixed parameters: while frozen != 0 the packed / pre-split / pre-scaled weight
  * blocks the tensor-core kernels consume are built once per (weight pointers, shape) and kept in

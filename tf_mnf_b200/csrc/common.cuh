@@ -16,7 +16,7 @@ struct mnf_ctx {
   void* ws;  // grow-only device workspace
   size_t ws_bytes;
   bool capturing;
-  int math_mode;  // MNF_MATH_FP32 (FFMA) or MNF_MATH_TF32X3 (tcgen05, 3xTF32 split)
+  int math_mode;  // MNF_MATH_FP32 (FFMA), MNF_MATH_TF32X3 (tcgen05, 3xTF32 split) or MNF_MATH_BF16 (dense: one bf16 MMA)
   // timing probe: bracket the probe_skip-th launch of kernel family probe_kind with events
   int probe_kind;
   int probe_skip;
@@ -73,6 +73,10 @@ int mnf_tc_paired_forward(mnf_ctx* ctx, int conv, int64_t M, int K, int N, const
                           const float* mean_W, const float* log_std_W, const float* mean_b, const float* log_var_b,
                           float max_std, const NoiseDev& eps, float* y, float* mean_out, float* sd_out,
                           const int* geo, int act = 0);  // conv geo: H,W,C,kh,kw,Ho,Wo,stride,pad_t,pad_l,pool; act 1 = ReLU (dense)
+// dense_bf16.cu: MNF_MATH_BF16, one kind::f16 (bf16) MMA per product, TMA-fed from pre-packed operands
+int mnf_dense_bf16_forward(mnf_ctx* ctx, int64_t M, int K, int N, const float* x, const float* z, const float* mean_W,
+                           const float* log_std_W, const float* mean_b, const float* log_var_b, float max_std,
+                           const NoiseDev& eps, float* y, float* sd_out, int act);
 void* mnf_workspace(mnf_ctx* ctx, size_t bytes);  // nullptr on failure (error set)
 void mnf_note_path(const char* name);              // which kernel family served the last forward call (mnf_last_path)
 // Where a call's packed weights go.  Not frozen: the transient workspace, *fresh = true (pack every

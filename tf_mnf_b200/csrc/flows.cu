@@ -493,7 +493,7 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
   // tensor-core flow step (re-used step after step: launches are ordered on the stream)
   float* scal = nullptr;
   float* pack_ws = nullptr;
-  const bool use_tc = ctx->math_mode == MNF_MATH_TF32X3 && B >= 32 && D <= 2048;  // smem: biases + mask bits scale with D
+  const bool use_tc = ctx->math_mode != MNF_MATH_FP32 && B >= 32 && D <= 2048;  // smem: biases + mask bits scale with D
   {
     const size_t scal_floats = ((size_t)2 * T + 63) & ~(size_t)63;
     const size_t pack_floats = use_tc ? mnf_flow_umma_pack_floats((int)D) : 0;

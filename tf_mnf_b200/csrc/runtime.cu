@@ -202,7 +202,7 @@ int mnf_ctx_launch_count(mnf_ctx* ctx, int64_t* out) {
 
 int mnf_ctx_set_math(mnf_ctx* ctx, int mode) {
   MNF_CHECK_ARG(ctx, "ctx is NULL");
-  MNF_CHECK_ARG(mode == MNF_MATH_FP32 || mode == MNF_MATH_TF32X3, "mnf_ctx_set_math: unknown mode %d", mode);
+  MNF_CHECK_ARG(mode == MNF_MATH_FP32 || mode == MNF_MATH_TF32X3 || mode == MNF_MATH_BF16, "mnf_ctx_set_math: unknown mode %d", mode);
   ctx->math_mode = mode;
   return MNF_OK;
 }

@@ -105,8 +105,9 @@ class Context:
 
     def set_math(self, mode: str) -> None:
         """"fp32": FFMA kernels; "tf32x3": tcgen05 tensor cores with hi/lo operand splitting
-        (fp32-level accuracy).  Applies to the dense / conv forward contractions."""
-        codes = {"fp32": 0, "tf32x3": 1}
+        (fp32-level accuracy); "bf16": as tf32x3, but MNFDense contractions use one bf16 MMA per
+        product (tolerance in include/mnf_b200.h).  Applies to the dense / conv forward contractions."""
+        codes = {"fp32": 0, "tf32x3": 1, "bf16": 2}
         if mode not in codes:
             raise ValueError(f"math mode must be one of {sorted(codes)}, got {mode!r}")
         L.check(self.lib.mnf_ctx_set_math(self.handle, codes[mode]))
