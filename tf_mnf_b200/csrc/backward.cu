@@ -138,15 +138,21 @@ __global__ void dy_split_kernel(int64_t M, int N, int64_t HoWo, const float* __r
   }
 }
 
-// out0[n] = sum_m a0[m,n], out1[n] = sum_m a1[m,n]   (block = 32 columns x 8 row lanes)
+// out0[n] = sum_m a0[m,n], out1[n] = sum_m a1[m,n]   (block = 32 columns x 8 row lanes).
+// The rows are split over gridDim.y CTAs (a conv layer's bias gradient sums B*Ho*Wo rows of a
+// 20- or 50-column matrix: one CTA per 32 columns walked 73,728 rows alone, 3.4 ms); each writes
+// its partial sums to part[split][2][N] and colsum2_fold adds them in a fixed order.
+#define COLSUM_SPLITS 256
 __global__ void colsum2_kernel(int64_t M, int N, const float* __restrict__ a0, const float* __restrict__ a1,
-                               float* __restrict__ out0, float* __restrict__ out1) {
+                               float* __restrict__ part) {
   __shared__ float s0[8][33], s1[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + cx;
+  const int64_t chunk = (M + gridDim.y - 1) / gridDim.y;
+  const int64_t mlo = blockIdx.y * chunk, mhi = (mlo + chunk < M) ? mlo + chunk : M;
   float t0 = 0.f, t1 = 0.f;
   if (n < N)
-    for (int64_t m = ry; m < M; m += 8) {
+    for (int64_t m = mlo + ry; m < mhi; m += 8) {
       t0 += a0[m * N + n];
       if (a1) t1 += a1[m * N + n];
     }
@@ -155,9 +161,34 @@ __global__ void colsum2_kernel(int64_t M, int N, const float* __restrict__ a0, c
   __syncthreads();
   if (ry == 0 && n < N) {
     for (int r = 1; r < 8; ++r) { t0 += s0[r][cx]; t1 += s1[r][cx]; }
-    if (out0) out0[n] = t0;
-    if (out1 && a1) out1[n] = t1;
+    part[((int64_t)blockIdx.y * 2 + 0) * N + n] = t0;
+    part[((int64_t)blockIdx.y * 2 + 1) * N + n] = t1;
   }
+}
+__global__ void colsum2_fold(int N, int splits, const float* __restrict__ part, float* __restrict__ out0,
+                             float* __restrict__ out1) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float t0 = 0.f, t1 = 0.f;
+  for (int sp = 0; sp < splits; ++sp) {
+    t0 += part[((int64_t)sp * 2 + 0) * N + n];
+    t1 += part[((int64_t)sp * 2 + 1) * N + n];
+  }
+  if (out0) out0[n] = t0;
+  if (out1) out1[n] = t1;
+}
+static inline size_t colsum2_scratch_floats(int64_t N) { return (size_t)COLSUM_SPLITS * 2 * (size_t)N; }
+// part: colsum2_scratch_floats(N) floats of scratch
+static int colsum2(mnf_ctx* ctx, int64_t M, int N, const float* a0, const float* a1, float* out0, float* out1,
+                   float* part) {
+  int splits = (int)cdiv(M, 64);
+  if (splits > COLSUM_SPLITS) splits = COLSUM_SPLITS;
+  if (splits < 1) splits = 1;
+  colsum2_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)splits), 256, 0, ctx->stream>>>(M, N, a0, a1, part);
+  MNF_LAUNCHED(ctx);
+  colsum2_fold<<<(unsigned)cdiv(N, 128), 128, 0, ctx->stream>>>(N, splits, part, out0, a1 ? out1 : nullptr);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
 }
 
 // d_log_std_W = in_range ? 2 Vw dVw : 0 (in place on g); d_log_var_b = in_range ? vb dvb : 0
@@ -198,7 +229,8 @@ extern "C" int mnf_dense_backward(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N,
   MNF_CHECK_ARG(B >= 1 && K >= 1 && N >= 1 && K < (1 << 30) && N < (1 << 30) && B < (1ll << 31),
                 "mnf_dense_backward: bad shape");
   const int64_t KN = K * N, BK = B * K, BN = B * N;
-  size_t bytes = pad256(4 * KN) + pad256(4 * N) * 2 + pad256(4 * BN) + 4 * pad256(4 * BK) + 4096;
+  size_t bytes = pad256(4 * KN) + pad256(4 * N) * 2 + pad256(4 * BN) + 4 * pad256(4 * BK) + 4096 +
+                 pad256(4 * colsum2_scratch_floats(N));
   char* ws = (char*)mnf_workspace(ctx, bytes);
   if (!ws) return MNF_ERR_CUDA;
   Bump bp = {ws, 0};
@@ -210,15 +242,15 @@ extern "C" int mnf_dense_backward(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N,
   float* X2 = bp.take<float>(BK);
   float* dA = bp.take<float>(BK);
   float* dX2 = bp.take<float>(BK);
+  float* csum = bp.take<float>(colsum2_scratch_floats(N));
   bwd_prep_var<<<ew_grid(ctx, KN), 256, 0, ctx->stream>>>(KN, log_std_W, max_std, Vw, (int)N, log_var_b, vb);
   MNF_LAUNCHED(ctx);
   dy_split_kernel<<<ew_grid(ctx, BN), 256, 0, ctx->stream>>>(B, (int)N, 1, dy, sd, nullptr, make_noise(eps), dV, nullptr);
   MNF_LAUNCHED(ctx);
-  if (d_mean_b || d_log_var_b) {
-    colsum2_kernel<<<(unsigned)cdiv(N, 32), 256, 0, ctx->stream>>>(B, (int)N, dy, dV, d_mean_b, dvb);
-    MNF_LAUNCHED(ctx);
-  }
   int rc;
+  if (d_mean_b || d_log_var_b) {
+    if ((rc = colsum2(ctx, B, (int)N, dy, dV, d_mean_b, dvb, csum))) return rc;
+  }
   if (dx || dz) {
     // dA = dy @ mean_W^T ; dX2 = dV @ Vw^T
     if ((rc = gemm(ctx, (int)B, (int)K, (int)N, dy, N, 1, mean_W, 1, N, dA, K, false))) return rc;
@@ -342,7 +374,8 @@ extern "C" int mnf_conv2d_backward(mnf_ctx* ctx, const mnf_conv_shape* s, const 
   if (Bc > s->B) Bc = s->B;
   const int64_t Mc_max = Bc * HoWo;
   MNF_CHECK_ARG(Mc_max < (1ll << 31) && Kc < (1 << 30), "mnf_conv2d_backward: shape too large");
-  size_t bytes = pad256(4 * KF) * 2 + pad256(4 * F) * 2 + pad256(4 * MF) * 2 + 4 * pad256(4 * Mc_max * Kc) + 4096;
+  size_t bytes = pad256(4 * KF) * 2 + pad256(4 * F) * 2 + pad256(4 * MF) * 2 + 4 * pad256(4 * Mc_max * Kc) + 4096 +
+                 pad256(4 * colsum2_scratch_floats(F));
   char* ws = (char*)mnf_workspace(ctx, bytes);
   if (!ws) return MNF_ERR_CUDA;
   Bump bp = {ws, 0};
@@ -356,13 +389,13 @@ extern "C" int mnf_conv2d_backward(mnf_ctx* ctx, const mnf_conv_shape* s, const 
   float* cols2 = bp.take<float>(Mc_max * Kc);
   float* dcols = bp.take<float>(Mc_max * Kc);
   float* dcols2 = bp.take<float>(Mc_max * Kc);
+  float* csum = bp.take<float>(colsum2_scratch_floats(F));
   bwd_prep_var<<<ew_grid(ctx, KF), 256, 0, ctx->stream>>>(KF, log_std_W, max_std, Vw, F, log_var_b, vb);
   MNF_LAUNCHED(ctx);
   dy_split_kernel<<<ew_grid(ctx, MF), 256, 0, ctx->stream>>>(M, F, HoWo, dy, sd, z, make_noise(eps), dv, dm);
   MNF_LAUNCHED(ctx);
   if (d_mean_b || d_log_var_b) {
-    colsum2_kernel<<<(unsigned)cdiv(F, 32), 256, 0, ctx->stream>>>(M, F, dm, dv, d_mean_b, dvb);
-    MNF_LAUNCHED(ctx);
+    if ((rc = colsum2(ctx, M, F, dm, dv, d_mean_b, dvb, csum))) return rc;
   }
   if (dz) {
     conv_dz_kernel<<<(unsigned)s->B, 128, 0, ctx->stream>>>(s->B, HoWo, F, dy, mean_saved, dz);
@@ -419,9 +452,15 @@ struct FlowBwdArgs {
   int64_t ld2;
   NoiseDev bern;
   float *gw1, *gb1, *gws, *gbs, *gwt, *gbt;
+  float* dhbuf;  // [B,H] zeroed scratch: dL/dh summed over the column splits (PHASE 1 -> PHASE 2)
+  int chunks_per_split;
 };
 
-template <int KIND>
+// PHASE 0: the whole step in one CTA per 32 rows.  With few rows (a 128-row minibatch, or the single
+// row of kl_div's chains) that is 1-4 CTAs walking D/32 barrier-separated column chunks twice
+// (0.4-0.6 ms at D = 800): PHASE 1 / PHASE 2 run stage A resp. stages B + C with the column chunks
+// spread over blockIdx.y, exchanging dL/dh through dhbuf (atomic adds, like the weight gradients).
+template <int KIND, int PHASE>
 __global__ void __launch_bounds__(FB_THREADS) flow_mlp_step_bwd(FlowBwdArgs a) {
   __shared__ float hs[FB_ROWS][FB_HMAX + 1];
   __shared__ float dps[FB_ROWS][FB_HMAX + 1];
@@ -431,6 +470,8 @@ __global__ void __launch_bounds__(FB_THREADS) flow_mlp_step_bwd(FlowBwdArgs a) {
   const int64_t row0 = (int64_t)blockIdx.x * FB_ROWS, row = row0 + r;
   const bool row_ok = row < a.B;
   const int D = a.D, H = a.H;
+  const int c_lo = PHASE == 0 ? 0 : (int)blockIdx.y * a.chunks_per_split * 32;
+  const int c_hi = PHASE == 0 ? D : ((c_lo + a.chunks_per_split * 32 < D) ? c_lo + a.chunks_per_split * 32 : D);
   float (*xs)[33] = dss;  // stage C reuses dss for the input chunk
 
   for (int e = tid; e < FB_ROWS * H; e += FB_THREADS) {
@@ -444,7 +485,7 @@ __global__ void __launch_bounds__(FB_THREADS) flow_mlp_step_bwd(FlowBwdArgs a) {
   __syncthreads();
 
   // ---- stage A: recompute (s,t), form (ds,dt), direct dx term, dh, head weight grads
-  for (int c0 = 0; c0 < D; c0 += 32) {
+  for (int c0 = c_lo; c0 < c_hi && PHASE != 2; c0 += 32) {
     for (int e = tid; e < H * 32; e += FB_THREADS) {
       int h = e >> 5, cc = e & 31, c = c0 + cc;
       float vs = 0.f, vt = 0.f;
@@ -530,6 +571,22 @@ __global__ void __launch_bounds__(FB_THREADS) flow_mlp_step_bwd(FlowBwdArgs a) {
     __syncthreads();
   }
 
+  if (PHASE == 1) {
+#pragma unroll
+    for (int j = 0; j < FB_JMAX; ++j) {
+      int h = g + 8 * j;
+      if (h < H && row_ok) atomicAdd(a.dhbuf + row * H + h, dh[j]);
+    }
+    return;
+  }
+  if (PHASE == 2) {
+#pragma unroll
+    for (int j = 0; j < FB_JMAX; ++j) {
+      int h = g + 8 * j;
+      dh[j] = (h < H && row_ok) ? a.dhbuf[row * H + h] : 0.f;
+    }
+  }
+
   // ---- stage B: through the hidden activation
 #pragma unroll
   for (int j = 0; j < FB_JMAX; ++j) {
@@ -541,14 +598,14 @@ __global__ void __launch_bounds__(FB_THREADS) flow_mlp_step_bwd(FlowBwdArgs a) {
     }
   }
   __syncthreads();
-  if (tid < H) {
+  if (tid < H && (PHASE == 0 || blockIdx.y == 0)) {
     float acc = 0.f;
     for (int rr = 0; rr < FB_ROWS; ++rr) acc += dps[rr][tid];
     atomicAdd(a.gb1 + tid, acc);
   }
 
   // ---- stage C: dW1 and the MLP-path term of dx
-  for (int d0 = 0; d0 < D; d0 += 32) {
+  for (int d0 = c_lo; d0 < c_hi; d0 += 32) {
     __syncthreads();
     for (int e = tid; e < 32 * H; e += FB_THREADS) {
       int dd = e / H, h = e - dd * H, d = d0 + dd;
@@ -712,11 +769,13 @@ extern "C" int mnf_flow_backward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, 
   MNF_CHECK_ARG(T == 0 || (steps && gsteps), "mnf_flow_backward: steps/grad steps NULL");
   const int64_t BD = B * D;
   // running gradient buffers (ping-pong) + planar temporaries live in the workspace
-  size_t bytes = 2 * pad256(4 * BD) + pad256(4 * (2 * D + 2)) * (T + 1) + pad256(8 * (T + 1)) + 4096;
+  size_t bytes = 2 * pad256(4 * BD) + pad256(4 * (2 * D + 2)) * (T + 1) + pad256(8 * (T + 1)) + 4096 +
+                 pad256(4 * (size_t)B * FB_HMAX);
   char* ws = (char*)mnf_workspace(ctx, bytes);
   if (!ws) return MNF_ERR_CUDA;
   Bump bp = {ws, 0};
   float* buf[2] = {bp.take<float>(BD), bp.take<float>(BD)};
+  float* dhbuf = bp.take<float>((size_t)B * FB_HMAX);
   float* scal = bp.take<float>(2 * (T + 1));
   // g = d_states[T] + d_zT
   float* cur = buf[0];
@@ -749,9 +808,29 @@ extern "C" int mnf_flow_backward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, 
       a.bern = make_noise(&st.bern);
       a.gw1 = (float*)gs.w1; a.gb1 = (float*)gs.b1; a.gws = (float*)gs.ws; a.gbs = (float*)gs.bs;
       a.gwt = (float*)gs.wt; a.gbt = (float*)gs.bt;
-      int grid = (int)cdiv(B, FB_ROWS);
-      if (st.kind == MNF_FLOW_IAF) flow_mlp_step_bwd<MNF_FLOW_IAF><<<grid, FB_THREADS, 0, ctx->stream>>>(a);
-      else flow_mlp_step_bwd<MNF_FLOW_RNVP><<<grid, FB_THREADS, 0, ctx->stream>>>(a);
+      const int grid = (int)cdiv(B, FB_ROWS), nchunks = (int)cdiv(D, 32);
+      int nsplit = (2 * ctx->sm_count) / grid;  // column splits that fill the machine about twice
+      if (nsplit > nchunks) nsplit = nchunks;
+      if (nsplit >= 2) {
+        a.chunks_per_split = (int)cdiv(nchunks, nsplit);
+        nsplit = (int)cdiv(nchunks, a.chunks_per_split);
+        a.dhbuf = dhbuf;
+        MNF_CUDA(cudaMemsetAsync(dhbuf, 0, sizeof(float) * B * st.hidden, ctx->stream));
+        const dim3 g2((unsigned)grid, (unsigned)nsplit);
+        if (st.kind == MNF_FLOW_IAF) {
+          flow_mlp_step_bwd<MNF_FLOW_IAF, 1><<<g2, FB_THREADS, 0, ctx->stream>>>(a);
+          flow_mlp_step_bwd<MNF_FLOW_IAF, 2><<<g2, FB_THREADS, 0, ctx->stream>>>(a);
+        } else {
+          flow_mlp_step_bwd<MNF_FLOW_RNVP, 1><<<g2, FB_THREADS, 0, ctx->stream>>>(a);
+          flow_mlp_step_bwd<MNF_FLOW_RNVP, 2><<<g2, FB_THREADS, 0, ctx->stream>>>(a);
+        }
+        ctx->launches++;
+      } else {
+        a.chunks_per_split = nchunks;
+        a.dhbuf = nullptr;
+        if (st.kind == MNF_FLOW_IAF) flow_mlp_step_bwd<MNF_FLOW_IAF, 0><<<grid, FB_THREADS, 0, ctx->stream>>>(a);
+        else flow_mlp_step_bwd<MNF_FLOW_RNVP, 0><<<grid, FB_THREADS, 0, ctx->stream>>>(a);
+      }
       MNF_LAUNCHED(ctx);
     } else if (st.kind == MNF_FLOW_PLANAR) {
       MNF_CHECK_ARG(gs.w1 && gs.b1 && gs.wt, "planar step %d: NULL grad pointer", k);

@@ -122,6 +122,85 @@ __global__ void __launch_bounds__(256) planar_step_fwd(PlanarArgs a) {
   }
 }
 
+// The same step for D % 4 == 0, D <= 128 NV: the row lives in registers (NV float4 per lane,
+// coalesced 16-byte accesses), so z is read once, a sampled z0 costs one Philox call per 4
+// elements, and wide rows (D = 4096: 32 KB in + out per row) move at HBM speed.
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+template <int NV>
+__global__ void __launch_bounds__(256) planar_step_vec(PlanarArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= a.B) return;
+  const int D = a.D;
+  float4 zv[NV];
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int d0 = 4 * (j * 32 + lane);
+    zv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d0 < D) {
+      if (a.zin) {
+        zv[j] = ld4(a.zin + row * D + d0);
+      } else {
+        float n[4];
+        if (a.eps.injected) {
+          const float4 t = ld4(a.eps.injected + row * D + d0);
+          n[0] = t.x; n[1] = t.y; n[2] = t.z; n[3] = t.w;
+        } else {
+          philox_normal4(a.eps, a.eps.row_offset + (uint64_t)row, 0u, (uint32_t)(d0 >> 2), n);
+        }
+        const float4 qm = ld4(a.q0_mean + d0), ql = ld4(a.q0_log_var + d0);
+        zv[j].x = qm.x + expf(0.5f * ql.x) * n[0];
+        zv[j].y = qm.y + expf(0.5f * ql.y) * n[1];
+        zv[j].z = qm.z + expf(0.5f * ql.z) * n[2];
+        zv[j].w = qm.w + expf(0.5f * ql.w) * n[3];
+        if (a.z0_out) *reinterpret_cast<float4*>(a.z0_out + row * D + d0) = zv[j];
+      }
+      const float4 w = ld4(a.w + d0);
+      dot = fmaf(zv[j].x, w.x, dot);
+      dot = fmaf(zv[j].y, w.y, dot);
+      dot = fmaf(zv[j].z, w.z, dot);
+      dot = fmaf(zv[j].w, w.w, dot);
+    }
+  }
+  dot = warp_sum(dot);
+  const float th = tanhf(dot + a.b[0]);
+  const float k = a.scal[0], wu = a.scal[1];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int d0 = 4 * (j * 32 + lane);
+    if (d0 < D) {
+      const float4 w = ld4(a.w + d0), u = ld4(a.u + d0);
+      float4 o;
+      o.x = fmaf(th, u.x + k * w.x, zv[j].x);
+      o.y = fmaf(th, u.y + k * w.y, zv[j].y);
+      o.z = fmaf(th, u.z + k * w.z, zv[j].z);
+      o.w = fmaf(th, u.w + k * w.w, zv[j].w);
+      *reinterpret_cast<float4*>(a.zout + row * D + d0) = o;
+    }
+  }
+  if (lane == 0 && a.ld_out) {
+    float ld = logf(fabsf(1.f + (1.f - th * th) * wu));
+    a.ld_out[row] = (a.ld_in ? a.ld_in[row] : 0.f) + ld;
+  }
+}
+static bool planar_vec_ok(const PlanarArgs& a) {
+  auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  return a.D % 4 == 0 && a.D <= 4096 && al(a.zin) && al(a.zout) && al(a.z0_out) && al(a.w) && al(a.u) &&
+         al(a.q0_mean) && al(a.q0_log_var) && al(a.eps.injected);
+}
+static void planar_launch(mnf_ctx* ctx, const PlanarArgs& a) {
+  const int grid = (int)cdiv(a.B, 8);
+  if (!planar_vec_ok(a)) { planar_step_fwd<<<grid, 256, 0, ctx->stream>>>(a); return; }
+  const int nv = (a.D + 127) / 128;  // which variant depends on D only: any row split takes the same path
+  if (nv <= 1) planar_step_vec<1><<<grid, 256, 0, ctx->stream>>>(a);
+  else if (nv <= 2) planar_step_vec<2><<<grid, 256, 0, ctx->stream>>>(a);
+  else if (nv <= 4) planar_step_vec<4><<<grid, 256, 0, ctx->stream>>>(a);
+  else if (nv <= 8) planar_step_vec<8><<<grid, 256, 0, ctx->stream>>>(a);
+  else if (nv <= 16) planar_step_vec<16><<<grid, 256, 0, ctx->stream>>>(a);
+  else planar_step_vec<32><<<grid, 256, 0, ctx->stream>>>(a);
+}
+
 // T == 0: states[0] = z0 (sampled or copied), log_dets = 0.  One thread per 4 consecutive
 // elements of a row: one Philox call yields the four normals.
 __global__ void sample_z0_kernel(int64_t B, int D, const float* zin, const float* q0_mean, const float* q0_log_var,
@@ -557,7 +636,7 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
       a.B = B; a.D = (int)D; a.zin = zin; a.q0_mean = q0_mean; a.q0_log_var = q0_log_var; a.eps = eps;
       a.z0_out = z0_out; a.zout = zout; a.ld_in = first ? nullptr : log_dets; a.ld_out = log_dets;
       a.w = st.w1; a.b = st.b1; a.u = st.wt; a.scal = scal + 2 * k;
-      planar_step_fwd<<<(int)cdiv(B, 8), 256, 0, ctx->stream>>>(a);
+      planar_launch(ctx, a);
       MNF_LAUNCHED(ctx);
     } else {
       MNF_CHECK_ARG(false, "flow step %d: unknown kind %d", k, st.kind);

@@ -5,6 +5,13 @@ these lines document the other configs of SURVEY.md section 8(d).
 
   python tools/bench_configs.py --config c4 [--math bf16|tf32x3] [--steps K]
 
+c1: MNFLeNet train step, batch 128 (configs[0]): forward + softmax cross-entropy + backward +
+    kl_div + KL backward + Adam; images/s.
+c2: MNFFeedForward (100, 50, 10) on 136 features, IAF/MADE flows, batch 1024 (configs[1]):
+    forward + MSE + backward + KL + Adam; rows/s.
+c5: MNFVGG on 32x32x3, batch 256 split over the ranks, data-parallel training with one NCCL
+    all-reduce over the flat fp32 gradient buffer (configs[4]); run under torchrun for N > 1;
+    images/s (whole job), max over ranks.
 c4: one MNFDense(4096) on x ~ N(0,1) [8192, 4096], planar q/r flows x2, bf16 operands / fp32
     accumulate (configs[3]).  A step = layer(x) (sample_z through the planar chain + the paired
     contraction with in-kernel Philox eps).  Roofline: tensor (2 products x 2*M*K*N FLOP against the
@@ -34,15 +41,116 @@ def tensor_peak():
     return 1662.7, "SURVEY.md 8(d) (measured cuBLAS bf16 burst)"
 
 
+def train_config(args) -> None:
+    import torch
+
+    import tf_mnf_b200 as M
+    from tf_mnf_b200 import _lib as L
+    from tf_mnf_b200.models import MNFFeedForward, MNFLeNet, MNFVGG
+    from tf_mnf_b200.train import Trainer
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    M.runtime.set_default_device(local)
+    M.set_seed(0)
+    ctx = M.default_context(local)
+    ctx.set_math("tf32x3" if args.math == "bf16" else args.math)
+    lib = ctx.lib
+    rng = np.random.RandomState(0)
+    if args.config == "c1":
+        GB, unit = 128, "images/s"
+        model = MNFLeNet(max_std=1, flow_h_sizes=[50], std_init=10.0, flow_type="rnvp")
+        x = rng.uniform(size=(GB, 28, 28, 1)).astype(np.float32)
+        y = np.eye(10, dtype=np.float32)[rng.randint(0, 10, size=GB)]
+        loss, klw, name = "xent", 1.0 / 60000, "MNF-LeNet5 (RNVP flows) train step, synthetic 28x28x1 batch 128 (configs[0])"
+    elif args.config == "c2":
+        GB, unit = 1024, "rows/s"
+        model = MNFFeedForward(layer_sizes=(100, 50, 10), std_init=1e-2)
+        x = rng.standard_normal((GB, 136)).astype(np.float32)
+        y = rng.standard_normal((GB, 10)).astype(np.float32)
+        loss, klw, name = "mse", 1.0 / 128, "MNF-MLP regressor 136->100->50->10 (IAF/MADE flows) fwd+bwd+KL, batch 1024 (configs[1])"
+    else:
+        GB, unit = 256, "images/s"
+        model = MNFVGG()
+        x = rng.uniform(size=(GB, 32, 32, 3)).astype(np.float32)
+        y = np.eye(10, dtype=np.float32)[rng.randint(0, 10, size=GB)]
+        loss, klw, name = "xent", 1.0 / 50000, "MNF VGG-style conv net, synthetic 32x32x3 global batch 256, data-parallel (configs[4])"
+    lo, hi = rank * GB // world, (rank + 1) * GB // world
+    model.set_row_offset(lo)
+    xd, yd = ctx.to_device(x[lo:hi]), ctx.to_device(y[lo:hi])
+    tr = Trainer(model, loss=loss, kl_weight=klw, world=world)
+
+    def ev():
+        p = C.c_void_p()
+        L.check(lib.mnf_event_create(C.byref(p)))
+        return p
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        tr.step(xd, yd)
+    barrier()
+    n0 = ctx.launches
+    tr.step(xd, yd)
+    per_step = ctx.launches - n0
+    barrier()
+    import time
+    starts, stops = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        L.check(lib.mnf_event_record(ctx.handle, starts[i]))
+        tr.step(xd, yd)
+        L.check(lib.mnf_event_record(ctx.handle, stops[i]))
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    ms = C.c_float()
+    per = []
+    for a, b in zip(starts, stops):
+        L.check(lib.mnf_event_elapsed_ms(a, b, C.byref(ms)))
+        per.append(ms.value)
+    # a step contains host synchronisation (the all-reduce hands the gradient buffer to torch), so the
+    # wall clock per step (barrier to barrier) is the honest figure; the event time is reported beside it
+    mine = torch.tensor([wall_ms, float(np.mean(per))], device="cuda")
+    if dist is not None:
+        dist.all_reduce(mine, op=dist.ReduceOp.MAX)
+    wall_ms, dev_ms = (float(v) for v in mine.cpu())
+    n_params = sum(p.size for _, p, _ in tr._named_params())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "train-step throughput (fwd + loss + bwd + KL + KL bwd + allreduce + Adam)", "value": GB / (wall_ms * 1e-3),
+            "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": wall_ms,
+            "device_ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "global_batch": GB, "math": ctx.math, "n_params": int(n_params),
+                       "allreduce_bytes": int(n_params) * 4 if world > 1 else 0,
+                       "timing": "wall clock barrier to barrier, max over ranks (steps contain host syncs)"},
+            "gpu_launches": per_step * args.steps}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="c4", choices=["c4"])
+    ap.add_argument("--config", default="c4", choices=["c1", "c2", "c4", "c5"])
     ap.add_argument("--math", default="bf16", choices=["bf16", "tf32x3", "fp32"])
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rows", type=int, default=8192)
     ap.add_argument("--width", type=int, default=4096)
     args = ap.parse_args()
+    if args.config != "c4":
+        train_config(args)
+        return
 
     import tf_mnf_b200 as M
     from tf_mnf_b200 import _lib as L
