@@ -25,7 +25,12 @@ class Trainer:
         self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
         self.world, self.group = int(world), group
         self.t = 0
-        self.state: dict[int, tuple[DeviceArray, DeviceArray]] = {}
+        # flat training state (built on the first step): parameters, gradients and the two Adam
+        # moments each live in ONE buffer; the layers' variables / grads are views into them
+        self.flat_p: DeviceArray | None = None
+        self.flat_g: DeviceArray | None = None
+        self.flat_m: DeviceArray | None = None
+        self.flat_v: DeviceArray | None = None
 
     def _forward_layers(self):
         layers = list(self.model.layers)
@@ -33,20 +38,55 @@ class Trainer:
             layers = layers[:-1]  # cross-entropy is fused with the softmax
         return layers
 
+    def _ensure_flat(self, x: DeviceArray) -> None:
+        """Move every trainable variable into one flat parameter buffer (the live variable objects
+        are re-pointed, so layers and flows keep working unchanged) and make the gradients views of
+        one flat gradient buffer: zeroing, the data-parallel all-reduce and Adam then are ONE
+        memset / collective / launch per step instead of one per tensor (LeNet: 132 tensors)."""
+        if self.flat_p is not None:
+            return
+        ctx = default_context()
+        model = self.model
+        if not all(l.built for l in model.mnf_layers):
+            idx = [(l.call_index, l.kl_index) for l in model.mnf_layers]
+            model.set_training(False)
+            model(x)  # Keras build protocol: variables are created by the first call
+            for l, (ci, ki) in zip(model.mnf_layers, idx):
+                l.call_index, l.kl_index = ci, ki
+        for c in [ctx, *getattr(model, "_sides", [])]:
+            c.sync()
+        for l in model.mnf_layers:
+            l._pre = None  # a z drawn ahead carries pointers to the old parameter buffers
+            l.zero_grads()
+        items = [(lyr, name, v) for lyr in model.mnf_layers for name, v in lyr.trainable_variables.items()]
+        offs, total = [], 0
+        for _, _, v in items:
+            offs.append(total)
+            total += (v.size + 63) // 64 * 64  # 256-byte aligned slots
+        self.flat_p, self.flat_g = ctx.zeros((total,)), ctx.zeros((total,))
+        self.flat_m, self.flat_v = ctx.zeros((total,)), ctx.zeros((total,))
+        for (lyr, name, v), off in zip(items, offs):
+            slot = self.flat_p[off:off + v.size].reshape(v.shape)
+            slot.assign(v)
+            ctx.sync()
+            v.ptr, v.owner = slot.ptr, slot.owner
+            lyr.grads[name] = self.flat_g[off:off + v.size].reshape(v.shape)
+        ctx.sync()
+
     def loss_and_grads(self, x: Any, target: Any, noise: list | None = None):
         """Forward + backward: returns (loss [1], kl [1]); gradients land in layer.grads."""
         ctx = default_context()
         model = self.model
-        model.set_training(True)
         x = as_device(x, ctx)
         target = as_device(target, ctx)
+        self._ensure_flat(x)
+        model.set_training(True)
         layers = self._forward_layers()
         it = iter(noise or [])
         h = x
         for lyr in layers:
             h = lyr(h, noise=next(it, None)) if hasattr(lyr, "kl_div") else lyr(h)
-        for lyr in model.mnf_layers:
-            lyr.zero_grads()
+        L.check(ctx.lib.mnf_memset(ctx.handle, _p(self.flat_g), 0, self.flat_g.nbytes))
         B = h.shape[0]
         gb = B * self.world  # global batch: every rank holds B rows
         loss = ctx.empty((1,))
@@ -73,22 +113,18 @@ class Trainer:
             return
         import torch
 
-        from .parallel import allreduce_gradients
+        import torch.distributed as dist
 
         default_context().sync()
-        grads = [torch.as_tensor(g, device="cuda") for _, _, g in self._named_params()]
-        allreduce_gradients(grads, None, self.group)
+        flat = torch.as_tensor(self.flat_g, device="cuda")  # zero-copy view: one in-place collective
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         torch.cuda.synchronize()
 
     def apply(self) -> None:
         ctx = default_context()
         self.t += 1
-        for key, p, g in self._named_params():
-            st = self.state.get(key)
-            if st is None:
-                st = self.state[key] = (ctx.zeros(p.shape), ctx.zeros(p.shape))
-            L.check(ctx.lib.mnf_adam_step(ctx.handle, p.size, _p(p), _p(g), _p(st[0]), _p(st[1]), self.lr, self.beta1,
-                                          self.beta2, self.eps, self.t))
+        L.check(ctx.lib.mnf_adam_step(ctx.handle, self.flat_p.size, _p(self.flat_p), _p(self.flat_g), _p(self.flat_m),
+                                      _p(self.flat_v), self.lr, self.beta1, self.beta2, self.eps, self.t))
 
     def step(self, x: Any, target: Any):
         loss, kl = self.loss_and_grads(x, target)
