@@ -14,11 +14,16 @@ RTOL = 1e-5   # activations-like tensors (dx, dz)
 RTOL_G = 2e-5  # parameter gradients (fp32 atomics / split-K accumulate over the batch)
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["fp32", "tf32x3"])
+def ctx(request):
+    """Both arithmetic modes: FFMA everywhere, and the tensor-core mode, whose backward
+    contractions run as 3xTF32 on tcgen05 (csrc/gemm_umma.cu) -- same fp32 parity bar."""
     import tf_mnf_b200 as M
 
-    return M.default_context()
+    c = M.default_context()
+    c.set_math(request.param)
+    yield c
+    c.set_math("fp32")
 
 
 def _f32(a):

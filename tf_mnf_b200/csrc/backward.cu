@@ -3,6 +3,8 @@
 // formulas: SURVEY.md App. A-1, A-1c, A-2, validated against finite differences in
 // tests/test_oracle_grad.py).  Correctness-first fp32 kernels: a strided SGEMM with split-K,
 // explicit im2col/col2im for the conv gradients, and fused row-tile kernels for the flows.
+#include <cstdlib>
+
 #include "common.cuh"
 
 // ----------------------------------------------------------------------- workspace bump
@@ -88,13 +90,17 @@ __global__ void __launch_bounds__(256) sgemm_strided(GemmArgs g) {
 static int gemm(mnf_ctx* ctx, int M, int N, int K, const float* A, int64_t sAm, int64_t sAk, const float* B,
                 int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate) {
   if (M <= 0 || N <= 0) return MNF_OK;
+  // tensor-core math modes: 3xTF32 on tcgen05 (gemm_umma.cu) unless the product is tiny
+  static const bool no_tc = getenv("MNF_NO_TC_BWD") != nullptr;
+  if (ctx->math_mode != MNF_MATH_FP32 && !no_tc && K >= 1 && (int64_t)M * N * K >= (1 << 18))
+    return mnf_gemm_umma(ctx, M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, accumulate);
   GemmArgs g = {M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, accumulate ? 1 : 0, K};
   dim3 grid((unsigned)cdiv(M, 64), (unsigned)cdiv(N, 64), 1);
   int tiles = grid.x * grid.y;
   int split = 1;
-  if (tiles < ctx->sm_count && K >= 2048) {
+  if (tiles < ctx->sm_count && K >= 512 && (accumulate || ldc == N)) {
     split = (int)cdiv(2 * ctx->sm_count, tiles);
-    int maxsplit = (int)cdiv(K, 256);
+    int maxsplit = (int)cdiv(K, 128);
     if (split > maxsplit) split = maxsplit;
     if (split < 1) split = 1;
   }
