@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(THREADS, 3) gemm_tf32x3(Args a) {
     const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter of this warp, column half
     const int m = m0 + q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool vec_ok = (a.ldc & 3) == 0 && ((uintptr_t)a.C & 15) == 0;
 #pragma unroll 1
     for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 16) {
       if (c0 >= n_eff) break;  // warp-uniform
@@ -165,12 +166,19 @@ __global__ void __launch_bounds__(THREADS, 3) gemm_tf32x3(Args a) {
       tmem_ld16(trow + c0, acc);
       if (m < a.M) {
         float* crow = a.C + (int64_t)m * a.ldc + n0 + c0;
+        if (!a.atomic && vec_ok && n0 + c0 + 16 <= a.N) {
+          // 64 contiguous bytes of this thread's row: four 16-byte stores fill two whole sectors
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (n0 + c0 + j < a.N) {
-            if (a.atomic) atomicAdd(crow + j, acc[j]);
-            else crow[j] = acc[j];
-          }
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j < a.N) {
+              if (a.atomic) atomicAdd(crow + j, acc[j]);
+              else crow[j] = acc[j];
+            }
+        }
       }
     }
     tc_fence_before();
