@@ -122,25 +122,31 @@ __global__ void __launch_bounds__(256) planar_step_fwd(PlanarArgs a) {
   }
 }
 
-// The same step for D % 4 == 0, D <= 128 NV: the row lives in registers (NV float4 per lane,
-// coalesced 16-byte accesses), so z is read once, a sampled z0 costs one Philox call per 4
-// elements, and wide rows (D = 4096: 32 KB in + out per row) move at HBM speed.
+// The same step for D % 4 == 0, D <= 4096: the row lives in registers (NV float4 per lane, WPR
+// warps per row, coalesced 16-byte accesses), so z is read once, a sampled z0 costs one Philox
+// call per 4 elements, and wide rows (D = 4096: 32 KB in + out per row) move at HBM speed.  All
+// loads of a row are issued before the first use (the scalar kernel's load -> use -> load chain
+// costs a memory round trip per 32 columns); at most 8 float4 per lane keep 32 warps per SM.
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-template <int NV>
+template <int NV, int WPR, bool SAMPLE>
 __global__ void __launch_bounds__(256) planar_step_vec(PlanarArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= a.B) return;
+  __shared__ float part[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int sub = wid % WPR;                                   // this warp's slice of the row
+  const int64_t row = (int64_t)blockIdx.x * (8 / WPR) + wid / WPR;
+  const bool row_ok = row < a.B;
   const int D = a.D;
+  const float* __restrict__ zin = a.zin;
+  const float* __restrict__ wv = a.w;
+  const float* __restrict__ uv = a.u;
   float4 zv[NV];
-  float dot = 0.f;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    const int d0 = 4 * (j * 32 + lane);
+    const int d0 = 4 * ((j * WPR + sub) * 32 + lane);
     zv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (d0 < D) {
-      if (a.zin) {
-        zv[j] = ld4(a.zin + row * D + d0);
+    if (row_ok && d0 < D) {
+      if (!SAMPLE) {
+        zv[j] = ld4(zin + row * D + d0);
       } else {
         float n[4];
         if (a.eps.injected) {
@@ -154,9 +160,16 @@ __global__ void __launch_bounds__(256) planar_step_vec(PlanarArgs a) {
         zv[j].y = qm.y + expf(0.5f * ql.y) * n[1];
         zv[j].z = qm.z + expf(0.5f * ql.z) * n[2];
         zv[j].w = qm.w + expf(0.5f * ql.w) * n[3];
-        if (a.z0_out) *reinterpret_cast<float4*>(a.z0_out + row * D + d0) = zv[j];
       }
-      const float4 w = ld4(a.w + d0);
+    }
+  }
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int d0 = 4 * ((j * WPR + sub) * 32 + lane);
+    if (row_ok && d0 < D) {
+      if (SAMPLE && a.z0_out) *reinterpret_cast<float4*>(a.z0_out + row * D + d0) = zv[j];
+      const float4 w = ld4(wv + d0);
       dot = fmaf(zv[j].x, w.x, dot);
       dot = fmaf(zv[j].y, w.y, dot);
       dot = fmaf(zv[j].z, w.z, dot);
@@ -164,13 +177,20 @@ __global__ void __launch_bounds__(256) planar_step_vec(PlanarArgs a) {
     }
   }
   dot = warp_sum(dot);
+  if (WPR > 1) {
+    if (lane == 0) part[wid] = dot;
+    __syncthreads();
+    dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < WPR; ++i) dot += part[(wid / WPR) * WPR + i];  // fixed order: same sum in every warp
+  }
   const float th = tanhf(dot + a.b[0]);
   const float k = a.scal[0], wu = a.scal[1];
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    const int d0 = 4 * (j * 32 + lane);
-    if (d0 < D) {
-      const float4 w = ld4(a.w + d0), u = ld4(a.u + d0);
+    const int d0 = 4 * ((j * WPR + sub) * 32 + lane);
+    if (row_ok && d0 < D) {
+      const float4 w = ld4(wv + d0), u = ld4(uv + d0);
       float4 o;
       o.x = fmaf(th, u.x + k * w.x, zv[j].x);
       o.y = fmaf(th, u.y + k * w.y, zv[j].y);
@@ -179,7 +199,7 @@ __global__ void __launch_bounds__(256) planar_step_vec(PlanarArgs a) {
       *reinterpret_cast<float4*>(a.zout + row * D + d0) = o;
     }
   }
-  if (lane == 0 && a.ld_out) {
+  if (row_ok && sub == 0 && lane == 0 && a.ld_out) {
     float ld = logf(fabsf(1.f + (1.f - th * th) * wu));
     a.ld_out[row] = (a.ld_in ? a.ld_in[row] : 0.f) + ld;
   }
@@ -189,16 +209,21 @@ static bool planar_vec_ok(const PlanarArgs& a) {
   return a.D % 4 == 0 && a.D <= 4096 && al(a.zin) && al(a.zout) && al(a.z0_out) && al(a.w) && al(a.u) &&
          al(a.q0_mean) && al(a.q0_log_var) && al(a.eps.injected);
 }
+template <int NV, int WPR>
+static void planar_launch2(mnf_ctx* ctx, const PlanarArgs& a) {
+  const int grid = (int)cdiv(a.B, 8 / WPR);
+  if (a.zin) planar_step_vec<NV, WPR, false><<<grid, 256, 0, ctx->stream>>>(a);
+  else planar_step_vec<NV, WPR, true><<<grid, 256, 0, ctx->stream>>>(a);
+}
 static void planar_launch(mnf_ctx* ctx, const PlanarArgs& a) {
-  const int grid = (int)cdiv(a.B, 8);
-  if (!planar_vec_ok(a)) { planar_step_fwd<<<grid, 256, 0, ctx->stream>>>(a); return; }
+  if (!planar_vec_ok(a)) { planar_step_fwd<<<(int)cdiv(a.B, 8), 256, 0, ctx->stream>>>(a); return; }
   const int nv = (a.D + 127) / 128;  // which variant depends on D only: any row split takes the same path
-  if (nv <= 1) planar_step_vec<1><<<grid, 256, 0, ctx->stream>>>(a);
-  else if (nv <= 2) planar_step_vec<2><<<grid, 256, 0, ctx->stream>>>(a);
-  else if (nv <= 4) planar_step_vec<4><<<grid, 256, 0, ctx->stream>>>(a);
-  else if (nv <= 8) planar_step_vec<8><<<grid, 256, 0, ctx->stream>>>(a);
-  else if (nv <= 16) planar_step_vec<16><<<grid, 256, 0, ctx->stream>>>(a);
-  else planar_step_vec<32><<<grid, 256, 0, ctx->stream>>>(a);
+  if (nv <= 1) planar_launch2<1, 1>(ctx, a);
+  else if (nv <= 2) planar_launch2<2, 1>(ctx, a);
+  else if (nv <= 4) planar_launch2<4, 1>(ctx, a);
+  else if (nv <= 8) planar_launch2<8, 1>(ctx, a);
+  else if (nv <= 16) planar_launch2<8, 2>(ctx, a);
+  else planar_launch2<8, 4>(ctx, a);
 }
 
 // T == 0: states[0] = z0 (sampled or copied), log_dets = 0.  One thread per 4 consecutive
@@ -630,7 +655,7 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
       MNF_LAUNCHED(ctx);
     } else if (st.kind == MNF_FLOW_PLANAR) {
       MNF_CHECK_ARG(st.w1 && st.b1 && st.wt, "planar step %d: NULL pointer", k);
-      planar_prep<<<1, 256, 0, ctx->stream>>>((int)D, st.w1, st.wt, scal + 2 * k);
+      planar_prep<<<1, 1024, 0, ctx->stream>>>((int)D, st.w1, st.wt, scal + 2 * k);
       MNF_LAUNCHED(ctx);
       PlanarArgs a;
       a.B = B; a.D = (int)D; a.zin = zin; a.q0_mean = q0_mean; a.q0_log_var = q0_log_var; a.eps = eps;
