@@ -143,6 +143,85 @@ def time_cpu(flow: str, rows: int, steps: int, warmup: int):
     return float(np.mean(ts)), ts
 
 
+
+def cpu_train_step_factory(flow: str = "rnvp", batch: int = 128):
+    """BASELINE configs[0] on host cores: one MNF-LeNet5 training step (forward, mean softmax
+    cross-entropy + kl/60000, backward through every layer and both KL terms -- what
+    tape.gradient computes in notebooks/lenet_mnist.py:108-114) with the NumPy float32
+    restatement of the reference (oracle/), noise drawn inside the step.  The Adam update
+    (1.7 M parameters, < 1 % of the step) is not included."""
+    from oracle import mnf_oracle as O
+
+    Ps = O.make_lenet_params(seed=0, flow=flow, std_init=10.0, dtype=np.float32)
+    rng = np.random.RandomState(0)
+    x = rng.uniform(size=(batch, 28, 28, 1)).astype(np.float32)
+    y = np.eye(10, dtype=np.float32)[rng.randint(0, 10, size=batch)]
+    Ds = [20, 50, 800, 500]
+    outs = [(batch, 24, 24, 20), (batch, 8, 8, 50), (batch, 500), (batch, 10)]
+    kl_shapes = [(25,), (500,), (500,), (10,)]
+    f32 = np.float32
+
+    def pool_fwd(h):  # ReLU + MaxPool2D(2x2, SAME) on even sizes, keeping what the backward needs
+        B, H, W, Cc = h.shape
+        r = np.maximum(h, 0).reshape(B, H // 2, 2, W // 2, 2, Cc)
+        p = r.max(axis=(2, 4))
+        return p, (r, p, h.shape)
+
+    def pool_bwd(g, c):
+        r, p, shp = c
+        mask = (r == p[:, :, None, :, None, :]) & (r > 0)
+        mask = mask / np.maximum(mask.sum(axis=(2, 4), keepdims=True), 1)  # ties share the gradient
+        return (mask * g[:, :, None, :, None, :]).reshape(shp).astype(f32)
+
+    def step():
+        noise, bern = [], []
+        for D, o in zip(Ds, outs):
+            noise.append((rng.standard_normal((batch, D)).astype(f32), rng.standard_normal(o).astype(f32)))
+            bern.append([(rng.uniform(size=(batch, D)) <= 0.5).astype(f32) for _ in range(2)] if flow == "rnvp" else None)
+        h, c1 = O.conv_call(Ps[0], x, *noise[0], max_std=1.0, bern_q=bern[0])
+        h, p1 = pool_fwd(h)
+        h, c2 = O.conv_call(Ps[1], h, *noise[1], max_std=1.0, bern_q=bern[1])
+        h, p2 = pool_fwd(h)
+        flat_shape = h.shape
+        h, c3 = O.dense_call(Ps[2], h.reshape(batch, -1), *noise[2], max_std=1.0, bern_q=bern[2])
+        a3 = h
+        h, c4 = O.dense_call(Ps[3], np.maximum(h, 0), *noise[3], max_std=1.0, bern_q=bern[3])
+        probs = O.softmax(h)
+        loss = float(-np.mean(np.log(np.maximum(probs[y > 0], 1e-30))))
+        g = ((probs - y) / batch).astype(f32)
+        g, g4 = O.dense_call_backward(Ps[3], c4, g)
+        g, g3 = O.dense_call_backward(Ps[2], c3, (g * (a3 > 0)).astype(f32))
+        g, g2 = O.conv_call_backward(Ps[1], c2, pool_bwd(g.reshape(flat_shape), p2))
+        g, g1 = O.conv_call_backward(Ps[0], c1, pool_bwd(g, p1))
+        kl = 0.0
+        for i, (D, ks) in enumerate(zip(Ds, kl_shapes)):
+            ez, ea = rng.standard_normal((1, D)).astype(f32), rng.standard_normal(ks).astype(f32)
+            b = [(rng.uniform(size=(1, D)) <= 0.5).astype(f32) for _ in range(4)] if flow == "rnvp" else [None] * 4
+            bq, br = (b[:2], b[2:]) if flow == "rnvp" else (None, None)
+            if i < 2:
+                k, c = O.conv_kl(Ps[i], ez, ea, f32(rng.standard_normal()), bern_q=bq, bern_r=br)
+                O.conv_kl_backward(Ps[i], c, G=1.0 / 60000)
+            else:
+                k, c = O.dense_kl(Ps[i], ez, ea, bern_q=bq, bern_r=br)
+                O.dense_kl_backward(Ps[i], c, G=1.0 / 60000)
+            kl += float(k)
+        return loss, kl, (g1, g2, g3, g4)
+
+    return step
+
+
+def time_cpu_train(flow: str = "rnvp", batch: int = 128, steps: int = 5, warmup: int = 1):
+    step = cpu_train_step_factory(flow, batch)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts)), ts
+
+
 def blas_threads() -> int:
     try:
         from threadpoolctl import threadpool_info

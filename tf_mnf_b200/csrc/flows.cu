@@ -558,9 +558,10 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
     MNF_LAUNCHED(ctx);
     return MNF_OK;
   }
-  bool any_planar = false, all_mlp = true;
+  bool any_planar = false, all_mlp = true, any_rnvp = false;
   for (int k = 0; k < T; ++k) {
     any_planar |= steps[k].kind == MNF_FLOW_PLANAR;
+    any_rnvp |= steps[k].kind == MNF_FLOW_RNVP;
     all_mlp &= (steps[k].kind == MNF_FLOW_IAF || steps[k].kind == MNF_FLOW_RNVP) && steps[k].hidden >= 1 &&
                steps[k].hidden <= FT_HMAX && steps[k].w1 && steps[k].b1 && steps[k].ws && steps[k].bs && steps[k].wt &&
                steps[k].bt;
@@ -597,7 +598,8 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
   // tensor-core flow step (re-used step after step: launches are ordered on the stream)
   float* scal = nullptr;
   float* pack_ws = nullptr;
-  const bool use_tc = ctx->math_mode != MNF_MATH_FP32 && B >= 32 && D <= 2048;  // smem: biases + mask bits scale with D
+  // smem: biases (8 D bytes) and, for RNVP, mask bits (16 D bytes) scale with D
+  const bool use_tc = ctx->math_mode != MNF_MATH_FP32 && B >= 32 && D <= (any_rnvp ? 2048 : 4096);
   {
     const size_t scal_floats = ((size_t)2 * T + 63) & ~(size_t)63;
     const size_t pack_floats = use_tc ? mnf_flow_umma_pack_floats((int)D) : 0;

@@ -657,7 +657,8 @@ int mnf_flow_umma_step(mnf_ctx* ctx, int64_t B, int D, int H, int kind, int pari
     MNF_LAUNCHED(ctx);
   }
   const size_t smem = (size_t)S2 * B2_STAGE + 2 * H_VAR + sizeof(float) * 4 * BM + 256 +
-                      sizeof(float) * 2 * (size_t)a.chunks * CN + sizeof(uint16_t) * (size_t)BM * a.kblocks + 16;
+                      sizeof(float) * 2 * (size_t)a.chunks * CN +
+                      (kind == MNF_FLOW_RNVP ? sizeof(uint16_t) * (size_t)BM * a.kblocks : 0) + 16;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     MNF_CUDA(cudaFuncSetAttribute(flow_umma_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -126,8 +126,18 @@ def train_config(args) -> None:
         dist.all_reduce(mine, op=dist.ReduceOp.MAX)
     wall_ms, dev_ms = (float(v) for v in mine.cpu())
     n_params = sum(p.size for _, p, _ in tr._named_params())
+    cpu = None
+    if rank == 0 and args.config == "c1" and not args.no_cpu:
+        import bench  # the CPU leg lives in bench.py (the one place besides tests/ that runs oracle/)
+
+        t_cpu, _ = bench.time_cpu_train("rnvp", GB, steps=5, warmup=1)
+        cores = bench.blas_threads()
+        cpu = {"value": GB / t_cpu, "unit": unit, "cores": cores, "kind": "port", "ms_per_step": t_cpu * 1e3,
+               "sample": f"5 full steps (batch {GB}): forward + cross-entropy + backward + KL + KL backward, NumPy float32 "
+                         f"restatement of the reference TF path (oracle/), {cores} BLAS threads; Adam not included"}
     if rank == 0:
         print(json.dumps({
+            "cpu_baseline": cpu,
             "metric": "train-step throughput (fwd + loss + bwd + KL + KL bwd + allreduce + Adam)", "value": GB / (wall_ms * 1e-3),
             "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": wall_ms,
             "device_ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
@@ -145,6 +155,7 @@ def main() -> None:
     ap.add_argument("--math", default="bf16", choices=["bf16", "tf32x3", "fp32"])
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="c1: skip the CPU (NumPy restatement) train-step baseline")
     ap.add_argument("--rows", type=int, default=8192)
     ap.add_argument("--width", type=int, default=4096)
     args = ap.parse_args()
