@@ -207,6 +207,9 @@ int mnf_gemm_umma(mnf_ctx* ctx, int M, int N, int K, const float* A, int64_t sAm
     if (split > maxsplit) split = maxsplit;
     if (split < 1) split = 1;
   }
+  // the tensor core's fp32 accumulation is not round-to-nearest: keep every TMEM accumulation chain
+  // to <= 1024 terms (error stays below 1e-5 of the maximum) and let fp32 atomics combine the slices
+  if ((accumulate || ldc == N) && cdiv(K, split) > 1024) split = (int)cdiv(K, 1024);
   a.kchunk = (int)(cdiv(cdiv(K > 0 ? K : 1, split), BK) * BK);
   grid.z = (unsigned)cdiv(K > 0 ? K : 1, a.kchunk);
   if (grid.z > 1 && !accumulate) {

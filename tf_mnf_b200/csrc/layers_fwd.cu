@@ -661,7 +661,7 @@ int mnf_conv2d_can_fuse_pool(mnf_ctx* ctx, const mnf_conv_shape* s, int32_t* ok)
       return MNF_OK;
     }
   }
-  if (ctx->math_mode != MNF_MATH_FP32 && s->F <= 64 && s->F > 20 && 128 % (2 * Wo) == 0) *ok = 1;
+  if (mnf_tc_k_ok(ctx, (int64_t)s->kh * s->kw * s->C) && s->F <= 64 && s->F > 20 && 128 % (2 * Wo) == 0) *ok = 1;
   return MNF_OK;
 }
 
@@ -669,7 +669,7 @@ int mnf_conv2d_can_fuse_pool(mnf_ctx* ctx, const mnf_conv_shape* s, int32_t* ok)
 static bool dense_act_ok(const mnf_ctx* ctx, int64_t K, int64_t N, const float* x, const float* z, int act) {
   if (act == MNF_ACT_NONE) return true;
   if (small_dense_ok(K, N, x, z)) return act == MNF_ACT_RELU || act == MNF_ACT_SOFTMAX;
-  return act == MNF_ACT_RELU && ctx->math_mode != MNF_MATH_FP32;
+  return act == MNF_ACT_RELU && mnf_tc_k_ok(ctx, K);
 }
 
 int mnf_dense_can_fuse_act(mnf_ctx* ctx, int64_t K, int64_t N, int32_t act, int32_t* ok) {
@@ -723,7 +723,7 @@ int mnf_dense_forward_act(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const f
   if (ctx->math_mode == MNF_MATH_BF16)
     return mnf_dense_bf16_forward(ctx, B, (int)K, (int)N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std,
                                   make_noise(eps), y, sd_out, act);
-  if (ctx->math_mode == MNF_MATH_TF32X3)
+  if (ctx->math_mode == MNF_MATH_TF32X3 && mnf_tc_k_ok(ctx, K))
     return mnf_tc_paired_forward(ctx, 0, B, (int)K, (int)N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std,
                                  make_noise(eps), y, nullptr, sd_out, nullptr, act);
   float *Vw, *vb;
@@ -798,13 +798,14 @@ int mnf_conv2d_forward(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, co
     rc = mnf_conv_win_umma_forward(ctx, s->B, geo, a.N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std, a.eps, y, &used);
     if (rc || used) return rc;
   }
-  if (ctx->math_mode == MNF_MATH_FP32 || (a.N <= 20 && a.K <= 256)) {  // shapes of the direct FFMA kernel
+  const bool tc_ok = mnf_tc_k_ok(ctx, a.K);  // long contractions stay on FFMA in the fp32-parity mode
+  if (!tc_ok || (a.N <= 20 && a.K <= 256)) {  // shapes of the direct FFMA kernel
     rc = need_var();
     if (rc) return rc;
     rc = launch_direct(ctx, a, pad_b, pad_r, &used);
     if (rc || used) return rc;
   }
-  if (ctx->math_mode != MNF_MATH_FP32) {
+  if (tc_ok) {
     if (!pad_b && !pad_r) {  // raw-tile kernel: im2col expressed by UMMA descriptors (8-wide output rows)
       if (!getenv("MNF_NO_F16")) {  // scaled fp16 hi/lo operands: half the weight stream and MMAs
         rc = mnf_conv_raw_f16_forward(ctx, s->B, geo, a.N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std, a.eps, y,

@@ -236,43 +236,50 @@ class MNFLayerBase:
                 L.check(ctx.lib.mnf_memset(ctx.handle, _p(g), 0, g.nbytes))
         return self.grads
 
-    def _grad_steps(self, tag: str, nf: NormalizingFlow):
+    def _grad_steps(self, tag: str, nf: NormalizingFlow, grads: dict | None = None):
         """mnf_flow_step array whose pointer slots name the GRADIENT buffers of flow `tag`."""
+        grads = self.grads if grads is None else grads
         steps = (L.FlowStep * max(len(nf.flows), 1))()
         for k, fl in enumerate(nf.flows):
-            by_id = {id(v): self.grads[f"{tag}/{k}/{n}"] for n, v in fl.variables().items()}
+            by_id = {id(v): grads[f"{tag}/{k}/{n}"] for n, v in fl.variables().items()}
             fl.fill_step(steps[k], ptr_of=lambda a, m=by_id: m[id(a)].ptr)
         return steps
 
-    def _flow_backward(self, tag: str, nf: NormalizingFlow, run: ChainRun, d_states, d_zT, d_ld) -> DeviceArray:
-        ctx = self.ctx
+    def _flow_backward(self, tag: str, nf: NormalizingFlow, run: ChainRun, d_states, d_zT, d_ld,
+                       ctx: Context | None = None, grads: dict | None = None) -> DeviceArray:
+        ctx = ctx or self.ctx
         B, D, T = run.B, run.D, len(nf.flows)
         d_z0 = ctx.empty((B, D))
-        gsteps = self._grad_steps(tag, nf)
+        gsteps = self._grad_steps(tag, nf, grads)
         L.check(ctx.lib.mnf_flow_backward(ctx.handle, B, D, T, run.steps, _p(run.states), _p(run.saved),
                                           _p(d_states), _p(d_zT), _p(d_ld), _p(d_z0), gsteps))
         return d_z0
 
-    def _sample_z_backward(self, run: ChainRun, dz: DeviceArray, d_ld: DeviceArray | None) -> None:
+    def _sample_z_backward(self, run: ChainRun, dz: DeviceArray, d_ld: DeviceArray | None,
+                           ctx: Context | None = None, grads: dict | None = None) -> None:
         """Through flow_q back to q0_mean / q0_log_var; accumulates."""
-        ctx = self.ctx
-        d_z0 = self._flow_backward("flow_q", self.flow_q, run, None, dz, d_ld)
+        ctx = ctx or self.ctx
+        grads = self.grads if grads is None else grads
+        d_z0 = self._flow_backward("flow_q", self.flow_q, run, None, dz, d_ld, ctx, grads)
         L.check(ctx.lib.mnf_sample_z_backward(ctx.handle, run.B, run.D, _p(d_z0), _p(self.q0_log_var),
-                                              C.byref(run.eps), _p(self.grads["q0_mean"]), _p(self.grads["q0_log_var"])))
+                                              C.byref(run.eps), _p(grads["q0_mean"]), _p(grads["q0_log_var"])))
 
-    def _add_grad(self, name: str, src: DeviceArray) -> None:
-        dst = self.grads[name]
-        L.check(self.ctx.lib.mnf_axpy(self.ctx.handle, dst.size, 1.0, _p(src), _p(dst)))
+    def _add_grad(self, name: str, src: DeviceArray, ctx: Context | None = None, grads: dict | None = None) -> None:
+        dst = (self.grads if grads is None else grads)[name]
+        ctx = ctx or self.ctx
+        L.check(ctx.lib.mnf_axpy(ctx.handle, dst.size, 1.0, _p(src), _p(dst)))
 
-    def kl_backward(self, scale: float = 1.0) -> None:
+    def kl_backward(self, scale: float = 1.0, ctx: Context | None = None, grads: dict | None = None) -> None:
         """Gradient of scale * kl_div() (the most recent kl_div() call made with
-        `training=True`) accumulated into self.grads."""
+        `training=True`) accumulated into self.grads.
+        `ctx` / `grads`: run on the (forked) context kl_div() ran on and accumulate into another
+        set of buffers, so the KL branch of a training step runs beside the likelihood branch."""
         t = self._kl_tape
         if not t:
             raise RuntimeError(f"{self.name}: call kl_div() with layer.training = True before kl_backward()")
-        if not self.grads:
+        if grads is None and not self.grads:
             self.zero_grads()
-        ctx, D = self.ctx, self._flow_dim()
+        ctx, D = ctx or self.ctx, self._flow_dim()
         a: L.KlArgs = t["args"]
         g = L.KlGrads()
         names = ["mean_W", "log_std_W", "mean_b", "log_var_b"]
@@ -290,9 +297,16 @@ class MNFLayerBase:
             g.d_z, g.d_r_states = d_z.ptr, d_rst.ptr
         L.check(ctx.lib.mnf_kl_backward(ctx.handle, C.byref(a), float(scale), C.byref(g)))
         for n, buf in scratch.items():
-            self._add_grad(n, buf)
+            self._add_grad(n, buf, ctx, grads)
         if self.use_z:
-            d_ld = ctx.to_device(np.array([-float(scale)], np.float32))  # dKL/d(ld_q) = dKL/d(ld_r) = -scale
-            dz_r = self._flow_backward("flow_r", self.flow_r, t["rrun"], d_rst, None, d_ld)
+            # dKL/d(ld_q) = dKL/d(ld_r) = -scale; the one-element array is cached per (context, scale):
+            # uploading it synchronises the stream
+            key = (id(ctx), float(scale))
+            d_ld = self._dld_cache.get(key) if hasattr(self, "_dld_cache") else None
+            if d_ld is None:
+                if not hasattr(self, "_dld_cache"):
+                    self._dld_cache = {}
+                d_ld = self._dld_cache[key] = ctx.to_device(np.array([-float(scale)], np.float32))
+            dz_r = self._flow_backward("flow_r", self.flow_r, t["rrun"], d_rst, None, d_ld, ctx, grads)
             L.check(ctx.lib.mnf_axpy(ctx.handle, D, 1.0, _p(dz_r), _p(d_z)))
-            self._sample_z_backward(t["qrun"], d_z, d_ld)
+            self._sample_z_backward(t["qrun"], d_z, d_ld, ctx, grads)

@@ -31,6 +31,11 @@ class Trainer:
         self.flat_g: DeviceArray | None = None
         self.flat_m: DeviceArray | None = None
         self.flat_v: DeviceArray | None = None
+        # the KL branch (kl_div + its backward: single-row flow chains, latency-bound) runs on a forked
+        # context beside the likelihood branch and accumulates into its own flat buffer
+        self.kl_ctx = None
+        self.flat_gk: DeviceArray | None = None
+        self.kl_grads: list[dict] = []
 
     def _forward_layers(self):
         layers = list(self.model.layers)
@@ -65,12 +70,17 @@ class Trainer:
             total += (v.size + 63) // 64 * 64  # 256-byte aligned slots
         self.flat_p, self.flat_g = ctx.zeros((total,)), ctx.zeros((total,))
         self.flat_m, self.flat_v = ctx.zeros((total,)), ctx.zeros((total,))
+        self.flat_gk = ctx.zeros((total,))
+        self.kl_ctx = ctx.fork()
+        per_layer = {id(l): {} for l in model.mnf_layers}
         for (lyr, name, v), off in zip(items, offs):
             slot = self.flat_p[off:off + v.size].reshape(v.shape)
             slot.assign(v)
             ctx.sync()
             v.ptr, v.owner = slot.ptr, slot.owner
             lyr.grads[name] = self.flat_g[off:off + v.size].reshape(v.shape)
+            per_layer[id(lyr)][name] = self.flat_gk[off:off + v.size].reshape(v.shape)
+        self.kl_grads = [per_layer[id(l)] for l in model.mnf_layers]
         ctx.sync()
 
     def loss_and_grads(self, x: Any, target: Any, noise: list | None = None):
@@ -95,11 +105,19 @@ class Trainer:
             L.check(ctx.lib.mnf_softmax_xent(ctx.handle, B, h.shape[1], _p(h), _p(target), 1.0 / gb, _p(loss), _p(dh)))
         else:
             L.check(ctx.lib.mnf_mse_loss(ctx.handle, h.size, _p(h), _p(target), 1.0 / (gb * h.size // B), _p(loss), _p(dh)))
+        # KL branch on the forked context (ordered after everything enqueued so far, i.e. after the
+        # previous step's Adam update); it does not depend on x, so it runs beside the backward pass
+        kc = self.kl_ctx
+        kc.wait(ctx)
+        L.check(kc.lib.mnf_memset(kc.handle, _p(self.flat_gk), 0, self.flat_gk.nbytes))
+        kl = model.kl_div(ctx=kc)
+        for lyr, kg in zip(model.mnf_layers, self.kl_grads):
+            lyr.kl_backward(self.kl_weight / self.world, ctx=kc, grads=kg)  # summed over ranks = contributed once
         for lyr in reversed(layers):
             dh = lyr.backward(dh)
-        kl = model.kl_div()
-        for lyr in model.mnf_layers:
-            lyr.kl_backward(self.kl_weight / self.world)  # summed over ranks = contributed once
+        ctx.wait(kc)
+        L.check(ctx.lib.mnf_axpy(ctx.handle, self.flat_g.size, 1.0, _p(self.flat_gk), _p(self.flat_g)))
+        kc.wait(ctx)  # the KL buffers are re-used next step only after this sum
         model.set_training(False)
         return loss, kl
 

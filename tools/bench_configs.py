@@ -60,7 +60,7 @@ def train_config(args) -> None:
     M.runtime.set_default_device(local)
     M.set_seed(0)
     ctx = M.default_context(local)
-    ctx.set_math("tf32x3" if args.math == "bf16" else args.math)
+    ctx.set_math(args.math or "tf32x3")
     lib = ctx.lib
     rng = np.random.RandomState(0)
     if args.config == "c1":
@@ -152,7 +152,8 @@ def train_config(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c4", choices=["c1", "c2", "c4", "c5"])
-    ap.add_argument("--math", default="bf16", choices=["bf16", "tf32x3", "fp32"])
+    ap.add_argument("--math", default=None, choices=["bf16", "tf32x3", "fp32"],
+                    help="default: bf16 for c4, tf32x3 (fp32 parity) for the training configs")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="c1: skip the CPU (NumPy restatement) train-step baseline")
@@ -162,6 +163,7 @@ def main() -> None:
     if args.config != "c4":
         train_config(args)
         return
+    args.math = args.math or "bf16"
 
     import tf_mnf_b200 as M
     from tf_mnf_b200 import _lib as L
