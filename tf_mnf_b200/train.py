@@ -133,10 +133,15 @@ class Trainer:
 
         import torch.distributed as dist
 
-        default_context().sync()
-        flat = torch.as_tensor(self.flat_g, device="cuda")  # zero-copy view: one in-place collective
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-        torch.cuda.synchronize()
+        ctx = default_context()
+        if getattr(self, "_flat_t", None) is None:
+            ctx.sync()
+            self._flat_t = torch.as_tensor(self.flat_g, device="cuda")  # zero-copy view, made once
+            self._tstream = torch.cuda.ExternalStream(ctx.stream, device=self._flat_t.device)
+        # the collective is enqueued behind the backward pass on the context's own stream (NCCL's stream
+        # waits for it and the context's stream waits for NCCL): no host synchronisation in the step
+        with torch.cuda.stream(self._tstream):
+            dist.all_reduce(self._flat_t, op=dist.ReduceOp.SUM, group=self.group)
 
     def apply(self) -> None:
         ctx = default_context()
