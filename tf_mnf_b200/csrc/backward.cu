@@ -35,6 +35,7 @@ struct GemmArgs {
   float* C; int64_t ldc;
   int accumulate;
   int kchunk;  // K range per z-slice
+  int sqA;     // use A(m,k)^2 (the variance twin of a contraction reads the same operand)
 };
 
 __global__ void __launch_bounds__(256) sgemm_strided(GemmArgs g) {
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(256) sgemm_strided(GemmArgs g) {
       if (a_kfast) { k = tid & 15; m = (tid >> 4) + 16 * q; } else { m = tid & 63; k = (tid >> 6) + 4 * q; }
       float v = 0.f;
       if (m0 + m < g.M && k0 + k < kend) v = __ldg(g.A + (int64_t)(m0 + m) * g.sAm + (int64_t)(k0 + k) * g.sAk);
-      As[k][m] = v;
+      As[k][m] = g.sqA ? v * v : v;
       int n, kb;
       if (b_nfast) { n = tid & 63; kb = (tid >> 6) + 4 * q; } else { kb = tid & 15; n = (tid >> 4) + 16 * q; }
       float w = 0.f;
@@ -88,13 +89,13 @@ __global__ void __launch_bounds__(256) sgemm_strided(GemmArgs g) {
 }
 
 static int gemm(mnf_ctx* ctx, int M, int N, int K, const float* A, int64_t sAm, int64_t sAk, const float* B,
-                int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate) {
+                int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate, bool sqA = false) {
   if (M <= 0 || N <= 0) return MNF_OK;
   // tensor-core math modes: 3xTF32 on tcgen05 (gemm_umma.cu) unless the product is tiny
   static const bool no_tc = getenv("MNF_NO_TC_BWD") != nullptr;
   if (ctx->math_mode != MNF_MATH_FP32 && !no_tc && K >= 1 && (int64_t)M * N * K >= (1 << 18))
-    return mnf_gemm_umma(ctx, M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, accumulate);
-  GemmArgs g = {M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, accumulate ? 1 : 0, K};
+    return mnf_gemm_umma(ctx, M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, accumulate, sqA);
+  GemmArgs g = {M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, accumulate ? 1 : 0, K, sqA ? 1 : 0};
   dim3 grid((unsigned)cdiv(M, 64), (unsigned)cdiv(N, 64), 1);
   int tiles = grid.x * grid.y;
   int split = 1;
@@ -284,9 +285,8 @@ struct ConvGeo {
   int H, W, C, kh, kw, F, Ho, Wo, stride, pad_t, pad_l;
 };
 
-// cols[m, (i,j,c)] = x[b, ho*s+i-pt, wo*s+j-pl, c] (0 outside), cols2 = cols^2; m local to the chunk
-__global__ void im2col_kernel(ConvGeo g, int64_t b0, int64_t Mc, const float* __restrict__ x, float* __restrict__ cols,
-                              float* __restrict__ cols2) {
+// cols[m, (i,j,c)] = x[b, ho*s+i-pt, wo*s+j-pl, c] (0 outside); m local to the chunk.  The variance twin squares it inside the GEMM.
+__global__ void im2col_kernel(ConvGeo g, int64_t b0, int64_t Mc, const float* __restrict__ x, float* __restrict__ cols) {
   const int Kc = g.kh * g.kw * g.C;
   const int64_t total = Mc * Kc;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -300,7 +300,6 @@ __global__ void im2col_kernel(ConvGeo g, int64_t b0, int64_t Mc, const float* __
     float v = 0.f;
     if (hi >= 0 && hi < g.H && wi >= 0 && wi < g.W) v = x[((b * g.H + hi) * g.W + wi) * g.C + c];
     cols[idx] = v;
-    cols2[idx] = v * v;
   }
 }
 
@@ -380,7 +379,7 @@ extern "C" int mnf_conv2d_backward(mnf_ctx* ctx, const mnf_conv_shape* s, const 
   if (Bc > s->B) Bc = s->B;
   const int64_t Mc_max = Bc * HoWo;
   MNF_CHECK_ARG(Mc_max < (1ll << 31) && Kc < (1 << 30), "mnf_conv2d_backward: shape too large");
-  size_t bytes = pad256(4 * KF) * 2 + pad256(4 * F) * 2 + pad256(4 * MF) * 2 + 4 * pad256(4 * Mc_max * Kc) + 4096 +
+  size_t bytes = pad256(4 * KF) * 2 + pad256(4 * F) * 2 + pad256(4 * MF) * 2 + 3 * pad256(4 * Mc_max * Kc) + 4096 +
                  pad256(4 * colsum2_scratch_floats(F));
   char* ws = (char*)mnf_workspace(ctx, bytes);
   if (!ws) return MNF_ERR_CUDA;
@@ -392,7 +391,6 @@ extern "C" int mnf_conv2d_backward(mnf_ctx* ctx, const mnf_conv_shape* s, const 
   float* dm = bp.take<float>(MF);
   float* dv = bp.take<float>(MF);
   float* cols = bp.take<float>(Mc_max * Kc);
-  float* cols2 = bp.take<float>(Mc_max * Kc);
   float* dcols = bp.take<float>(Mc_max * Kc);
   float* dcols2 = bp.take<float>(Mc_max * Kc);
   float* csum = bp.take<float>(colsum2_scratch_floats(F));
@@ -416,11 +414,12 @@ extern "C" int mnf_conv2d_backward(mnf_ctx* ctx, const mnf_conv_shape* s, const 
     const float* dmc = dm + b0 * HoWo * F;
     const float* dvc = dv + b0 * HoWo * F;
     if (wgrad) {
-      im2col_kernel<<<ew_grid(ctx, Mc * Kc), 256, 0, ctx->stream>>>(g, b0, Mc, x, cols, cols2);
+      im2col_kernel<<<ew_grid(ctx, Mc * Kc), 256, 0, ctx->stream>>>(g, b0, Mc, x, cols);
       MNF_LAUNCHED(ctx);
       // dW += cols^T @ dm   (M=Kc, N=F, K=Mc)
       if (d_mean_W && (rc = gemm(ctx, (int)Kc, F, (int)Mc, cols, 1, Kc, dmc, F, 1, d_mean_W, F, true))) return rc;
-      if (d_log_std_W && (rc = gemm(ctx, (int)Kc, F, (int)Mc, cols2, 1, Kc, dvc, F, 1, dVw, F, true))) return rc;
+      // the variance twin squares the same patches on the fly (no second im2col matrix)
+      if (d_log_std_W && (rc = gemm(ctx, (int)Kc, F, (int)Mc, cols, 1, Kc, dvc, F, 1, dVw, F, true, true))) return rc;
     }
     if (dx) {
       // dcols = dm @ W^T  (M=Mc, N=Kc, K=F): B(k=f, n=kc) = W[kc*F + f]

@@ -35,6 +35,7 @@ struct Args {
   float* C; int64_t ldc;
   int atomic;   // accumulate into C (split-K or C += ...)
   int kchunk;   // K range per z-slice (multiple of BK)
+  int sqA;      // multiply with A(m,k)^2 (variance twin of a contraction over the same operand)
 };
 
 // 8 elements of a [128 rows x 16 k] operand tile per thread.  kfast: the operand's k axis has unit
@@ -144,6 +145,10 @@ __global__ void __launch_bounds__(THREADS, 3) gemm_tf32x3(Args a) {
       Frag fa, fb;
       load_frag(fa, a.A, a.sAm, a.sAk, m0, a.M, BM, k0, kend, a_kfast, pt);
       load_frag(fb, a.B, a.sBn, a.sBk, n0, a.N, n_eff, k0, kend, b_kfast, pt);
+      if (a.sqA) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) fa.v[e] *= fa.v[e];
+      }
       mbar_wait(&empty[stage], (uint32_t)(((it / STAGES) & 1) ^ 1));
       uint8_t* st = smem + stage * STAGE_BYTES;
       store_frag(fa, st, a_kfast, pt);
@@ -194,10 +199,10 @@ __global__ void __launch_bounds__(THREADS, 3) gemm_tf32x3(Args a) {
 
 // backward.cu's gemm() routes here when the context's math mode is a tensor-core one.
 int mnf_gemm_umma(mnf_ctx* ctx, int M, int N, int K, const float* A, int64_t sAm, int64_t sAk, const float* B,
-                  int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate) {
+                  int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate, bool sqA) {
   using namespace gu;
   if (M <= 0 || N <= 0) return MNF_OK;
-  Args a = {M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, accumulate ? 1 : 0, 0};
+  Args a = {M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, accumulate ? 1 : 0, 0, sqA ? 1 : 0};
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(N, BN), 1);
   const int64_t tiles = (int64_t)grid.x * grid.y, slots = 3ll * ctx->sm_count;
   int split = 1;

@@ -105,9 +105,10 @@ class MNFConv2D(MNFLayerBase):
 
     __call__ = call
 
-    def backward(self, dy: Any) -> DeviceArray:
+    def backward(self, dy: Any, need_dx: bool = True) -> DeviceArray | None:
         """Gradient of the most recent call() (made with `training=True`) given dL/dy:
-        returns dL/dx and ACCUMULATES parameter gradients into self.grads (App. A-1c, A-2)."""
+        returns dL/dx (None with need_dx=False: the first layer of a model has no use for it)
+        and ACCUMULATES parameter gradients into self.grads (App. A-1c, A-2)."""
         t = self._tape
         if not t:
             raise RuntimeError(f"{self.name}: call the layer with layer.training = True before backward()")
@@ -118,7 +119,7 @@ class MNFConv2D(MNFLayerBase):
         x, z = t["x"], t["z"]
         if dy.shape != t["sd"].shape:
             raise ValueError(f"dy must have shape {t['sd'].shape}, got {dy.shape}")
-        dx = ctx.empty(x.shape)
+        dx = ctx.empty(x.shape) if need_dx else None
         dz = ctx.empty((x.shape[0], self.n_filters)) if self.use_z else None
         tmp = {n: ctx.empty(getattr(self, n).shape) for n in ("mean_W", "log_std_W", "mean_b", "log_var_b")}
         L.check(ctx.lib.mnf_conv2d_backward(ctx.handle, C.byref(t["shape"]), _p(x), _p(z), _p(self.mean_W),

@@ -72,9 +72,10 @@ class MNFDense(MNFLayerBase):
 
     __call__ = call
 
-    def backward(self, dy: Any) -> DeviceArray:
+    def backward(self, dy: Any, need_dx: bool = True) -> DeviceArray | None:
         """Gradient of the most recent call() (made with `training=True`) given dL/dy:
-        returns dL/dx and ACCUMULATES parameter gradients into self.grads (App. A-1, A-2)."""
+        returns dL/dx (None with need_dx=False: the first layer of a model has no use for it)
+        and ACCUMULATES parameter gradients into self.grads (App. A-1, A-2)."""
         t = self._tape
         if not t:
             raise RuntimeError(f"{self.name}: call the layer with layer.training = True before backward()")
@@ -86,7 +87,7 @@ class MNFDense(MNFLayerBase):
         B = x.shape[0]
         if dy.shape != (B, self.n_out):
             raise ValueError(f"dy must have shape {(B, self.n_out)}, got {dy.shape}")
-        dx = ctx.empty(x.shape)
+        dx = ctx.empty(x.shape) if need_dx else None
         dz = ctx.empty(x.shape) if self.use_z else None
         tmp = {n: ctx.empty(getattr(self, n).shape) for n in ("mean_W", "log_std_W", "mean_b", "log_var_b")}
         L.check(ctx.lib.mnf_dense_backward(ctx.handle, B, self.n_in, self.n_out, _p(x), _p(z), _p(self.mean_W),

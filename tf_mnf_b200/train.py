@@ -113,8 +113,11 @@ class Trainer:
         kl = model.kl_div(ctx=kc)
         for lyr, kg in zip(model.mnf_layers, self.kl_grads):
             lyr.kl_backward(self.kl_weight / self.world, ctx=kc, grads=kg)  # summed over ranks = contributed once
-        for lyr in reversed(layers):
-            dh = lyr.backward(dh)
+        for i in range(len(layers) - 1, -1, -1):
+            if i == 0 and hasattr(layers[0], "kl_div"):
+                layers[0].backward(dh, need_dx=False)  # nobody consumes dL/d(input)
+            else:
+                dh = layers[i].backward(dh)
         ctx.wait(kc)
         L.check(ctx.lib.mnf_axpy(ctx.handle, self.flat_g.size, 1.0, _p(self.flat_gk), _p(self.flat_g)))
         kc.wait(ctx)  # the KL buffers are re-used next step only after this sum
