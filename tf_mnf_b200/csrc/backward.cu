@@ -145,6 +145,45 @@ __global__ void dy_split_kernel(int64_t M, int N, int64_t HoWo, const float* __r
   }
 }
 
+// N % 4 == 0: a thread per four consecutive columns -- one Philox call instead of four, 16-byte accesses
+__global__ void dy_split_kernel4(int64_t M, int N, int64_t HoWo, const float* __restrict__ dy,
+                                 const float* __restrict__ sd, const float* __restrict__ z, NoiseDev eps,
+                                 float* __restrict__ dV, float* __restrict__ dm) {
+  const int N4 = N >> 2;
+  const int64_t total = M * N4;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = q / N4;
+    const int n = (int)(q - m * N4) * 4;
+    const int64_t b = m / HoWo, i = m * N + n;
+    const uint32_t outer = (uint32_t)(m - b * HoWo);
+    float e[4];
+    if (eps.injected) {
+      const float4 t = *reinterpret_cast<const float4*>(eps.injected + i);
+      e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+    } else {
+      philox_normal4(eps, eps.row_offset + (uint64_t)b, outer, (uint32_t)(n >> 2), e);
+    }
+    const float4 g = *reinterpret_cast<const float4*>(dy + i), s = *reinterpret_cast<const float4*>(sd + i);
+    *reinterpret_cast<float4*>(dV + i) =
+        make_float4(g.x * e[0] / (2.f * s.x), g.y * e[1] / (2.f * s.y), g.z * e[2] / (2.f * s.z), g.w * e[3] / (2.f * s.w));
+    if (dm) {
+      float4 zz = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (z) zz = *reinterpret_cast<const float4*>(z + b * N + n);
+      *reinterpret_cast<float4*>(dm + i) = make_float4(g.x * zz.x, g.y * zz.y, g.z * zz.z, g.w * zz.w);
+    }
+  }
+}
+static int dy_split(mnf_ctx* ctx, int64_t M, int N, int64_t HoWo, const float* dy, const float* sd, const float* z,
+                    const NoiseDev& eps, float* dV, float* dm) {
+  auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  if (N % 4 == 0 && al(dy) && al(sd) && al(z) && al(dV) && al(dm) && al(eps.injected))
+    dy_split_kernel4<<<ew_grid(ctx, M * (N / 4)), 256, 0, ctx->stream>>>(M, N, HoWo, dy, sd, z, eps, dV, dm);
+  else
+    dy_split_kernel<<<ew_grid(ctx, M * N), 256, 0, ctx->stream>>>(M, N, HoWo, dy, sd, z, eps, dV, dm);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
 // out0[n] = sum_m a0[m,n], out1[n] = sum_m a1[m,n]   (block = 32 columns x 8 row lanes).
 // The rows are split over gridDim.y CTAs (a conv layer's bias gradient sums B*Ho*Wo rows of a
 // 20- or 50-column matrix: one CTA per 32 columns walked 73,728 rows alone, 3.4 ms); each writes
@@ -252,8 +291,10 @@ extern "C" int mnf_dense_backward(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N,
   float* csum = bp.take<float>(colsum2_scratch_floats(N));
   bwd_prep_var<<<ew_grid(ctx, KN), 256, 0, ctx->stream>>>(KN, log_std_W, max_std, Vw, (int)N, log_var_b, vb);
   MNF_LAUNCHED(ctx);
-  dy_split_kernel<<<ew_grid(ctx, BN), 256, 0, ctx->stream>>>(B, (int)N, 1, dy, sd, nullptr, make_noise(eps), dV, nullptr);
-  MNF_LAUNCHED(ctx);
+  {
+    int rc0 = dy_split(ctx, B, (int)N, 1, dy, sd, nullptr, make_noise(eps), dV, nullptr);
+    if (rc0) return rc0;
+  }
   int rc;
   if (d_mean_b || d_log_var_b) {
     if ((rc = colsum2(ctx, B, (int)N, dy, dV, d_mean_b, dvb, csum))) return rc;
@@ -287,35 +328,41 @@ struct ConvGeo {
 
 // cols[m, (i,j,c)] = x[b, ho*s+i-pt, wo*s+j-pl, c] (0 outside); m local to the chunk.  The variance twin squares it inside the GEMM.
 __global__ void im2col_kernel(ConvGeo g, int64_t b0, int64_t Mc, const float* __restrict__ x, float* __restrict__ cols) {
-  const int Kc = g.kh * g.kw * g.C;
-  const int64_t total = Mc * Kc;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t m = idx / Kc;
-    int k = (int)(idx - m * Kc);
-    int i = k / (g.kw * g.C), rem = k - i * g.kw * g.C, j = rem / g.C, c = rem - j * g.C;
-    int pix = (int)(m % ((int64_t)g.Ho * g.Wo));
-    int64_t b = b0 + m / ((int64_t)g.Ho * g.Wo);
-    int ho = pix / g.Wo, wo = pix - ho * g.Wo;
-    int hi = ho * g.stride - g.pad_t + i, wi = wo * g.stride - g.pad_l + j;
-    float v = 0.f;
-    if (hi >= 0 && hi < g.H && wi >= 0 && wi < g.W) v = x[((b * g.H + hi) * g.W + wi) * g.C + c];
-    cols[idx] = v;
+  // a warp per output pixel: the 64-bit index arithmetic is done once per row, the lanes walk the
+  // patch (a filter row is kw*C contiguous input elements) with 32-bit divisions only
+  const int Kc = g.kh * g.kw * g.C, kwC = g.kw * g.C, HoWo = g.Ho * g.Wo;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int64_t m = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); m < Mc; m += (int64_t)gridDim.x * wpb) {
+    const int64_t bl = m / HoWo;
+    const int pix = (int)(m - bl * HoWo), ho = pix / g.Wo, wo = pix - ho * g.Wo;
+    const int hi0 = ho * g.stride - g.pad_t, wi0 = wo * g.stride - g.pad_l;
+    const float* xb = x + (b0 + bl) * (int64_t)g.H * g.W * g.C;
+    float* dst = cols + m * Kc;
+    for (int k = lane; k < Kc; k += 32) {
+      const int i = k / kwC, rem = k - i * kwC, j = rem / g.C;
+      const int hi = hi0 + i, wi = wi0 + j;
+      float v = 0.f;
+      if (hi >= 0 && hi < g.H && wi >= 0 && wi < g.W) v = __ldg(xb + ((int64_t)hi * g.W + wi0) * g.C + rem);
+      dst[k] = v;
+    }
   }
 }
 
 // dx[b,hi,wi,c] = sum_{i,j} dcols[m(b,ho,wo),(i,j,c)] + 2 x * sum dcols2[...], gather form (no atomics)
+// IDX = int when the chunk's element count fits (64-bit divisions cost ~100 instructions each)
+template <typename IDX>
 __global__ void col2im_kernel(ConvGeo g, int64_t b0, int64_t Bc, const float* __restrict__ x,
                               const float* __restrict__ dcols, const float* __restrict__ dcols2,
                               float* __restrict__ dx) {
   const int Kc = g.kh * g.kw * g.C;
-  const int64_t total = Bc * g.H * g.W * g.C;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+  const IDX total = (IDX)(Bc * g.H * g.W * g.C);
+  for (IDX idx = (IDX)blockIdx.x * (IDX)blockDim.x + (IDX)threadIdx.x; idx < total; idx += (IDX)gridDim.x * (IDX)blockDim.x) {
     int c = (int)(idx % g.C);
-    int64_t t = idx / g.C;
+    IDX t = idx / g.C;
     int wi = (int)(t % g.W);
     t /= g.W;
     int hi = (int)(t % g.H);
-    int64_t bl = t / g.H;
+    int64_t bl = (int64_t)(t / g.H);
     float s1 = 0.f, s2 = 0.f;
     for (int i = 0; i < g.kh; ++i) {
       int hh = hi + g.pad_t - i;
@@ -396,8 +443,7 @@ extern "C" int mnf_conv2d_backward(mnf_ctx* ctx, const mnf_conv_shape* s, const 
   float* csum = bp.take<float>(colsum2_scratch_floats(F));
   bwd_prep_var<<<ew_grid(ctx, KF), 256, 0, ctx->stream>>>(KF, log_std_W, max_std, Vw, F, log_var_b, vb);
   MNF_LAUNCHED(ctx);
-  dy_split_kernel<<<ew_grid(ctx, MF), 256, 0, ctx->stream>>>(M, F, HoWo, dy, sd, z, make_noise(eps), dv, dm);
-  MNF_LAUNCHED(ctx);
+  if ((rc = dy_split(ctx, M, F, HoWo, dy, sd, z, make_noise(eps), dv, dm))) return rc;
   if (d_mean_b || d_log_var_b) {
     if ((rc = colsum2(ctx, M, F, dm, dv, d_mean_b, dvb, csum))) return rc;
   }
@@ -425,7 +471,10 @@ extern "C" int mnf_conv2d_backward(mnf_ctx* ctx, const mnf_conv_shape* s, const 
       // dcols = dm @ W^T  (M=Mc, N=Kc, K=F): B(k=f, n=kc) = W[kc*F + f]
       if ((rc = gemm(ctx, (int)Mc, (int)Kc, F, dmc, F, 1, mean_W, 1, F, dcols, Kc, false))) return rc;
       if ((rc = gemm(ctx, (int)Mc, (int)Kc, F, dvc, F, 1, Vw, 1, F, dcols2, Kc, false))) return rc;
-      col2im_kernel<<<ew_grid(ctx, bc * g.H * g.W * g.C), 256, 0, ctx->stream>>>(g, b0, bc, x, dcols, dcols2, dx);
+      if (bc * g.H * g.W * g.C < (1ll << 30))
+        col2im_kernel<int><<<ew_grid(ctx, bc * g.H * g.W * g.C), 256, 0, ctx->stream>>>(g, b0, bc, x, dcols, dcols2, dx);
+      else
+        col2im_kernel<int64_t><<<ew_grid(ctx, bc * g.H * g.W * g.C), 256, 0, ctx->stream>>>(g, b0, bc, x, dcols, dcols2, dx);
       MNF_LAUNCHED(ctx);
     }
   }

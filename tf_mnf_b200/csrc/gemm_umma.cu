@@ -4,11 +4,10 @@
 // need no copy.  fp32 parity as in tc_gemm.cu: both operands are split hi + lo (round-to-nearest
 // TF32) and each product is hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM.
 //
-// One 128 x 128 tile (x one K slice) per CTA, three CTAs resident per SM (64 KB smem, 128 TMEM
-// columns each) so that one CTA's global loads overlap another's MMAs:
-//   warps 0-7 producers: 8 + 8 operand elements per thread and 16-wide k-block, loaded BEFORE
-//             waiting for the stage to drain (the loads of block i fly while block i-2 is
-//             multiplied), split, stored K-major (no-swizzle UMMA layout); thread -> element
+// One 128 x 128 tile (x one K slice) per CTA, two CTAs resident per SM (96 KB smem, 128 TMEM
+// columns each), each with a three-deep register prefetch ring in its producers:
+//   warps 0-7 producers: 8 + 8 operand elements per thread and 16-wide k-block, loaded three
+//             blocks ahead, split, stored K-major (no-swizzle UMMA layout); thread -> element
 //             mapping follows the operand's unit-stride axis so the loads coalesce either way;
 //             afterwards the same warps are the epilogue (tcgen05.ld, store / atomic add)
 //   warp 8    MMA issue (warp-converged, elect.sync): 6 x tcgen05.mma.kind::tf32 per k-block,
@@ -23,7 +22,7 @@ constexpr int BM = 128, BN = 128, BK = 16, KC = BK / 4;
 constexpr int VAR_BYTES = KC * 128 * 16;    // hi or lo part of one operand tile: 8 KB
 constexpr int OP_BYTES = 2 * VAR_BYTES;
 constexpr int STAGE_BYTES = 2 * OP_BYTES;   // A hi, A lo, B hi, B lo: 32 KB
-constexpr int STAGES = 2;
+constexpr int STAGES = 3;                   // == depth of the producers' register prefetch ring
 constexpr int PROD_WARPS = 8;
 constexpr int THREADS = (PROD_WARPS + 1) * 32;
 constexpr int TMEM_COLS = 128;
@@ -43,27 +42,36 @@ struct Args {
 struct Frag {
   float v[8];
 };
+// FULLK: the whole 16-wide k-block lies inside the slice (every block but possibly the last): no
+// per-element k predicate.  vec4: unit-stride k rows that are 16-byte aligned load as one float4.
+// Addresses advance by pointer increments; the producers are instruction-bound otherwise.
+template <bool FULLK>
 __device__ __forceinline__ void load_frag(Frag& f, const float* __restrict__ base, int64_t s_row, int64_t s_k,
-                                          int row0, int nrows, int rows_used, int k0, int kend, bool kfast, int pt) {
+                                          int row0, int nrows, int rows_used, int k0, int kend, bool kfast, bool vec4,
+                                          int pt) {
   if (kfast) {
-    const int kc = pt & 3, r0 = pt >> 2;
+    const int kc = pt & 3, r0 = pt >> 2, kk = k0 + kc * 4;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int rl = r0 + 64 * h, row = row0 + rl;
       const bool rok = rl < rows_used && row < nrows;
-      const float* p = base + (int64_t)row * s_row + (int64_t)(k0 + kc * 4) * s_k;
+      const float* p = base + (int64_t)row * s_row + kk;  // s_k == 1
+      if (rok && vec4 && (FULLK || kk + 4 <= kend)) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        f.v[h * 4 + 0] = t.x; f.v[h * 4 + 1] = t.y; f.v[h * 4 + 2] = t.z; f.v[h * 4 + 3] = t.w;
+      } else {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) f.v[h * 4 + e] = (rok && k0 + kc * 4 + e < kend) ? __ldg(p + e * s_k) : 0.f;
+        for (int e = 0; e < 4; ++e) f.v[h * 4 + e] = (rok && (FULLK || kk + e < kend)) ? __ldg(p + e) : 0.f;
+      }
     }
   } else {
-    const int rl = pt & 127, kh = pt >> 7, row = row0 + rl;
+    const int rl = pt & 127, kh = pt >> 7, row = row0 + rl, kk = k0 + kh * 8;
     const bool rok = rl < rows_used && row < nrows;
+    const float* p = base + (int64_t)row * s_row + (int64_t)kk * s_k;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int kk = k0 + (2 * kh + c) * 4;
-      const float* p = base + (int64_t)row * s_row + (int64_t)kk * s_k;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) f.v[c * 4 + e] = (rok && kk + e < kend) ? __ldg(p + e * s_k) : 0.f;
+    for (int e = 0; e < 8; ++e) {
+      f.v[e] = (rok && (FULLK || kk + e < kend)) ? __ldg(p) : 0.f;
+      p += s_k;
     }
   }
 }
@@ -81,7 +89,7 @@ __device__ __forceinline__ void store_frag(const Frag& f, uint8_t* dst, bool kfa
   }
 }
 
-__global__ void __launch_bounds__(THREADS, 3) gemm_tf32x3(Args a) {
+__global__ void __launch_bounds__(THREADS, 2) gemm_tf32x3(Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
@@ -140,22 +148,43 @@ __global__ void __launch_bounds__(THREADS, 3) gemm_tf32x3(Args a) {
     // ======================================================================== producers
     const int pt = threadIdx.x;  // 0..255
     const bool a_kfast = a.sAk == 1, b_kfast = a.sBk == 1;
-    for (int it = 0; it < nblk; ++it) {
-      const int stage = it % STAGES, k0 = kbeg + it * BK;
-      Frag fa, fb;
-      load_frag(fa, a.A, a.sAm, a.sAk, m0, a.M, BM, k0, kend, a_kfast, pt);
-      load_frag(fb, a.B, a.sBn, a.sBk, n0, a.N, n_eff, k0, kend, b_kfast, pt);
-      if (a.sqA) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) fa.v[e] *= fa.v[e];
+    // register ring: the loads of k-blocks it+1 .. it+STAGES-1 are in flight while block it is split and
+    // stored (a synchronous load -> store loop pays one L2 round trip, ~2 us under load, per block)
+    Frag fa[STAGES], fb[STAGES];
+    const bool a_vec = a_kfast && (a.sAm & 3) == 0 && ((uintptr_t)a.A & 15) == 0;
+    const bool b_vec = b_kfast && (a.sBn & 3) == 0 && ((uintptr_t)a.B & 15) == 0;
+    auto issue = [&](Frag& xa, Frag& xb, int it) {
+      const int k0 = kbeg + it * BK;
+      if (k0 + BK <= kend) {
+        load_frag<true>(xa, a.A, a.sAm, a.sAk, m0, a.M, BM, k0, kend, a_kfast, a_vec, pt);
+        load_frag<true>(xb, a.B, a.sBn, a.sBk, n0, a.N, n_eff, k0, kend, b_kfast, b_vec, pt);
+      } else {
+        load_frag<false>(xa, a.A, a.sAm, a.sAk, m0, a.M, BM, k0, kend, a_kfast, a_vec, pt);
+        load_frag<false>(xb, a.B, a.sBn, a.sBk, n0, a.N, n_eff, k0, kend, b_kfast, b_vec, pt);
       }
-      mbar_wait(&empty[stage], (uint32_t)(((it / STAGES) & 1) ^ 1));
-      uint8_t* st = smem + stage * STAGE_BYTES;
-      store_frag(fa, st, a_kfast, pt);
-      store_frag(fb, st + OP_BYTES, b_kfast, pt);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[stage]);
+    };
+#pragma unroll
+    for (int d = 0; d < STAGES; ++d)
+      if (d < nblk) issue(fa[d], fb[d], d);
+    for (int it0 = 0; it0 < nblk; it0 += STAGES) {
+#pragma unroll
+      for (int d = 0; d < STAGES; ++d) {  // it0 is a multiple of STAGES: stage == ring slot == d
+        const int it = it0 + d;
+        if (it < nblk) {
+          if (a.sqA) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) fa[d].v[e] *= fa[d].v[e];
+          }
+          mbar_wait(&empty[d], (uint32_t)(((it / STAGES) & 1) ^ 1));
+          uint8_t* st = smem + d * STAGE_BYTES;
+          store_frag(fa[d], st, a_kfast, pt);
+          store_frag(fb[d], st + OP_BYTES, b_kfast, pt);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[d]);
+          if (it + STAGES < nblk) issue(fa[d], fb[d], it + STAGES);
+        }
+      }
     }
     // ========================================================================= epilogue
     mbar_wait(done, 0u);
@@ -204,7 +233,7 @@ int mnf_gemm_umma(mnf_ctx* ctx, int M, int N, int K, const float* A, int64_t sAm
   if (M <= 0 || N <= 0) return MNF_OK;
   Args a = {M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, accumulate ? 1 : 0, 0, sqA ? 1 : 0};
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(N, BN), 1);
-  const int64_t tiles = (int64_t)grid.x * grid.y, slots = 3ll * ctx->sm_count;
+  const int64_t tiles = (int64_t)grid.x * grid.y, slots = 2ll * ctx->sm_count;
   int split = 1;
   if (tiles < slots && K > 8 * BK && (accumulate || ldc == N)) {
     split = (int)(slots / tiles);
