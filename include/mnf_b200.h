@@ -78,10 +78,10 @@ int mnf_ctx_launch_count(mnf_ctx* ctx, int64_t* out);
  *                  per product, fp32 accumulation (BASELINE config "wide MNFDense 4096 -> 4096,
  *                  bf16 tensor-core path"): x*z and x^2 are formed in fp32 and rounded to nearest
  *                  bf16, as are W and sigma^2; mean and variance are then within 2^-7 relative of
- *                  the fp32 result term by term, ~1e-3 relative in L2 norm for K >= 64.  Flow steps
- *                  of rows wider than 1024 also run on tcgen05 (3xTF32; 5e-5 instead of 1e-5 of
- *                  the maximum, see csrc/flows.cu).  Everything else (conv, KL, heads with
- *                  N <= 16) runs as under MNF_MATH_TF32X3. */
+ *                  the fp32 result term by term, ~1e-3 relative in L2 norm for K >= 64.  Conv
+ *                  contractions of any length stay on the tensor cores (3xTF32; beyond 1280
+ *                  terms the accumulation drift exceeds the 1e-5 bar, csrc/common.cuh).
+ *                  Everything else (flows, KL, heads with N <= 16) runs as under MNF_MATH_TF32X3. */
 enum { MNF_MATH_FP32 = 0, MNF_MATH_TF32X3 = 1, MNF_MATH_BF16 = 2 };
 int mnf_ctx_set_math(mnf_ctx* ctx, int mode);
 /* Inference with fixed parameters: while frozen != 0 the packed / pre-split / pre-scaled weight

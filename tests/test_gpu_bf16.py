@@ -94,34 +94,3 @@ def test_bf16_is_deterministic_and_close_to_tf32x3(bf_ctx):
     rel = np.linalg.norm(outs["bf16"].astype(np.float64) - outs["tf32x3"]) / np.linalg.norm(outs["tf32x3"])
     assert 1e-6 < rel <= 1e-2, rel
 
-
-@pytest.mark.parametrize("kind,D", [("iaf", 4096), ("iaf", 2048), ("rnvp", 2048)])
-def test_wide_flow_chain_on_tensor_cores(bf_ctx, kind, D):
-    """Under the bf16 mode the flow steps of wide layers (the VGG config's 4096-wide dense layer)
-    run on tcgen05 as 3xTF32; one TMEM accumulator then sums D terms, which costs accuracy the
-    fp32-parity mode does not spend (csrc/flows.cu).  Stated tolerance: 5e-5 of the tensor's
-    maximum for states, log-dets and saved activations (measured: 4e-6, 1.3e-5, 2.2e-5)."""
-    from gpu_util import close, make_flows
-
-    from tf_mnf_b200 import _lib as L
-    from tf_mnf_b200.flows import NormalizingFlow
-
-    B = 33
-    rng = np.random.RandomState(D + B)
-    steps = O.make_flow(rng, kind, D, 3, (50,), "ones", np.float64)
-    for st in steps:
-        for k, v in st.items():
-            if k.startswith("b"):
-                for b in v if isinstance(v, list) else [v]:
-                    b[...] = 0.1 * rng.standard_normal(b.shape)
-        if kind == "iaf":
-            st["W"][1] *= 0.25
-    z = rng.standard_normal((B, D))
-    bern = [(rng.uniform(size=(B, D)) <= 0.5).astype(np.float64) for _ in range(3)]
-    ref_states, ref_ld, _ = O.flow_forward(z, steps, bern)
-    nf = NormalizingFlow(make_flows(steps, D))
-    states, ld = nf.forward(_f32(z), bern=[_f32(b) for b in bern] if kind == "rnvp" else None, record=True)
-    assert L.last_path() == "flow_umma", L.last_path()
-    for k, (a, b) in enumerate(zip(states, ref_states)):
-        close(a.numpy(), b, 5e-5, f"state {k}")
-    close(ld.numpy(), ref_ld, 5e-5, "log_dets")

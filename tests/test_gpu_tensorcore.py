@@ -168,7 +168,7 @@ def test_flow_chain_tensorcore(tc_ctx, kind, D, B, masks):
     h_ref = caches[0]["acts"][1] if kind == "iaf" else caches[0]["hs"][0]
     h_got = nf.last_run.saved.numpy()[: B * 50].reshape(B, 50)
     close(h_got, h_ref, RTOL, "saved hidden")
-    assert L.last_path() == ("flow_mlp" if D > 800 else "flow_umma"), L.last_path()
+    assert L.last_path() == ("flow_umma" if D <= 800 else "flow_gemm" if kind == "iaf" else "flow_mlp"), L.last_path()
 
 
 @pytest.mark.parametrize("math", ["tf32x3", "fp32"])
@@ -232,3 +232,34 @@ def test_dense_fused_activation(tc_ctx, math, K, N, B, act):
     else:  # FFMA path for wide layers has no fused epilogue: the call stayed unfused
         assert math == "fp32" and N > 16
         np.testing.assert_array_equal(y_fused.numpy(), y_plain.numpy())
+
+
+@pytest.mark.parametrize("math", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("D,B", [(1536, 70), (4096, 33)])
+def test_wide_iaf_chain_as_gemms(tc_ctx, math, D, B):
+    """Wide IAF steps on few rows run their two MLP contractions as whole-chip GEMMs (csrc/flows.cu
+    `flow_gemm`; split-K keeps every tensor-core accumulation chain <= 1024 terms): fp32 parity in
+    both math modes, sampled z0 included, parity reversal, log-dets and the saved activations."""
+    from gpu_util import make_flows
+
+    from tf_mnf_b200 import _lib as L
+    from tf_mnf_b200.flows import NormalizingFlow
+
+    tc_ctx.set_math(math)
+    rng = np.random.RandomState(D + B)
+    steps = O.make_flow(rng, "iaf", D, 2, (50,), "ones", np.float64)
+    for st in steps:
+        for k, v in st.items():
+            if k.startswith("b"):
+                for b in v if isinstance(v, list) else [v]:
+                    b[...] = 0.1 * rng.standard_normal(b.shape)
+        st["W"][1] *= 0.25
+    z = rng.standard_normal((B, D))
+    ref_states, ref_ld, caches = O.flow_forward(z, steps, None)
+    nf = NormalizingFlow(make_flows(steps, D))
+    states, ld = nf.forward(_f32(z), record=True)
+    assert L.last_path() == "flow_gemm", L.last_path()
+    for k, (a, b) in enumerate(zip(states, ref_states)):
+        close(a.numpy(), b, RTOL, f"state {k}")
+    close(ld.numpy(), ref_ld, RTOL, "log_dets")
+    close(nf.last_run.saved.numpy()[: B * 50].reshape(B, 50), caches[0]["acts"][1], RTOL, "saved hidden")

@@ -118,6 +118,12 @@ static int gemm(mnf_ctx* ctx, int M, int N, int K, const float* A, int64_t sAm, 
   return MNF_OK;
 }
 
+// the same GEMM for other translation units (flows.cu: wide IAF steps on few rows)
+int mnf_gemm_any(mnf_ctx* ctx, int M, int N, int K, const float* A, int64_t sAm, int64_t sAk, const float* B,
+                 int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate) {
+  return gemm(ctx, M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, accumulate);
+}
+
 // ------------------------------------------------------------------- shared small kernels
 __global__ void bwd_prep_var(int64_t nW, const float* __restrict__ Ls, float max_std, float* __restrict__ Vw, int N,
                              const float* __restrict__ lvb, float* __restrict__ vb) {

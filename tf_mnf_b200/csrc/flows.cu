@@ -226,6 +226,37 @@ static void planar_launch(mnf_ctx* ctx, const PlanarArgs& a) {
   else planar_launch2<8, 4>(ctx, a);
 }
 
+// Wide IAF steps on few rows (the VGG config's 4096-wide dense layer at batch 256): the row-tile
+// kernel would run 8 CTAs through D/32 barrier-separated chunks twice (2.4 ms per step).  Here the two
+// MLP contractions are plain GEMMs over the whole chip (split-K; tcgen05 in the tensor-core modes,
+// with TMEM chains of <= 1024 terms) and two small kernels do the rest.
+__global__ void iaf_hidden_kernel(int64_t n, int H, const float* __restrict__ b1, float* __restrict__ pre,
+                                  float* __restrict__ hid_save) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = fmaxf(pre[i] + b1[(int)(i % H)], 0.f);
+    pre[i] = v;
+    if (hid_save) hid_save[i] = v;
+  }
+}
+// y = z * exp(s) + t (reversed when parity), ld = sum_d s; a warp per row, st = [B][s(D) | t(D)] without biases
+__global__ void __launch_bounds__(256) iaf_combine_kernel(int64_t B, int D, int parity, const float* __restrict__ zin,
+                                                          const float* __restrict__ st, const float* __restrict__ bs,
+                                                          const float* __restrict__ bt, float* __restrict__ zout,
+                                                          const float* __restrict__ ld_in, float* __restrict__ ld_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const float* srow = st + row * 2 * D;
+  float ld = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float s = srow[c] + bs[c], t = srow[D + c] + bt[c];
+    zout[row * D + (parity ? D - 1 - c : c)] = fmaf(zin[row * D + c], expf(s), t);
+    ld += s;
+  }
+  ld = warp_sum(ld);
+  if (lane == 0 && ld_out) ld_out[row] = (ld_in ? ld_in[row] : 0.f) + ld;
+}
+
 // T == 0: states[0] = z0 (sampled or copied), log_dets = 0.  One thread per 4 consecutive
 // elements of a row: one Philox call yields the four normals.
 __global__ void sample_z0_kernel(int64_t B, int D, const float* zin, const float* q0_mean, const float* q0_log_var,
@@ -598,21 +629,25 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
   // tensor-core flow step (re-used step after step: launches are ordered on the stream)
   float* scal = nullptr;
   float* pack_ws = nullptr;
-  // Tensor-core flow steps.  Shared memory (biases 8 D bytes; RNVP mask bits 16 D bytes) allows
-  // D <= 4096 (IAF) / 2048 (RNVP), but the stage-1 contraction accumulates D terms in ONE TMEM
-  // accumulator and the tensor core's fp32 accumulation is not round-to-nearest: measured against
-  // the float64 oracle the states stay at 2e-6 but log-dets / hidden activations reach 1.1e-5 at
-  // D = 2048 and 2.2e-5 at D = 4096 (FFMA: 4e-7), outside the 1e-5 parity bar.  So the fp32-parity
-  // mode uses tcgen05 up to D = 800 (the hidden activations cross 1e-5 at D = 896) and the bf16 mode (whose tolerance the caller accepted) beyond.
-  const int tc_dmax = ctx->math_mode == MNF_MATH_BF16 ? (any_rnvp ? 2048 : 4096) : 800;
+  // Tensor-core flow steps (flows_umma.cu).  Its stage-1 contraction accumulates D terms in ONE TMEM
+  // accumulator and the tensor core's fp32 accumulation is not round-to-nearest: measured against the
+  // float64 oracle the states stay at 2e-6 but log-dets / hidden activations reach 1.1e-5 at D = 2048
+  // and 2.2e-5 at D = 4096 (FFMA: 4e-7), and the hidden activations cross the 1e-5 parity bar at
+  // D = 896.  Wider rows take the GEMM formulation below (chains of <= 1024 terms) or the FFMA tiles.
+  const int tc_dmax = 800;
   const bool use_tc = ctx->math_mode != MNF_MATH_FP32 && B >= 32 && D <= tc_dmax;
+  // wide rows on few row tiles: the MLP contractions as whole-chip GEMMs (iaf_combine_kernel above)
+  const bool use_gemm = !use_tc && D >= 1024 && B >= 2 && cdiv(B, FT_ROWS) * 2 <= ctx->sm_count;
+  float* gemm_ws = nullptr;
   {
     const size_t scal_floats = ((size_t)2 * T + 63) & ~(size_t)63;
     const size_t pack_floats = use_tc ? mnf_flow_umma_pack_floats((int)D) : 0;
-    if (any_planar || use_tc) {
-      scal = (float*)mnf_workspace(ctx, sizeof(float) * (scal_floats + pack_floats));
+    const size_t gemm_floats = use_gemm ? (size_t)B * (64 + 2 * (size_t)D) : 0;
+    if (any_planar || use_tc || use_gemm) {
+      scal = (float*)mnf_workspace(ctx, sizeof(float) * (scal_floats + pack_floats + gemm_floats));
       if (!scal) return MNF_ERR_CUDA;
       pack_ws = scal + scal_floats;
+      gemm_ws = pack_ws + pack_floats;
     }
   }
   int64_t saved_off = 0;  // saved is packed: step k starts after sum_{j<k} B*hidden_j
@@ -652,6 +687,31 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
         int rc = mnf_flow_umma_step(ctx, B, (int)D, st.hidden, st.kind, st.parity, zin_tc, q0_mean, q0_log_var, eps, z0_tc,
                                     zout, a.ld_in, a.ld_out, a.hid_save, st, a.bern, pack_ws);
         if (rc) return rc;
+        continue;
+      }
+      if (use_gemm && st.kind == MNF_FLOW_IAF && !st.m1 && !st.m2 && st.wt == st.ws + D && st.ld2 == 2 * D) {
+        const float* zg = zin;
+        if (!zg) {  // sample z0 for all rows first (same Philox counters as the fused draw)
+          const int64_t n4 = B * ((D + 3) / 4);
+          int g0 = (int)(cdiv(n4, 256) < ctx->sm_count * 8 ? cdiv(n4, 256) : ctx->sm_count * 8);
+          sample_z0_kernel<<<g0, 256, 0, ctx->stream>>>(B, (int)D, nullptr, q0_mean, q0_log_var, eps, states, nullptr);
+          MNF_LAUNCHED(ctx);
+          zg = states;
+        }
+        const int H = st.hidden;
+        float* hbuf = gemm_ws;                   // [B, H]
+        float* stbuf = gemm_ws + (size_t)B * 64;  // [B, 2D]
+        int rc = mnf_gemm_any(ctx, (int)B, H, (int)D, zg, D, 1, st.w1, H, 1, hbuf, H, false);
+        if (rc) return rc;
+        const int64_t nh = B * H;
+        iaf_hidden_kernel<<<(int)cdiv(nh, 256), 256, 0, ctx->stream>>>(nh, H, st.b1, hbuf, a.hid_save);
+        MNF_LAUNCHED(ctx);
+        rc = mnf_gemm_any(ctx, (int)B, (int)(2 * D), H, hbuf, H, 1, st.ws, 2 * D, 1, stbuf, 2 * D, false);
+        if (rc) return rc;
+        mnf_note_path("flow_gemm");
+        iaf_combine_kernel<<<(int)cdiv(B, 8), 256, 0, ctx->stream>>>(B, (int)D, st.parity, zg, stbuf, st.bs, st.bt, zout,
+                                                                   a.ld_in, a.ld_out);
+        MNF_LAUNCHED(ctx);
         continue;
       }
       int grid = (int)cdiv(B, FT_ROWS);
