@@ -101,9 +101,12 @@ def train_config(args) -> None:
     for _ in range(max(args.warmup, 3)):
         tr.step(xd, yd)
     barrier()
-    n0 = ctx.launches
+    def all_launches():  # the main context, the KL branch's forked context and the model's side contexts
+        return ctx.launches + (tr.kl_ctx.launches if tr.kl_ctx else 0) + sum(c.launches for c in getattr(model, "_sides", []))
+
+    n0 = all_launches()
     tr.step(xd, yd)
-    per_step = ctx.launches - n0
+    per_step = all_launches() - n0
     barrier()
     import time
     starts, stops = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
