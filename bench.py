@@ -263,6 +263,11 @@ def workload_config(args, rows_per_step=ROWS) -> dict:
                       "as one CUDA graph, see launch_modes_ms_per_step; e2e: graph replay unless --no-graph (a device-side "
                       "replay counter advances the Philox call indices: replays are bit-identical to eager calls)",
             "weights": "frozen (Sequential.freeze_weights): packed / pre-split weight blocks are kept across steps",
+            "first_layer": ("every one of the 10240 rows convolved (--no-share)" if getattr(args, "no_share", False) else
+                            "model.mc_predict(images[10], 1024): conv1's two convolutions are evaluated once per distinct "
+                            "image and the noise (z, eps) is drawn per posterior sample -- mnf_conv.py:190-197 applies the "
+                            "noise after the contractions, so outputs equal those of the 10240-row repeated batch (same "
+                            "Philox counters; tests/test_gpu_mc.py); resident_tiled_batch times that batch"),
             "streams": "KL terms on 4 sibling streams and the z chains of layers 2-4 on 3 side streams, all forked from "
                        "the step's stream after its start event and joined before its stop event",
             "parallelism": f"row-sharded x{args.gpus}, no collective"}
@@ -319,6 +324,24 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
         kl = model.kl_div(ctx=kl_lanes)  # lanes were forked above, so this still starts at the step's start
         ctx.wait(kl_ctx)
         return probs, kl
+
+    # The workload as the API states it: the 10 distinct images (resident in HBM) under 1024 posterior
+    # samples each.  mc_predict lets the first layer convolve every distinct image once and draw only
+    # the noise per sample (mnf_conv.py:190-197 applies z and eps after the contractions; SURVEY.md
+    # 8f-2) -- same rows, same Philox counters as the forward of the 10240-row repeated batch, which
+    # is timed too (`resident_tiled_batch`; --no-share makes it the headline again).
+    imgs_dev = ctx.to_device(imgs)
+    model.mc_share_first = not args.no_share
+
+    def step_mc():
+        for c in kl_lanes:
+            c.wait(ctx)
+        probs = model.mc_predict(imgs_dev, N_SAMPLES)
+        kl = model.kl_div(ctx=kl_lanes)
+        ctx.wait(kl_ctx)
+        return probs, kl
+
+    main_step = (lambda: step(x_dev)) if args.no_share else step_mc
 
     def side_launches():  # the model's own side context (z of the later layers, drawn ahead)
         return sum(c.launches for c in getattr(model, "_sides", []))
@@ -406,7 +429,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     for i in range(n_probe):
         L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
         L.check(lib.mnf_ctx_probe(ctx.handle, 1, int(os.environ.get("MNF_BENCH_PROBE_SKIP", "1")), kst[i], ksp[i]))  # 2nd conv GEMM launch = conv2
-        step(x_dev)
+        main_step()
     barrier()
     launches_per_step = (all_launches() - launches0) // n_probe
 
@@ -419,7 +442,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
         from tf_mnf_b200.graph import CapturedStep
 
         try:
-            graph = CapturedStep(ctx, lambda: step(x_dev), forks=kl_lanes + list(model._sides), layers=model.mnf_layers,
+            graph = CapturedStep(ctx, main_step, forks=kl_lanes + list(model._sides), layers=model.mnf_layers,
                                  models=[model])
             for _ in range(3):
                 graph.launch()
@@ -446,9 +469,10 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
         return per, t0, t1
 
     # both ways of launching the same step are timed (K steps each); the faster one is `value`
-    modes = {"eager": timed_steps(lambda: step(x_dev))}
+    modes = {"eager": timed_steps(main_step)}
     if graph is not None:
         modes["graph"] = timed_steps(graph.launch)
+    tiled_ms = float(np.mean(timed_steps(lambda: step(x_dev))[0])) if not args.no_share else None
     launch_mode = min(modes, key=lambda k: float(np.mean(modes[k][0])))
     step_ms, t_wall0, t_wall1 = modes[launch_mode]
     t_wall = t_wall1 - t_wall0
@@ -570,6 +594,10 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
             "gpu_launches": int(launches),
             "clocks": clk.summary(min(v[1] for v in modes.values()), max(v[2] for v in modes.values())),
             "launch_modes_ms_per_step": {k: float(np.mean(v[0])) for k, v in modes.items()},
+            "resident_tiled_batch": None if tiled_ms is None else {
+                "value": ROWS / (tiled_ms * 1e-3), "unit": UNIT, "ms_per_step": tiled_ms, "n_gpus": 1,
+                "note": "rank 0, eager: model(x) on the resident 10240-row repeated batch + kl_div() -- the first layer "
+                        "convolves every row (no sharing between the samples of an image)"},
             "roofline": {"bound": "hbm",
                          "kernel": ("cf::conv_raw_f16" if args.math == "tf32x3" else "paired_gemm_fwd<CONV,64>")
                          + " (conv2: 12x12x20 -> 8x8x50, 5x5, + fused ReLU/2x2 max-pool)",
@@ -613,6 +641,9 @@ def main() -> None:
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--hostprof", action="store_true", help="cProfile of 20 steps' host-side enqueue (stderr)")
+    ap.add_argument("--no-share", action="store_true",
+                    help="forward the 10240-row repeated batch instead of mc_predict(images, 1024): the first layer then "
+                         "convolves every row")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--breakdown", action="store_true", help="print per-layer device times of one step (stderr)")
     args = ap.parse_args()

@@ -319,6 +319,17 @@ int mnf_u32_add(mnf_ctx* ctx, uint32_t* counter, uint32_t inc);
  * prediction (every input row `repeat` times, np.repeat(x, repeat, axis=0)) formed on the
  * device, so only the distinct rows cross PCIe. */
 int mnf_tile_rows(mnf_ctx* ctx, int64_t n_rows, int64_t row_elems, int64_t repeat, const float* src, float* dst);
+/* Monte-Carlo predictive through a FIRST MNFConv2D layer: the batch repeats every
+ * image n_rep times (lenet_mnist.py:84) and MNFConv2D.call (mnf_conv.py:182-197) applies z and eps
+ * after the contractions, so conv(x, W_mu) + b_mu and sqrt(conv(x^2, sigma^2) + vb) are computed once
+ * per DISTINCT image (mnf_conv2d_forward's mean_out / sd_out on the distinct rows) and expanded here:
+ *   y[b] = mean[b / n_rep] * z[b] + sd[b / n_rep] * eps[b]      (+ ReLU and 2x2 max-pool when asked)
+ * with the Philox counters of the full-batch kernels (global row, output pixel, filter quad).
+ * mean, sd: [ceil(B / n_rep), Ho, Wo, F]; z: [B, F] or NULL; y: [B, Ho, Wo, F] or [B, Ho/2, Wo/2, F].
+ * Needs F % 4 == 0 (and even Ho, Wo when pooling): mnf_conv2d_mc_can_expand tells. */
+int mnf_conv2d_mc_can_expand(mnf_ctx* ctx, int64_t Ho, int64_t Wo, int64_t F, int32_t fuse_relu_pool, int32_t* ok);
+int mnf_conv2d_mc_expand(mnf_ctx* ctx, int64_t B, int64_t n_rep, int64_t Ho, int64_t Wo, int64_t F, const float* mean,
+                         const float* sd, const float* z, const mnf_noise* eps, int32_t fuse_relu_pool, float* y);
 /* Adam update on a flat parameter buffer (lenet_mnist.py:47,115). */
 int mnf_adam_step(mnf_ctx* ctx, int64_t n, float* param, const float* grad, float* m, float* v,
                   float lr, float beta1, float beta2, float eps, int32_t step);

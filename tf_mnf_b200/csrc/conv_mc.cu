@@ -1,0 +1,124 @@
+// Monte-Carlo predictive through a FIRST MNFConv2D layer ("rows sharing an image
+// share conv(x, W)").  MNFConv2D.call (mnf_conv.py:182-197) applies the multiplicative noise AFTER
+// the contractions:  y = (conv(x, W_mu) + b_mu) * z + sqrt(conv(x^2, sigma^2) + vb) * eps,  so for a
+// batch that repeats every image n times (lenet_mnist.py:84, x.repeat(...)) the two convolutions
+// are the same for all n posterior samples of an image.  mnf_conv2d_forward computes the
+// pre-noise mean and standard-deviation maps once per DISTINCT image; this kernel then draws
+// z-scaled, eps-perturbed outputs for every (image, sample) row -- the part that is really
+// per-row -- optionally with the ReLU + 2x2 max-pool that follows the layer in MNF-LeNet.
+// Noise counters are those of the full-batch kernels (global row, output pixel, filter quad), so
+// the draws are the same numbers either way.
+//
+// One CTA per output row: the per-row constants (image, z, Philox row) are set up once and the
+// threads walk the row's (pooled pixel, filter quad) items; the per-image maps (460 KB for
+// MNF-LeNet conv1) stay in L2 / L1.  Issue-bound on Philox4x32-10 + Box-Muller like every noise
+// consumer here, but with every warp of the SM on it instead of the 16 epilogue warps of a GEMM CTA.
+#include "common.cuh"
+
+namespace {
+
+struct McArgs {
+  int64_t B, n_rep;
+  int Ho, Wo, F;
+  const float* mean;  // [I, Ho, Wo, F]  conv(x, W_mu) + b_mu
+  const float* sd;    // [I, Ho, Wo, F]  sqrt(conv(x^2, sigma^2) + vb)
+  const float* z;     // [B, F] or nullptr
+  NoiseDev eps;
+  float* y;           // [B, Ho, Wo, F] or pooled [B, Ho/2, Wo/2, F]
+};
+
+__device__ __forceinline__ float4 ld4g(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// four outputs (one pixel, one filter quad) of row `brow`
+__device__ __forceinline__ void mc_quad(const McArgs& a, int64_t brow, uint64_t grow, const float* mimg, const float* simg,
+                                        const float4& zq, int pix, int q, float o[4]) {
+  float e[4];
+  if (a.eps.injected) {
+    const float4 t = ld4g(a.eps.injected + (brow * a.Ho * a.Wo + pix) * a.F + 4 * q);
+    e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+  } else {
+    philox_normal4(a.eps, grow, (uint32_t)pix, (uint32_t)q, e);
+  }
+  const float4 m = ld4g(mimg + (int64_t)pix * a.F + 4 * q), s = ld4g(simg + (int64_t)pix * a.F + 4 * q);
+  o[0] = fmaf(s.x, e[0], m.x * zq.x);
+  o[1] = fmaf(s.y, e[1], m.y * zq.y);
+  o[2] = fmaf(s.z, e[2], m.z * zq.z);
+  o[3] = fmaf(s.w, e[3], m.w * zq.w);
+}
+
+template <bool POOL>
+__global__ void __launch_bounds__(256) conv_mc_expand(McArgs a) {
+  const int64_t brow = blockIdx.x;
+  const int64_t img = brow / a.n_rep;
+  const uint64_t grow = a.eps.row_offset + (uint64_t)brow;
+  const int Q = a.F >> 2;
+  const int64_t map = (int64_t)a.Ho * a.Wo * a.F;
+  const float* mimg = a.mean + img * map;
+  const float* simg = a.sd + img * map;
+  const float* zrow = a.z ? a.z + brow * a.F : nullptr;
+  if (POOL) {
+    const int Hp = a.Ho >> 1, Wp = a.Wo >> 1, items = Hp * Wp * Q;
+    float* yrow = a.y + brow * (int64_t)items * 4;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int q = it % Q, pp = it / Q, wp = pp % Wp, hp = pp / Wp;
+      const float4 zq = zrow ? ld4g(zrow + 4 * q) : make_float4(1.f, 1.f, 1.f, 1.f);
+      float best[4] = {0.f, 0.f, 0.f, 0.f};  // max(., 0) folds the ReLU in
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int pix = (2 * hp + (d >> 1)) * a.Wo + 2 * wp + (d & 1);
+        float o[4];
+        mc_quad(a, brow, grow, mimg, simg, zq, pix, q, o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) best[j] = fmaxf(best[j], o[j]);
+      }
+      *reinterpret_cast<float4*>(yrow + (int64_t)it * 4) = make_float4(best[0], best[1], best[2], best[3]);
+    }
+  } else {
+    const int items = a.Ho * a.Wo * Q;
+    float* yrow = a.y + brow * (int64_t)items * 4;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int q = it % Q, pix = it / Q;
+      const float4 zq = zrow ? ld4g(zrow + 4 * q) : make_float4(1.f, 1.f, 1.f, 1.f);
+      float o[4];
+      mc_quad(a, brow, grow, mimg, simg, zq, pix, q, o);
+      *reinterpret_cast<float4*>(yrow + (int64_t)it * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mnf_conv2d_mc_can_expand(mnf_ctx* ctx, int64_t Ho, int64_t Wo, int64_t F, int32_t fuse_relu_pool, int32_t* ok) {
+  MNF_CHECK_ARG(ctx && ok && Ho >= 1 && Wo >= 1 && F >= 1, "mnf_conv2d_mc_can_expand: bad argument");
+  *ok = (F % 4 == 0 && Ho * Wo * F < (1 << 28) && (!fuse_relu_pool || (Ho % 2 == 0 && Wo % 2 == 0))) ? 1 : 0;
+  return MNF_OK;
+}
+
+int mnf_conv2d_mc_expand(mnf_ctx* ctx, int64_t B, int64_t n_rep, int64_t Ho, int64_t Wo, int64_t F, const float* mean,
+                         const float* sd, const float* z, const mnf_noise* eps, int32_t fuse_relu_pool, float* y) {
+  MNF_CHECK_ARG(ctx && mean && sd && eps && y, "mnf_conv2d_mc_expand: NULL argument");
+  MNF_CHECK_ARG(B >= 0 && n_rep >= 1 && Ho >= 1 && Wo >= 1 && F >= 1 && B < (1ll << 31), "mnf_conv2d_mc_expand: bad shape");
+  int32_t ok = 0;
+  int rc = mnf_conv2d_mc_can_expand(ctx, Ho, Wo, F, fuse_relu_pool, &ok);
+  if (rc) return rc;
+  if (!ok) {
+    mnf_set_error("mnf_conv2d_mc_expand: unsupported shape Ho=%lld Wo=%lld F=%lld (F %% 4 == 0; even Ho, Wo when pooling)",
+                  (long long)Ho, (long long)Wo, (long long)F);
+    return MNF_ERR_UNSUPPORTED;
+  }
+  auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  MNF_CHECK_ARG(al(mean) && al(sd) && al(z) && al(y) && al(eps->injected), "mnf_conv2d_mc_expand: buffers must be 16-byte aligned");
+  if (B == 0) return MNF_OK;
+  McArgs a;
+  a.B = B; a.n_rep = n_rep; a.Ho = (int)Ho; a.Wo = (int)Wo; a.F = (int)F;
+  a.mean = mean; a.sd = sd; a.z = z; a.eps = make_noise(eps); a.y = y;
+  mnf_note_path(fuse_relu_pool ? "conv_mc_expand<pool>" : "conv_mc_expand");
+  if (fuse_relu_pool) conv_mc_expand<true><<<(unsigned)B, 256, 0, ctx->stream>>>(a);
+  else conv_mc_expand<false><<<(unsigned)B, 256, 0, ctx->stream>>>(a);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+}  // extern "C"

@@ -688,7 +688,10 @@ static int launch(mnf_ctx* ctx, Args& a, const float* mean_W, const float* log_s
     attr_smem = smem;
   }
   const int64_t tiles = cdiv(a.M, BM) * a.ntiles;
-  const int g = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+  // as many CTAs as the busiest one needs rounds: 320 tiles on 148 SMs are 3 rounds either way, and
+  // 107 CTAs x 3 tiles leave 41 SMs to the flow kernels running beside this one on the side streams
+  const int64_t rounds = cdiv(tiles, ctx->sm_count);
+  const int g = (int)cdiv(tiles, rounds);
   const bool probed = mnf_probe_begin(ctx, CONV ? MNF_PROBE_CONV_GEMM : MNF_PROBE_DENSE_GEMM);
   mnf_note_path(BN == 128 ? "paired_umma<128>" : "paired_umma<64>");
   paired_umma_fwd<BN, CONV><<<g, THREADS, smem, ctx->stream>>>(a);

@@ -105,6 +105,56 @@ class MNFConv2D(MNFLayerBase):
 
     __call__ = call
 
+    def mc_supported(self, x_shape, fuse_relu_pool: bool = False) -> bool:
+        """Whether call_mc() covers this input shape (else tile the rows and use call())."""
+        if self.training:
+            return False
+        ctx = self.ctx or default_context()
+        Ho, Wo = conv_out_hw(x_shape[1], x_shape[2], *self.kernel_size, self.strides, self.padding)
+        ok = C.c_int32(0)
+        L.check(ctx.lib.mnf_conv2d_mc_can_expand(ctx.handle, Ho, Wo, self.n_filters, int(fuse_relu_pool), C.byref(ok)))
+        return bool(ok.value)
+
+    def call_mc(self, x: Any, n_samples: int, noise: dict | None = None, fuse_relu_pool: bool = False) -> DeviceArray:  # noqa: A002
+        """call(np.repeat(x, n_samples, axis=0)) for a FIRST layer: z and eps enter
+        after the contractions (mnf_conv.py:190-197), so the two convolutions are evaluated once per
+        distinct input row and only the noise is drawn per (row, sample).  Same Philox counters as
+        call() on the repeated batch; inference only.  noise: {eps_z [B,F], bern_q, eps_out [B,Ho,Wo,F]}
+        with B = len(x) * n_samples."""
+        self.ctx = self.ctx or default_context()
+        x = as_device(x, self.ctx)
+        if x.ndim != 4:
+            raise ValueError(f"MNFConv2D expects NHWC input, got shape {x.shape}")
+        if not self.built:
+            self.build(x.shape)
+        if x.shape[3] != self.stack_size:
+            raise ValueError(f"MNFConv2D built for {self.stack_size} input channels, got {x.shape[3]}")
+        if self.training:
+            raise RuntimeError("call_mc() is an inference path: backward() needs the per-row tape of call()")
+        ctx, n, rows = self.ctx, int(n_samples), x.shape[0]
+        B = rows * n
+        Ho, Wo = conv_out_hw(x.shape[1], x.shape[2], *self.kernel_size, self.strides, self.padding)
+        F = self.n_filters
+        inj = noise or {}
+        z, _, _ = self._sample_z(B, nz.CALL_Z, nz.BERN_Q_CALL, inj, False, self.row_offset)
+        eo = as_device(inj["eps_out"], ctx) if inj.get("eps_out") is not None else None
+        if eo is not None and eo.shape != (B, Ho, Wo, F):
+            raise ValueError(f"injected eps_out must have shape {(B, Ho, Wo, F)}, got {eo.shape}")
+        # pre-noise mean / standard-deviation maps of the distinct rows (y of this call is not used)
+        s = self._shape(x)
+        mean, sd, scratch = ctx.empty((rows, Ho, Wo, F)), ctx.empty((rows, Ho, Wo, F)), ctx.empty((rows, Ho, Wo, F))
+        eps0 = nz.make(self.seed, self.call_index, self.uid, nz.CALL_OUT, self.row_offset, None)
+        L.check(ctx.lib.mnf_conv2d_forward(ctx.handle, C.byref(s), _p(x), None, _p(self.mean_W), _p(self.log_std_W),
+                                           _p(self.mean_b), _p(self.log_var_b), self.max_std, C.byref(eps0),
+                                           _p(scratch), _p(mean), _p(sd)))
+        eps = nz.make(self.seed, self.call_index, self.uid, nz.CALL_OUT, self.row_offset, eo)
+        self.last_fused = bool(fuse_relu_pool)
+        y = ctx.empty((B, Ho // 2, Wo // 2, F) if fuse_relu_pool else (B, Ho, Wo, F))
+        L.check(ctx.lib.mnf_conv2d_mc_expand(ctx.handle, B, n, Ho, Wo, F, _p(mean), _p(sd), _p(z), C.byref(eps),
+                                             int(bool(fuse_relu_pool)), _p(y)))
+        self.call_index += 1
+        return y
+
     def backward(self, dy: Any, need_dx: bool = True) -> DeviceArray | None:
         """Gradient of the most recent call() (made with `training=True`) given dL/dy:
         returns dL/dx (None with need_dx=False: the first layer of a model has no use for it)

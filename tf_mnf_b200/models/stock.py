@@ -109,15 +109,21 @@ class Sequential:
         self.layers = list(layers or [])
         self.presample_z = True   # draw the later layers' z on side streams beside the first layers
         self.presample_first = True  # ... and the first layer's z one call ahead (off inside captured graphs)
+        self.mc_share_first = True   # mc_predict(): a first MNFConv2D convolves each distinct row once
         self._sides: list = []    # one forked context per later MNF layer: their flow chains
         #                           (80-CTA kernels at 10k rows) pack the SMs side by side
 
-    def __call__(self, x: Any, noise: list | None = None) -> DeviceArray:  # noqa: A002
-        """noise: optional list with one injected-draw dict per MNF layer (program order)."""
+    def __call__(self, x: Any, noise: list | None = None, mc_samples: int = 0) -> DeviceArray:  # noqa: A002
+        """noise: optional list with one injected-draw dict per MNF layer (program order).
+        mc_samples = n > 0: x holds DISTINCT rows and the result is that of the batch
+        np.repeat(x, n, axis=0); the first layer (an MNFConv2D that supports it) evaluates its
+        contractions once per distinct row (MNFConv2D.call_mc) -- see mc_predict()."""
         x = as_device(x, default_context())
         it = iter(noise or [])
         skip = False
-        self._first_rows = x.shape[0]
+        n_mc = int(mc_samples)
+        rows = x.shape[0] * (n_mc or 1)
+        self._first_rows = rows
         first = None
         if self.presample_z and not noise:
             mnf = [l for l in self.mnf_layers if l.built and l.use_z and l.ctx is x.ctx]
@@ -129,14 +135,18 @@ class Sequential:
                         if self.presample_first:
                             first = (lyr, side)   # its z for THIS call was drawn during the previous call
                     else:
-                        lyr.presample(x.shape[0], side)
+                        lyr.presample(rows, side)
         for i, lyr in enumerate(self.layers):
             if skip:  # this ReLU+MaxPool was folded into the preceding conv's epilogue
                 skip = False
                 continue
             if hasattr(lyr, "kl_div"):
                 nxt = self.layers[i + 1] if i + 1 < len(self.layers) else None
-                if isinstance(nxt, ReLUMaxPool2D) and hasattr(lyr, "n_filters") and not lyr.training:
+                if n_mc and i == 0:
+                    fuse = isinstance(nxt, ReLUMaxPool2D) and lyr.mc_supported(x.shape, True)
+                    x = lyr.call_mc(x, n_mc, noise=next(it, None), fuse_relu_pool=fuse)
+                    skip = lyr.last_fused
+                elif isinstance(nxt, ReLUMaxPool2D) and hasattr(lyr, "n_filters") and not lyr.training:
                     x = lyr.call(x, noise=next(it, None), fuse_relu_pool=True)
                     skip = lyr.last_fused
                 elif type(nxt) in (ReLU, Softmax) and hasattr(lyr, "n_out") and not lyr.training:
@@ -165,11 +175,18 @@ class Sequential:
         """Monte-Carlo predictive: every input row under `n_samples` independent posterior draws
         (what the reference's notebooks do by calling the model n_samples times on one batch).
         The repeated batch np.repeat(x, n_samples, axis=0) is formed on the device, so only the
-        distinct rows cross PCIe; returns [len(x) * n_samples, ...] in that row order."""
+        distinct rows cross PCIe; returns [len(x) * n_samples, ...] in that row order.  When the
+        first layer is an MNFConv2D its two convolutions are evaluated once per distinct row and
+        only the noise is drawn per sample (mc_share_first; same Philox counters either way)."""
         x = as_device(x, default_context())
         n = int(n_samples)
         if n < 1:
             raise ValueError("n_samples must be >= 1")
+        first = self.layers[0] if self.layers else None
+        if (n > 1 and self.mc_share_first and hasattr(first, "call_mc") and (first.built or x.ndim == 4)
+                and x.ndim == 4 and first.mc_supported(x.shape)):
+            # the samples of an image share the first layer's contractions (SURVEY.md 8f-2)
+            return self(x, mc_samples=n)
         rows = x.shape[0]
         tiled = x.ctx.empty((rows * n, *x.shape[1:]))
         L.check(x.ctx.lib.mnf_tile_rows(x.ctx.handle, rows, x.size // max(rows, 1), n, _p(x), _p(tiled)))
