@@ -428,7 +428,9 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     launches0 = all_launches()
     for i in range(n_probe):
         L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
-        L.check(lib.mnf_ctx_probe(ctx.handle, 1, int(os.environ.get("MNF_BENCH_PROBE_SKIP", "1")), kst[i], ksp[i]))  # 2nd conv GEMM launch = conv2
+        # conv2 = the 2nd conv-GEMM launch of a step that convolves every row, the 1st when conv1 is shared
+        L.check(lib.mnf_ctx_probe(ctx.handle, 1, int(os.environ.get("MNF_BENCH_PROBE_SKIP", "1" if args.no_share else "0")),
+                                  kst[i], ksp[i]))
         main_step()
     barrier()
     launches_per_step = (all_launches() - launches0) // n_probe

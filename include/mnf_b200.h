@@ -327,6 +327,9 @@ int mnf_tile_rows(mnf_ctx* ctx, int64_t n_rows, int64_t row_elems, int64_t repea
  * with the Philox counters of the full-batch kernels (global row, output pixel, filter quad).
  * mean, sd: [ceil(B / n_rep), Ho, Wo, F]; z: [B, F] or NULL; y: [B, Ho, Wo, F] or [B, Ho/2, Wo/2, F].
  * Needs F % 4 == 0 (and even Ho, Wo when pooling): mnf_conv2d_mc_can_expand tells. */
+/* the per-image maps (a handful of images: one thread per output element) */
+int mnf_conv2d_mc_maps(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, const float* mean_W, const float* log_std_W,
+                       const float* mean_b, const float* log_var_b, float max_std, float* mean, float* sd);
 int mnf_conv2d_mc_can_expand(mnf_ctx* ctx, int64_t Ho, int64_t Wo, int64_t F, int32_t fuse_relu_pool, int32_t* ok);
 int mnf_conv2d_mc_expand(mnf_ctx* ctx, int64_t B, int64_t n_rep, int64_t Ho, int64_t Wo, int64_t F, const float* mean,
                          const float* sd, const float* z, const mnf_noise* eps, int32_t fuse_relu_pool, float* y);

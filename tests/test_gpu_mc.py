@@ -20,9 +20,11 @@ def _f32(a):
 
 @pytest.mark.parametrize("math", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("flow", ["iaf", "rnvp"])
-@pytest.mark.parametrize("shape,wshape,n,pool", [((3, 28, 28, 1), (5, 5, 1, 20), 7, True), ((2, 12, 12, 20), (5, 5, 20, 48), 5, True),
-                                                 ((4, 9, 11, 3), (3, 3, 3, 8), 3, False), ((1, 10, 10, 2), (3, 3, 2, 4), 33, True)])
-def test_call_mc_matches_oracle_on_repeated_batch(math, flow, shape, wshape, n, pool):
+@pytest.mark.parametrize("shape,wshape,n,pool,padding", [
+    ((3, 28, 28, 1), (5, 5, 1, 20), 7, True, "VALID"), ((2, 12, 12, 20), (5, 5, 20, 48), 5, True, "VALID"),
+    ((4, 9, 11, 3), (3, 3, 3, 8), 3, False, "VALID"), ((1, 10, 10, 2), (3, 3, 2, 4), 33, True, "VALID"),
+    ((2, 8, 6, 3), (3, 3, 3, 12), 4, True, "SAME"), ((3, 7, 9, 2), (2, 3, 2, 4), 2, False, "SAME")])
+def test_call_mc_matches_oracle_on_repeated_batch(math, flow, shape, wshape, n, pool, padding):
     import tf_mnf_b200 as M
     from tf_mnf_b200 import _lib as L
 
@@ -37,13 +39,13 @@ def test_call_mc_matches_oracle_on_repeated_batch(math, flow, shape, wshape, n, 
         x = rng.uniform(size=shape)
         xr = np.repeat(x, n, axis=0)
         B = xr.shape[0]
-        y0 = O.conv2d(xr, P["mean_W"], 1, "VALID")
+        y0 = O.conv2d(xr, P["mean_W"], 1, padding)
         eps_z, eps = rng.standard_normal((B, F)), rng.standard_normal(y0.shape)
         bern = [(rng.uniform(size=(B, F)) <= 0.5).astype(np.float64) for _ in range(2)]
-        ref, _ = O.conv_call(P, xr, eps_z, eps, 1.0, bern_q=bern)
+        ref, _ = O.conv_call(P, xr, eps_z, eps, 1.0, padding=padding, bern_q=bern)
         if pool:
             ref = O.maxpool2x2_same(O.relu(ref))
-        lyr = make_layer(P, x.shape)
+        lyr = make_layer(P, x.shape, padding=padding)
         inj = dict(eps_z=_f32(eps_z), eps_out=_f32(eps), bern_q=[_f32(b) for b in bern] if flow == "rnvp" else None)
         assert lyr.mc_supported(x.shape, pool)
         got = lyr.call_mc(_f32(x), n, noise=inj, fuse_relu_pool=pool)

@@ -118,6 +118,7 @@ SIGNATURES = {
     "mnf_scale": [vp, _i64, _f, vp, vp],
     "mnf_axpy": [vp, _i64, _f, vp, vp],
     "mnf_tile_rows": [vp, _i64, _i64, _i64, vp, vp],
+    "mnf_conv2d_mc_maps": [vp, C.POINTER(ConvShape), vp, vp, vp, vp, vp, _f, vp, vp],
     "mnf_conv2d_mc_can_expand": [vp, _i64, _i64, _i64, _i32, C.POINTER(_i32)],
     "mnf_conv2d_mc_expand": [vp, _i64, _i64, _i64, _i64, _i64, vp, vp, vp, C.POINTER(Noise), _i32, vp],
     "mnf_u32_add": [vp, vp, C.c_uint32],

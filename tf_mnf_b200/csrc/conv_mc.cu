@@ -2,8 +2,8 @@
 // share conv(x, W)").  MNFConv2D.call (mnf_conv.py:182-197) applies the multiplicative noise AFTER
 // the contractions:  y = (conv(x, W_mu) + b_mu) * z + sqrt(conv(x^2, sigma^2) + vb) * eps,  so for a
 // batch that repeats every image n times (lenet_mnist.py:84, x.repeat(...)) the two convolutions
-// are the same for all n posterior samples of an image.  mnf_conv2d_forward computes the
-// pre-noise mean and standard-deviation maps once per DISTINCT image; this kernel then draws
+// are the same for all n posterior samples of an image.  conv_mc_maps computes the pre-noise
+// mean and standard-deviation maps once per DISTINCT image; conv_mc_expand then draws
 // z-scaled, eps-perturbed outputs for every (image, sample) row -- the part that is really
 // per-row -- optionally with the ReLU + 2x2 max-pool that follows the layer in MNF-LeNet.
 // Noise counters are those of the full-batch kernels (global row, output pixel, filter quad), so
@@ -44,6 +44,49 @@ __device__ __forceinline__ void mc_quad(const McArgs& a, int64_t brow, uint64_t 
   o[1] = fmaf(s.y, e[1], m.y * zq.y);
   o[2] = fmaf(s.z, e[2], m.z * zq.z);
   o[3] = fmaf(s.w, e[3], m.w * zq.w);
+}
+
+// Pre-noise maps of the DISTINCT images: mean = conv(x, W_mu) + b_mu, sd = sqrt(conv(x^2, s^2) + vb)
+// with s = min(exp(L_sigma), max_std), vb = min(exp(l_vb), max_std^2) (mnf_conv.py:184-191).  A handful
+// of images (10 in the MC-predictive config): one thread per output element walks the K = kh*kw*C
+// filter taps; the general kernels would run it on one or two CTAs (116 us on the critical path).
+struct MapArgs {
+  int64_t I;
+  int H, W, C, kh, kw, F, Ho, Wo, stride, pad_t, pad_l;
+  const float *x, *Wm, *Ls, *bm, *lvb;
+  float max_std;
+  float *mean, *sd;
+};
+__global__ void __launch_bounds__(128) conv_mc_maps(MapArgs a) {
+  const int64_t total = a.I * a.Ho * a.Wo * a.F;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(idx % a.F);
+    int64_t t = idx / a.F;
+    const int wo = (int)(t % a.Wo);
+    t /= a.Wo;
+    const int ho = (int)(t % a.Ho);
+    const int64_t img = t / a.Ho;
+    const float* xi = a.x + img * (int64_t)a.H * a.W * a.C;
+    float m = 0.f, v = 0.f;
+    for (int i = 0; i < a.kh; ++i) {
+      const int hi = ho * a.stride - a.pad_t + i;
+      if (hi < 0 || hi >= a.H) continue;
+      for (int j = 0; j < a.kw; ++j) {
+        const int wi = wo * a.stride - a.pad_l + j;
+        if (wi < 0 || wi >= a.W) continue;
+        const float* xp = xi + ((int64_t)hi * a.W + wi) * a.C;
+        const int64_t wbase = ((int64_t)(i * a.kw + j) * a.C) * a.F + f;
+        for (int c = 0; c < a.C; ++c) {
+          const float xv = __ldg(xp + c);
+          const float sg = fminf(expf(__ldg(a.Ls + wbase + (int64_t)c * a.F)), a.max_std);
+          m = fmaf(xv, __ldg(a.Wm + wbase + (int64_t)c * a.F), m);
+          v = fmaf(xv * xv, sg * sg, v);
+        }
+      }
+    }
+    a.mean[idx] = m + __ldg(a.bm + f);
+    a.sd[idx] = sqrtf(v + fminf(expf(__ldg(a.lvb + f)), a.max_std * a.max_std));
+  }
 }
 
 template <bool POOL>
@@ -93,6 +136,30 @@ extern "C" {
 int mnf_conv2d_mc_can_expand(mnf_ctx* ctx, int64_t Ho, int64_t Wo, int64_t F, int32_t fuse_relu_pool, int32_t* ok) {
   MNF_CHECK_ARG(ctx && ok && Ho >= 1 && Wo >= 1 && F >= 1, "mnf_conv2d_mc_can_expand: bad argument");
   *ok = (F % 4 == 0 && Ho * Wo * F < (1 << 28) && (!fuse_relu_pool || (Ho % 2 == 0 && Wo % 2 == 0))) ? 1 : 0;
+  return MNF_OK;
+}
+
+int mnf_conv2d_mc_maps(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, const float* mean_W, const float* log_std_W,
+                       const float* mean_b, const float* log_var_b, float max_std, float* mean, float* sd) {
+  MNF_CHECK_ARG(ctx && s && x && mean_W && log_std_W && mean_b && log_var_b && mean && sd, "mnf_conv2d_mc_maps: NULL argument");
+  int64_t Ho, Wo;
+  int rc = mnf_conv_out_hw(s, &Ho, &Wo);
+  if (rc) return rc;
+  if (s->B == 0) return MNF_OK;
+  MapArgs a;
+  a.I = s->B; a.H = (int)s->H; a.W = (int)s->W; a.C = (int)s->C; a.kh = (int)s->kh; a.kw = (int)s->kw; a.F = (int)s->F;
+  a.Ho = (int)Ho; a.Wo = (int)Wo; a.stride = (int)s->stride; a.pad_t = a.pad_l = 0;
+  if (s->same) {  // TF SAME: smaller half of the padding first
+    int64_t ph = (Ho - 1) * s->stride + s->kh - s->H, pw = (Wo - 1) * s->stride + s->kw - s->W;
+    a.pad_t = (int)((ph > 0 ? ph : 0) / 2);
+    a.pad_l = (int)((pw > 0 ? pw : 0) / 2);
+  }
+  a.x = x; a.Wm = mean_W; a.Ls = log_std_W; a.bm = mean_b; a.lvb = log_var_b; a.max_std = max_std; a.mean = mean; a.sd = sd;
+  const int64_t total = a.I * Ho * Wo * a.F;
+  const int64_t cap = (int64_t)ctx->sm_count * 16;
+  const int grid = (int)(cdiv(total, 128) < cap ? cdiv(total, 128) : cap);
+  conv_mc_maps<<<grid, 128, 0, ctx->stream>>>(a);
+  MNF_LAUNCHED(ctx);
   return MNF_OK;
 }
 

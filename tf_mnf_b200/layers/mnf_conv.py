@@ -140,13 +140,11 @@ class MNFConv2D(MNFLayerBase):
         eo = as_device(inj["eps_out"], ctx) if inj.get("eps_out") is not None else None
         if eo is not None and eo.shape != (B, Ho, Wo, F):
             raise ValueError(f"injected eps_out must have shape {(B, Ho, Wo, F)}, got {eo.shape}")
-        # pre-noise mean / standard-deviation maps of the distinct rows (y of this call is not used)
+        # pre-noise mean / standard-deviation maps of the distinct rows
         s = self._shape(x)
-        mean, sd, scratch = ctx.empty((rows, Ho, Wo, F)), ctx.empty((rows, Ho, Wo, F)), ctx.empty((rows, Ho, Wo, F))
-        eps0 = nz.make(self.seed, self.call_index, self.uid, nz.CALL_OUT, self.row_offset, None)
-        L.check(ctx.lib.mnf_conv2d_forward(ctx.handle, C.byref(s), _p(x), None, _p(self.mean_W), _p(self.log_std_W),
-                                           _p(self.mean_b), _p(self.log_var_b), self.max_std, C.byref(eps0),
-                                           _p(scratch), _p(mean), _p(sd)))
+        mean, sd = ctx.empty((rows, Ho, Wo, F)), ctx.empty((rows, Ho, Wo, F))
+        L.check(ctx.lib.mnf_conv2d_mc_maps(ctx.handle, C.byref(s), _p(x), _p(self.mean_W), _p(self.log_std_W),
+                                           _p(self.mean_b), _p(self.log_var_b), self.max_std, _p(mean), _p(sd)))
         eps = nz.make(self.seed, self.call_index, self.uid, nz.CALL_OUT, self.row_offset, eo)
         self.last_fused = bool(fuse_relu_pool)
         y = ctx.empty((B, Ho // 2, Wo // 2, F) if fuse_relu_pool else (B, Ho, Wo, F))
