@@ -220,6 +220,37 @@ __device__ __forceinline__ void philox_normal4(const NoiseDev& n, uint64_t grow,
   box_muller(p.z, p.w, out[2], out[3]);
 }
 
+// Round keys hoisted out of the call: the key schedule (k += W per round, 20 integer adds) does not
+// depend on the counter, but with the call index read from memory (NoiseDev::delta) the compiler
+// re-derives it inside every call.  A kernel that draws many blocks per thread computes the ten
+// round keys once and keeps them in registers.
+struct PhiloxKeys {
+  uint32_t k0[10], k1[10];
+};
+__device__ __forceinline__ PhiloxKeys philox_keys(const NoiseDev& n) {
+  PhiloxKeys K;
+  const uint32_t k1 = n.delta ? n.k1 + __ldg(n.delta) : n.k1;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    K.k0[r] = n.k0 + (uint32_t)r * 0x9E3779B9u;
+    K.k1[r] = k1 + (uint32_t)r * 0xBB67AE85u;
+  }
+  return K;
+}
+__device__ __forceinline__ void philox_normal4_keys(const NoiseDev& n, const PhiloxKeys& K, uint64_t grow, uint32_t outer,
+                                                    uint32_t inner4, float out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t c0 = inner4, c1 = outer, c2 = (uint32_t)grow, c3 = n.stream ^ ((uint32_t)(grow >> 32) << 24);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0, hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ K.k0[r], n2 = hi0 ^ c3 ^ K.k1[r];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  box_muller(c0, c1, out[0], out[1]);
+  box_muller(c2, c3, out[2], out[3]);
+}
+
 // one normal at (row, outer, inner); `stride_*` describe the injected layout [rows, outer, inner]
 __device__ __forceinline__ float noise_normal1(const NoiseDev& n, int64_t lrow, uint32_t outer, uint32_t inner,
                                                int64_t n_outer, int64_t n_inner) {
