@@ -333,10 +333,10 @@ int mnf_dense_bf16_forward(mnf_ctx* ctx, int64_t M, int K, int N, const float* x
   }
   a.Ap = Ap; a.Bp = Bp; a.vb = vb;
   const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // per device: function attributes belong to the device's copy of the kernel
+  if (!attr_set[ctx->device & 63]) {
     MNF_CUDA(cudaFuncSetAttribute(paired_bf16_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set[ctx->device & 63] = true;
   }
   const int64_t tiles = a.mtiles * a.ntiles;
   const int g = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);

@@ -251,10 +251,10 @@ int mnf_gemm_umma(mnf_ctx* ctx, int M, int N, int K, const float* A, int64_t sAm
     a.atomic = 1;
   }
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // per device: function attributes belong to the device's copy of the kernel
+  if (!attr_set[ctx->device & 63]) {
     MNF_CUDA(cudaFuncSetAttribute(gemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set[ctx->device & 63] = true;
   }
   gemm_tf32x3<<<grid, THREADS, smem, ctx->stream>>>(a);
   MNF_LAUNCHED(ctx);
