@@ -269,7 +269,8 @@ class MNFLayerBase:
         ctx = ctx or self.ctx
         L.check(ctx.lib.mnf_axpy(ctx.handle, dst.size, 1.0, _p(src), _p(dst)))
 
-    def kl_backward(self, scale: float = 1.0, ctx: Context | None = None, grads: dict | None = None) -> None:
+    def kl_backward(self, scale: float = 1.0, ctx: Context | None = None, grads: dict | None = None,
+                    fresh_grads: bool = False) -> None:
         """Gradient of scale * kl_div() (the most recent kl_div() call made with
         `training=True`) accumulated into self.grads.
         `ctx` / `grads`: run on the (forked) context kl_div() ran on and accumulate into another
@@ -287,7 +288,10 @@ class MNFLayerBase:
             names += ["prior_var_r_p", "prior_var_r_p_bias"]
         if self.use_z:
             names += ["q0_log_var", "r0_mean", "r0_log_var", "r0_apvar"]
-        scratch = {n: ctx.empty(getattr(self, n).shape) for n in names}
+        # fresh_grads: the target buffers were just zeroed and nothing else has written them yet, so
+        # the kernel's (overwriting) outputs go there directly instead of through temporaries + axpy
+        target = self.grads if grads is None else grads
+        scratch = {n: target[n] for n in names} if fresh_grads else {n: ctx.empty(getattr(self, n).shape) for n in names}
         for n, buf in scratch.items():
             setattr(g, n, buf.ptr)
         d_z = d_rst = None
@@ -296,8 +300,9 @@ class MNFLayerBase:
             d_rst = ctx.empty((a.n_r_states, 1, D))
             g.d_z, g.d_r_states = d_z.ptr, d_rst.ptr
         L.check(ctx.lib.mnf_kl_backward(ctx.handle, C.byref(a), float(scale), C.byref(g)))
-        for n, buf in scratch.items():
-            self._add_grad(n, buf, ctx, grads)
+        if not fresh_grads:
+            for n, buf in scratch.items():
+                self._add_grad(n, buf, ctx, grads)
         if self.use_z:
             # dKL/d(ld_q) = dKL/d(ld_r) = -scale; the one-element array is cached per (context, scale):
             # uploading it synchronises the stream

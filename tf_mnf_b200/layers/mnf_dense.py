@@ -72,10 +72,12 @@ class MNFDense(MNFLayerBase):
 
     __call__ = call
 
-    def backward(self, dy: Any, need_dx: bool = True) -> DeviceArray | None:
+    def backward(self, dy: Any, need_dx: bool = True, fresh_grads: bool = False) -> DeviceArray | None:
         """Gradient of the most recent call() (made with `training=True`) given dL/dy:
         returns dL/dx (None with need_dx=False: the first layer of a model has no use for it)
-        and ACCUMULATES parameter gradients into self.grads (App. A-1, A-2)."""
+        and ACCUMULATES parameter gradients into self.grads (fresh_grads=True: the caller has just
+        zeroed them, so the kernels write the four weight / bias gradients in place instead of into
+        temporaries that are then added) (App. A-1, A-2)."""
         t = self._tape
         if not t:
             raise RuntimeError(f"{self.name}: call the layer with layer.training = True before backward()")
@@ -89,13 +91,15 @@ class MNFDense(MNFLayerBase):
             raise ValueError(f"dy must have shape {(B, self.n_out)}, got {dy.shape}")
         dx = ctx.empty(x.shape) if need_dx else None
         dz = ctx.empty(x.shape) if self.use_z else None
-        tmp = {n: ctx.empty(getattr(self, n).shape) for n in ("mean_W", "log_std_W", "mean_b", "log_var_b")}
+        names = ("mean_W", "log_std_W", "mean_b", "log_var_b")
+        tmp = {n: self.grads[n] for n in names} if fresh_grads else {n: ctx.empty(getattr(self, n).shape) for n in names}
         L.check(ctx.lib.mnf_dense_backward(ctx.handle, B, self.n_in, self.n_out, _p(x), _p(z), _p(self.mean_W),
                                            _p(self.log_std_W), _p(self.log_var_b), self.max_std, C.byref(t["eps"]),
                                            _p(t["sd"]), _p(dy), _p(dx), _p(dz), _p(tmp["mean_W"]),
                                            _p(tmp["log_std_W"]), _p(tmp["mean_b"]), _p(tmp["log_var_b"])))
-        for n, buf in tmp.items():
-            self._add_grad(n, buf)
+        if not fresh_grads:
+            for n, buf in tmp.items():
+                self._add_grad(n, buf)
         if self.use_z:
             self._sample_z_backward(t["run"], dz, None)
         return dx

@@ -112,12 +112,14 @@ class Trainer:
         L.check(kc.lib.mnf_memset(kc.handle, _p(self.flat_gk), 0, self.flat_gk.nbytes))
         kl = model.kl_div(ctx=kc)
         for lyr, kg in zip(model.mnf_layers, self.kl_grads):
-            lyr.kl_backward(self.kl_weight / self.world, ctx=kc, grads=kg)  # summed over ranks = contributed once
+            # summed over ranks = contributed once; the KL buffer was zeroed above: outputs land in place
+            lyr.kl_backward(self.kl_weight / self.world, ctx=kc, grads=kg, fresh_grads=True)
         for i in range(len(layers) - 1, -1, -1):
-            if i == 0 and hasattr(layers[0], "kl_div"):
-                layers[0].backward(dh, need_dx=False)  # nobody consumes dL/d(input)
+            mnf = hasattr(layers[i], "kl_div")  # MNF layers: the flat gradient buffer was zeroed above
+            if i == 0 and mnf:
+                layers[0].backward(dh, need_dx=False, fresh_grads=True)  # nobody consumes dL/d(input)
             else:
-                dh = layers[i].backward(dh)
+                dh = layers[i].backward(dh, fresh_grads=True) if mnf else layers[i].backward(dh)
         ctx.wait(kc)
         L.check(ctx.lib.mnf_axpy(ctx.handle, self.flat_g.size, 1.0, _p(self.flat_gk), _p(self.flat_g)))
         kc.wait(ctx)  # the KL buffers are re-used next step only after this sum
