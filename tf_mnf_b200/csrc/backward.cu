@@ -955,8 +955,12 @@ __global__ void sample_z_bwd_kernel(int64_t B, int D, const float* __restrict__ 
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int d = blockIdx.x * 32 + cx;
   float t0 = 0.f, t1 = 0.f;
+  // rows are split over gridDim.y (a handful of CTAs walking the whole batch was 45 us per call);
+  // the outputs accumulate, so the slices combine with atomic adds
+  const int64_t chunk = (B + gridDim.y - 1) / gridDim.y;
+  const int64_t blo = blockIdx.y * chunk, bhi = (blo + chunk < B) ? blo + chunk : B;
   if (d < D)
-    for (int64_t b = ry; b < B; b += 8) {
+    for (int64_t b = blo + ry; b < bhi; b += 8) {
       float g = dz0[b * D + d];
       t0 += g;
       t1 = fmaf(g, noise_normal1(eps, b, 0u, (uint32_t)d, 1, D), t1);
@@ -966,8 +970,8 @@ __global__ void sample_z_bwd_kernel(int64_t B, int D, const float* __restrict__ 
   __syncthreads();
   if (ry == 0 && d < D) {
     for (int r = 1; r < 8; ++r) { t0 += s0[r][cx]; t1 += s1[r][cx]; }
-    if (gm) gm[d] += t0;
-    if (glv) glv[d] += t1 * 0.5f * expf(0.5f * lv[d]);
+    if (gm) atomicAdd(gm + d, t0);
+    if (glv) atomicAdd(glv + d, t1 * 0.5f * expf(0.5f * lv[d]));
   }
 }
 
@@ -975,8 +979,12 @@ extern "C" int mnf_sample_z_backward(mnf_ctx* ctx, int64_t B, int64_t D, const f
                                      const mnf_noise* eps_z, float* d_q0_mean, float* d_q0_log_var) {
   MNF_CHECK_ARG(ctx && d_z0 && q0_log_var && eps_z, "mnf_sample_z_backward: NULL argument");
   MNF_CHECK_ARG(B >= 1 && D >= 1 && D < (1 << 30), "mnf_sample_z_backward: bad shape");
-  sample_z_bwd_kernel<<<(unsigned)cdiv(D, 32), 256, 0, ctx->stream>>>(B, (int)D, d_z0, q0_log_var, make_noise(eps_z),
-                                                                     d_q0_mean, d_q0_log_var);
+  int64_t splits = cdiv(B, 32);
+  const int64_t want = cdiv(2 * ctx->sm_count, cdiv(D, 32));
+  if (splits > want) splits = want;
+  if (splits < 1) splits = 1;
+  sample_z_bwd_kernel<<<dim3((unsigned)cdiv(D, 32), (unsigned)splits), 256, 0, ctx->stream>>>(
+      B, (int)D, d_z0, q0_log_var, make_noise(eps_z), d_q0_mean, d_q0_log_var);
   MNF_LAUNCHED(ctx);
   return MNF_OK;
 }
