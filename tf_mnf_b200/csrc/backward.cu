@@ -392,15 +392,31 @@ __global__ void col2im_kernel(ConvGeo g, int64_t b0, int64_t Bc, const float* __
 }
 
 // dz[b,f] = sum_pix dy * mean   (one block per image, threads over f)
-__global__ void conv_dz_kernel(int64_t B, int64_t HoWo, int F, const float* __restrict__ dy,
-                               const float* __restrict__ mean, float* __restrict__ dz) {
+__global__ void __launch_bounds__(256) conv_dz_kernel(int64_t B, int64_t HoWo, int F, const float* __restrict__ dy,
+                                                      const float* __restrict__ mean, float* __restrict__ dz) {
+  // one CTA per image.  F <= 256: the threads form G = 256 / F pixel groups x F filters (all lanes
+  // busy, consecutive threads on consecutive addresses), partial sums folded through shared memory;
+  // wider layers keep a thread per filter.
+  __shared__ float red[256];
   const int64_t b = blockIdx.x;
+  const float* dyb = dy + b * HoWo * F;
+  const float* mb = mean + b * HoWo * F;
+  if (F <= 256) {
+    const int G = 256 / F, f = threadIdx.x % F, g = threadIdx.x / F;
+    float s = 0.f;
+    if (g < G)
+      for (int64_t p = g; p < HoWo; p += G) s = fmaf(dyb[p * F + f], mb[p * F + f], s);
+    red[threadIdx.x] = g < G ? s : 0.f;
+    __syncthreads();
+    if (threadIdx.x < F) {
+      for (int gg = 1; gg < G; ++gg) s += red[gg * F + threadIdx.x];
+      dz[b * F + threadIdx.x] = s;
+    }
+    return;
+  }
   for (int f = threadIdx.x; f < F; f += blockDim.x) {
     float s = 0.f;
-    for (int64_t p = 0; p < HoWo; ++p) {
-      int64_t o = (b * HoWo + p) * F + f;
-      s = fmaf(dy[o], mean[o], s);
-    }
+    for (int64_t p = 0; p < HoWo; ++p) s = fmaf(dyb[p * F + f], mb[p * F + f], s);
     dz[b * F + f] = s;
   }
 }
@@ -454,7 +470,7 @@ extern "C" int mnf_conv2d_backward(mnf_ctx* ctx, const mnf_conv_shape* s, const 
     if ((rc = colsum2(ctx, M, F, dm, dv, d_mean_b, dvb, csum))) return rc;
   }
   if (dz) {
-    conv_dz_kernel<<<(unsigned)s->B, 128, 0, ctx->stream>>>(s->B, HoWo, F, dy, mean_saved, dz);
+    conv_dz_kernel<<<(unsigned)s->B, 256, 0, ctx->stream>>>(s->B, HoWo, F, dy, mean_saved, dz);
     MNF_LAUNCHED(ctx);
   }
   const bool wgrad = d_mean_W || d_log_std_W;

@@ -799,7 +799,9 @@ int mnf_conv2d_forward(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, co
     if (rc || used) return rc;
   }
   const bool tc_ok = mnf_tc_k_ok(ctx, a.K);  // long contractions stay on FFMA in the fp32-parity mode
-  if (!tc_ok || (a.N <= 20 && a.K <= 256)) {  // shapes of the direct FFMA kernel
+  // shapes of the direct FFMA kernel; a training call on the tensor-core modes (mean / sd saved for the
+  // backward pass) takes the implicit GEMM instead: the direct kernel is tuned for inference row counts
+  if (!tc_ok || (a.N <= 20 && a.K <= 256 && !(tc_ok && (mean_out || sd_out)))) {
     rc = need_var();
     if (rc) return rc;
     rc = launch_direct(ctx, a, pad_b, pad_r, &used);
