@@ -217,17 +217,24 @@ __global__ void colsum2_kernel(int64_t M, int N, const float* __restrict__ a0, c
     part[((int64_t)blockIdx.y * 2 + 1) * N + n] = t1;
   }
 }
-__global__ void colsum2_fold(int N, int splits, const float* __restrict__ part, float* __restrict__ out0,
-                             float* __restrict__ out1) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) colsum2_fold(int N, int splits, const float* __restrict__ part,
+                                                    float* __restrict__ out0, float* __restrict__ out1) {
+  // a warp per column: lanes stride over the row splits, then a butterfly (fixed order, and 8 dependent
+  // loads per lane instead of a 256-long serial chain in one thread)
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
   float t0 = 0.f, t1 = 0.f;
-  for (int sp = 0; sp < splits; ++sp) {
+  for (int sp = lane; sp < splits; sp += 32) {
     t0 += part[((int64_t)sp * 2 + 0) * N + n];
     t1 += part[((int64_t)sp * 2 + 1) * N + n];
   }
-  if (out0) out0[n] = t0;
-  if (out1) out1[n] = t1;
+  t0 = warp_sum(t0);
+  t1 = warp_sum(t1);
+  if (lane == 0) {
+    if (out0) out0[n] = t0;
+    if (out1) out1[n] = t1;
+  }
 }
 static inline size_t colsum2_scratch_floats(int64_t N) { return (size_t)COLSUM_SPLITS * 2 * (size_t)N; }
 // part: colsum2_scratch_floats(N) floats of scratch
@@ -238,7 +245,7 @@ static int colsum2(mnf_ctx* ctx, int64_t M, int N, const float* a0, const float*
   if (splits < 1) splits = 1;
   colsum2_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)splits), 256, 0, ctx->stream>>>(M, N, a0, a1, part);
   MNF_LAUNCHED(ctx);
-  colsum2_fold<<<(unsigned)cdiv(N, 128), 128, 0, ctx->stream>>>(N, splits, part, out0, a1 ? out1 : nullptr);
+  colsum2_fold<<<(unsigned)cdiv(N, 8), 256, 0, ctx->stream>>>(N, splits, part, out0, a1 ? out1 : nullptr);
   MNF_LAUNCHED(ctx);
   return MNF_OK;
 }

@@ -34,6 +34,7 @@ class Trainer:
         # the KL branch (kl_div + its backward: single-row flow chains, latency-bound) runs on a forked
         # context beside the likelihood branch and accumulates into its own flat buffer
         self.kl_ctx = None
+        self._z_sides: list = []  # one forked context per MNF layer: the z chains of a step run side by side
         self.flat_gk: DeviceArray | None = None
         self.kl_grads: list[dict] = []
 
@@ -93,6 +94,16 @@ class Trainer:
         model.set_training(True)
         layers = self._forward_layers()
         it = iter(noise or [])
+        if not noise:
+            # z does not depend on x: every layer's flow chain (one CTA per 128 rows, latency-bound at
+            # minibatch sizes) is enqueued up front on its own stream instead of in line, one after another
+            # (only the wide ones: for a 50-wide chain the extra stream fork / join costs the host more than it saves)
+            zl = [l for l in model.mnf_layers if l.use_z and l._flow_dim() >= 256]
+            while len(self._z_sides) < len(zl):
+                self._z_sides.append(ctx.fork())
+            for lyr, side in zip(zl, self._z_sides):
+                side.wait(ctx)  # behind the previous step's parameter update
+                lyr.presample(x.shape[0], side)
         h = x
         for lyr in layers:
             h = lyr(h, noise=next(it, None)) if hasattr(lyr, "kl_div") else lyr(h)
