@@ -82,3 +82,40 @@ def test_feed_forward_mse_step():
     tr = Trainer(model, loss="mse", kl_weight=1e-6, lr=1e-2)
     losses = [float(tr.step(x, t)[0].numpy()[0]) for _ in range(30)]
     assert np.all(np.isfinite(losses)) and np.mean(losses[-5:]) < np.mean(losses[:5])
+
+
+def test_trainer_flat_state_keeps_the_model_usable():
+    """Trainer moves the variables into one flat buffer (re-pointing the live objects) and makes the
+    gradients views of another: layers, flows and inference calls must keep working on them, a
+    second trainer may take the model over, and the KL branch's forked stream must leave the same
+    gradients as a serial evaluation (checked through the parameter update being deterministic)."""
+    import tf_mnf_b200 as M
+    from tf_mnf_b200.train import Trainer
+
+    def run(seed):
+        model, x, y = _model_and_batch(seed=seed)
+        tr = Trainer(model, loss="xent", kl_weight=1e-3, lr=1e-3)
+        for _ in range(3):
+            tr.step(x, y)
+        return model, tr, x, y
+
+    model, tr, x, y = run(7)
+    lo, hi = tr.flat_p.ptr, tr.flat_p.ptr + tr.flat_p.nbytes
+    for lyr in model.mnf_layers:
+        for name, v in lyr.trainable_variables.items():
+            assert lo <= v.ptr < hi, (lyr.name, name)
+            g = lyr.grads[name]
+            assert tr.flat_g.ptr <= g.ptr < tr.flat_g.ptr + tr.flat_g.nbytes and g.shape == v.shape
+    p = model.mc_predict(x[:2], 5).numpy()  # inference on the re-pointed variables (shared first layer)
+    assert p.shape == (10, 10) and np.all(np.isfinite(p))
+    np.testing.assert_allclose(p.sum(1), 1.0, rtol=1e-5)
+    # the same three steps from the same seed give the same parameters, up to the order of the
+    # fp32 atomic adds in the weight-gradient kernels
+    model2, tr2, _, _ = run(7)
+    a, b = tr.flat_p.numpy(), tr2.flat_p.numpy()
+    assert np.max(np.abs(a - b)) <= 1e-5 * max(np.max(np.abs(a)), 1.0)
+    # a second trainer takes the model over
+    tr3 = Trainer(model, loss="xent", kl_weight=1e-3, lr=1e-3)
+    loss, kl = tr3.step(x, y)
+    assert np.isfinite(float(loss.numpy()[0])) and np.isfinite(float(kl.numpy()[0]))
+    M.default_context().sync()
