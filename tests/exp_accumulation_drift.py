@@ -1,4 +1,6 @@
-"""Experiment: error of the IAF / RNVP chain vs the float64 oracle at large D, FFMA vs tcgen05."""
+"""Diagnostic (run by hand on a GPU box: python tests/exp_accumulation_drift.py): error of the flow chains and
+of the dense contraction against the float64 oracle at large D / K, FFMA vs tcgen05 -- the numbers quoted in
+DESIGN.md section 4 and csrc/common.cuh.  Lives in tests/ because it uses the oracle."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

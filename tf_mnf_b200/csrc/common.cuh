@@ -128,7 +128,7 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // The tensor core adds each MMA's result to the fp32 accumulator in TMEM without round-to-nearest,
 // so a chain of K/8 x 3 accumulations drifts: against the float64 oracle the 3xTF32 contraction is
 // at 6e-6 of the tensor's maximum for K = 800 and 2.7e-5 for K = 4096 (FFMA: 9e-7 / 2.7e-6;
-// tools/exp_bigD_flow.py).  The fp32-parity mode therefore keeps contractions longer than this on
+// tests/exp_accumulation_drift.py).  The fp32-parity mode therefore keeps contractions longer than this on
 // the FFMA kernels (every MNF-LeNet / MLP layer is shorter); the bf16 mode, whose caller accepted a
 // tolerance, uses the tensor cores for any K.
 #define MNF_TC_PARITY_KMAX 1280
