@@ -263,3 +263,29 @@ def test_wide_iaf_chain_as_gemms(tc_ctx, math, D, B):
         close(a.numpy(), b, RTOL, f"state {k}")
     close(ld.numpy(), ref_ld, RTOL, "log_dets")
     close(nf.last_run.saved.numpy()[: B * 50].reshape(B, 50), caches[0]["acts"][1], RTOL, "saved hidden")
+
+
+@pytest.mark.parametrize("K,N,B,use_z,act", [(4096, 512, 256, True, None), (1500, 70, 33, True, "relu"), (2048, 24, 5, False, None)])
+def test_dense_long_contraction_keeps_fp32_parity(tc_ctx, K, N, B, use_z, act):
+    """K > 1280 in the fp32-parity tensor-core mode: one TMEM accumulation chain of K terms would
+    drift past 1e-5 (2.7e-5 measured at K = 4096), so the layer runs as split-K tcgen05 GEMMs with
+    chains of <= 1024 terms plus an epilogue kernel (`dense_long_gemm`)."""
+    from tf_mnf_b200 import _lib as L
+
+    rng = np.random.RandomState(K + N)
+    P = O.make_layer_params(rng, (K, N), flow="planar", std_init=10.0, dtype=np.float64)
+    P["q0_log_var"][...] = -3 + 0.5 * rng.standard_normal(K)
+    P["mean_b"][...] = 0.1 * rng.standard_normal(N)
+    x = rng.standard_normal((B, K))
+    eps_z, eps = rng.standard_normal((B, K)), rng.standard_normal((B, N))
+    ref, _ = O.dense_call(P, x, eps_z, eps, 1.0, use_z=use_z)
+    if act == "relu":
+        ref = np.maximum(ref, 0)
+    lyr = make_layer(P, x.shape, use_z=use_z)
+    inj = dict(eps_out=_f32(eps))
+    if use_z:
+        inj["eps_z"] = _f32(eps_z)
+    y = lyr.call(_f32(x), noise=inj, activation=act)
+    assert L.last_path() == "dense_long_gemm", L.last_path()
+    assert act is None or lyr.last_fused
+    close(y.numpy(), ref, RTOL, "dense call (long K, tf32x3)")

@@ -120,8 +120,8 @@ static int gemm(mnf_ctx* ctx, int M, int N, int K, const float* A, int64_t sAm, 
 
 // the same GEMM for other translation units (flows.cu: wide IAF steps on few rows)
 int mnf_gemm_any(mnf_ctx* ctx, int M, int N, int K, const float* A, int64_t sAm, int64_t sAk, const float* B,
-                 int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate) {
-  return gemm(ctx, M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, accumulate);
+                 int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate, bool sqA) {
+  return gemm(ctx, M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, accumulate, sqA);
 }
 
 // ------------------------------------------------------------------- shared small kernels

@@ -82,7 +82,7 @@ int mnf_gemm_umma(mnf_ctx* ctx, int M, int N, int K, const float* A, int64_t sAm
                   int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate, bool sqA = false);
 // backward.cu: C (+)= A B with arbitrary strides (FFMA, or tcgen05 3xTF32 in the tensor-core math modes)
 int mnf_gemm_any(mnf_ctx* ctx, int M, int N, int K, const float* A, int64_t sAm, int64_t sAk, const float* B,
-                 int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate);
+                 int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate, bool sqA = false);
 void* mnf_workspace(mnf_ctx* ctx, size_t bytes);  // nullptr on failure (error set)
 void mnf_note_path(const char* name);              // which kernel family served the last forward call (mnf_last_path)
 // Where a call's packed weights go.  Not frozen: the transient workspace, *fresh = true (pack every

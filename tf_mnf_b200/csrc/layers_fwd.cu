@@ -621,6 +621,72 @@ static int prep_var(mnf_ctx* ctx, int64_t KN, int N, const float* Ls, const floa
   return MNF_OK;
 }
 
+// ---- long contractions in the fp32-parity tensor-core mode (K > MNF_TC_PARITY_KMAX): the fused
+// tcgen05 kernel would sum K terms in one TMEM accumulator (drift beyond the 1e-5 bar) and the FFMA
+// kernel is ~8x slower, so the two products run as split-K GEMMs (gemm_umma.cu: chains of <= 1024
+// terms combined by fp32 atomics) and a small kernel applies the local-reparameterisation epilogue.
+__global__ void dense_xz_kernel(int64_t n, const float* __restrict__ x, const float* __restrict__ z, float* __restrict__ A) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) A[i] = x[i] * z[i];
+}
+__global__ void dense_long_epilogue(int64_t B, int N, const float* __restrict__ mean, const float* __restrict__ var,
+                                    const float* __restrict__ bm, const float* __restrict__ vb, NoiseDev eps, int act,
+                                    float* __restrict__ y, float* __restrict__ sd_out) {
+  const int N4 = (N + 3) >> 2;
+  const int64_t total = B * N4;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = q / N4;
+    const int nb = (int)(q - m * N4) * 4;
+    float e[4];
+    if (eps.injected) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) e[j] = nb + j < N ? eps.injected[m * N + nb + j] : 0.f;
+    } else {
+      philox_normal4(eps, eps.row_offset + (uint64_t)m, 0u, (uint32_t)(nb >> 2), e);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = nb + j;
+      if (n < N) {
+        const float sd = sqrtf(var[m * N + n] + vb[n]);
+        const float out = fmaf(sd, e[j], mean[m * N + n] + bm[n]);
+        y[m * N + n] = act == MNF_ACT_RELU ? fmaxf(out, 0.f) : out;
+        if (sd_out) sd_out[m * N + n] = sd;
+      }
+    }
+  }
+}
+static int dense_long_forward(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const float* x, const float* z,
+                              const float* mean_W, const float* log_std_W, const float* mean_b, const float* log_var_b,
+                              float max_std, const NoiseDev& eps, int act, float* y, float* sd_out) {
+  const size_t pv_floats = (((size_t)(K * N + N + 8)) + 63) & ~(size_t)63;  // prep_var's block comes first
+  const size_t BK = (size_t)B * K, BN = (size_t)B * N;
+  float* ws = (float*)mnf_workspace(ctx, sizeof(float) * (pv_floats + (z ? BK : 0) + 2 * BN + 64));
+  if (!ws) return MNF_ERR_CUDA;
+  float *Vw, *vb;
+  int rc = prep_var(ctx, K * N, (int)N, log_std_W, log_var_b, max_std, &Vw, &vb);  // same base pointer: no growth
+  if (rc) return rc;
+  float* A = ws + pv_floats;
+  float* mean = A + (z ? BK : 0);
+  float* var = mean + BN;
+  const float* Aop = x;
+  const int cap = ctx->sm_count * 8;
+  if (z) {
+    const int64_t g = cdiv((int64_t)BK, 256);
+    dense_xz_kernel<<<(int)(g < cap ? g : cap), 256, 0, ctx->stream>>>((int64_t)BK, x, z, A);
+    MNF_LAUNCHED(ctx);
+    Aop = A;
+  }
+  const bool probed = mnf_probe_begin(ctx, MNF_PROBE_DENSE_GEMM);  // brackets both GEMMs and the epilogue
+  if ((rc = mnf_gemm_any(ctx, (int)B, (int)N, (int)K, Aop, K, 1, mean_W, N, 1, mean, N, false, false))) return rc;
+  if ((rc = mnf_gemm_any(ctx, (int)B, (int)N, (int)K, x, K, 1, Vw, N, 1, var, N, false, true))) return rc;
+  const int64_t g = cdiv(B * ((N + 3) / 4), 256);
+  mnf_note_path("dense_long_gemm");
+  dense_long_epilogue<<<(int)(g < cap ? g : cap), 256, 0, ctx->stream>>>(B, (int)N, mean, var, mean_b, vb, eps, act, y, sd_out);
+  mnf_probe_end(ctx, probed);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
 extern "C" {
 
 int mnf_conv_out_hw(const mnf_conv_shape* s, int64_t* Ho, int64_t* Wo) {
@@ -669,7 +735,7 @@ int mnf_conv2d_can_fuse_pool(mnf_ctx* ctx, const mnf_conv_shape* s, int32_t* ok)
 static bool dense_act_ok(const mnf_ctx* ctx, int64_t K, int64_t N, const float* x, const float* z, int act) {
   if (act == MNF_ACT_NONE) return true;
   if (small_dense_ok(K, N, x, z)) return act == MNF_ACT_RELU || act == MNF_ACT_SOFTMAX;
-  return act == MNF_ACT_RELU && mnf_tc_k_ok(ctx, K);
+  return act == MNF_ACT_RELU && ctx->math_mode != MNF_MATH_FP32;
 }
 
 int mnf_dense_can_fuse_act(mnf_ctx* ctx, int64_t K, int64_t N, int32_t act, int32_t* ok) {
@@ -723,6 +789,9 @@ int mnf_dense_forward_act(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const f
   if (ctx->math_mode == MNF_MATH_BF16)
     return mnf_dense_bf16_forward(ctx, B, (int)K, (int)N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std,
                                   make_noise(eps), y, sd_out, act);
+  if (ctx->math_mode == MNF_MATH_TF32X3 && !mnf_tc_k_ok(ctx, K) && B < (1ll << 31))
+    return dense_long_forward(ctx, B, K, N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std, make_noise(eps), act, y,
+                              sd_out);
   if (ctx->math_mode == MNF_MATH_TF32X3 && mnf_tc_k_ok(ctx, K))
     return mnf_tc_paired_forward(ctx, 0, B, (int)K, (int)N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std,
                                  make_noise(eps), y, nullptr, sd_out, nullptr, act);
