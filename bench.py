@@ -264,8 +264,9 @@ def workload_config(args, rows_per_step=ROWS) -> dict:
                       "replay counter advances the Philox call indices: replays are bit-identical to eager calls)",
             "weights": "frozen (Sequential.freeze_weights): packed / pre-split weight blocks are kept across steps",
             "first_layer": ("every one of the 10240 rows convolved (--no-share)" if getattr(args, "no_share", False) else
-                            "model.mc_predict(images[10], 1024): conv1's two convolutions are evaluated once per distinct "
-                            "image and the noise (z, eps) is drawn per posterior sample -- mnf_conv.py:190-197 applies the "
+                            "model.mc_predict(images[10], 1024): in EVERY step (nothing is cached between steps) conv1's two "
+                            "convolutions are evaluated once per distinct image and the noise (z, eps) is drawn per "
+                            "posterior sample -- SURVEY.md 8f-2; mnf_conv.py:190-197 applies the "
                             "noise after the contractions, so outputs equal those of the 10240-row repeated batch (same "
                             "Philox counters; tests/test_gpu_mc.py); resident_tiled_batch times that batch"),
             "streams": "KL terms on 4 sibling streams and the z chains of layers 2-4 on 3 side streams, all forked from "
