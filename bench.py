@@ -243,7 +243,9 @@ def run_reference(args, rank: int) -> None:
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, rows_per_step=rows),
+        "config": {**workload_config(args, rows_per_step=rows),
+                   "first_layer": "every row convolved, as the reference does (the B200 arm's mc_predict shares conv1's "
+                                  "contractions between the samples of an image; same outputs)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{rows} of {ROWS} rows per step (same images, same model), NumPy float32 "
                                    f"restatement of the reference TF path, {cores} BLAS threads of {os.cpu_count()} host cores; "
