@@ -71,9 +71,9 @@ int mnf_ctx_sm_count(mnf_ctx* ctx, int* out);
 int mnf_ctx_launch_count(mnf_ctx* ctx, int64_t* out);
 
 /* Arithmetic of the paired mean/variance contractions (dense and conv forward):
- *  MNF_MATH_FP32   register-blocked FFMA kernels (default)
- *  MNF_MATH_TF32X3 tcgen05.mma kind::tf32 with hi/lo operand splitting (3 MMAs per product,
- *                  fp32 accumulation in TMEM): fp32-level accuracy (<= 1e-5 rel.) on tensor cores
+ *  MNF_MATH_FP32   register-blocked FFMA kernels
+ *  MNF_MATH_TF32X3 (default) tcgen05.mma with hi/lo operand splitting (3 MMAs per product, fp32
+ *                  accumulation in TMEM): fp32-level accuracy (<= 1e-5 rel.) on tensor cores
  *  MNF_MATH_BF16   MNFDense contractions (N > 16) with bf16 operands, one tcgen05.mma kind::f16
  *                  per product, fp32 accumulation (BASELINE config "wide MNFDense 4096 -> 4096,
  *                  bf16 tensor-core path"): x*z and x^2 are formed in fp32 and rounded to nearest

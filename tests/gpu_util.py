@@ -117,3 +117,91 @@ def close(a, b, rtol=1e-5, what=""):
     err = np.max(np.abs(a - b)) / scale
     assert err <= rtol, f"{what}: max err / max|ref| = {err:.3e} > {rtol:g}"
     return err
+
+
+# ----------------------------------------------------------------- the timed (in-kernel Philox) mode
+def params_from_layer(lyr, dtype=np.float64):
+    """Oracle-layout parameter dict read back from a host layer's device variables."""
+    P = {}
+    for n in ("mean_W", "log_std_W", "mean_b", "log_var_b", "q0_mean", "q0_log_var", "r0_mean", "r0_log_var",
+              "r0_apvar", "prior_var_r_p", "prior_var_r_p_bias"):
+        if hasattr(lyr, n) and getattr(lyr, n) is not None:
+            P[n] = getattr(lyr, n).numpy().astype(dtype)
+    for tag in ("flow_q", "flow_r"):
+        steps = []
+        for fl in getattr(lyr, tag).flows:
+            v = {k: a.numpy().astype(dtype) for k, a in fl.variables().items()}
+            name = type(fl).__name__
+            if name in ("IAF", "MAF"):
+                ls = fl.net.layers
+                steps.append(dict(kind="iaf", parity=fl.parity, W=[l.kernel.numpy().astype(dtype) for l in ls],
+                                  b=[l.bias.numpy().astype(dtype) for l in ls],
+                                  masks=None if ls[0].mask is None else [l.mask_host.astype(dtype) for l in ls]))
+            elif name == "RNVP":
+                steps.append(dict(kind="rnvp", Wn=[v["net_kernel"]], bn=[v["net_bias"]], Wt=v["t_kernel"],
+                                  bt=v["t_bias"], Ws=v["s_kernel"], bs=v["s_bias"]))
+            else:
+                steps.append(dict(kind="planar", u=v["u"].reshape(-1, 1), w=v["w"].reshape(-1, 1), b=v["b"].reshape(1)))
+        P[tag] = steps
+    return P
+
+
+def draw_normal(lyr, draw, call_index, rows, outer, inner, row_offset=0):
+    """Exactly the normals a kernel draws for this layer's (draw id, call index): mnf_philox_normal."""
+    import ctypes as C
+
+    from tf_mnf_b200 import _lib as L
+    from tf_mnf_b200 import noise as nz
+
+    ctx = lyr.ctx
+    out = ctx.empty((rows, outer, inner))
+    seed = (int(lyr.seed) & 0xFFFFFFFF) | ((int(call_index) & 0xFFFFFFFF) << 32)
+    L.check(ctx.lib.mnf_philox_normal(ctx.handle, seed, nz.stream_id(lyr.uid, draw), int(row_offset), rows, outer, inner,
+                                      C.c_void_p(out.ptr)))
+    return out.numpy().astype(np.float64)
+
+
+def draw_bern(lyr, draw, call_index, rows, inner, row_offset=0):
+    import ctypes as C
+
+    from tf_mnf_b200 import _lib as L
+    from tf_mnf_b200 import noise as nz
+
+    ctx = lyr.ctx
+    out = ctx.empty((rows, inner))
+    seed = (int(lyr.seed) & 0xFFFFFFFF) | ((int(call_index) & 0xFFFFFFFF) << 32)
+    L.check(ctx.lib.mnf_philox_bernoulli(ctx.handle, seed, nz.stream_id(lyr.uid, draw), int(row_offset), rows, inner,
+                                         C.c_float(0.5), C.c_void_p(out.ptr)))
+    return out.numpy().astype(np.float64)
+
+
+def call_noise(lyr, B, out_shape, call_index, row_offset=0):
+    """(eps_z [B,D], eps_out [B,...], bern_q list) of one call() of `lyr`, as its kernels draw them in
+    the timed mode (no injection): draw ids of tf_mnf_b200/noise.py, counters of include/mnf_b200.h."""
+    from tf_mnf_b200 import noise as nz
+
+    D = lyr._flow_dim()
+    eps_z = draw_normal(lyr, nz.CALL_Z, call_index, B, 1, D, row_offset).reshape(B, D)
+    inner = out_shape[-1]
+    outer = int(np.prod(out_shape[1:-1])) if len(out_shape) > 2 else 1
+    eps_out = draw_normal(lyr, nz.CALL_OUT, call_index, B, outer, inner, row_offset).reshape(out_shape)
+    bern = None
+    if lyr.flow_type == "rnvp":
+        bern = [draw_bern(lyr, nz.BERN_Q_CALL + k, call_index, B, D, row_offset) for k in range(lyr.n_flows_q)]
+    return eps_z, eps_out, bern
+
+
+def kl_noise(lyr, kl_index):
+    """Draws of one kl_div() call: (eps_z [1,D], eps_a, eps_b | None, bern_q, bern_r)."""
+    from tf_mnf_b200 import noise as nz
+
+    D = lyr._flow_dim()
+    rows, cols = lyr._kl_shape()
+    eps_z = draw_normal(lyr, nz.KL_Z, kl_index, 1, 1, D).reshape(1, D)
+    eps_a = draw_normal(lyr, nz.KL_A, kl_index, 1, 1, rows if lyr._conv else cols).reshape(-1)
+    eps_b = float(draw_normal(lyr, nz.KL_B, kl_index, 1, 1, 1).reshape(())) if lyr._conv else None
+    bq = br = None
+    if lyr.flow_type == "rnvp":
+        bq = [draw_bern(lyr, nz.BERN_Q_KL + k, kl_index, 1, D) for k in range(lyr.n_flows_q)]
+        br = [draw_bern(lyr, nz.BERN_R_KL + k, kl_index, 1, D) for k in range(lyr.n_flows_r)]
+    return eps_z, eps_a, eps_b, bq, br

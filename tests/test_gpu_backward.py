@@ -23,7 +23,7 @@ def ctx(request):
     c = M.default_context()
     c.set_math(request.param)
     yield c
-    c.set_math("fp32")
+    c.set_math("tf32x3")
 
 
 def _f32(a):

@@ -25,7 +25,7 @@ def bf_ctx():
     ctx = M.default_context()
     ctx.set_math("bf16")
     yield ctx
-    ctx.set_math("fp32")
+    ctx.set_math("tf32x3")
 
 
 def _f32(a):

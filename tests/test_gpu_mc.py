@@ -52,7 +52,7 @@ def test_call_mc_matches_oracle_on_repeated_batch(math, flow, shape, wshape, n, 
         assert L.last_path().startswith("conv_mc_expand"), L.last_path()
         close(got.numpy(), ref, RTOL, "call_mc")
     finally:
-        ctx.set_math("fp32")
+        ctx.set_math("tf32x3")
 
 
 def test_mc_predict_shared_equals_tiled_batch():
@@ -88,7 +88,7 @@ def test_mc_predict_shared_equals_tiled_batch():
         model.set_row_offset(1000)
         close(model(np.repeat(x, 40, axis=0)).numpy(), outs[True][0], RTOL, "model(np.repeat)")
     finally:
-        ctx.set_math("fp32")
+        ctx.set_math("tf32x3")
 
 
 def test_mc_predict_falls_back_when_unsupported():

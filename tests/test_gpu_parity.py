@@ -15,11 +15,15 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["tf32x3", "fp32"])
+def ctx(request):
+    """Both arithmetic modes: the library default (tcgen05, hi/lo operand splitting) and the FFMA kernels."""
     import tf_mnf_b200 as M
 
-    return M.default_context()
+    c = M.default_context()
+    c.set_math(request.param)
+    yield c
+    c.set_math("tf32x3")
 
 
 # ------------------------------------------------------------------------------- noise

@@ -38,7 +38,7 @@ def test_presampled_z_is_bit_identical(flow_type, math):
             np.testing.assert_array_equal(a, b)
         assert not np.array_equal(outs[0][1], outs[0][2])  # fresh noise per call
     finally:
-        ctx.set_math("fp32")
+        ctx.set_math("tf32x3")
 
 
 def test_presample_survives_changed_batch_and_training_flag():
@@ -126,7 +126,7 @@ def test_frozen_weights_are_bit_identical_and_unfreeze_sees_updates(math):
         assert not np.array_equal(y_new, ys_ref[1])
     finally:
         ctx.freeze_weights(False)
-        ctx.set_math("fp32")
+        ctx.set_math("tf32x3")
 
 
 def test_captured_step_replays_match_eager_calls():
@@ -174,4 +174,4 @@ def test_captured_step_replays_match_eager_calls():
         g.close()
     finally:
         ctx.freeze_weights(False)
-        ctx.set_math("fp32")
+        ctx.set_math("tf32x3")

@@ -19,7 +19,7 @@ def tc_ctx():
     ctx = M.default_context()
     ctx.set_math("tf32x3")
     yield ctx
-    ctx.set_math("fp32")
+    ctx.set_math("tf32x3")
 
 
 def _f32(a):

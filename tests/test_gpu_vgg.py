@@ -26,7 +26,7 @@ def test_vgg_full_size_forward_and_kl():
         p = model(x).numpy()
         kl = float(model.kl_div().numpy()[0])
     finally:
-        ctx.set_math("fp32")
+        ctx.set_math("tf32x3")
     assert p.shape == (16, 10) and np.all(np.isfinite(p))
     np.testing.assert_allclose(p.sum(1), 1.0, rtol=1e-5)
     assert np.isfinite(kl) and kl > 0
@@ -54,7 +54,7 @@ def test_vgg_tensorcore_matches_ffma():
             model.presample_first = False
             out[mode] = model(x).numpy()
         finally:
-            ctx.set_math("fp32")
+            ctx.set_math("tf32x3")
     np.testing.assert_allclose(out["tf32x3"], out["fp32"], rtol=2e-4, atol=1e-6)
 
 

@@ -120,6 +120,7 @@ int mnf_ctx_create(int device, void* stream, mnf_ctx** out) {
   MNF_CUDA(cudaSetDevice(device));
   mnf_ctx* c = (mnf_ctx*)calloc(1, sizeof(mnf_ctx));
   c->device = device;
+  c->math_mode = MNF_MATH_TF32X3;  // tensor cores with fp32-level accuracy: what a drop-in user gets
   if (stream) {
     c->stream = (cudaStream_t)stream;
     c->owns_stream = false;

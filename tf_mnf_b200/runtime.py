@@ -31,6 +31,7 @@ class Context:
         L.check(self.lib.mnf_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
         self.handle = h
         self.device = device
+        self.math = "tf32x3"  # the library's default (mnf_b200.h): tcgen05 with hi/lo operand splitting
         # Host-side free list of stream-ordered allocations, by size.  A block released by Python
         # and handed out again is only ever touched by LATER work of this context's stream, which
         # is exactly the guarantee of cudaFreeAsync + cudaMallocAsync on one stream -- without
