@@ -57,7 +57,9 @@ const char* mnf_last_error(void);
  * "flow_umma", "flow_mlp", ...): lets tests assert which path a shape exercised. */
 const char* mnf_last_path(void);
 int mnf_device_count(int* out);
-/* stream: a cudaStream_t owned by the caller, or NULL to let the context create its own. */
+/* stream: a cudaStream_t owned by the caller, or NULL to let the context create its own.
+ * One device per process (one process per GPU): a context for a second device in the same
+ * process is refused with MNF_ERR_UNSUPPORTED. */
 int mnf_ctx_create(int device, void* stream, mnf_ctx** out);
 int mnf_ctx_destroy(mnf_ctx* ctx);
 int mnf_ctx_set_stream(mnf_ctx* ctx, void* stream);
@@ -66,6 +68,11 @@ int mnf_ctx_sync(mnf_ctx* ctx);
 /* Make all FUTURE work on ctx's stream wait for everything enqueued so far on other's stream
  * (event fork/join; lets kl_div(), which does not depend on x, run on a second context). */
 int mnf_ctx_wait(mnf_ctx* ctx, mnf_ctx* other);
+/* The same against a FOREIGN stream (the producer's stream of a tensor that enters through DLPack /
+ * __cuda_array_interface__): a cudaStream_t, or 1 = legacy default stream, 2 = per-thread default
+ * stream (the __cuda_array_interface__ v3 encoding).  Contexts own a non-blocking stream, so there is
+ * no implicit ordering with a framework's streams. */
+int mnf_ctx_wait_stream(mnf_ctx* ctx, void* stream);
 int mnf_ctx_sm_count(mnf_ctx* ctx, int* out);
 /* kernels launched by this context since creation (bench.py reports it as gpu_launches) */
 int mnf_ctx_launch_count(mnf_ctx* ctx, int64_t* out);
@@ -113,6 +120,11 @@ int mnf_event_elapsed_ms(void* start, void* stop, float* out); /* synchronises o
 
 /* CUDA-graph capture of everything enqueued between begin/end on the context's stream */
 int mnf_graph_begin(mnf_ctx* ctx);
+/* Mark a context whose stream JOINS a capture (forked from the capturing context via mnf_ctx_wait):
+ * while set, workspace growth / packed-weight cache misses on it fail with a clear message
+ * ("run one eager step first") instead of issuing calls that invalidate the capture.
+ * mnf_graph_begin / mnf_graph_end set and clear it on the capturing context itself. */
+int mnf_ctx_set_capturing(mnf_ctx* ctx, int32_t capturing);
 int mnf_graph_end(mnf_ctx* ctx, void** graph_exec_out);
 int mnf_graph_launch(mnf_ctx* ctx, void* graph_exec);
 int mnf_graph_destroy(void* graph_exec);
@@ -310,7 +322,21 @@ int mnf_softmax_xent(mnf_ctx* ctx, int64_t B, int64_t N, const float* logits, co
  * count; bandgap_regression.py:57-69); dy (may be NULL) = 2 (y - target) * inv_global_n. */
 int mnf_mse_loss(mnf_ctx* ctx, int64_t n, const float* y, const float* target, float inv_global_n,
                  float* loss_out, float* dy);
-/* y = a*x + b (inference-mode BatchNormalization in MNFFeedForward), generic axpby helpers */
+/* tf.keras.layers.BatchNormalization over the last axis of x [B,N] (mnf_feed_forward.py:20; Keras
+ * defaults: momentum 0.99, epsilon 1e-3).  training != 0 (what model.fit runs, bandgap_regression.py:76):
+ * the batch mean and biased batch variance normalise and moving_mean / moving_var move towards them
+ * by (1 - momentum), in place; training == 0 (model(x) in the reference's GradientTape loop and at
+ * prediction time): the moving statistics normalise.  save_mean / save_invstd [N] (NULL together to
+ * skip) keep what the backward needs.  Backward: dx [B,N], d_gamma, d_beta [N] (each may be NULL;
+ * overwritten); `training` must be the flag of the forward call.  Per-rank batch statistics under
+ * data parallelism (no sync-BN), as Keras does per replica. */
+int mnf_batchnorm_forward(mnf_ctx* ctx, int64_t B, int64_t N, const float* x, const float* gamma, const float* beta,
+                          float* moving_mean, float* moving_var, float eps, float momentum, int32_t training, float* y,
+                          float* save_mean, float* save_invstd);
+int mnf_batchnorm_backward(mnf_ctx* ctx, int64_t B, int64_t N, const float* x, const float* gamma, const float* save_mean,
+                           const float* save_invstd, int32_t training, const float* dy, float* dx, float* d_gamma,
+                           float* d_beta);
+/* y = a*x, generic axpby helpers */
 int mnf_scale(mnf_ctx* ctx, int64_t n, float a, const float* x, float* y);
 int mnf_axpy(mnf_ctx* ctx, int64_t n, float a, const float* x, float* y); /* y += a*x */
 /* *counter += inc on the device (the replay counter of a captured step, see mnf_noise.call_delta) */
@@ -333,6 +359,26 @@ int mnf_conv2d_mc_maps(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, co
 int mnf_conv2d_mc_can_expand(mnf_ctx* ctx, int64_t Ho, int64_t Wo, int64_t F, int32_t fuse_relu_pool, int32_t* ok);
 int mnf_conv2d_mc_expand(mnf_ctx* ctx, int64_t B, int64_t n_rep, int64_t Ho, int64_t Wo, int64_t F, const float* mean,
                          const float* sd, const float* z, const mnf_noise* eps, int32_t fuse_relu_pool, float* y);
+/* ---- the data-parallel gradient all-reduce ---------------------------------------
+ * The only collective of the design: where the reference applies its gradients
+ * (notebooks/lenet_mnist.py:114-115, tape.gradient -> adam.apply_gradients), a data-parallel run sums
+ * the flat fp32 gradient buffer over the ranks first.  One process per GPU; NCCL over NVLink, bound at
+ * run time (dlopen of libnccl.so.2 -- the copy a host framework already loaded is re-used; override
+ * with MNF_NCCL_LIB); without NCCL these calls return MNF_ERR_UNSUPPORTED, never a fallback.
+ *   rank 0:    mnf_comm_unique_id(id)            -- host code ships the 128 bytes to the other ranks
+ *   all ranks: mnf_comm_init(ctx, id, rank, world, &comm)          (collective; blocks until all joined)
+ *   per step:  mnf_allreduce_grads(comm, ctx, grads, n)            in place, sum, on ctx's stream
+ * The caller scales: likelihood gradients by 1/global batch (mnf_softmax_xent / mnf_mse_loss do), KL
+ * gradients by 1/world, so that the plain sum is the gradient of the single-process loss. */
+#define MNF_COMM_ID_BYTES 128
+typedef struct mnf_comm mnf_comm;
+int mnf_comm_nccl_version(int* out);
+int mnf_comm_unique_id(uint8_t* h_id /* [MNF_COMM_ID_BYTES], host */);
+int mnf_comm_init(mnf_ctx* ctx, const uint8_t* h_id, int rank, int world, mnf_comm** out);
+int mnf_comm_info(mnf_comm* comm, int* rank, int* world);
+int mnf_comm_destroy(mnf_comm* comm);
+int mnf_allreduce_grads(mnf_comm* comm, mnf_ctx* ctx, float* grads, int64_t n);
+
 /* Adam update on a flat parameter buffer (lenet_mnist.py:47,115). */
 int mnf_adam_step(mnf_ctx* ctx, int64_t n, float* param, const float* grad, float* m, float* v,
                   float lr, float beta1, float beta2, float eps, int32_t step);

@@ -581,6 +581,36 @@ def softmax(x):
     return e / e.sum(axis=-1, keepdims=True)
 
 
+# ------------------------------------------------ stock BatchNormalization (mnf_feed_forward.py:20)
+def batchnorm_forward(x, gamma, beta, moving_mean, moving_var, eps=1e-3, momentum=0.99, training=True):
+    """tf.keras.layers.BatchNormalization() on [B, N] (Keras defaults; third-party: tensorflow==2.1.0
+    keras/layers/normalization.py, non-fused path for rank-2 inputs).  training=True is what
+    model.fit runs (bandgap_regression.py:76): batch mean / biased variance normalise and the moving
+    statistics move by (1 - momentum) towards them; training=False (model(x), :83,:107) uses the
+    moving statistics.  Returns y, cache, (new_moving_mean, new_moving_var)."""
+    if training:
+        mean = x.mean(axis=0)
+        var = ((x - mean) ** 2).mean(axis=0)
+        new = (moving_mean * momentum + mean * (1 - momentum), moving_var * momentum + var * (1 - momentum))
+    else:
+        mean, var, new = moving_mean, moving_var, (moving_mean, moving_var)
+    inv = 1.0 / np.sqrt(var + eps)
+    xhat = (x - mean) * inv
+    return xhat * gamma + beta, dict(xhat=xhat, inv=inv, gamma=gamma, training=training), new
+
+
+def batchnorm_backward(dy, c):
+    """Gradient of batchnorm_forward: (dx, dgamma, dbeta)."""
+    xhat, inv, gamma = c["xhat"], c["inv"], c["gamma"]
+    dgamma, dbeta = (dy * xhat).sum(axis=0), dy.sum(axis=0)
+    if c["training"]:
+        B = dy.shape[0]
+        dx = gamma * inv / B * (B * dy - dbeta - xhat * dgamma)
+    else:
+        dx = dy * gamma * inv
+    return dx, dgamma, dbeta
+
+
 def lenet_forward(Ps, x, noise, max_std=1.0, bern=None):
     """MNFLeNet, mnf_lenet.py:22-33.  Ps = [conv1, conv2, dense1, dense2] param dicts;
     noise = [(eps_z, eps_out)] * 4 in program order (App. A-6)."""

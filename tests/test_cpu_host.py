@@ -199,3 +199,25 @@ def test_philox_reference_vector():
     assert [hex(v) for v in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
     out = philox4x32_10(np.full((1, 4), 0xFFFFFFFF, np.uint32), (0xFFFFFFFF, 0xFFFFFFFF))[0]
     assert [hex(v) for v in out] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+
+
+def test_tf_glue_is_import_guarded():
+    """The package never imports TensorFlow; tf_glue imports cleanly and only fails when used."""
+    import importlib
+    import sys
+
+    sys.modules.pop("tensorflow", None)
+    mod = importlib.import_module("tf_mnf_b200.tf_glue")
+    with pytest.raises(ImportError, match="TensorFlow"):
+        mod.make_keras_layers()
+
+
+def test_nccl_binds_at_run_time():
+    """mnf_comm_* resolve NCCL with dlopen (csrc/comm.cu): the version query needs no GPU."""
+    import ctypes as C
+
+    from tf_mnf_b200 import _lib as L
+
+    v = C.c_int()
+    L.check(L.load().mnf_comm_nccl_version(C.byref(v)))
+    assert v.value >= 20000

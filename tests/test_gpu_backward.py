@@ -3,6 +3,8 @@
 no gradients of its own: it relies on TF autodiff of the forward the oracle restates."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import pytest
 from gpu_util import close, make_flows, make_layer
@@ -11,7 +13,7 @@ from oracle import mnf_oracle as O
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5   # activations-like tensors (dx, dz)
-RTOL_G = 2e-5  # parameter gradients (fp32 atomics / split-K accumulate over the batch)
+RTOL_G = float(os.environ.get("MNF_RTOL_G", 2e-5))  # parameter gradients (fp32 atomics / split-K accumulate over the batch)
 
 
 @pytest.fixture(scope="module", params=["fp32", "tf32x3"])

@@ -175,3 +175,26 @@ def test_captured_step_replays_match_eager_calls():
     finally:
         ctx.freeze_weights(False)
         ctx.set_math("tf32x3")
+
+
+def test_presampled_z_is_discarded_when_parameters_change():
+    """Sequential draws the first layer's z for the NEXT call ahead of time; a parameter assigned in
+    between must not leave that call with a z drawn from the old q0_mean (it is redrawn in line, with
+    the same Philox counters, from the current parameters)."""
+    import tf_mnf_b200 as M
+    from tf_mnf_b200.models import MNFLeNet
+
+    x = np.random.RandomState(0).uniform(size=(6, 28, 28, 1)).astype(np.float32)
+    outs = []
+    for ahead in (True, False):
+        M.set_seed(9)
+        model = MNFLeNet(4, 6, 16, 10, max_std=1, flow_h_sizes=[8], std_init=1.0)
+        model.presample_first = model.presample_z = ahead
+        model(x)  # builds the layers (Keras protocol); nothing can be drawn ahead before that
+        model(x)  # draws the first layer's z for the next call beside the rest of this one
+        l0 = model.mnf_layers[0]
+        assert (l0._pre is not None) == ahead
+        l0.q0_mean.assign(l0.q0_mean.numpy() + 0.5)
+        l0.flow_q.flows[0].net.layers[0].kernel.assign(l0.flow_q.flows[0].net.layers[0].kernel.numpy() * 0.5)
+        outs.append(model(x).numpy())
+    np.testing.assert_array_equal(outs[0], outs[1])

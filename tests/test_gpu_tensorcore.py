@@ -289,3 +289,37 @@ def test_dense_long_contraction_keeps_fp32_parity(tc_ctx, K, N, B, use_z, act):
     assert L.last_path() == "dense_long_gemm", L.last_path()
     assert act is None or lyr.last_fused
     close(y.numpy(), ref, RTOL, "dense call (long K, tf32x3)")
+
+
+@pytest.mark.parametrize("K,N,B,use_z", [(800, 500, 1300, True), (64, 17, 1024, False), (1280, 130, 1025, True)])
+def test_dense_f16x3_many_rows(tc_ctx, K, N, B, use_z):
+    """dense_f16x3.cu (M >= 1024): injected noise against the float64 oracle, sd_out included; rows whose
+    magnitudes differ by 1e8 and weight columns 7 decades apart must each meet the bar relative to
+    THEIR OWN output scale (per-row and per-column power-of-two scales)."""
+    from tf_mnf_b200 import _lib as L
+
+    rng = np.random.RandomState(K + N)
+    P = O.make_layer_params(rng, (K, N), flow="iaf", std_init=10.0, dtype=np.float64)
+    P["q0_log_var"][...] = -3 + 0.5 * rng.standard_normal(K)
+    P["mean_b"][...] = 0.0
+    P["log_var_b"][...] = -60.0
+    P["mean_W"] *= np.exp(rng.uniform(-8, 8, size=N))
+    x = rng.standard_normal((B, K))
+    x *= np.exp(rng.uniform(-9, 9, size=(B, 1)))
+    x[5] = 0.0
+    eps_z, eps = rng.standard_normal((B, K)), rng.standard_normal((B, N))
+    ref, c = O.dense_call(P, x, eps_z, eps, 1.0, use_z=use_z)
+    lyr = make_layer(P, x.shape, use_z=use_z)
+    lyr.training = True  # sd_out is written
+    inj = dict(eps_out=_f32(eps))
+    if use_z:
+        inj["eps_z"] = _f32(eps_z)
+    got = lyr(_f32(x), noise=inj).numpy()
+    assert L.last_path() == "paired_f16x3<128>", L.last_path()
+    close(got, ref, RTOL, "whole tensor")
+    close(lyr._tape["sd"].numpy(), c["sq"], RTOL, "sd_out")
+    for b in range(0, B, 97):
+        if np.max(np.abs(ref[b])) > 1e-30:
+            close(got[b], ref[b], 2e-5, f"row {b}")
+    for n in range(0, N, 7):
+        close(got[:, n], ref[:, n], 2e-5, f"column {n}")

@@ -46,6 +46,9 @@ DENSE_CASES = [
     (800, 500, 300, "relu", "paired_umma<128>"),
     (800, 500, 129, None, "paired_umma<128>"),
     (136, 100, 64, None, "paired_umma<64>"),
+    (800, 500, 1100, "relu", "paired_f16x3<128>"),   # many rows: packed split-fp16 operands (dense_f16x3.cu)
+    (136, 100, 1024, None, "paired_f16x3<128>"),
+    (130, 70, 1031, None, "paired_f16x3<128>"),      # ragged: K % 32, N % 4, M % 128 all non-zero
     (500, 10, 257, "softmax", "dense_small"),
     (500, 10, 33, None, "dense_small"),
 ]

@@ -119,3 +119,71 @@ def test_trainer_flat_state_keeps_the_model_usable():
     loss, kl = tr3.step(x, y)
     assert np.isfinite(float(loss.numpy()[0])) and np.isfinite(float(kl.numpy()[0]))
     M.default_context().sync()
+
+
+@pytest.mark.parametrize("batch_stats", [True, False])
+def test_batchnorm_layer_matches_oracle(batch_stats):
+    """BatchNormalization (mnf_feed_forward.py:20) forward, moving-average update and backward against
+    the oracle: fit-mode batch statistics and the tape loop's moving statistics; 1e-5 of the maximum."""
+    import tf_mnf_b200 as M
+    from gpu_util import close
+    from tf_mnf_b200.models.stock import BatchNormalization
+
+    from oracle import mnf_oracle as O
+
+    ctx = M.default_context()
+    rng = np.random.RandomState(8)
+    B, N = 1024, 100
+    x = (3 + 2 * rng.standard_normal((B, N))).astype(np.float32)
+    dy = rng.standard_normal((B, N)).astype(np.float32)
+    bn = BatchNormalization(batch_stats=batch_stats)
+    bn.build((B, N), ctx)
+    g, b = 1 + 0.3 * rng.standard_normal(N), 0.2 * rng.standard_normal(N)
+    mm, mv = 0.1 * rng.standard_normal(N), 1 + 0.2 * rng.uniform(size=N)
+    for arr, v in ((bn.gamma, g), (bn.beta, b), (bn.moving_mean, mm), (bn.moving_variance, mv)):
+        arr.assign(v.astype(np.float32))
+    g, b, mm, mv = (a.numpy().astype(np.float64) for a in (bn.gamma, bn.beta, bn.moving_mean, bn.moving_variance))
+    x64 = x.astype(np.float64)
+    # inference call: moving statistics, nothing updated
+    y_inf = bn(ctx.to_device(x)).numpy()
+    ref_inf, _, _ = O.batchnorm_forward(x64, g, b, mm, mv, training=False)
+    close(y_inf, ref_inf, 1e-5, "inference")
+    bn.training = True
+    y = bn(ctx.to_device(x)).numpy()
+    ref, c, (nm, nv) = O.batchnorm_forward(x64, g, b, mm, mv, training=batch_stats)
+    close(y, ref, 1e-5, "training-call y")
+    close(bn.moving_mean.numpy(), nm, 1e-6, "moving mean")
+    close(bn.moving_variance.numpy(), nv, 1e-6, "moving variance")
+    bn.zero_grads()
+    dx = bn.backward(ctx.to_device(dy)).numpy()
+    rdx, rdg, rdb = O.batchnorm_backward(dy.astype(np.float64), c)
+    close(dx, rdx, 1e-5, "dx")
+    close(bn.grads["gamma"].numpy(), rdg, 1e-5, "dgamma")
+    close(bn.grads["beta"].numpy(), rdb, 1e-5, "dbeta")
+
+
+def test_feed_forward_trains_batchnorm_parameters():
+    """BASELINE configs[1] (MNF-MLP regressor): gamma / beta of the BatchNormalization layers are
+    trainable variables of the step (they live in the Trainer's flat buffer and move), the moving
+    statistics follow the batches, and a prediction afterwards uses them."""
+    import tf_mnf_b200 as M
+    from tf_mnf_b200.models import MNFFeedForward
+    from tf_mnf_b200.train import Trainer
+
+    M.set_seed(6)
+    model = MNFFeedForward(layer_sizes=(32, 16, 4), flow_h_sizes=[8], std_init=1e-2)
+    rng = np.random.RandomState(2)
+    x = (1.5 + rng.standard_normal((64, 24))).astype(np.float32)
+    t = (x[:, :4] * 0.5).astype(np.float32)
+    tr = Trainer(model, loss="mse", kl_weight=1e-6, lr=1e-2)
+    for _ in range(5):
+        tr.step(x, t)
+    bns = [l for l in model.layers if type(l).__name__ == "BatchNormalization"]
+    assert len(bns) == 2
+    lo, hi = tr.flat_p.ptr, tr.flat_p.ptr + tr.flat_p.nbytes
+    for bn in bns:
+        assert lo <= bn.gamma.ptr < hi and lo <= bn.beta.ptr < hi
+        assert np.max(np.abs(bn.gamma.numpy() - 1)) > 1e-4 and np.max(np.abs(bn.beta.numpy())) > 1e-4
+        assert np.max(np.abs(bn.moving_mean.numpy())) > 1e-4  # relu outputs have a positive mean
+    p = model(x).numpy()
+    assert p.shape == (64, 4) and np.all(np.isfinite(p))

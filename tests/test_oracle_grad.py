@@ -170,3 +170,28 @@ def test_kl_grad_no_z():
     g = O.dense_kl_backward(P, c, 1.0, learn_p=True)
     tree = dict(P={k: P[k] for k in ("mean_W", "log_std_W", "mean_b", "log_var_b", "prior_var_r_p", "prior_var_r_p_bias")})
     fd_check(lambda: O.dense_kl(P, None, None, use_z=False)[0], tree, dict(P=g), rng)
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_batchnorm_backward_fd(training):
+    """Stock BatchNormalization of MNFFeedForward (mnf_feed_forward.py:20): the oracle's analytic
+    backward against finite differences, batch-statistics (model.fit) and moving-statistics modes."""
+    rng = np.random.RandomState(3)
+    B, N = 9, 5
+    P = dict(x=rng.standard_normal((B, N)), gamma=1 + 0.3 * rng.standard_normal(N), beta=0.2 * rng.standard_normal(N))
+    mm, mv = 0.1 * rng.standard_normal(N), 1 + 0.2 * rng.uniform(size=N)
+    w = rng.standard_normal((B, N))
+
+    def f():
+        y, _, _ = O.batchnorm_forward(P["x"], P["gamma"], P["beta"], mm, mv, training=training)
+        return float((y * w).sum())
+
+    y, c, (nm, nv) = O.batchnorm_forward(P["x"], P["gamma"], P["beta"], mm, mv, training=training)
+    dx, dg, db = O.batchnorm_backward(w, c)
+    fd_check(f, P, dict(x=dx, gamma=dg, beta=db), rng, n=12)
+    if training:
+        np.testing.assert_allclose(nm, mm * 0.99 + P["x"].mean(0) * 0.01)
+        np.testing.assert_allclose(nv, mv * 0.99 + P["x"].var(0) * 0.01)
+        np.testing.assert_allclose(y.mean(0), P["beta"], atol=1e-12)
+    else:
+        assert nm is mm and nv is mv

@@ -66,6 +66,7 @@ SIGNATURES = {
     "mnf_ctx_get_stream": [vp, C.POINTER(vp)],
     "mnf_ctx_sync": [vp],
     "mnf_ctx_wait": [vp, vp],
+    "mnf_ctx_wait_stream": [vp, vp],
     "mnf_ctx_sm_count": [vp, C.POINTER(C.c_int)],
     "mnf_ctx_launch_count": [vp, C.POINTER(_i64)],
     "mnf_ctx_set_math": [vp, C.c_int],
@@ -116,6 +117,8 @@ SIGNATURES = {
     "mnf_softmax_xent": [vp, _i64, _i64, vp, vp, _f, vp, vp],
     "mnf_mse_loss": [vp, _i64, vp, vp, _f, vp, vp],
     "mnf_scale": [vp, _i64, _f, vp, vp],
+    "mnf_batchnorm_forward": [vp, _i64, _i64, vp, vp, vp, vp, vp, _f, _f, _i32, vp, vp, vp],
+    "mnf_batchnorm_backward": [vp, _i64, _i64, vp, vp, vp, vp, _i32, vp, vp, vp, vp],
     "mnf_axpy": [vp, _i64, _f, vp, vp],
     "mnf_tile_rows": [vp, _i64, _i64, _i64, vp, vp],
     "mnf_conv2d_mc_maps": [vp, C.POINTER(ConvShape), vp, vp, vp, vp, vp, _f, vp, vp],
@@ -123,7 +126,15 @@ SIGNATURES = {
     "mnf_conv2d_mc_expand": [vp, _i64, _i64, _i64, _i64, _i64, vp, vp, vp, C.POINTER(Noise), _i32, vp],
     "mnf_u32_add": [vp, vp, C.c_uint32],
     "mnf_adam_step": [vp, _i64, vp, vp, vp, vp, _f, _f, _f, _f, _i32],
+    "mnf_ctx_set_capturing": [vp, _i32],
+    "mnf_comm_nccl_version": [C.POINTER(C.c_int)],
+    "mnf_comm_unique_id": [vp],
+    "mnf_comm_init": [vp, vp, C.c_int, C.c_int, C.POINTER(vp)],
+    "mnf_comm_info": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "mnf_comm_destroy": [vp],
+    "mnf_allreduce_grads": [vp, vp, vp, _i64],
 }
+MNF_COMM_ID_BYTES = 128
 MNF_ACT_NONE, MNF_ACT_RELU, MNF_ACT_SOFTMAX = 0, 1, 2
 NON_STATUS = {"mnf_version": ([], C.c_int), "mnf_last_error": ([], C.c_char_p), "mnf_last_path": ([], C.c_char_p)}
 ALL_SYMBOLS = sorted([*SIGNATURES, *NON_STATUS])

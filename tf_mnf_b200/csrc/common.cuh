@@ -77,6 +77,12 @@ int mnf_tc_paired_forward(mnf_ctx* ctx, int conv, int64_t M, int K, int N, const
 int mnf_dense_bf16_forward(mnf_ctx* ctx, int64_t M, int K, int N, const float* x, const float* z, const float* mean_W,
                            const float* log_std_W, const float* mean_b, const float* log_var_b, float max_std,
                            const NoiseDev& eps, float* y, float* sd_out, int act);
+// dense_f16x3.cu: many-row dense layers in the fp32-parity mode: operands packed once into scaled fp16 hi/lo
+// planes, three kind::f16 MMAs per product, both operand streams by cp.async.bulk
+bool mnf_dense_f16x3_ok(const mnf_ctx* ctx, int64_t M, int K, int N);
+int mnf_dense_f16x3_forward(mnf_ctx* ctx, int64_t M, int K, int N, const float* x, const float* z, const float* mean_W,
+                            const float* log_std_W, const float* mean_b, const float* log_var_b, float max_std,
+                            const NoiseDev& eps, float* y, float* sd_out, int act);
 // gemm_umma.cu: strided fp32 GEMM C (+)= A B as 3xTF32 on tcgen05 (backward contractions)
 int mnf_gemm_umma(mnf_ctx* ctx, int M, int N, int K, const float* A, int64_t sAm, int64_t sAk, const float* B,
                   int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate, bool sqA = false);

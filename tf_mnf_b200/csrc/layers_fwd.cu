@@ -792,6 +792,11 @@ int mnf_dense_forward_act(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const f
   if (ctx->math_mode == MNF_MATH_TF32X3 && !mnf_tc_k_ok(ctx, K) && B < (1ll << 31))
     return dense_long_forward(ctx, B, K, N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std, make_noise(eps), act, y,
                               sd_out);
+  // many rows: operands packed once into split fp16 planes, GEMM fed by bulk copies (dense_f16x3.cu);
+  // few rows (training minibatches): the one-launch tile kernel whose producer warps split in place
+  if (mnf_dense_f16x3_ok(ctx, B, (int)K, (int)N) && !getenv("MNF_NO_F16X3"))
+    return mnf_dense_f16x3_forward(ctx, B, (int)K, (int)N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std,
+                                   make_noise(eps), y, sd_out, act);
   if (ctx->math_mode == MNF_MATH_TF32X3 && mnf_tc_k_ok(ctx, K))
     return mnf_tc_paired_forward(ctx, 0, B, (int)K, (int)N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std,
                                  make_noise(eps), y, nullptr, sd_out, nullptr, act);

@@ -117,7 +117,17 @@ int mnf_ctx_create(int device, void* stream, mnf_ctx** out) {
     return MNF_ERR_CUDA;
   }
   MNF_CHECK_ARG(device >= 0 && device < n, "mnf_ctx_create: device %d out of range [0,%d)", device, n);
+  // One device per process (one process per GPU): the entry points launch on the
+  // CURRENT device and the kernels' function attributes are set once per process, so a second
+  // device in the same process is refused instead of failing later with an opaque CUDA error.
+  static int first_device = -1;
+  if (first_device >= 0 && device != first_device) {
+    mnf_set_error("mnf_ctx_create: this process already drives device %d; libmnf_b200 uses one process per GPU "
+                  "(asked for device %d)", first_device, device);
+    return MNF_ERR_UNSUPPORTED;
+  }
   MNF_CUDA(cudaSetDevice(device));
+  first_device = device;
   mnf_ctx* c = (mnf_ctx*)calloc(1, sizeof(mnf_ctx));
   c->device = device;
   c->math_mode = MNF_MATH_TF32X3;  // tensor cores with fp32-level accuracy: what a drop-in user gets
@@ -184,6 +194,23 @@ int mnf_ctx_wait(mnf_ctx* ctx, mnf_ctx* other) {
   cudaEventDestroy(ev);  // released once the recorded work completes
   if (e != cudaSuccess) {
     mnf_set_error("mnf_ctx_wait failed: %s", cudaGetErrorString(e));
+    return MNF_ERR_CUDA;
+  }
+  return MNF_OK;
+}
+
+int mnf_ctx_wait_stream(mnf_ctx* ctx, void* stream) {
+  MNF_CHECK_ARG(ctx, "mnf_ctx_wait_stream: ctx is NULL");
+  // __cuda_array_interface__ v3 stream encoding: 1 = legacy default stream, 2 = per-thread default
+  cudaStream_t s = stream == (void*)1 ? cudaStreamLegacy : stream == (void*)2 ? cudaStreamPerThread : (cudaStream_t)stream;
+  if (s == ctx->stream) return MNF_OK;
+  cudaEvent_t ev;
+  MNF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaError_t e = cudaEventRecord(ev, s);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev, 0);
+  cudaEventDestroy(ev);
+  if (e != cudaSuccess) {
+    mnf_set_error("mnf_ctx_wait_stream failed: %s", cudaGetErrorString(e));
     return MNF_ERR_CUDA;
   }
   return MNF_OK;
@@ -297,6 +324,12 @@ int mnf_graph_begin(mnf_ctx* ctx) {
   MNF_CHECK_ARG(!ctx->capturing, "mnf_graph_begin: already capturing");
   MNF_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
   ctx->capturing = true;
+  return MNF_OK;
+}
+
+int mnf_ctx_set_capturing(mnf_ctx* ctx, int32_t capturing) {
+  MNF_CHECK_ARG(ctx, "ctx is NULL");
+  ctx->capturing = capturing != 0;
   return MNF_OK;
 }
 

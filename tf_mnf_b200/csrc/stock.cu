@@ -142,6 +142,97 @@ __global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __res
   }
 }
 
+
+// ---- tf.keras.layers.BatchNormalization over the last axis of [B, N] (mnf_feed_forward.py:20; Keras
+// defaults momentum 0.99, epsilon 1e-3).  Block = 32 columns x 8 row groups: lanes walk columns
+// (coalesced), row groups stride the batch; reductions over the batch through shared memory,
+// accumulated in double (B terms of either sign).
+//   training: batch mean and BIASED variance normalise (the rank-2, non-fused Keras path), and the
+//             moving statistics move by (1 - momentum) towards them;
+//   inference: the moving statistics normalise.
+constexpr int BN_COLS = 32, BN_RG = 8;
+
+__device__ __forceinline__ double bn_block_sum(double v, double (*red)[BN_COLS]) {
+  const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  red[rg][c] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int g = 0; g < BN_RG; ++g) s += red[g][c];
+  __syncthreads();
+  return s;
+}
+
+__global__ void __launch_bounds__(BN_COLS* BN_RG) batchnorm_fwd_kernel(
+    int64_t B, int N, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+    float* __restrict__ mov_mean, float* __restrict__ mov_var, float eps, float momentum, int training,
+    float* __restrict__ y, float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  __shared__ double red[BN_RG][BN_COLS];
+  const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int n = blockIdx.x * BN_COLS + c;
+  const bool ok = n < N;
+  float mean, var;
+  if (training) {
+    double s = 0.0;
+    if (ok)
+      for (int64_t b = rg; b < B; b += BN_RG) s += (double)x[b * N + n];
+    const double m = bn_block_sum(s, red) / (double)B;
+    double q = 0.0;
+    if (ok)
+      for (int64_t b = rg; b < B; b += BN_RG) {
+        const double d = (double)x[b * N + n] - m;
+        q += d * d;
+      }
+    const double v = bn_block_sum(q, red) / (double)B;
+    mean = (float)m;
+    var = (float)v;
+    if (ok && rg == 0) {
+      mov_mean[n] = mov_mean[n] * momentum + mean * (1.f - momentum);
+      mov_var[n] = mov_var[n] * momentum + var * (1.f - momentum);
+    }
+  } else {
+    mean = ok ? mov_mean[n] : 0.f;
+    var = ok ? mov_var[n] : 1.f;
+  }
+  if (!ok) return;
+  const float inv = 1.0f / sqrtf(var + eps);
+  if (rg == 0 && save_mean) { save_mean[n] = mean; save_invstd[n] = inv; }
+  const float g = gamma[n], bt = beta[n];
+  for (int64_t b = rg; b < B; b += BN_RG) y[b * N + n] = (x[b * N + n] - mean) * inv * g + bt;
+}
+
+// training: dx = gamma * inv / B * (B dy - sum(dy) - xhat sum(dy xhat));  inference: dx = dy gamma inv
+__global__ void __launch_bounds__(BN_COLS* BN_RG) batchnorm_bwd_kernel(
+    int64_t B, int N, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ save_mean,
+    const float* __restrict__ save_invstd, int training, const float* __restrict__ dy, float* __restrict__ dx,
+    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ double red[BN_RG][BN_COLS];
+  const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int n = blockIdx.x * BN_COLS + c;
+  const bool ok = n < N;
+  const float mean = ok ? save_mean[n] : 0.f, inv = ok ? save_invstd[n] : 0.f;
+  double s1 = 0.0, s2 = 0.0;
+  if (ok)
+    for (int64_t b = rg; b < B; b += BN_RG) {
+      const float g = dy[b * N + n];
+      s1 += (double)g;
+      s2 += (double)g * (double)((x[b * N + n] - mean) * inv);
+    }
+  const double sum_dy = bn_block_sum(s1, red), sum_dyx = bn_block_sum(s2, red);
+  if (!ok) return;
+  if (rg == 0) {
+    if (dgamma) dgamma[n] = (float)sum_dyx;
+    if (dbeta) dbeta[n] = (float)sum_dy;
+  }
+  if (!dx) return;
+  const float gi = gamma[n] * inv;
+  const float m1 = (float)(sum_dy / (double)B), m2 = (float)(sum_dyx / (double)B);
+  for (int64_t b = rg; b < B; b += BN_RG) {
+    const float g = dy[b * N + n];
+    dx[b * N + n] = training ? gi * (g - m1 - (x[b * N + n] - mean) * inv * m2) : gi * g;
+  }
+}
+
 extern "C" {
 
 int mnf_relu_maxpool2(mnf_ctx* ctx, int64_t B, int64_t H, int64_t W, int64_t C, const float* x, float* y,
@@ -208,6 +299,29 @@ int mnf_mse_loss(mnf_ctx* ctx, int64_t n, const float* y, const float* target, f
   MNF_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), ctx->stream));
   if (n == 0) return MNF_OK;
   mse_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(n, y, target, inv_global_n, loss_out, dy);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+int mnf_batchnorm_forward(mnf_ctx* ctx, int64_t B, int64_t N, const float* x, const float* gamma, const float* beta,
+                          float* moving_mean, float* moving_var, float eps, float momentum, int32_t training, float* y,
+                          float* save_mean, float* save_invstd) {
+  MNF_CHECK_ARG(ctx && x && gamma && beta && moving_mean && moving_var && y, "mnf_batchnorm_forward: NULL argument");
+  MNF_CHECK_ARG(B >= 1 && N >= 1 && N < (1 << 30), "mnf_batchnorm_forward: bad shape [%lld,%lld]", (long long)B, (long long)N);
+  MNF_CHECK_ARG((save_mean == nullptr) == (save_invstd == nullptr), "mnf_batchnorm_forward: save_mean / save_invstd go together");
+  batchnorm_fwd_kernel<<<(int)cdiv(N, BN_COLS), BN_COLS * BN_RG, 0, ctx->stream>>>(
+      B, (int)N, x, gamma, beta, moving_mean, moving_var, eps, momentum, training, y, save_mean, save_invstd);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+int mnf_batchnorm_backward(mnf_ctx* ctx, int64_t B, int64_t N, const float* x, const float* gamma, const float* save_mean,
+                           const float* save_invstd, int32_t training, const float* dy, float* dx, float* d_gamma,
+                           float* d_beta) {
+  MNF_CHECK_ARG(ctx && x && gamma && save_mean && save_invstd && dy, "mnf_batchnorm_backward: NULL argument");
+  MNF_CHECK_ARG(B >= 1 && N >= 1 && N < (1 << 30), "mnf_batchnorm_backward: bad shape [%lld,%lld]", (long long)B, (long long)N);
+  batchnorm_bwd_kernel<<<(int)cdiv(N, BN_COLS), BN_COLS * BN_RG, 0, ctx->stream>>>(B, (int)N, x, gamma, save_mean, save_invstd,
+                                                                                 training, dy, dx, d_gamma, d_beta);
   MNF_LAUNCHED(ctx);
   return MNF_OK;
 }

@@ -68,6 +68,9 @@ class CapturedStep:
         try:
             for c in self.forks:
                 c.wait(ctx)  # fork: the other streams join the capture
+                # ... and must fail as clearly as the capturing context if they would grow a workspace
+                # or miss the packed-weight cache now (cudaFree / cudaMalloc would invalidate the capture)
+                L.check(ctx.lib.mnf_ctx_set_capturing(c.handle, 1))
             # z drawn one call ahead (Sequential.presample_first): the captured step reads the z the
             # previous replay drew (buffer X, filled eagerly for replay 0 by the stocking pass above)
             # and draws the next one into another buffer Y; Y is copied onto X at the end of the graph.
@@ -89,6 +92,8 @@ class CapturedStep:
             for c in every:
                 c._capture_keep = None
                 c._capturing = False
+            for c in self.forks:
+                ctx.lib.mnf_ctx_set_capturing(c.handle, 0)
             g = C.c_void_p()
             rc = ctx.lib.mnf_graph_end(ctx.handle, C.byref(g))
         L.check(rc)

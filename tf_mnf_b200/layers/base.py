@@ -12,7 +12,7 @@ from .. import init
 from .. import noise as nz
 from ..flows import IAF, RNVP, NormalizingFlow, PlanarFlow
 from ..flows.base import ChainRun
-from ..runtime import Context, DeviceArray, as_device, default_context
+from ..runtime import Context, DeviceArray, as_device, default_context, param_version
 
 _VP = C.c_void_p
 
@@ -136,7 +136,8 @@ class MNFLayerBase:
         pre, self._pre = (self._pre, None) if z_draw == nz.CALL_Z else (None, self._pre)
         if pre is not None:
             ctx.wait(pre["side"])  # also orders the buffers' (stream-ordered) release after the side work
-            if (not inject and pre["key"] == (B, index, row_offset, bool(record)) and ctx is self.ctx):
+            # ... drawn from the CURRENT parameters: a z sampled before an assign() / optimiser step is stale
+            if (not inject and pre["key"] == (B, index, row_offset, bool(record), param_version()) and ctx is self.ctx):
                 return pre["z"], pre["ld"], pre["run"]
         eps_inj = as_device(inject["eps_z"], ctx) if inject.get("eps_z") is not None else None
         if eps_inj is not None and eps_inj.shape != (B, D):
@@ -164,7 +165,8 @@ class MNFLayerBase:
         self._pre = None
         B = int(batch_size)
         z, ld, run = self._sample_z(B, nz.CALL_Z, nz.BERN_Q_CALL, None, self.training, self.row_offset, side, self.ctx)
-        self._pre = dict(key=(B, self.call_index, self.row_offset, bool(self.training)), z=z, ld=ld, run=run, side=side)
+        self._pre = dict(key=(B, self.call_index, self.row_offset, bool(self.training), param_version()), z=z, ld=ld,
+                         run=run, side=side)
 
     def sample_z(self, batch_size: int, noise: dict | None = None):  # noqa: A002 - mirrors reference name
         self._require_built()

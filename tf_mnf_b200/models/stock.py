@@ -88,19 +88,74 @@ class Softmax(StockLayer):
 
 
 class BatchNormalization(StockLayer):
-    """Inference mode (what `model(x)` evaluates in the reference's loops): moving mean 0,
-    variance 1, epsilon 1e-3, gamma 1, beta 0  ->  y = x / sqrt(1 + 1e-3)."""
+    """tf.keras.layers.BatchNormalization() as MNFFeedForward uses it (mnf_feed_forward.py:20): last
+    axis, momentum 0.99, epsilon 1e-3, trainable gamma / beta, moving mean / variance.
 
-    scale = float(1.0 / np.sqrt(1.0 + 1e-3))
+    Keras picks the mode per call: `model.fit` (bandgap_regression.py:76) normalises with the batch
+    statistics and updates the moving averages; a plain `model(x)` -- the reference's GradientTape
+    loop (:106-107) and its predictions (:83) -- normalises with the moving statistics while gamma
+    and beta still receive gradients.  Here `batch_stats` selects the mode of a TRAINING call
+    (`layer.training`): True = fit semantics (default, what Trainer runs), False = the tape loop's.
+    Inference calls always use the moving statistics."""
+
+    def __init__(self, momentum: float = 0.99, epsilon: float = 1e-3, batch_stats: bool = True) -> None:
+        self.momentum, self.epsilon, self.batch_stats = float(momentum), float(epsilon), bool(batch_stats)
+        self.built = False
+        self.grads: dict = {}
+        self.name = "batch_normalization"
+
+    def build(self, input_shape, ctx=None) -> None:
+        ctx = ctx or default_context()
+        n = int(input_shape[-1])
+        self.gamma, self.beta = ctx.to_device(np.ones(n, np.float32)), ctx.zeros((n,))
+        self.moving_mean, self.moving_variance = ctx.zeros((n,)), ctx.to_device(np.ones(n, np.float32))
+        self.built = True
+
+    @property
+    def trainable_variables(self) -> dict:
+        return {"gamma": self.gamma, "beta": self.beta} if self.built else {}
+
+    def variables(self) -> dict:
+        return {**self.trainable_variables, "moving_mean": self.moving_mean, "moving_variance": self.moving_variance}
+
+    def zero_grads(self) -> dict:
+        for name, v in self.trainable_variables.items():
+            g = self.grads.get(name)
+            if g is None or g.shape != v.shape:
+                self.grads[name] = v.ctx.zeros(v.shape)
+            else:
+                L.check(v.ctx.lib.mnf_memset(v.ctx.handle, _p(g), 0, g.nbytes))
+        return self.grads
 
     def __call__(self, x: DeviceArray) -> DeviceArray:
-        y = x.ctx.empty(x.shape)
-        L.check(x.ctx.lib.mnf_scale(x.ctx.handle, x.size, self.scale, _p(x), _p(y)))
+        if x.ndim != 2:
+            raise NotImplementedError("BatchNormalization: [batch, features] inputs (MNFFeedForward) only")
+        if not self.built:
+            self.build(x.shape, x.ctx)
+        ctx, (B, N) = x.ctx, x.shape
+        y = ctx.empty(x.shape)
+        mode = int(self.training and self.batch_stats)
+        sm = si = None
+        if self.training:
+            sm, si = ctx.empty((N,)), ctx.empty((N,))
+            self._tape = dict(x=x, mean=sm, invstd=si, mode=mode)
+        L.check(ctx.lib.mnf_batchnorm_forward(ctx.handle, B, N, _p(x), _p(self.gamma), _p(self.beta), _p(self.moving_mean),
+                                              _p(self.moving_variance), self.epsilon, self.momentum, mode, _p(y), _p(sm), _p(si)))
         return y
 
-    def backward(self, dy):
-        dx = dy.ctx.empty(dy.shape)
-        L.check(dy.ctx.lib.mnf_scale(dy.ctx.handle, dy.size, self.scale, _p(dy), _p(dx)))
+    def backward(self, dy: DeviceArray, fresh_grads: bool = False) -> DeviceArray:
+        """dL/dx; ACCUMULATES d gamma / d beta into self.grads (fresh_grads: written in place)."""
+        t = self._tape
+        ctx, x = dy.ctx, t["x"]
+        if not self.grads:
+            self.zero_grads()
+        dx = ctx.empty(x.shape)
+        tmp = self.grads if fresh_grads else {n: ctx.empty(v.shape) for n, v in self.trainable_variables.items()}
+        L.check(ctx.lib.mnf_batchnorm_backward(ctx.handle, x.shape[0], x.shape[1], _p(x), _p(self.gamma), _p(t["mean"]),
+                                               _p(t["invstd"]), t["mode"], _p(dy), _p(dx), _p(tmp["gamma"]), _p(tmp["beta"])))
+        if not fresh_grads:
+            for n, buf in tmp.items():
+                L.check(ctx.lib.mnf_axpy(ctx.handle, buf.size, 1.0, _p(buf), _p(self.grads[n])))
         return dx
 
 
@@ -218,6 +273,11 @@ class Sequential:
     @property
     def mnf_layers(self) -> list:
         return [l for l in self.layers if hasattr(l, "kl_div")]
+
+    @property
+    def param_layers(self) -> list:
+        """Every layer that owns trainable variables: the MNF layers and BatchNormalization."""
+        return [l for l in self.layers if hasattr(type(l), "trainable_variables")]
 
     def set_training(self, flag: bool) -> None:
         for lyr in self.layers:

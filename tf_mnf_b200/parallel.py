@@ -7,8 +7,8 @@
   gradient is identical on every rank and must be contributed once: one all-reduce (NCCL over
   NVLink on GPUs, gloo in the CPU tests) over a flat fp32 buffer.
 
-torch.distributed is plumbing here (process group + collective); tensors handed to it are
-zero-copy views of DeviceArrays (`torch.as_tensor(arr)` via __cuda_array_interface__).
+The collective itself is libmnf_b200's mnf_allreduce_grads (tf_mnf_b200/comm.py: NCCL bound inside
+the C ABI); this module holds the host-side rules and is free of torch.
 """
 from __future__ import annotations
 
@@ -31,27 +31,28 @@ def shard_model_rows(model: Any, n_rows: int, rank: int, world: int) -> tuple[in
     return lo, hi
 
 
-def allreduce_gradients(like_grads: Sequence[Any], kl_grads: Sequence[Any] | None = None, group: Any = None) -> None:
-    """In place: like_grads[i] <- sum_ranks(like_grads[i]) / world  (+ kl_grads[i] once).
+def allreduce_gradients(like_grads: Sequence[Any], kl_grads: Sequence[Any] | None = None, comm: Any = None) -> None:
+    """In place: like_grads[i] <- sum_ranks(like_grads[i])  (+ kl_grads[i] once).
 
-    `like_grads` hold each rank's gradient of ITS OWN shard's mean loss times (local rows /
-    global rows) -- i.e. already scaled so that the plain SUM over ranks is the gradient of the
-    global-batch mean (softmax_xent's inv_global_batch does this).  Tensors are torch tensors
-    (CPU for gloo, CUDA views for NCCL); they are flattened into ONE buffer so a single
-    collective is issued (lenet: 1.70 M parameters = 6.8 MB)."""
-    import torch
-    import torch.distributed as dist
+    The list form of what `Trainer` does on its flat device buffer, on HOST arrays (NumPy): `like_grads`
+    hold each rank's gradient of ITS OWN shard's loss already scaled by 1 / global batch
+    (mnf_softmax_xent's inv_global_batch does this), so that the plain SUM over ranks is the gradient
+    of the global-batch mean; the KL gradient is identical on every rank and is added once behind the
+    sum (or, as Trainer does, pre-scaled by 1 / world and folded into the summed buffer).  The arrays
+    are flattened into ONE buffer so a single collective is issued (lenet: 1.70 M parameters =
+    6.8 MB).  `comm`: any object with `.world` and `.allreduce_host(flat: np.ndarray)` (in-place sum)."""
+    import numpy as np
 
-    tensors = [t for t in like_grads]
+    tensors = list(like_grads)
     if not tensors:
         return
-    flat = torch.cat([t.reshape(-1) for t in tensors])
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat = np.concatenate([np.asarray(t, np.float32).reshape(-1) for t in tensors])
+    if comm is not None and getattr(comm, "world", 1) > 1:
+        comm.allreduce_host(flat)
     off = 0
     for i, t in enumerate(tensors):
-        n = t.numel()
-        t.copy_(flat[off:off + n].view_as(t))
+        n = t.size
+        t[...] = flat[off:off + n].reshape(t.shape)
         if kl_grads is not None and kl_grads[i] is not None:
-            t.add_(kl_grads[i])
+            t += kl_grads[i]
         off += n

@@ -104,6 +104,11 @@ class Context:
         """Order this context's future work after everything enqueued so far on `other`."""
         L.check(self.lib.mnf_ctx_wait(self.handle, other.handle))
 
+    def wait_stream(self, stream: int) -> None:
+        """Order this context's future work after everything enqueued so far on a foreign stream
+        (cudaStream_t handle; 1 = legacy default, 2 = per-thread default)."""
+        L.check(self.lib.mnf_ctx_wait_stream(self.handle, C.c_void_p(int(stream))))
+
     def set_math(self, mode: str) -> None:
         """"fp32": FFMA kernels; "tf32x3": tcgen05 tensor cores with hi/lo operand splitting
         (fp32-level accuracy); "bf16": as tf32x3, but MNFDense contractions use one bf16 MMA per
@@ -165,6 +170,21 @@ class _Owned:
 
 
 _tls = threading.local()
+
+# Bumped whenever a parameter buffer may have changed (DeviceArray.assign / copy_from_host, the
+# optimiser step): anything derived from parameters AHEAD of its use -- the z a layer draws one call
+# early (MNFLayerBase.presample) -- records the version it was computed under and is discarded when
+# the version has moved on.
+_param_version = 0
+
+
+def param_version() -> int:
+    return _param_version
+
+
+def bump_param_version() -> None:
+    global _param_version
+    _param_version += 1
 
 
 def default_context(device: int | None = None) -> Context:
@@ -253,6 +273,7 @@ class DeviceArray:
             raise ValueError(f"shape mismatch: {h.shape} vs {self.shape}")
         L.check(self.ctx.lib.mnf_memcpy_h2d(self.ctx.handle, C.c_void_p(self.ptr), h.ctypes.data, h.nbytes))
         self.ctx.sync()
+        bump_param_version()
         return self
 
     def copy(self) -> "DeviceArray":
@@ -266,6 +287,7 @@ class DeviceArray:
             if value.shape != self.shape:
                 raise ValueError(f"shape mismatch: {value.shape} vs {self.shape}")
             L.check(self.ctx.lib.mnf_memcpy_d2d(self.ctx.handle, C.c_void_p(self.ptr), C.c_void_p(value.ptr), self.nbytes))
+            bump_param_version()
             return self
         return self.copy_from_host(value)
 
@@ -367,6 +389,9 @@ def as_device(x: Any, ctx: Context | None = None) -> DeviceArray:
                 exp *= s
             if not ok:
                 raise ValueError("device tensor must be C-contiguous")
+        # the producer's stream (interface v3): our non-blocking stream has no implicit ordering with
+        # it, so wait for what it has enqueued; without the field, order against the legacy default stream
+        ctx.wait_stream(cai.get("stream") or 1)
         return DeviceArray(ctx, cai["data"][0], cai["shape"], "f4", owner=x)
     if isinstance(x, np.ndarray) or isinstance(x, (list, tuple, float, int)):
         return ctx.to_device(np.asarray(x, dtype=np.float32))
@@ -374,7 +399,11 @@ def as_device(x: Any, ctx: Context | None = None) -> DeviceArray:
         dev = x.__dlpack_device__() if hasattr(x, "__dlpack_device__") else (2, ctx.device)
         if int(dev[0]) not in (2, 13):
             raise ValueError(f"tensor is on DLPack device type {int(dev[0])}, not CUDA: tf_mnf_b200 has no CPU path")
-        cap = x.__dlpack__()
+        try:  # DLPack protocol: the producer makes the data safe to use on the consumer's stream
+            cap = x.__dlpack__(stream=ctx.stream)
+        except TypeError:  # pre-protocol producer: no stream argument
+            cap = x.__dlpack__()
+            ctx.wait_stream(1)
         tv = dlpack_view(cap)
         if (tv.dtype_code, tv.dtype_bits) != (2, 32) or not tv.contiguous:
             raise ValueError("expected a C-contiguous float32 tensor")
@@ -383,9 +412,14 @@ def as_device(x: Any, ctx: Context | None = None) -> DeviceArray:
     raise TypeError(f"cannot interpret {type(x).__name__} as a device tensor")
 
 
-def from_dlpack_capsule(capsule, ctx: Context | None = None) -> DeviceArray:
-    """For TF 2.1-style `tf.experimental.dlpack.to_dlpack(t)` capsules."""
+def from_dlpack_capsule(capsule, ctx: Context | None = None, producer_stream: int | None = 1) -> DeviceArray:
+    """For TF 2.1-style `tf.experimental.dlpack.to_dlpack(t)` capsules.  They carry no stream: the
+    context's stream is ordered behind `producer_stream` (default 1 = the legacy default stream; pass
+    the framework's compute stream, or None when the caller has synchronised / adopted that stream
+    with Context.set_stream)."""
     ctx = ctx or default_context()
+    if producer_stream is not None:
+        ctx.wait_stream(producer_stream)
     tv = dlpack_view(capsule)
     if (tv.dtype_code, tv.dtype_bits) != (2, 32) or not tv.contiguous:
         raise ValueError("expected a C-contiguous float32 tensor")

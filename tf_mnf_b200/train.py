@@ -13,17 +13,17 @@ import numpy as np
 from . import _lib as L
 from .layers.base import _p
 from .models.stock import Softmax
-from .runtime import DeviceArray, as_device, default_context
+from .runtime import DeviceArray, as_device, bump_param_version, default_context
 
 
 class Trainer:
     def __init__(self, model: Any, loss: str = "xent", kl_weight: float = 1.0, lr: float = 1e-3, beta1: float = 0.9,
-                 beta2: float = 0.999, eps: float = 1e-7, world: int = 1, group: Any = None) -> None:
+                 beta2: float = 0.999, eps: float = 1e-7, world: int = 1, comm: Any = None) -> None:
         if loss not in ("xent", "mse"):
             raise ValueError("loss must be 'xent' (softmax cross-entropy) or 'mse'")
         self.model, self.loss, self.kl_weight = model, loss, float(kl_weight)
         self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
-        self.world, self.group = int(world), group
+        self.world, self.comm = int(world), comm
         self.t = 0
         # flat training state (built on the first step): parameters, gradients and the two Adam
         # moments each live in ONE buffer; the layers' variables / grads are views into them
@@ -53,7 +53,7 @@ class Trainer:
             return
         ctx = default_context()
         model = self.model
-        if not all(l.built for l in model.mnf_layers):
+        if not all(l.built for l in model.param_layers):
             idx = [(l.call_index, l.kl_index) for l in model.mnf_layers]
             model.set_training(False)
             model(x)  # Keras build protocol: variables are created by the first call
@@ -63,8 +63,10 @@ class Trainer:
             c.sync()
         for l in model.mnf_layers:
             l._pre = None  # a z drawn ahead carries pointers to the old parameter buffers
+        for l in model.param_layers:
             l.zero_grads()
-        items = [(lyr, name, v) for lyr in model.mnf_layers for name, v in lyr.trainable_variables.items()]
+        # MNF layers and BatchNormalization (gamma, beta); moving statistics are not trained
+        items = [(lyr, name, v) for lyr in model.param_layers for name, v in lyr.trainable_variables.items()]
         offs, total = [], 0
         for _, _, v in items:
             offs.append(total)
@@ -73,7 +75,7 @@ class Trainer:
         self.flat_m, self.flat_v = ctx.zeros((total,)), ctx.zeros((total,))
         self.flat_gk = ctx.zeros((total,))
         self.kl_ctx = ctx.fork()
-        per_layer = {id(l): {} for l in model.mnf_layers}
+        per_layer = {id(l): {} for l in model.param_layers}
         for (lyr, name, v), off in zip(items, offs):
             slot = self.flat_p[off:off + v.size].reshape(v.shape)
             slot.assign(v)
@@ -129,8 +131,10 @@ class Trainer:
             mnf = hasattr(layers[i], "kl_div")  # MNF layers: the flat gradient buffer was zeroed above
             if i == 0 and mnf:
                 layers[0].backward(dh, need_dx=False, fresh_grads=True)  # nobody consumes dL/d(input)
+            elif mnf or hasattr(type(layers[i]), "trainable_variables"):
+                dh = layers[i].backward(dh, fresh_grads=True)
             else:
-                dh = layers[i].backward(dh, fresh_grads=True) if mnf else layers[i].backward(dh)
+                dh = layers[i].backward(dh)
         ctx.wait(kc)
         L.check(ctx.lib.mnf_axpy(ctx.handle, self.flat_g.size, 1.0, _p(self.flat_gk), _p(self.flat_g)))
         kc.wait(ctx)  # the KL buffers are re-used next step only after this sum
@@ -138,32 +142,29 @@ class Trainer:
         return loss, kl
 
     def _named_params(self):
-        for li, lyr in enumerate(self.model.mnf_layers):
+        for li, lyr in enumerate(self.model.param_layers):
             for name, v in lyr.trainable_variables.items():
                 yield (li, name), v, lyr.grads[name]
 
     def allreduce(self) -> None:
+        """One in-place sum of the flat gradient buffer over the ranks (mnf_allreduce_grads: NCCL,
+        enqueued behind the backward pass on the context's own stream -- no host synchronisation).
+        `comm`: a tf_mnf_b200.comm.Communicator, created from the torchrun environment on first use;
+        any object with `.allreduce(flat: DeviceArray)` works (the CPU tests plug in a gloo one)."""
         if self.world <= 1:
             return
-        import torch
+        if self.comm is None:
+            from .comm import Communicator
 
-        import torch.distributed as dist
-
-        ctx = default_context()
-        if getattr(self, "_flat_t", None) is None:
-            ctx.sync()
-            self._flat_t = torch.as_tensor(self.flat_g, device="cuda")  # zero-copy view, made once
-            self._tstream = torch.cuda.ExternalStream(ctx.stream, device=self._flat_t.device)
-        # the collective is enqueued behind the backward pass on the context's own stream (NCCL's stream
-        # waits for it and the context's stream waits for NCCL): no host synchronisation in the step
-        with torch.cuda.stream(self._tstream):
-            dist.all_reduce(self._flat_t, op=dist.ReduceOp.SUM, group=self.group)
+            self.comm = Communicator(default_context(), world=self.world)
+        self.comm.allreduce(self.flat_g)
 
     def apply(self) -> None:
         ctx = default_context()
         self.t += 1
         L.check(ctx.lib.mnf_adam_step(ctx.handle, self.flat_p.size, _p(self.flat_p), _p(self.flat_g), _p(self.flat_m),
                                       _p(self.flat_v), self.lr, self.beta1, self.beta2, self.eps, self.t))
+        bump_param_version()  # a z drawn ahead of the next call is stale now
 
     def step(self, x: Any, target: Any):
         loss, kl = self.loss_and_grads(x, target)
