@@ -36,18 +36,32 @@ N_IMAGES, N_SAMPLES = 10, 1024
 ROWS = N_IMAGES * N_SAMPLES
 # algorithmic bytes of the dominant kernel (conv2 paired implicit GEMM), SURVEY.md 8(d):
 # per row read x 12*12*20*4 + write y 8*8*50*4, plus mean_W + var_W once per launch
-CONV2_BYTES_PER_ROW = 12 * 12 * 20 * 4 + 8 * 8 * 50 * 4
+# The fused kernel reads x [12,12,20] and writes the ReLU'd, 2x2-pooled output [4,4,50] (the
+# un-pooled [8,8,50] of 8(d) never reaches HBM); the launch also reads mean_W and log_std_W once.
+CONV2_BYTES_PER_ROW = 12 * 12 * 20 * 4 + 4 * 4 * 50 * 4
 CONV2_WEIGHT_BYTES = 2 * 5 * 5 * 20 * 50 * 4
-CONV2_FLOP_PER_ROW = 2 * 2 * 64 * 500 * 50
+CONV2_FLOP_PER_ROW = 2 * 2 * 64 * 500 * 50   # two products (mean, variance), SURVEY.md 8(d)
+# per-row algorithmic work of the other stages (fused outputs where a stock layer is folded in)
+STAGES = {
+    # name: (bytes per row, weight bytes per launch, FLOP per row)
+    "conv1 (mc_expand: mean*z + sd*eps, ReLU, 2x2 pool; 11520 normals per row)": (12 * 12 * 20 * 4 + 20 * 4, 2 * 10 * 24 * 24 * 20 * 4, 4 * 24 * 24 * 20),
+    "conv2 (conv_raw_f16)": (CONV2_BYTES_PER_ROW, CONV2_WEIGHT_BYTES, CONV2_FLOP_PER_ROW),
+    "d1 (row_pack + paired_f16x3, ReLU fused)": (2 * 800 * 4 + 500 * 4, 2 * 800 * 500 * 4, 2 * 2 * 800 * 500),
+    "d2 (dense_small, Softmax fused)": (2 * 500 * 4 + 10 * 4, 2 * 500 * 10 * 4, 2 * 2 * 500 * 10),
+}
+LENET_BYTES_PER_ROW = 80776 + 5111520 / 10240   # SURVEY.md 8(d), layer-API boundary, B = 10240
+LENET_FLOP_PER_ROW = 9.994e6
 
 
 def peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s burst, sustained, source)."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return (float(p["hbm_gbs"]), float(p.get("bf16_tflops", 1662.7)), float(p.get("bf16_tflops_sustained", 1402.8)),
+                "measured (MEASURED_PEAKS.json)")
+    return 6650.0, 1662.7, 1402.8, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -261,8 +275,8 @@ def workload_config(args, rows_per_step=ROWS) -> dict:
             "rows_per_gpu": rows_per_step, "flow_type": args.flow, "n_flows_q": 2, "n_flows_r": 2, "flow_h_sizes": [50],
             "std_init": 10.0, "max_std": 1.0, "noise": "in-kernel Philox4x32-10", "l2": "flushed between timed steps "
             "(256 MiB memset outside the per-step event pairs)",
-            "launch": "value: the faster of eager enqueue (the host runs ahead of the device) and replaying the step "
-                      "as one CUDA graph, see launch_modes_ms_per_step; e2e: graph replay unless --no-graph (a device-side "
+            "launch": "value: eager enqueue (the host runs ahead of the device); the same step replayed as one CUDA "
+                      "graph is in launch_modes_ms_per_step; e2e: graph replay unless --no-graph (a device-side "
                       "replay counter advances the Philox call indices: replays are bit-identical to eager calls)",
             "weights": "frozen (Sequential.freeze_weights): packed / pre-split weight blocks are kept across steps",
             "first_layer": ("every one of the 10240 rows convolved (--no-share)" if getattr(args, "no_share", False) else
@@ -424,19 +438,50 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     def all_launches():
         return ctx.launches + sum(c.launches for c in kl_lanes) + side_launches()
 
-    # ---- the dominant kernel (conv2) timed in place: a probe brackets that one launch in a few
-    # eager steps (a captured graph has no place for the probe's events)
+    # ---- the kernels of a step timed in place: a probe (mnf_ctx_probe) brackets ONE launch family of
+    # one context with CUDA events inside eager steps, side streams running (a captured graph has no
+    # place for the probe's events).  One probe per context and step, so the table takes a few rounds.
     n_probe = min(args.steps, 10)
-    kst, ksp = [ev() for _ in range(n_probe)], [ev() for _ in range(n_probe)]
+    sides = list(getattr(model, "_sides", []))
+    PR_CONV, PR_DENSE, PR_FLOW, PR_KL, PR_EXPAND = 1, 2, 3, 4, 5
+    share = not args.no_share
+    plan = [
+        ("conv2", ctx, PR_CONV, 0 if share else 1),
+        ("conv1", ctx, PR_EXPAND if share else PR_CONV, 0),
+        ("d1", ctx, PR_DENSE, 0),
+        ("d2", ctx, PR_DENSE, 1),
+    ]
+    for name, si in (("conv2.z", 1), ("d1.z", 2), ("d2.z", 3)):   # the z chains of layers 2-4 (their own streams)
+        if si < len(sides):
+            plan += [(f"flow step 1 of {name}", sides[si], PR_FLOW, 0), (f"flow step 2 of {name}", sides[si], PR_FLOW, 1)]
+    kernel_ms: dict[str, list] = {}
     launches0 = all_launches()
-    for i in range(n_probe):
-        L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
-        # conv2 = the 2nd conv-GEMM launch of a step that convolves every row, the 1st when conv1 is shared
-        L.check(lib.mnf_ctx_probe(ctx.handle, 1, int(os.environ.get("MNF_BENCH_PROBE_SKIP", "1" if args.no_share else "0")),
-                                  kst[i], ksp[i]))
-        main_step()
-    barrier()
-    launches_per_step = (all_launches() - launches0) // n_probe
+    probe_steps = 0
+    pending = list(plan)
+    while pending:
+        batch, rest, used = [], [], set()
+        for item in pending:
+            (rest if id(item[1]) in used else batch).append(item)
+            used.add(id(item[1]))
+        pending = rest
+        evs = {name: ([ev() for _ in range(n_probe)], [ev() for _ in range(n_probe)]) for name, *_ in batch}
+        for i in range(n_probe):
+            L.check(lib.mnf_memset(ctx.handle, C.c_void_p(flush.ptr), 0, flush.nbytes))
+            for name, c, kind, skip in batch:
+                L.check(lib.mnf_ctx_probe(c.handle, kind, skip, evs[name][0][i], evs[name][1][i]))
+            main_step()
+            probe_steps += 1
+        barrier()
+        for name, c, kind, skip in batch:
+            L.check(lib.mnf_ctx_probe(c.handle, 0, 0, None, None))
+            ms_ = C.c_float()
+            vals = []
+            for a_, b_ in zip(*evs[name]):
+                if lib.mnf_event_elapsed_ms(a_, b_, C.byref(ms_)) == 0:
+                    vals.append(ms_.value)
+            kernel_ms[name] = vals
+    launches_per_step = (all_launches() - launches0) // max(probe_steps, 1)
+    kern_ms = kernel_ms.get("conv2") or [float("nan")]
 
     # ---- timed: K steps, device-resident input, per-step CUDA events, L2 flushed in between.
     # The step is captured once into a CUDA graph (tf_mnf_b200/graph.py) and replayed: one launch
@@ -478,7 +523,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     if graph is not None:
         modes["graph"] = timed_steps(graph.launch)
     tiled_ms = float(np.mean(timed_steps(lambda: step(x_dev))[0])) if not args.no_share else None
-    launch_mode = min(modes, key=lambda k: float(np.mean(modes[k][0])))
+    launch_mode = "eager"  # `value` is the plain API call; the graph replay of the same step is reported beside it
     step_ms, t_wall0, t_wall1 = modes[launch_mode]
     t_wall = t_wall1 - t_wall0
     clk.__exit__()
@@ -489,7 +534,6 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
         L.check(lib.mnf_event_elapsed_ms(a, b, C.byref(ms)))
         return ms.value
 
-    kern_ms = [elapsed(a, b) for a, b in zip(kst, ksp)]
     my_ms = float(np.mean(step_ms))
     print(f"[rank {rank}] step_ms={np.round(step_ms, 3).tolist()} conv2_ms={np.round(kern_ms, 3).tolist()} "
           f"wall_per_step_ms={t_wall / args.steps * 1e3:.3f} launch={launch_mode} "
@@ -571,18 +615,56 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     my_e2e = time_e2e(e2e_mc)
     my_e2e_tiled = time_e2e(e2e_tiled)
 
+    # ---- BASELINE configs[4] beside the headline: the MNF VGG-style net's data-parallel train step, the one
+    # place of the design with a collective (mnf_allreduce_grads: NCCL over NVLink, inside the C ABI)
+    c5 = None
+    if not args.no_train:
+        try:
+            c5 = time_c5_train(ctx, rank, world, dist, barrier, ev, elapsed, args.train_steps)
+        except Exception as exc:  # never lose the headline to the secondary measurement
+            print(f"[rank {rank}] C5 train step unavailable ({exc!r})", file=sys.stderr, flush=True)
+            barrier()
+
     # ---- max over ranks
+    names = sorted(kernel_ms)
+    mine = [my_ms, my_e2e, my_e2e_tiled] + [float(np.mean(kernel_ms[n])) if kernel_ms[n] else float("nan") for n in names]
     if dist is not None:
-        t = torch.tensor([my_ms, my_e2e, float(np.mean(kern_ms)), my_e2e_tiled], device="cuda")
+        t = torch.tensor(mine, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, k_ms, e2e_tiled_ms = (float(v) for v in t.tolist())
-    else:
-        ms, e2e_ms, k_ms, e2e_tiled_ms = my_ms, my_e2e, float(np.mean(kern_ms)), my_e2e_tiled
+        mine = [float(v) for v in t.tolist()]
+    ms, e2e_ms, e2e_tiled_ms = mine[:3]
+    kms = dict(zip(names, mine[3:]))
+    k_ms = kms.get("conv2", float("nan"))
 
     if rank == 0:
-        hbm, which = peaks()
+        hbm, tc_burst, tc_sus, which = peaks()
+        tc = args.math == "tf32x3"
+        # conv2's arithmetic intensity (263 FLOP/B fused) is above the ridge (254), and the fp32-parity mode
+        # spends THREE kind::f16 MMAs per product (hi*hi + lo*hi + hi*lo): its roof is the tensor pipe / 3.
+        # `peak` is the burst figure (the kernel is timed alone by its probe), per the contract.
+        k_flop = CONV2_FLOP_PER_ROW * ROWS
         k_bytes = CONV2_BYTES_PER_ROW * ROWS + CONV2_WEIGHT_BYTES
-        achieved = k_bytes / (k_ms * 1e-3) / 1e9
+        ach_tf = k_flop / (k_ms * 1e-3) / 1e12
+        ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        peak_tf = tc_burst / 3 if tc else ffma_peak
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if tc and os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj.get("conv2_dram_bytes_per_launch")
+        table = {}
+        for name, (bpr, wb, fpr) in STAGES.items():
+            key = name.split(" ")[0]
+            if key in kms and kms[key] == kms[key]:
+                t_ms = kms[key]
+                table[name] = {"ms": t_ms, "share_of_step": t_ms / ms, "algorithmic_GBps": (bpr * ROWS + wb) / (t_ms * 1e-3) / 1e9,
+                               "hbm_frac": (bpr * ROWS + wb) / (t_ms * 1e-3) / 1e9 / hbm,
+                               "algorithmic_TFLOPs": fpr * ROWS / (t_ms * 1e-3) / 1e12}
+        for name in names:
+            if name.startswith("flow"):
+                table[name] = {"ms": kms[name], "stream": "side (beside the main stream)"}
+        step_roof = hbm * 1e9 / LENET_BYTES_PER_ROW
         line = {
             "metric": METRIC, "value": ROWS * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
@@ -603,22 +685,37 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
                 "value": ROWS / (tiled_ms * 1e-3), "unit": UNIT, "ms_per_step": tiled_ms, "n_gpus": 1,
                 "note": "rank 0, eager: model(x) on the resident 10240-row repeated batch + kl_div() -- the first layer "
                         "convolves every row (no sharing between the samples of an image)"},
-            "roofline": {"bound": "hbm",
-                         "kernel": ("cf::conv_raw_f16" if args.math == "tf32x3" else "paired_gemm_fwd<CONV,64>")
-                         + " (conv2: 12x12x20 -> 8x8x50, 5x5, + fused ReLU/2x2 max-pool)",
-                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
-                         # (profiles/r01_ncu_full_prof_conv_f16.txt); the pooled output partly stays in L2
-                         "traffic": (120378624 + 14185472) if args.math == "tf32x3" else None,
-                         "peak_source": which, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms,
-                         "algorithmic_bytes_per_launch": k_bytes,
+            "roofline": {"bound": "tensor",
+                         "kernel": ("cf::conv_raw_f16" if tc else "paired_gemm_fwd<CONV,64>")
+                         + " (conv2: 12x12x20 -> 8x8x50, 5x5, + fused ReLU/2x2 max-pool), the dominant kernel of the step",
+                         "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch, from the ncu --set full
+                         # capture named in profiles/roofline_traffic.json (null when no capture of this round exists)
+                         "traffic": traffic,
+                         "peak_source": which + (": dense bf16/fp16 burst / 3 (three MMAs per fp32-parity product)" if tc else
+                                                 ": FFMA 148 SM x 128 lanes x 2 x 1.965 GHz"),
+                         "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms,
+                         "algorithmic_flop_per_launch": k_flop, "algorithmic_bytes_per_launch": k_bytes,
+                         "hbm_view": {"achieved_GBps": k_bytes / (k_ms * 1e-3) / 1e9, "peak_GBps": hbm,
+                                      "frac": k_bytes / (k_ms * 1e-3) / 1e9 / hbm,
+                                      "note": "the same launch against the HBM roof: algorithmic bytes of the FUSED kernel "
+                                              "(pooled output); not what binds it"},
                          "pipe": ("tcgen05.mma kind::f16, power-of-two scaled fp16 hi/lo split of both operands, fp32 "
-                                  "accumulate (fp32 parity <=1e-5 rel.); bound in practice by the shared-memory operand fetch of its "
-                                  "N=64 SS-mode MMAs (DESIGN.md section 4); kernel_ms is the in-situ time, side streams running"
-                                  if args.math == "tf32x3" else "fp32 FFMA (parity path, <=1e-5 rel.)"),
-                         "algorithmic_tflops": CONV2_FLOP_PER_ROW * ROWS / (k_ms * 1e-3) / 1e12},
+                                  "accumulate (fp32 parity <=1e-5 rel.); kernel_ms is the in-situ time, side streams running"
+                                  if tc else "fp32 FFMA (parity path, <=1e-5 rel.)"),
+                         "step": {"rows_per_s_per_gpu": ROWS / (ms * 1e-3), "hbm_roof_rows_per_s": step_roof,
+                                  "frac": ROWS / (ms * 1e-3) / step_roof,
+                                  "tensor_roof_rows_per_s": tc_sus * 1e12 / 3 / LENET_FLOP_PER_ROW,
+                                  "frac_of_tensor_roof": ROWS / (ms * 1e-3) / (tc_sus * 1e12 / 3 / LENET_FLOP_PER_ROW),
+                                  "no_share_frac": None if tiled_ms is None else ROWS / (tiled_ms * 1e-3) / step_roof,
+                                  "note": "whole step against SURVEY.md 8(d): 81,275 B/row at the layer-API boundary -> HBM roof; "
+                                          "9.994 MFLOP/row x 3 MMAs per fp32-parity product -> tensor roof (sustained bf16 / 3); "
+                                          "no_share = every row convolved by conv1 (resident_tiled_batch)"},
+                         "kernels": table},
             "wall_s_timed_region": t_wall,
         }
+        if c5 is not None:
+            line["c5_train_step"] = c5
         if world == 1 and not args.no_cpu:
             rows = args.cpu_rows
             t_cpu, _ = time_cpu(args.flow, rows, args.cpu_steps, 1)
@@ -631,6 +728,58 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def time_c5_train(ctx, rank, world, dist, barrier, ev, elapsed, steps: int = 8):
+    """BASELINE.json configs[4]: MNF VGG-style net, synthetic 32x32x3, GLOBAL batch 256 split
+    over the ranks (strong scaling), one training step = forward + cross-entropy + backward + kl_div + KL
+    backward + ONE in-place NCCL all-reduce of the flat fp32 gradient buffer (mnf_allreduce_grads, C ABI)
+    + Adam.  Device time per step (CUDA events on the context's stream), max over ranks."""
+    import torch
+
+    import tf_mnf_b200 as M
+    from tf_mnf_b200 import _lib as L
+    from tf_mnf_b200.models import MNFVGG
+    from tf_mnf_b200.train import Trainer
+
+    GB = 256
+    M.set_seed(0)  # same parameters and noise keys on every rank
+    model = MNFVGG()
+    rng = np.random.RandomState(0)
+    x = rng.uniform(size=(GB, 32, 32, 3)).astype(np.float32)
+    y = np.eye(10, dtype=np.float32)[rng.randint(0, 10, size=GB)]
+    lo, hi = rank * GB // world, (rank + 1) * GB // world
+    model.set_row_offset(lo)
+    xd, yd = ctx.to_device(x[lo:hi]), ctx.to_device(y[lo:hi])
+    tr = Trainer(model, loss="xent", kl_weight=1.0 / 50000, world=world)
+    for _ in range(3):
+        tr.step(xd, yd)
+    barrier()
+    starts, stops = [ev() for _ in range(steps)], [ev() for _ in range(steps)]
+    t0 = time.perf_counter()
+    for i in range(steps):
+        L.check(ctx.lib.mnf_event_record(ctx.handle, starts[i]))
+        tr.step(xd, yd)
+        L.check(ctx.lib.mnf_event_record(ctx.handle, stops[i]))
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / steps
+    dev_ms = float(np.mean([elapsed(a, b) for a, b in zip(starts, stops)]))
+    if dist is not None:
+        t = torch.tensor([wall_ms, dev_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall_ms, dev_ms = (float(v) for v in t.tolist())
+    n_params = int(tr.flat_g.size)
+    out = {"workload": "MNF VGG-style conv net (6 x MNFConv2D 3x3 SAME + 2 x MNFDense, IAF flows), synthetic 32x32x3, "
+                       "global batch 256, data-parallel train step (BASELINE.json configs[4])",
+           "value": GB / (wall_ms * 1e-3), "unit": "images/s", "n_gpus": world, "scaling": "strong", "steps": steps,
+           "ms_per_step": wall_ms, "device_ms_per_step": dev_ms, "per_gpu_batch": hi - lo,
+           "timing": "wall clock barrier to barrier per step, max over ranks (device-event time beside it)",
+           "collective": None if world == 1 else {
+               "op": "ncclAllReduce(sum), in place, fp32, on the context's stream (mnf_allreduce_grads)",
+               "bytes": n_params * 4, "nccl_version": tr.comm.nccl_version if tr.comm is not None else None}}
+    if tr.comm is not None:
+        tr.comm.close()
+    return out
 
 
 def main() -> None:
@@ -651,6 +800,8 @@ def main() -> None:
                          "convolves every row")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--breakdown", action="store_true", help="print per-layer device times of one step (stderr)")
+    ap.add_argument("--no-train", action="store_true", help="skip the C5 (MNF-VGG data-parallel train step) measurement")
+    ap.add_argument("--train-steps", type=int, default=8)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

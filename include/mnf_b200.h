@@ -99,7 +99,8 @@ int mnf_ctx_set_math(mnf_ctx* ctx, int mode);
 int mnf_ctx_freeze_weights(mnf_ctx* ctx, int32_t frozen);
 
 /* Timing probe for bench.py's roofline line: the (skip+1)-th launch of kernel family `kind`
- * (1 conv paired GEMM, 2 dense paired GEMM, 3 flow step, 4 KL; 0 disarms) is bracketed by
+ * (1 conv paired GEMM, 2 dense paired GEMM incl. its per-call operand packing, 3 flow step, 4 KL,
+ * 5 Monte-Carlo expansion of a first conv layer; 0 disarms) is bracketed by
  * cudaEventRecord(ev_start/ev_stop) on the context's stream, then the probe disarms. */
 int mnf_ctx_probe(mnf_ctx* ctx, int kind, int skip, void* ev_start, void* ev_stop);
 

@@ -33,7 +33,8 @@ struct mnf_packed_entry {
   size_t bytes;
 };
 
-enum { MNF_PROBE_NONE = 0, MNF_PROBE_CONV_GEMM = 1, MNF_PROBE_DENSE_GEMM = 2, MNF_PROBE_FLOW_STEP = 3, MNF_PROBE_KL = 4 };
+enum { MNF_PROBE_NONE = 0, MNF_PROBE_CONV_GEMM = 1, MNF_PROBE_DENSE_GEMM = 2, MNF_PROBE_FLOW_STEP = 3, MNF_PROBE_KL = 4,
+       MNF_PROBE_MC_EXPAND = 5 };
 
 // returns true when this launch is the probed one (and records the start event)
 static inline bool mnf_probe_begin(mnf_ctx* ctx, int kind) {

@@ -188,8 +188,10 @@ int mnf_conv2d_mc_expand(mnf_ctx* ctx, int64_t B, int64_t n_rep, int64_t Ho, int
   a.B = B; a.n_rep = n_rep; a.Ho = (int)Ho; a.Wo = (int)Wo; a.F = (int)F;
   a.mean = mean; a.sd = sd; a.z = z; a.eps = make_noise(eps); a.y = y;
   mnf_note_path(fuse_relu_pool ? "conv_mc_expand<pool>" : "conv_mc_expand");
+  const bool probed = mnf_probe_begin(ctx, MNF_PROBE_MC_EXPAND);
   if (fuse_relu_pool) conv_mc_expand<true><<<(unsigned)B, 256, 0, ctx->stream>>>(a);
   else conv_mc_expand<false><<<(unsigned)B, 256, 0, ctx->stream>>>(a);
+  mnf_probe_end(ctx, probed);
   MNF_LAUNCHED(ctx);
   return MNF_OK;
 }
