@@ -35,12 +35,14 @@ def philox_words(seed64, stream, row_offset, rows, outer, inner):
 
 
 def box_muller_f64(words):
-    """float64 restatement of csrc/common.cuh:box_muller on [..., 4k] words."""
-    w = words.reshape(*words.shape[:-1], -1, 2).astype(np.float64)
-    u = ((w[..., 0].astype(np.uint64) >> np.uint64(8)).astype(np.float64) + 0.5) / 16777216.0
-    v = ((w[..., 1].astype(np.uint64) >> np.uint64(8)).astype(np.float64) + 0.5) / 16777216.0
+    """float64 restatement of csrc/common.cuh:box_muller on [..., 4k] words: the top 23 bits of a word are
+    the mantissa of f in [1, 2); u = f - (1 - 2^-24), angle = 2 pi (f - 1.5)."""
+    w = words.reshape(*words.shape[:-1], -1, 2).astype(np.uint64)
+    fa = 1.0 + (w[..., 0] >> np.uint64(9)).astype(np.float64) / 8388608.0
+    fb = 1.0 + (w[..., 1] >> np.uint64(9)).astype(np.float64) / 8388608.0
+    u = fa - (1.0 - 2.0 ** -24)
     r = np.sqrt(-2 * np.log(u))
-    th = 2 * np.pi * (v - 0.5)
+    th = 2 * np.pi * (fb - 1.5)
     return np.stack([r * np.cos(th), r * np.sin(th)], -1).reshape(words.shape)
 
 

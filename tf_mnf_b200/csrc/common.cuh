@@ -209,13 +209,22 @@ __device__ __forceinline__ float sqrt_fast(float x) {
   return r;
 }
 
-// Box-Muller on two 32-bit words -> two N(0,1)
+// Box-Muller on two 32-bit words -> two N(0,1).  Every noise consumer is issue-bound on this transform
+// (conv_mc_expand: 118 M normals per step), so it is built from the cheapest instructions that keep the
+// distribution exact to fp32:
+//   word -> float without I2F (quarter-rate XU pipe, shared with MUFU): the top 23 bits become the
+//           mantissa of f in [1, 2);  u = f - (1 - 2^-24) is (k + 1/2) 2^-23 in (0, 1), symmetric about 1/2;
+//           the angle is 2 pi (f - 1.5), 2^23 equidistant angles in [-pi, pi);
+//   radius  sqrt(-2 ln u) = sqrt(lg2(u) * (-2 ln 2)): MUFU.LG2, one FMUL, MUFU.SQRT;
+//   sin / cos of the same argument share one range-reduction multiply (MUFU.SIN, MUFU.COS).
+// Four MUFU, five FMUL, two FADD and four integer operations per pair (before: four MUFU + two I2F, ten
+// FMUL, four FADD).  tests/gpu_util.py:box_muller_f64 restates it in float64.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
-  float u = u01_open(a);
-  float v = u01_open(b);
-  float r = sqrt_fast(-2.0f * __logf(u));
+  const float fa = __uint_as_float((a >> 9) | 0x3F800000u), fb = __uint_as_float((b >> 9) | 0x3F800000u);
+  const float u = fa - 0.99999994f;  // 1 - 2^-24, exact in fp32
+  const float r = sqrt_fast(__log2f(u) * -1.3862943611198906f);
   float s, c;
-  __sincosf(6.283185307179586f * (v - 0.5f), &s, &c);
+  __sincosf(6.283185307179586f * (fb - 1.5f), &s, &c);
   n0 = r * c;
   n1 = r * s;
 }
