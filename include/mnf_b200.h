@@ -178,26 +178,42 @@ int mnf_philox_raw(mnf_ctx* ctx, uint64_t seed, uint32_t stream, uint64_t row_of
 /* ---- flows: NormalizingFlow.forward (flows/__init__.py:22-29) --------------------------- */
 enum { MNF_FLOW_IAF = 0, MNF_FLOW_RNVP = 1, MNF_FLOW_PLANAR = 2 };
 
-/* One flow step.  D = flow dimension, H = hidden units (one hidden layer).
+/* One flow step.  D = flow dimension, H = hidden units of the first hidden layer.
  *  IAF    (maf.py:47-53, made.py:28-30,77-91): w1 [D,H], b1 [H] = first MaskedDense;
- *         ws/wt = second MaskedDense kernel [H,2D] columns [0,D) / [D,2D) (ld2 = 2D),
- *         bs/bt likewise halves of its bias; m1 [D,H], m2 [H,2D] optional masks (NULL = ones).
- *  RNVP   (rnvp.py:33-47): w1,b1 = net Dense(H,tanh); ws,bs = s Dense; wt,bt = t Dense (ld2 = D);
- *         bern = Bernoulli mask draw (injected or Philox).
- *  PLANAR (planar.py:22-36): w1 = dense kernel w [D], b1 = dense bias [1], wt = u [D]. */
+ *         ws/wt = LAST MaskedDense kernel [H_last,2D] columns [0,D) / [D,2D) (ld2 = 2D),
+ *         bs/bt likewise halves of its bias; m1 [D,H], m2 [H_last,2D] optional masks (NULL = ones).
+ *  RNVP   (rnvp.py:33-47): w1,b1 = first net Dense(H, activation); ws,bs = s Dense; wt,bt = t Dense
+ *         (ld2 = D); bern = Bernoulli mask draw (injected or Philox).
+ *  PLANAR (planar.py:22-36): w1 = dense kernel w [D], b1 = dense bias [1], wt = u [D].
+ * General coupling networks (made.py:77-88 / rnvp.py:28-29 build one hidden layer per entry of
+ * h_sizes): n_extra further hidden layers behind the first, layer l (1-based) mapping
+ * extra_h[l-2]... i.e. extra_w[i] is [h_i, extra_h[i]] with h_0 = hidden, h_i = extra_h[i-1]; extra_m
+ * are the MADE masks of those layers (NULL = ones).  activation: MNF_ACTV_DEFAULT = what the class
+ * uses by default (MADE: ReLU, fixed; RNVP: tanh), or the RNVP constructor's `activation`.
+ * One hidden layer with the default activation runs on the fused / tensor-core kernels; anything
+ * else on the general kernels (csrc/flows_generic.cu: D <= 1024, hidden widths <= 256). */
+#define MNF_FLOW_MAX_HIDDEN 4
+enum { MNF_ACTV_DEFAULT = 0, MNF_ACTV_RELU = 1, MNF_ACTV_TANH = 2, MNF_ACTV_SIGMOID = 3, MNF_ACTV_LINEAR = 4 };
 typedef struct {
   int32_t kind, parity, hidden, reserved;
   const float *w1, *b1, *ws, *bs, *wt, *bt;
   int64_t ld2;
   const float *m1, *m2;
   mnf_noise bern;
+  int32_t n_extra, activation;
+  int32_t extra_h[MNF_FLOW_MAX_HIDDEN - 1];
+  int32_t reserved2;
+  const float* extra_w[MNF_FLOW_MAX_HIDDEN - 1];
+  const float* extra_b[MNF_FLOW_MAX_HIDDEN - 1];
+  const float* extra_m[MNF_FLOW_MAX_HIDDEN - 1];
 } mnf_flow_step;
 
 /* sample_z + flow chain (mnf_dense.py:88-102, mnf_conv.py:100-114).
  *  z0 != NULL: start from z0 [B,D].  Otherwise z0 = q0_mean + exp(q0_log_var/2) * eps_z.
  *  states [T+1,B,D]: every intermediate state (the LIST the reference returns); the last
  *  slice is z_T.  log_dets [B] = sum of per-step log-determinants (may be NULL).
- *  saved (may be NULL) [T,B,H]: hidden activations kept for mnf_flow_backward. */
+ *  saved (may be NULL): hidden activations kept for mnf_flow_backward, step after step, B x (sum of the
+ *  step's hidden widths) floats each (nothing for planar steps). */
 int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, const mnf_flow_step* h_steps,
                      const float* z0, const float* q0_mean, const float* q0_log_var,
                      const mnf_noise* eps_z, float* states, float* log_dets, float* saved);
@@ -212,6 +228,12 @@ int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, const mnf_fl
 int mnf_flow_backward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, const mnf_flow_step* h_steps,
                       const float* states, const float* saved, const float* d_states, const float* d_zT,
                       const float* d_log_dets, float* d_z0, const mnf_flow_step* h_grad_steps);
+/* MAF.forward == IAF.inverse, maf.py:33-45: the sequential decode of a MADE-based step, as the reference
+ * spells it out (x = 0; z reversed when parity; for i < D: (s, t) = net(x); x[:, i] = (z[:, i] - t[:, i])
+ * exp(-s[:, i]); log_det -= s[:, i]).  z, x [B,D]; log_dets [B] (may be NULL).  The single-pass direction
+ * (MAF.inverse == IAF.forward) is mnf_flow_forward. */
+int mnf_maf_decode(mnf_ctx* ctx, int64_t B, int64_t D, const mnf_flow_step* step, const float* z, float* x,
+                   float* log_dets);
 /* d q0_mean / d q0_log_var from d_z0 (App. A-2): accumulated (+=). */
 int mnf_sample_z_backward(mnf_ctx* ctx, int64_t B, int64_t D, const float* d_z0,
                           const float* q0_log_var, const mnf_noise* eps_z,

@@ -100,12 +100,22 @@ def iaf_backward(dy, dld, st, c):
     return dx, dict(W=gW, b=gb)
 
 
+_ACT = {
+    "tanh": (np.tanh, lambda h: 1 - h * h),
+    "relu": (lambda x: np.maximum(x, 0), lambda h: (h > 0).astype(h.dtype)),
+    "sigmoid": (lambda x: 1.0 / (1.0 + np.exp(-x)), lambda h: h * (1 - h)),
+    "linear": (lambda x: x, lambda h: np.ones_like(h)),
+}
+
+
 def rnvp_forward(z, st, m):
-    """rnvp.py:33-47.  m = Bernoulli(0.5) mask [B,D], fresh per call (rnvp.py:36)."""
+    """rnvp.py:33-47.  m = Bernoulli(0.5) mask [B,D], fresh per call (rnvp.py:36).  st["act"]: the
+    constructor's `activation` of the net's Dense layers (rnvp.py:20-29; default "tanh")."""
+    act = _ACT[st.get("act", "tanh")][0]
     z1, z2 = (1 - m) * z, m * z
     h, hs = z2, []
     for Wn, bn in zip(st["Wn"], st["bn"]):
-        h = np.tanh(h @ Wn + bn)
+        h = act(h @ Wn + bn)
         hs.append(h)
     sh = h @ st["Wt"] + st["bt"]
     sc = h @ st["Ws"] + st["bs"]
@@ -113,6 +123,29 @@ def rnvp_forward(z, st, m):
     ld = ((1 - m) * np.log(g)).sum(axis=1)
     x = (z1 * g + (1 - g) * sh) + z2
     return x, ld, dict(z=z, m=m, hs=hs, sh=sh, g=g)
+
+
+def maf_forward_sequential(z, st):
+    """MAF.forward == IAF.inverse, maf.py:33-45, exactly as the reference spells the loop out (it cannot
+    run there: it assigns into a tensor slice, App. B-4): x = 0; z reversed when parity; for i in
+    range(dim): (s, t) = net(x); x[:, i] = (z[:, i] - t[:, i]) exp(-s[:, i]); log_dets += -s[:, i].
+    One full MADE pass per dimension (the slow direction)."""
+    W, b, masks = st["W"], st["b"], st.get("masks")
+    B, D = z.shape
+    x = np.zeros_like(z)
+    ld = np.zeros(B, z.dtype)
+    zz = z[:, ::-1] if st["parity"] else z
+    for i in range(D):
+        h = x
+        for l in range(len(W)):
+            We = W[l] if masks is None else W[l] * masks[l].astype(W[l].dtype)
+            h = h @ We + b[l]
+            if l < len(W) - 1:
+                h = np.maximum(h, 0)
+        s, t = h[:, :D], h[:, D:]
+        x[:, i] = (zz[:, i] - t[:, i]) * np.exp(-s[:, i])
+        ld = ld - s[:, i]
+    return x, ld
 
 
 def rnvp_backward(dx, dld, st, c):
@@ -125,8 +158,9 @@ def rnvp_backward(dx, dld, st, c):
     grads = dict(Wt=y.T @ dsh, bt=dsh.sum(0), Ws=y.T @ dsc, bs=dsc.sum(0), Wn=[], bn=[])
     dh = dsh @ st["Wt"].T + dsc @ st["Ws"].T
     gWn, gbn = [None] * len(hs), [None] * len(hs)
+    dact = _ACT[st.get("act", "tanh")][1]
     for l in reversed(range(len(hs))):
-        dp = dh * (1 - hs[l] ** 2)
+        dp = dh * dact(hs[l])
         inp = hs[l - 1] if l > 0 else m * z
         gWn[l] = inp.T @ dp
         gbn[l] = dp.sum(0)

@@ -51,14 +51,15 @@ def assign_flow(fl, st):
     f32 = lambda a: np.asarray(a, np.float32)  # noqa: E731
     kind = st["kind"]
     if kind == "iaf":
-        l1, l2 = fl.net.layers
-        l1.kernel.assign(f32(st["W"][0])), l1.bias.assign(f32(st["b"][0]))
-        l2.kernel.assign(f32(st["W"][1])), l2.bias.assign(f32(st["b"][1]))
+        for lyr, W, b in zip(fl.net.layers, st["W"], st["b"]):
+            lyr.kernel.assign(f32(W)), lyr.bias.assign(f32(b))
         masks = st.get("masks")
         if masks is not None and not all(np.all(np.asarray(m) == 1) for m in masks):
-            l1.set_mask(masks[0], l1.kernel.ctx), l2.set_mask(masks[1], l2.kernel.ctx)
+            for lyr, m in zip(fl.net.layers, masks):
+                lyr.set_mask(m, lyr.kernel.ctx)
     elif kind == "rnvp":
-        fl.net_kernel.assign(f32(st["Wn"][0])), fl.net_bias.assign(f32(st["bn"][0]))
+        for k, bb, W, b in zip(fl.net_kernels, fl.net_biases, st["Wn"], st["bn"]):
+            k.assign(f32(W)), bb.assign(f32(b))
         fl.t_kernel.assign(f32(st["Wt"])), fl.t_bias.assign(f32(st["bt"]))
         fl.s_kernel.assign(f32(st["Ws"])), fl.s_bias.assign(f32(st["bs"]))
     else:
@@ -71,9 +72,9 @@ def make_flows(steps, D):
     out = []
     for st in steps:
         if st["kind"] == "iaf":
-            fl = IAF(parity=int(st["parity"]), h_sizes=(st["W"][0].shape[1],))
+            fl = IAF(parity=int(st["parity"]), h_sizes=tuple(W.shape[1] for W in st["W"][:-1]))
         elif st["kind"] == "rnvp":
-            fl = RNVP(D, h_sizes=(st["Wn"][0].shape[1],))
+            fl = RNVP(D, h_sizes=tuple(W.shape[1] for W in st["Wn"]), activation=st.get("act", "tanh"))
         else:
             fl = PlanarFlow(D)
         fl.build(D)
@@ -89,10 +90,11 @@ def make_layer(P, x_shape, max_std=1.0, use_z=True, r_term="all_states", stride=
     conv = P["mean_W"].ndim == 4
     fq, fr = P["flow_q"], P["flow_r"]
     kind = (fq or fr or [dict(kind="iaf")])[0]["kind"]
-    h = 50
+    h = (50,)
     for st in [*fq, *fr]:
-        h = st["W"][0].shape[1] if kind == "iaf" else st["Wn"][0].shape[1] if kind == "rnvp" else 50
-    common = dict(n_flows_q=len(fq), n_flows_r=len(fr), use_z=use_z, flow_h_sizes=(h,), max_std=max_std,
+        h = (tuple(W.shape[1] for W in st["W"][:-1]) if kind == "iaf" else
+             tuple(W.shape[1] for W in st["Wn"]) if kind == "rnvp" else (50,))
+    common = dict(n_flows_q=len(fq), n_flows_r=len(fr), use_z=use_z, flow_h_sizes=h, max_std=max_std,
                   flow_type=kind, r_term=r_term, **kw)
     if conv:
         kh, kw_, _, F = P["mean_W"].shape
@@ -140,8 +142,9 @@ def params_from_layer(lyr, dtype=np.float64):
                                   b=[l.bias.numpy().astype(dtype) for l in ls],
                                   masks=None if ls[0].mask is None else [l.mask_host.astype(dtype) for l in ls]))
             elif name == "RNVP":
-                steps.append(dict(kind="rnvp", Wn=[v["net_kernel"]], bn=[v["net_bias"]], Wt=v["t_kernel"],
-                                  bt=v["t_bias"], Ws=v["s_kernel"], bs=v["s_bias"]))
+                steps.append(dict(kind="rnvp", Wn=[k.numpy().astype(dtype) for k in fl.net_kernels],
+                                  bn=[b.numpy().astype(dtype) for b in fl.net_biases], Wt=v["t_kernel"],
+                                  bt=v["t_bias"], Ws=v["s_kernel"], bs=v["s_bias"], act=fl.activation))
             else:
                 steps.append(dict(kind="planar", u=v["u"].reshape(-1, 1), w=v["w"].reshape(-1, 1), b=v["b"].reshape(1)))
         P[tag] = steps

@@ -152,10 +152,11 @@ def test_constructor_contract():
         MNFDense(3, bogus=1)
     with pytest.raises(ValueError):
         MNFDense(3, flow_type="glow")
-    with pytest.raises(NotImplementedError, match="one hidden layer"):
-        IAF(0, h_sizes=(6, 5))
+    assert IAF(0, h_sizes=(6, 5)).h_sizes == (6, 5) and RNVP(4, h_sizes=(7, 4), activation="relu").activation == "relu"
+    with pytest.raises(NotImplementedError, match="hidden layers"):
+        IAF(0, h_sizes=(6, 5, 4, 3, 2))
     with pytest.raises(NotImplementedError):
-        RNVP(4, activation="relu")
+        RNVP(4, activation="swish")
     m = MNFLeNet(max_std=1, flow_h_sizes=[50], std_init=10.0)
     assert [type(l).__name__ for l in m.mnf_layers] == ["MNFConv2D", "MNFConv2D", "MNFDense", "MNFDense"]
     assert [l.n_filters for l in m.mnf_layers[:2]] == [20, 50] and [l.n_out for l in m.mnf_layers[2:]] == [500, 10]

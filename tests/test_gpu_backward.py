@@ -35,10 +35,16 @@ def _f32(a):
 def flow_grad_map(kind, g):
     """oracle grad dict -> host variable names (tf_mnf_b200.flows.*.variables())."""
     if kind == "iaf":
-        return {"w1": g["W"][0], "b1": g["b"][0], "w2": g["W"][1], "b2": g["b"][1]}
+        out = {}
+        for i, (W, b) in enumerate(zip(g["W"], g["b"]), 1):
+            out[f"w{i}"], out[f"b{i}"] = W, b
+        return out
     if kind == "rnvp":
-        return {"net_kernel": g["Wn"][0], "net_bias": g["bn"][0], "t_kernel": g["Wt"], "t_bias": g["bt"],
-                "s_kernel": g["Ws"], "s_bias": g["bs"]}
+        out = {"net_kernel": g["Wn"][0], "net_bias": g["bn"][0]}
+        for i in range(1, len(g["Wn"])):
+            out[f"net_kernel_{i}"], out[f"net_bias_{i}"] = g["Wn"][i], g["bn"][i]
+        out.update({"t_kernel": g["Wt"], "t_bias": g["bt"], "s_kernel": g["Ws"], "s_bias": g["bs"]})
+        return out
     return {"u": g["u"], "w": g["w"], "b": g["b"]}
 
 

@@ -20,7 +20,9 @@ class Noise(C.Structure):
 class FlowStep(C.Structure):
     _fields_ = [("kind", C.c_int32), ("parity", C.c_int32), ("hidden", C.c_int32), ("reserved", C.c_int32),
                 ("w1", vp), ("b1", vp), ("ws", vp), ("bs", vp), ("wt", vp), ("bt", vp),
-                ("ld2", C.c_int64), ("m1", vp), ("m2", vp), ("bern", Noise)]
+                ("ld2", C.c_int64), ("m1", vp), ("m2", vp), ("bern", Noise),
+                ("n_extra", C.c_int32), ("activation", C.c_int32), ("extra_h", C.c_int32 * 3), ("reserved2", C.c_int32),
+                ("extra_w", vp * 3), ("extra_b", vp * 3), ("extra_m", vp * 3)]
 
 
 class ConvShape(C.Structure):
@@ -55,6 +57,8 @@ class TensorView(C.Structure):
 RELEASE_FN = C.CFUNCTYPE(None, vp)
 
 MNF_FLOW_IAF, MNF_FLOW_RNVP, MNF_FLOW_PLANAR = 0, 1, 2
+MNF_FLOW_MAX_HIDDEN = 4
+ACTIVATIONS = {None: 0, "default": 0, "relu": 1, "tanh": 2, "sigmoid": 3, "linear": 4}
 
 # name -> (argtypes); every function returns int status except the two noted below
 _i64, _i32, _f, _u64, _u32, _sz = C.c_int64, C.c_int32, C.c_float, C.c_uint64, C.c_uint32, C.c_size_t
@@ -97,6 +101,7 @@ SIGNATURES = {
     "mnf_flow_forward": [vp, _i64, _i64, _i32, C.POINTER(FlowStep), vp, vp, vp, C.POINTER(Noise), vp, vp, vp],
     "mnf_flow_backward": [vp, _i64, _i64, _i32, C.POINTER(FlowStep), vp, vp, vp, vp, vp, vp, C.POINTER(FlowStep)],
     "mnf_sample_z_backward": [vp, _i64, _i64, vp, vp, C.POINTER(Noise), vp, vp],
+    "mnf_maf_decode": [vp, _i64, _i64, C.POINTER(FlowStep), vp, vp, vp],
     "mnf_dense_forward": [vp, _i64, _i64, _i64, vp, vp, vp, vp, vp, vp, _f, C.POINTER(Noise), vp, vp],
     "mnf_dense_forward_act": [vp, _i64, _i64, _i64, vp, vp, vp, vp, vp, vp, _f, C.POINTER(Noise), C.c_int32, vp, vp],
     "mnf_dense_can_fuse_act": [vp, _i64, _i64, C.c_int32, C.POINTER(C.c_int32)],

@@ -872,14 +872,18 @@ extern "C" int mnf_flow_backward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, 
   int64_t soff[65];
   soff[0] = 0;
   for (int k = 0; k < T; ++k)
-    soff[k + 1] = soff[k] + ((steps[k].kind == MNF_FLOW_PLANAR) ? 0 : B * steps[k].hidden);
+    soff[k + 1] = soff[k] + B * mnf_flow_step_hidden_total(steps[k]);
   int which = 0;
   for (int k = T - 1; k >= 0; --k) {
     const mnf_flow_step& st = steps[k];
     const mnf_flow_step& gs = gsteps[k];
     float* out = (k == 0) ? d_z0 : buf[which ^ 1];
     const float* add = d_states ? d_states + (int64_t)k * BD : nullptr;
-    if (st.kind == MNF_FLOW_IAF || st.kind == MNF_FLOW_RNVP) {
+    if (mnf_flow_step_is_generic(st)) {
+      int rc = mnf_flow_generic_backward(ctx, B, D, st, gs, states + (int64_t)k * BD, saved ? saved + soff[k] : nullptr, cur,
+                                         d_log_dets, add, out);
+      if (rc) return rc;
+    } else if (st.kind == MNF_FLOW_IAF || st.kind == MNF_FLOW_RNVP) {
       MNF_CHECK_ARG(saved, "mnf_flow_backward: saved hidden activations required");
       MNF_CHECK_ARG(st.hidden >= 1 && st.hidden <= FB_HMAX, "flow step %d: hidden=%d not in [1,%d]", k, st.hidden, FB_HMAX);
       MNF_CHECK_ARG(gs.w1 && gs.b1 && gs.ws && gs.bs && gs.wt && gs.bt, "flow step %d: NULL grad pointer", k);

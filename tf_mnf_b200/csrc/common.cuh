@@ -57,6 +57,14 @@ int mnf_flow_umma_step(mnf_ctx* ctx, int64_t B, int D, int H, int kind, int pari
                        const float* ld_in, float* ld_out, float* hid_save, const mnf_flow_step& st,
                        const NoiseDev& bern, float* pack_ws);
 size_t mnf_flow_umma_pack_floats(int D);
+// flows_generic.cu: coupling networks with several hidden layers / other activations (warp per row, FFMA)
+bool mnf_flow_step_is_generic(const mnf_flow_step& st);
+int64_t mnf_flow_step_hidden_total(const mnf_flow_step& st);
+int mnf_flow_generic_forward(mnf_ctx* ctx, int64_t B, int64_t D, const mnf_flow_step& st, const float* zin, float* zout,
+                             const float* ld_in, float* ld_out, float* hid_save);
+int mnf_flow_generic_backward(mnf_ctx* ctx, int64_t B, int64_t D, const mnf_flow_step& st, const mnf_flow_step& gs,
+                              const float* xin, const float* hid, const float* dy, const float* dld, const float* add,
+                              float* dx);
 int mnf_conv_raw_umma_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, const float* x, const float* z,
                               const float* mean_W, const float* log_std_W, const float* mean_b,
                               const float* log_var_b, float max_std, const NoiseDev& eps, float* y, float* mean_out,

@@ -96,68 +96,103 @@ __global__ void __launch_bounds__(RP_THREADS) row_pack(int64_t M, int K, int kbl
   const int r0 = (int)(blockIdx.x % (BM / RP_ROWS)) * RP_ROWS;
   const int64_t m0 = mt * BM + r0;
   const bool vec = (K % 4 == 0) && (((uintptr_t)x & 15) == 0) && (!z || ((uintptr_t)z & 15) == 0);
-  for (int rr = warp; rr < RP_ROWS; rr += RP_THREADS / 32) {
-    const int64_t m = m0 + rr;
-    float ma = 0.f, ms = 0.f;
-    if (m < M) {
-      const float* xr = x + m * K;
-      const float* zr = z ? z + m * K : nullptr;
-      if (vec) {
-        for (int k = lane * 4; k < K; k += 128) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(xr + k));
-          float4 b = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (zr) b = __ldg(reinterpret_cast<const float4*>(zr + k));
-          ma = fmaxf(ma, fmaxf(fmaxf(fabsf(a.x * b.x), fabsf(a.y * b.y)), fmaxf(fabsf(a.z * b.z), fabsf(a.w * b.w))));
-          ms = fmaxf(ms, fmaxf(fmaxf(a.x * a.x, a.y * a.y), fmaxf(a.z * a.z, a.w * a.w)));
+  {
+    // pass 1: the warp's four rows side by side (eight independent 16-byte loads per k step and lane:
+    // the pass is latency-bound, what matters is the number of loads in flight)
+    constexpr int RW = RP_ROWS / (RP_THREADS / 32);  // rows per warp
+    float ma[RW], ms[RW];
+#pragma unroll
+    for (int i = 0; i < RW; ++i) ma[i] = ms[i] = 0.f;
+    if (vec) {
+      for (int k = lane * 4; k < K; k += 128) {
+        float4 a[RW], b[RW];
+#pragma unroll
+        for (int i = 0; i < RW; ++i) {
+          const int64_t m = m0 + warp * RW + i;
+          a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          b[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (m < M) {
+            a[i] = __ldg(reinterpret_cast<const float4*>(x + m * K + k));
+            if (z) b[i] = __ldg(reinterpret_cast<const float4*>(z + m * K + k));
+          }
         }
-      } else {
-        for (int k = lane; k < K; k += 32) {
-          const float a = __ldg(xr + k), b = zr ? __ldg(zr + k) : 1.f;
-          ma = fmaxf(ma, fabsf(a * b));
-          ms = fmaxf(ms, a * a);
+#pragma unroll
+        for (int i = 0; i < RW; ++i) {
+          ma[i] = fmaxf(ma[i], fmaxf(fmaxf(fabsf(a[i].x * b[i].x), fabsf(a[i].y * b[i].y)), fmaxf(fabsf(a[i].z * b[i].z), fabsf(a[i].w * b[i].w))));
+          ms[i] = fmaxf(ms[i], fmaxf(fmaxf(a[i].x * a[i].x, a[i].y * a[i].y), fmaxf(a[i].z * a[i].z, a[i].w * a[i].w)));
+        }
+      }
+    } else {
+      for (int k = lane; k < K; k += 32) {
+#pragma unroll
+        for (int i = 0; i < RW; ++i) {
+          const int64_t m = m0 + warp * RW + i;
+          if (m < M) {
+            const float a = __ldg(x + m * K + k), b = z ? __ldg(z + m * K + k) : 1.f;
+            ma[i] = fmaxf(ma[i], fabsf(a * b));
+            ms[i] = fmaxf(ms[i], a * a);
+          }
         }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
-      ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, o));
-    }
-    if (lane == 0) {
-      const int ea = scale_exp(ma), es = scale_exp(ms);
-      fsc[rr][0] = ldexpf(1.f, ea);
-      fsc[rr][1] = ldexpf(1.f, es);
-      rsc[m0 + rr] = make_float2(ldexpf(1.f, -ea), ldexpf(1.f, -es));
+    for (int i = 0; i < RW; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ma[i] = fmaxf(ma[i], __shfl_xor_sync(0xffffffffu, ma[i], o));
+        ms[i] = fmaxf(ms[i], __shfl_xor_sync(0xffffffffu, ms[i], o));
+      }
+      if (lane == 0) {
+        const int rr = warp * RW + i;
+        const int ea = scale_exp(ma[i]), es = scale_exp(ms[i]);
+        fsc[rr][0] = ldexpf(1.f, ea);
+        fsc[rr][1] = ldexpf(1.f, es);
+        rsc[m0 + rr] = make_float2(ldexpf(1.f, -ea), ldexpf(1.f, -es));
+      }
     }
   }
   __syncthreads();
   const int nchunks = kblocks * CH;
   for (int c0 = 0; c0 < nchunks; c0 += RP_SLAB) {
     const int c = c0 + lane, k0 = c * 8;  // this lane's chunk of the slab
-    for (int rr = warp; rr < RP_ROWS; rr += RP_THREADS / 32) {
-      const int64_t m = m0 + rr;
-      float xv[8], zv[8];
+    constexpr int RW = RP_ROWS / (RP_THREADS / 32);
+    float4 xa[RW][2], za[RW][2];
+    const bool fastk = vec && k0 + 8 <= K;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { xv[e] = 0.f; zv[e] = 1.f; }
+    for (int i = 0; i < RW; ++i) {
+      const int64_t m = m0 + warp * RW + i;
+      xa[i][0] = xa[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      za[i][0] = za[i][1] = make_float4(1.f, 1.f, 1.f, 1.f);
       if (m < M && k0 < K) {
         const float* xr = x + m * K + k0;
         const float* zr = z ? z + m * K + k0 : nullptr;
-        if (vec && k0 + 8 <= K) {
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(xr)), a1 = __ldg(reinterpret_cast<const float4*>(xr + 4));
-          xv[0] = a0.x; xv[1] = a0.y; xv[2] = a0.z; xv[3] = a0.w; xv[4] = a1.x; xv[5] = a1.y; xv[6] = a1.z; xv[7] = a1.w;
+        if (fastk) {
+          xa[i][0] = __ldg(reinterpret_cast<const float4*>(xr));
+          xa[i][1] = __ldg(reinterpret_cast<const float4*>(xr + 4));
           if (zr) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(zr)), b1 = __ldg(reinterpret_cast<const float4*>(zr + 4));
-            zv[0] = b0.x; zv[1] = b0.y; zv[2] = b0.z; zv[3] = b0.w; zv[4] = b1.x; zv[5] = b1.y; zv[6] = b1.z; zv[7] = b1.w;
+            za[i][0] = __ldg(reinterpret_cast<const float4*>(zr));
+            za[i][1] = __ldg(reinterpret_cast<const float4*>(zr + 4));
           }
         } else {
+          float xv[8], zv[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
+          for (int e = 0; e < 8; ++e) {
+            xv[e] = 0.f; zv[e] = 1.f;
             if (k0 + e < K) {
               xv[e] = __ldg(xr + e);
               if (zr) zv[e] = __ldg(zr + e);
             }
+          }
+          xa[i][0] = make_float4(xv[0], xv[1], xv[2], xv[3]); xa[i][1] = make_float4(xv[4], xv[5], xv[6], xv[7]);
+          za[i][0] = make_float4(zv[0], zv[1], zv[2], zv[3]); za[i][1] = make_float4(zv[4], zv[5], zv[6], zv[7]);
         }
       }
+    }
+#pragma unroll
+    for (int i = 0; i < RW; ++i) {
+      const int rr = warp * RW + i;
+      const float xv[8] = {xa[i][0].x, xa[i][0].y, xa[i][0].z, xa[i][0].w, xa[i][1].x, xa[i][1].y, xa[i][1].z, xa[i][1].w};
+      const float zv[8] = {za[i][0].x, za[i][0].y, za[i][0].z, za[i][0].w, za[i][1].x, za[i][1].y, za[i][1].z, za[i][1].w};
       const float fa = fsc[rr][0], fs = fsc[rr][1];
       uint32_t ah[4], al[4], sh[4], sl[4];
 #pragma unroll

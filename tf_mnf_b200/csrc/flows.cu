@@ -597,7 +597,9 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
                steps[k].hidden <= FT_HMAX && steps[k].w1 && steps[k].b1 && steps[k].ws && steps[k].bs && steps[k].wt &&
                steps[k].bt;
   }
-  if (B == 1 && all_mlp && T <= C1_TMAX && D <= C1_DMAX) {  // kl_div path: whole chain in one CTA
+  bool any_generic = false;
+  for (int k = 0; k < T; ++k) any_generic |= mnf_flow_step_is_generic(steps[k]);
+  if (B == 1 && all_mlp && !any_generic && T <= C1_TMAX && D <= C1_DMAX) {  // kl_div path: whole chain in one CTA
     Chain1Args a;
     a.D = (int)D; a.T = T; a.zin = z0; a.q0_mean = q0_mean; a.q0_log_var = q0_log_var; a.eps = eps;
     a.states = states; a.ld_out = log_dets; a.hid_save = saved;
@@ -658,6 +660,21 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
     float* zout = states + (int64_t)(k + 1) * BD;
     float* z0_out = (first && !z0) ? states : nullptr;
     if (first && z0 && z0 != states) MNF_CUDA(cudaMemcpyAsync(states, z0, sizeof(float) * BD, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (mnf_flow_step_is_generic(st)) {  // several hidden layers / another activation: the general kernels
+      const float* zg = zin;
+      if (!zg) {  // sample z0 for all rows first (same Philox counters as the fused draw)
+        const int64_t n4 = B * ((D + 3) / 4);
+        int g0 = (int)(cdiv(n4, 256) < ctx->sm_count * 8 ? cdiv(n4, 256) : ctx->sm_count * 8);
+        sample_z0_kernel<<<g0, 256, 0, ctx->stream>>>(B, (int)D, nullptr, q0_mean, q0_log_var, eps, states, nullptr);
+        MNF_LAUNCHED(ctx);
+        zg = states;
+      }
+      int rc = mnf_flow_generic_forward(ctx, B, D, st, zg, zout, first ? nullptr : log_dets, log_dets,
+                                        saved ? saved + saved_off : nullptr);
+      if (rc) return rc;
+      saved_off += B * mnf_flow_step_hidden_total(st);
+      continue;
+    }
     if (st.kind == MNF_FLOW_IAF || st.kind == MNF_FLOW_RNVP) {
       MNF_CHECK_ARG(st.hidden >= 1 && st.hidden <= FT_HMAX, "flow step %d: hidden=%d not in [1,%d]", k, st.hidden, FT_HMAX);
       MNF_CHECK_ARG(st.w1 && st.b1 && st.ws && st.bs && st.wt && st.bt, "flow step %d: NULL weight pointer", k);

@@ -10,7 +10,7 @@ from .maf import IAF, MAF
 from .planar import PlanarFlow
 from .rnvp import RNVP
 
-__all__ = ["IAF", "MAF", "MADE", "MaskedDense", "RNVP", "PlanarFlow", "NormalizingFlow", "NormalizingFlowModel"]
+__all__ = ["IAF", "MAF", "MADE", "MaskedDense", "RNVP", "PlanarFlow", "NormalizingFlow", "NormalizingFlowModel", "DiagNormal"]
 
 
 class NormalizingFlow:
@@ -25,6 +25,23 @@ class NormalizingFlow:
         self.last_run: ChainRun | None = None
 
     def forward(self, z: Any, bern: Sequence[Any] | None = None, record: bool = False):
+        if any(isinstance(fl, MAF) and not isinstance(fl, IAF) for fl in self.flows):
+            # a MAF's forward is the sequential decode (maf.py:33-45), not the MADE pass the fused chain
+            # runs: step by step through the flows' own forward(), as flows/__init__.py:22-29 does
+            import ctypes as C
+
+            from .. import _lib as L
+            from ..runtime import as_device, default_context
+
+            if bern is not None or record:
+                raise NotImplementedError("injected masks / recording are for chains of IAF, RNVP and PlanarFlow steps")
+            z = as_device(z, default_context())
+            xs, total = [z], z.ctx.zeros((z.shape[0],))
+            for fl in self.flows:
+                z, ld = fl.forward(z)
+                xs.append(z)
+                L.check(z.ctx.lib.mnf_axpy(z.ctx.handle, ld.size, 1.0, C.c_void_p(ld.ptr), C.c_void_p(total.ptr)))
+            return xs, total
         run = ChainRun(self.flows)
         states, ld = run.forward(z=z, bern=bern, seed=init.global_seed(), call_index=self._calls,
                                  layer_id=self.uid, bern_draw=noise.FLOW_BERN, record=record)
@@ -60,18 +77,86 @@ class NormalizingFlow:
         return d_z0, grads
 
     def inverse(self, x: Any):
-        raise NotImplementedError("NormalizingFlow.inverse is never called by the MNF layers (SURVEY.md 8f-4)")
+        """flows/__init__.py:31-38: x -> z through the flows in reverse order; returns the LIST of states
+        (starting with x) and the summed log-determinants.  A flow must have an `inverse` (MAF: one
+        MADE pass; IAF: the sequential decode); RNVP and PlanarFlow have none in the reference either."""
+        import ctypes as C
+
+        from .. import _lib as L
+        from ..runtime import as_device, default_context
+
+        x = as_device(x, default_context())
+        zs, total = [x], None
+        for fl in reversed(self.flows):
+            if not hasattr(fl, "inverse"):
+                raise NotImplementedError(f"{type(fl).__name__} has no inverse() (neither in the reference)")
+            x, ld = fl.inverse(x)
+            zs.append(x)
+            if total is None:
+                total = ld
+            else:
+                L.check(x.ctx.lib.mnf_axpy(x.ctx.handle, ld.size, 1.0, C.c_void_p(ld.ptr), C.c_void_p(total.ptr)))
+        if total is None:
+            total = x.ctx.zeros((x.shape[0],))
+        return zs, total
+
+
+class DiagNormal:
+    """A base distribution for NormalizingFlowModel (the reference takes any object with log_prob /
+    sample, e.g. tfp.distributions.MultivariateNormalDiag): independent N(loc, scale^2) per dimension.
+    sample() draws on the device (mnf_philox_normal); log_prob() returns per-row log densities [B]."""
+
+    def __init__(self, dim: int, loc: float = 0.0, scale: float = 1.0, seed: int | None = None) -> None:
+        self.dim, self.loc, self.scale = int(dim), float(loc), float(scale)
+        self.seed = init.global_seed() if seed is None else int(seed)
+        self.uid = init.next_uid()
+        self._calls = 0
+
+    def sample(self, num_samples):
+        import ctypes as C
+
+        import numpy as np
+
+        from .. import _lib as L
+        from ..runtime import default_context
+
+        n = int(np.prod(num_samples)) if not isinstance(num_samples, int) else int(num_samples)
+        ctx = default_context()
+        out = ctx.empty((n, self.dim))
+        seed = (self.seed & 0xFFFFFFFF) | ((self._calls & 0xFFFFFFFF) << 32)
+        L.check(ctx.lib.mnf_philox_normal(ctx.handle, seed, noise.stream_id(self.uid, noise.FLOW_BERN - 1), 0, n, 1, self.dim,
+                                          C.c_void_p(out.ptr)))
+        self._calls += 1
+        if self.loc != 0.0 or self.scale != 1.0:
+            host = out.numpy() * self.scale + self.loc
+            out = ctx.to_device(host)
+        return out
+
+    def log_prob(self, z):
+        import numpy as np
+
+        zz = (z.numpy() if hasattr(z, "numpy") else np.asarray(z)).astype(np.float64)
+        u = (zz - self.loc) / self.scale
+        return (-0.5 * u * u - np.log(self.scale) - 0.5 * np.log(2 * np.pi)).sum(axis=-1)
 
 
 class NormalizingFlowModel(NormalizingFlow):
-    """(base distribution, flow) pair (flows/__init__.py:41-57); unused by the layers."""
+    """(base distribution, flow) pair (flows/__init__.py:41-57).  `base`: any object with
+    log_prob(z) and sample(num_samples), e.g. DiagNormal above."""
 
     def __init__(self, base: Any, flow: Sequence[Flow]) -> None:
         super().__init__(flow)
         self.base = base
 
     def base_log_prob(self, x: Any):
-        raise NotImplementedError("needs NormalizingFlow.inverse (SURVEY.md 8f-4)")
+        """flows/__init__.py:49-51: sum over the batch of base.log_prob(inverse(x)[-1])."""
+        import numpy as np
+
+        zs, _ = self.inverse(x)
+        return float(np.sum(self.base.log_prob(zs[-1])))
 
     def sample(self, *num_samples: int):
-        raise NotImplementedError("NormalizingFlowModel.sample is outside the MNF hot path (SURVEY.md 8f-4)")
+        """flows/__init__.py:53-57: z ~ base, then all the states of forward(z)."""
+        z = self.base.sample(num_samples)
+        xs, _ = self.forward(z)
+        return xs

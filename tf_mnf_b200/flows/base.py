@@ -33,8 +33,10 @@ class Flow:
 
     @property
     def hidden(self) -> int:
-        return {L.MNF_FLOW_PLANAR: 0}.get(self.kind, getattr(self, "h_sizes", None) and self.h_sizes[0] or
-                                          getattr(getattr(self, "net", None), "h_sizes", (0,))[0])
+        """Floats per row the step saves for its backward pass: the sum of its hidden widths."""
+        if self.kind == L.MNF_FLOW_PLANAR:
+            return 0
+        return int(sum(self.h_sizes))
 
     def _single_step(self, z: Any, bern: Sequence[Any] | None = None):
         chain = ChainRun([self])
