@@ -63,7 +63,7 @@ def main() -> None:
         scale = max(np.max(np.abs(b)), 1e-12)
         err = float(np.max(np.abs(a - b)) / scale)
         worst = max(worst, err)
-        assert err <= 2e-4, (k, err)
+        assert err <= 2e-5, (k, err)  # measured 9e-7: the shards' fp32 sums differ from the single-process order only
     if world > 1:
         t = torch.from_numpy(params).cuda()
         mx, mn = t.clone(), t.clone()

@@ -13,7 +13,7 @@ from oracle import mnf_oracle as O
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5   # activations-like tensors (dx, dz)
-RTOL_G = float(os.environ.get("MNF_RTOL_G", 2e-5))  # parameter gradients (fp32 atomics / split-K accumulate over the batch)
+RTOL_G = float(os.environ.get("MNF_RTOL_G", 1e-5))  # parameter gradients: the same bar as activations (north_star)
 
 
 @pytest.fixture(scope="module", params=["fp32", "tf32x3"])
