@@ -84,6 +84,8 @@ CONV_CASES = [
     # x shape, filter shape, padding, fuse ReLU+pool, kernel family under tf32x3
     ((37, 12, 12, 20), (5, 5, 20, 50), "VALID", True, "conv_raw_f16"),
     ((130, 12, 12, 20), (5, 5, 20, 50), "VALID", False, "conv_raw_f16"),
+    ((701, 12, 12, 20), (5, 5, 20, 50), "VALID", True, "conv_raw_f16x2"),   # enough tiles for every CTA pair (cta_group::2), odd tile count
+    ((640, 12, 12, 20), (5, 5, 20, 36), "VALID", True, "conv_raw_f16x2"),
     ((9, 28, 28, 1), (5, 5, 1, 20), "VALID", True, "conv_win_umma"),
     ((5, 28, 28, 1), (5, 5, 1, 20), "VALID", False, "conv_win_umma"),
     ((3, 9, 7, 3), (3, 3, 3, 64), "SAME", False, None),

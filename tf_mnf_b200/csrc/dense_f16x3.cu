@@ -60,10 +60,13 @@ struct Args {
 };
 
 __device__ __forceinline__ void split_f16x2(float a0, float a1, uint32_t& hi, uint32_t& lo) {
-  const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
-  const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
-  hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-  lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  // packed conversions (F2FP.F16.F32.PACK_AB: one instruction per PAIR, not on the quarter-rate XU pipe that the
+  // scalar F2F.F16.F32 uses -- the plane producers convert 4 values per element)
+  const __half2 h = __floats2half2_rn(a0, a1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 // 2^e with m * 2^e in [2^13, 2^14) (e = 0 for m == 0 / non-finite)
 __device__ __forceinline__ int scale_exp(float m) {
