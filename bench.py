@@ -45,7 +45,7 @@ CONV2_FLOP_PER_ROW = 2 * 2 * 64 * 500 * 50   # two products (mean, variance), SU
 STAGES = {
     # name: (bytes per row, weight bytes per launch, FLOP per row)
     "conv1 (mc_expand: mean*z + sd*eps, ReLU, 2x2 pool; 11520 normals per row)": (12 * 12 * 20 * 4 + 20 * 4, 2 * 10 * 24 * 24 * 20 * 4, 4 * 24 * 24 * 20),
-    "conv2 (conv_raw_f16)": (CONV2_BYTES_PER_ROW, CONV2_WEIGHT_BYTES, CONV2_FLOP_PER_ROW),
+    "conv2 (conv_raw_f16x2: CTA pairs, tcgen05 cta_group::2)": (CONV2_BYTES_PER_ROW, CONV2_WEIGHT_BYTES, CONV2_FLOP_PER_ROW),
     "d1 (row_pack + paired_f16x3, ReLU fused)": (2 * 800 * 4 + 500 * 4, 2 * 800 * 500 * 4, 2 * 2 * 800 * 500),
     "d2 (dense_small, Softmax fused)": (2 * 500 * 4 + 10 * 4, 2 * 500 * 10 * 4, 2 * 2 * 500 * 10),
 }
@@ -686,7 +686,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
                 "note": "rank 0, eager: model(x) on the resident 10240-row repeated batch + kl_div() -- the first layer "
                         "convolves every row (no sharing between the samples of an image)"},
             "roofline": {"bound": "tensor",
-                         "kernel": ("cf::conv_raw_f16" if tc else "paired_gemm_fwd<CONV,64>")
+                         "kernel": ("cf::conv_raw_f16x2" if tc else "paired_gemm_fwd<CONV,64>")
                          + " (conv2: 12x12x20 -> 8x8x50, 5x5, + fused ReLU/2x2 max-pool), the dominant kernel of the step",
                          "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch, from the ncu --set full
@@ -700,8 +700,9 @@ def run_gpu(args, rank: int, local_rank: int, world: int) -> None:
                                       "frac": k_bytes / (k_ms * 1e-3) / 1e9 / hbm,
                                       "note": "the same launch against the HBM roof: algorithmic bytes of the FUSED kernel "
                                               "(pooled output); not what binds it"},
-                         "pipe": ("tcgen05.mma kind::f16, power-of-two scaled fp16 hi/lo split of both operands, fp32 "
-                                  "accumulate (fp32 parity <=1e-5 rel.); kernel_ms is the in-situ time, side streams running"
+                         "pipe": ("tcgen05.mma cta_group::2 kind::f16 (M = 256 over a CTA pair), power-of-two scaled fp16 hi/lo "
+                                  "split of both operands, fp32 accumulate (fp32 parity <=1e-5 rel.); kernel_ms is the in-situ "
+                                  "time, side streams running"
                                   if tc else "fp32 FFMA (parity path, <=1e-5 rel.)"),
                          "step": {"rows_per_s_per_gpu": ROWS / (ms * 1e-3), "hbm_roof_rows_per_s": step_roof,
                                   "frac": ROWS / (ms * 1e-3) / step_roof,

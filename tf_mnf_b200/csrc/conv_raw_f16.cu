@@ -511,20 +511,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// wait with cluster-scope acquire: the data behind the barrier may have been written in the peer CTA
-__device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t polls = 0; !done; ++polls) {
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P1;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (!done && polls > (1u << 24)) __trap();
-  }
-}
+// Waits stay at CTA scope (umma.cuh: mbar_wait).  A cluster-scope acquire on the polling side makes ptxas emit
+// CCTL.IVALL -- an L1 invalidate -- behind EVERY try_wait (6 % of this kernel's instructions when it was
+// tried, with the producers' and epilogue's global loads missing L1 ever after), and buys nothing here: what
+// the peer CTA publishes is shared memory read by its own SM's tensor-core datapath, ordered by the
+// arriving side's fence.proxy.async + release.cluster arrive and by tcgen05.commit.
+__device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 // arrive on the barrier at the same offset in CTA `rank` of the cluster (cluster-scope release)
 __device__ __forceinline__ void mbar_arrive_cl(uint64_t* bar, uint32_t rank) {
   uint32_t raddr;

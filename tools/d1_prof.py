@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""One MNF-LeNet d1 layer call (10240 x 800 -> 500, ReLU fused): device time of pack + GEMM; MNF_DENSE_PROF=1
+prints where the CTA-pair GEMM's MMA warp waits.   python tools/d1_prof.py [rows]"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import tf_mnf_b200 as M  # noqa: E402
+from tf_mnf_b200 import _lib as L  # noqa: E402
+from tf_mnf_b200.layers import MNFDense  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 10240
+M.set_seed(0)
+ctx = M.default_context()
+lyr = MNFDense(500, flow_type="rnvp", std_init=10.0)
+x = ctx.to_device(np.random.RandomState(0).uniform(size=(B, 800)).astype(np.float32))
+lyr.build(x.shape)
+ctx.freeze_weights(True)
+for _ in range(3):
+    lyr.call(x, activation="relu")
+ctx.sync()
+ks, ke = [], []
+for i in range(10):
+    a, b = C.c_void_p(), C.c_void_p()
+    L.check(ctx.lib.mnf_event_create(C.byref(a))), L.check(ctx.lib.mnf_event_create(C.byref(b)))
+    L.check(ctx.lib.mnf_ctx_probe(ctx.handle, 2, 0, a, b))
+    lyr.call(x, activation="relu")
+    ks.append(a), ke.append(b)
+ctx.sync()
+ms = C.c_float()
+t = []
+for a, b in zip(ks, ke):
+    L.check(ctx.lib.mnf_event_elapsed_ms(a, b, C.byref(ms)))
+    t.append(ms.value * 1e3)
+print(f"{L.last_path()} B={B}: pack + GEMM {np.mean(t):.1f} us (min {np.min(t):.1f})")
