@@ -57,6 +57,16 @@ int mnf_flow_umma_step(mnf_ctx* ctx, int64_t B, int D, int H, int kind, int pari
                        const float* ld_in, float* ld_out, float* hid_save, const mnf_flow_step& st,
                        const NoiseDev& bern, float* pack_ws);
 size_t mnf_flow_umma_pack_floats(int D);
+// flows_f16.cu: RNVP steps on kind::f16 (scaled fp16 hi/lo operands), z moved by bulk copies only
+bool mnf_flow_f16_ok(const mnf_ctx* ctx, int64_t B, int64_t D, const mnf_flow_step& st);
+size_t mnf_flow_f16_pack_bytes(int D);
+size_t mnf_flow_f16_tiles(int64_t B);
+int mnf_flow_f16_sample_z0(mnf_ctx* ctx, int64_t B, int D, const float* q0_mean, const float* q0_log_var, const NoiseDev& eps,
+                           float* zout, float* tmax);
+int mnf_flow_f16_absmax(mnf_ctx* ctx, int64_t B, int D, const float* z, float* tmax);
+int mnf_flow_f16_step(mnf_ctx* ctx, int64_t B, int D, const float* zin, float* zout, const float* ld_in, float* ld_out,
+                      float* hid_save, const mnf_flow_step& st, const NoiseDev& bern, const float* tmax_in, float* tmax_out,
+                      uint8_t* pack_ws);
 // flows_generic.cu: coupling networks with several hidden layers / other activations (warp per row, FFMA)
 bool mnf_flow_step_is_generic(const mnf_flow_step& st);
 int64_t mnf_flow_step_hidden_total(const mnf_flow_step& st);

@@ -641,15 +641,27 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
   // wide rows on few row tiles: the MLP contractions as whole-chip GEMMs (iaf_combine_kernel above)
   const bool use_gemm = !use_tc && D >= 1024 && B >= 2 && cdiv(B, FT_ROWS) * 2 <= ctx->sm_count;
   float* gemm_ws = nullptr;
+  // RNVP steps of many rows: flows_f16.cu (needs the max |z| of every 128-row tile: two ping-pong arrays)
+  bool any_f16 = false;
+  for (int k = 0; k < T; ++k) any_f16 |= use_tc && mnf_flow_f16_ok(ctx, B, D, steps[k]);
+  any_f16 = any_f16 && ((reinterpret_cast<uintptr_t>(states) | (z0 ? reinterpret_cast<uintptr_t>(z0) : 0)) & 15) == 0;
+  float *tmax_cur = nullptr, *tmax_nxt = nullptr;
+  uint8_t* pack16 = nullptr;
+  bool tmax_valid = false;
   {
     const size_t scal_floats = ((size_t)2 * T + 63) & ~(size_t)63;
     const size_t pack_floats = use_tc ? mnf_flow_umma_pack_floats((int)D) : 0;
     const size_t gemm_floats = use_gemm ? (size_t)B * (64 + 2 * (size_t)D) : 0;
+    const size_t tmax_floats = any_f16 ? ((mnf_flow_f16_tiles(B) + 63) & ~(size_t)63) : 0;
+    const size_t pack16_floats = any_f16 ? (mnf_flow_f16_pack_bytes((int)D) + 3) / 4 : 0;
     if (any_planar || use_tc || use_gemm) {
-      scal = (float*)mnf_workspace(ctx, sizeof(float) * (scal_floats + pack_floats + gemm_floats));
+      scal = (float*)mnf_workspace(ctx, sizeof(float) * (scal_floats + pack_floats + gemm_floats + 2 * tmax_floats + pack16_floats));
       if (!scal) return MNF_ERR_CUDA;
       pack_ws = scal + scal_floats;
       gemm_ws = pack_ws + pack_floats;
+      tmax_cur = gemm_ws + gemm_floats;
+      tmax_nxt = tmax_cur + tmax_floats;
+      pack16 = (uint8_t*)(tmax_nxt + tmax_floats);
     }
   }
   int64_t saved_off = 0;  // saved is packed: step k starts after sum_{j<k} B*hidden_j
@@ -659,6 +671,8 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
     const float* zin = first ? z0 : states + (int64_t)k * BD;
     float* zout = states + (int64_t)(k + 1) * BD;
     float* z0_out = (first && !z0) ? states : nullptr;
+    const bool had_tmax = tmax_valid;  // zin's tile maxima are known (written by the f16 step before this one)
+    tmax_valid = false;
     if (first && z0 && z0 != states) MNF_CUDA(cudaMemcpyAsync(states, z0, sizeof(float) * BD, cudaMemcpyDeviceToDevice, ctx->stream));
     if (mnf_flow_step_is_generic(st)) {  // several hidden layers / another activation: the general kernels
       const float* zg = zin;
@@ -688,6 +702,22 @@ extern "C" int mnf_flow_forward(mnf_ctx* ctx, int64_t B, int64_t D, int32_t T, c
       a.w1 = st.w1; a.b1 = st.b1; a.ws = st.ws; a.bs = st.bs; a.wt = st.wt; a.bt = st.bt;
       a.m1 = st.m1; a.m2 = st.m2; a.ld2 = st.ld2;
       a.bern = make_noise(&st.bern);
+      if (any_f16 && mnf_flow_f16_ok(ctx, B, D, st)) {  // tcgen05 kind::f16 path (flows_f16.cu)
+        const float* zin16 = zin;
+        if (!zin16) {  // z0 for all rows (same Philox counters as the fused draw) + its tile maxima
+          int rc = mnf_flow_f16_sample_z0(ctx, B, (int)D, q0_mean, q0_log_var, eps, states, tmax_cur);
+          if (rc) return rc;
+          zin16 = states;
+        } else if (!had_tmax) {
+          int rc = mnf_flow_f16_absmax(ctx, B, (int)D, zin16, tmax_cur);
+          if (rc) return rc;
+        }
+        int rc = mnf_flow_f16_step(ctx, B, (int)D, zin16, zout, a.ld_in, a.ld_out, a.hid_save, st, a.bern, tmax_cur, tmax_nxt, pack16);
+        if (rc) return rc;
+        float* t = tmax_cur; tmax_cur = tmax_nxt; tmax_nxt = t;
+        tmax_valid = true;
+        continue;
+      }
       if (use_tc && (z0_out || zin)) {  // tcgen05 path (3xTF32): same arithmetic contract, fp32 parity
         const float* zin_tc = zin;
         float* z0_tc = z0_out;
