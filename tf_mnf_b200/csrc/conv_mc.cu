@@ -29,17 +29,18 @@ struct McArgs {
 
 __device__ __forceinline__ float4 ld4g(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-// four outputs (one pixel, one filter quad) of row `brow`
-__device__ __forceinline__ void mc_quad(const McArgs& a, const PhiloxKeys& K, int64_t brow, uint64_t grow, const float* mimg,
-                                        const float* simg, const float4& zq, int pix, int q, float o[4]) {
+// four outputs (one pixel, one filter quad) of a row; `off` = pix * F + 4 q indexes the row's injected
+// noise and the image's maps alike (32-bit: the per-quad 64-bit address arithmetic was 10 % of the kernel)
+__device__ __forceinline__ void mc_quad(const McArgs& a, const PhiloxKeys& K, const float* inj, uint64_t grow, const float* mimg,
+                                        const float* simg, const float4& zq, int pix, int q, int off, float o[4]) {
   float e[4];
-  if (a.eps.injected) {
-    const float4 t = ld4g(a.eps.injected + (brow * a.Ho * a.Wo + pix) * a.F + 4 * q);
+  if (inj) {
+    const float4 t = ld4g(inj + off);
     e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
   } else {
     philox_normal4_keys(a.eps, K, grow, (uint32_t)pix, (uint32_t)q, e);
   }
-  const float4 m = ld4g(mimg + (int64_t)pix * a.F + 4 * q), s = ld4g(simg + (int64_t)pix * a.F + 4 * q);
+  const float4 m = ld4g(mimg + off), s = ld4g(simg + off);
   o[0] = fmaf(s.x, e[0], m.x * zq.x);
   o[1] = fmaf(s.y, e[1], m.y * zq.y);
   o[2] = fmaf(s.z, e[2], m.z * zq.z);
@@ -100,24 +101,27 @@ __global__ void __launch_bounds__(256) conv_mc_expand(McArgs a) {
   const float* simg = a.sd + img * map;
   const float* zrow = a.z ? a.z + brow * a.F : nullptr;
   const PhiloxKeys K = philox_keys(a.eps);
+  const float* inj = a.eps.injected ? a.eps.injected + brow * map : nullptr;
   if (POOL) {
     const int Hp = a.Ho >> 1, Wp = a.Wo >> 1, items = Hp * Wp * Q;
     float* yrow = a.y + brow * (int64_t)items * 4;
     // (q, wp, hp) of item `it`, advanced incrementally (runtime integer divisions cost ~20 instructions each)
     const int sq = (int)blockDim.x % Q, spp = (int)blockDim.x / Q, swp = spp % Wp, shp = spp / Wp;
     int q = (int)threadIdx.x % Q, pp0 = (int)threadIdx.x / Q, wp = pp0 % Wp, hp = pp0 / Wp;
+    const int dpix[4] = {0, 1, a.Wo, a.Wo + 1};
+    const int doff[4] = {0, a.F, a.Wo * a.F, (a.Wo + 1) * a.F};
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
       const float4 zq = zrow ? ld4g(zrow + 4 * q) : make_float4(1.f, 1.f, 1.f, 1.f);
       float best[4] = {0.f, 0.f, 0.f, 0.f};  // max(., 0) folds the ReLU in
+      const int pix0 = 2 * hp * a.Wo + 2 * wp, off0 = pix0 * a.F + 4 * q;
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
-        const int pix = (2 * hp + (d >> 1)) * a.Wo + 2 * wp + (d & 1);
         float o[4];
-        mc_quad(a, K, brow, grow, mimg, simg, zq, pix, q, o);
+        mc_quad(a, K, inj, grow, mimg, simg, zq, pix0 + dpix[d], q, off0 + doff[d], o);
 #pragma unroll
         for (int j = 0; j < 4; ++j) best[j] = fmaxf(best[j], o[j]);
       }
-      *reinterpret_cast<float4*>(yrow + (int64_t)it * 4) = make_float4(best[0], best[1], best[2], best[3]);
+      *reinterpret_cast<float4*>(yrow + it * 4) = make_float4(best[0], best[1], best[2], best[3]);
       q += sq; wp += swp; hp += shp;
       if (q >= Q) { q -= Q; ++wp; }
       if (wp >= Wp) { wp -= Wp; ++hp; }
@@ -129,8 +133,8 @@ __global__ void __launch_bounds__(256) conv_mc_expand(McArgs a) {
       const int q = it % Q, pix = it / Q;
       const float4 zq = zrow ? ld4g(zrow + 4 * q) : make_float4(1.f, 1.f, 1.f, 1.f);
       float o[4];
-      mc_quad(a, K, brow, grow, mimg, simg, zq, pix, q, o);
-      *reinterpret_cast<float4*>(yrow + (int64_t)it * 4) = make_float4(o[0], o[1], o[2], o[3]);
+      mc_quad(a, K, inj, grow, mimg, simg, zq, pix, q, it * 4, o);
+      *reinterpret_cast<float4*>(yrow + it * 4) = make_float4(o[0], o[1], o[2], o[3]);
     }
   }
 }

@@ -58,8 +58,7 @@ struct Args {
   const float* bt;
   const uint8_t* W1p;   // [kblocks][{hi, lo}][4 chunks][64 hidden][8 halves]
   const uint8_t* W2p;   // [kblocks][{hi, lo}][8 chunks][32 s | 32 t][8 halves]
-  const float* s1inv;   // [64] inverse column scales of W1
-  const float* s2inv;   // [2][kblocks * 32] inverse column scales of Ws, Wt
+  const float* sinv;    // [3] inverse power-of-two scales of W1, Ws, Wt
   const float* tmax_in; // [tiles] max |z| of each 128-row tile
   float* tmax_out;      // [tiles] same for zout (may be NULL)
   NoiseDev bern;
@@ -97,6 +96,17 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int 
 __device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
+// single MUFU instructions (no denormal / range fix-ups: the arguments here are normal and bounded)
+__device__ __forceinline__ float ex2_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
@@ -109,9 +119,9 @@ __global__ void __launch_bounds__(THREADS, 1) rnvp_f16_step(const __grid_constan
   uint8_t* Hs = smem + S2 * B2_STAGE;        // [2][8][BM][16 B]       32 KB (aliases A1 / B1)
   uint8_t* raw = smem + REGION_X;            // [NR][BM][128 B] (swizzled)
   uint32_t* mbits = (uint32_t*)(raw + NR * RAW_TILE);  // [kblocks][BM]: bit e set = element kept (m = 1)
-  float* colp = (float*)(mbits + a.kblocks * BM);      // [4][kblocks * 32]: bs | bt | inverse scales of Ws | Wt
-  float* b1s = colp + 4 * a.kblocks * TK;              // [64] b1 | [64] inverse scales of W1
-  float* ldp = b1s + 2 * HP;                           // [4][BM] log-det partials
+  float* colp = (float*)(mbits + a.kblocks * BM);      // [2][kblocks * 32]: bs | bt
+  float* b1s = colp + 2 * a.kblocks * TK;              // [64] b1
+  float* ldp = b1s + HP;                               // [4][BM] log-det partials
   float* zmx = ldp + 4 * BM;                           // [32] per-warp max |z'|
   uint64_t* bars = (uint64_t*)(zmx + 32);
   uint64_t* full1 = bars;              // [S1]
@@ -149,13 +159,8 @@ __global__ void __launch_bounds__(THREADS, 1) rnvp_f16_step(const __grid_constan
   for (int c = threadIdx.x; c < ncols; c += THREADS) {
     colp[c] = c < D ? a.bs[c] : 0.f;
     colp[ncols + c] = c < D ? a.bt[c] : 0.f;
-    colp[2 * ncols + c] = a.s2inv[c] * H_INV;
-    colp[3 * ncols + c] = a.s2inv[ncols + c] * H_INV;
   }
-  if (threadIdx.x < HP) {
-    b1s[threadIdx.x] = threadIdx.x < a.H ? a.b1[threadIdx.x] : 0.f;
-    b1s[HP + threadIdx.x] = a.s1inv[threadIdx.x];
-  }
+  if (threadIdx.x < HP) b1s[threadIdx.x] = threadIdx.x < a.H ? a.b1[threadIdx.x] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -164,7 +169,8 @@ __global__ void __launch_bounds__(THREADS, 1) rnvp_f16_step(const __grid_constan
 
   // power-of-two scale of this tile's z: max |z| * 2^e in [2^13, 2^14)
   const int ze = scale_exp(__ldg(a.tmax_in + blockIdx.x));
-  const float zscale = ldexpf(1.f, ze), zinv = ldexpf(1.f, -ze);
+  const float zscale = ldexpf(1.f, ze);
+  const float c1 = ldexpf(1.f, -ze) * __ldg(a.sinv), c2s = __ldg(a.sinv + 1) * H_INV, c2t = __ldg(a.sinv + 2) * H_INV;
 
   // instruction descriptor: D = F32 (bit 4), A = B = F16 (format 0), K-major both, N = 64, M = 128
   const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -183,9 +189,9 @@ __global__ void __launch_bounds__(THREADS, 1) rnvp_f16_step(const __grid_constan
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int h = c0 + 8 * q + e;
-        const float pre = fmaf(v[8 * q + e], zinv * b1s[HP + h], b1s[h]);
-        const float t = __expf(-2.f * fabsf(pre));        // in (0, 1]
-        const float th = __fdividef(1.f - t, 1.f + t);    // tanh(|pre|)
+        const float pre = fmaf(v[8 * q + e], c1, b1s[h]);
+        const float t = ex2_fast(-2.8853900817779268f * fabsf(pre));  // exp(-2 |pre|) in (0, 1]
+        const float th = (1.f - t) * rcp_fast(1.f + t);               // tanh(|pre|)
         hv[e] = h < a.H ? (pre < 0.f ? -th : th) : 0.f;
         if (a.hid_save && row < a.B && h < a.H) a.hid_save[row * a.H + h] = hv[e];
       }
@@ -251,9 +257,7 @@ __global__ void __launch_bounds__(THREADS, 1) rnvp_f16_step(const __grid_constan
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&raw_free[slot]);
-      uint32_t bits = mbits[kb * BM + r];
-      const int left = D - kb * TK;
-      if (left < TK) bits &= (1u << left) - 1u;  // columns beyond D were never loaded
+      const uint32_t bits = mbits[kb * BM + r];  // (columns beyond D: zero-filled by the load)
       uint32_t hi[TK / 2], lo[TK / 2];
 #pragma unroll
       for (int e = 0; e < TK / 2; ++e) {
@@ -344,8 +348,11 @@ __global__ void __launch_bounds__(THREADS, 1) rnvp_f16_step(const __grid_constan
         w[0] = ~q.x; w[1] = ~q.y; w[2] = ~q.z; w[3] = ~q.w;  // the draw is 1 when the bit is clear
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (k4 * 4 + i < a.kblocks) mbits[(k4 * 4 + i) * BM + r] = w[i];
+      for (int i = 0; i < 4; ++i) {
+        const int kb = k4 * 4 + i, left = D - kb * TK;
+        // columns beyond D count as kept (m = 1): z' = z = 0 (zero-filled by the TMA load) and no log-det term
+        if (kb < a.kblocks) mbits[kb * BM + r] = left < TK ? (w[i] | ~((1u << left) - 1u)) : w[i];
+      }
     }
     named_arrive(3, 128 + 512);
     h_epilogue(warp, 0);
@@ -383,22 +390,18 @@ __global__ void __launch_bounds__(THREADS, 1) rnvp_f16_step(const __grid_constan
       if (lane == 0) mbar_arrive(&aempty[buf]);
       const float* bs_s = colp + cb;
       const float* bt_s = colp + ncols + cb;
-      const float* is_s = colp + 2 * ncols + cb;
-      const float* it_s = colp + 3 * ncols + cb;
       float out[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const float s = fmaf(sv[e], is_s[e], bs_s[e]), t = fmaf(tv[e], it_s[e], bt_s[e]), zv = z16[e];
-        const float m = (mb >> e) & 1u ? 1.f : 0.f;
-        const float u = __expf(-fabsf(s));           // in (0, 1]
-        const float rcp = __fdividef(1.f, 1.f + u);
-        const float gate = s >= 0.f ? rcp : u * rcp;  // sigmoid(s)
-        const float lg = fminf(s, 0.f) - __logf(1.f + u);  // log(sigmoid(s))
-        out[e] = ((1.f - m) * zv * gate + (1.f - gate) * t) + m * zv;
-        if (row_ok && cb + e < D) {
-          ld += (1.f - m) * lg;
-          zm = fmaxf(zm, fabsf(out[e]));
-        }
+        const float s = fmaf(sv[e], c2s, bs_s[e]), t = fmaf(tv[e], c2t, bt_s[e]), zv = z16[e];
+        const bool keep = (mb >> e) & 1u;
+        const float u = ex2_fast(-1.4426950408889634f * fabsf(s));  // exp(-|s|) in (0, 1]
+        const float rcp = rcp_fast(1.f + u);                        // sigmoid(|s|) in [1/2, 1)
+        const float gate = s >= 0.f ? rcp : u * rcp;                // sigmoid(s)
+        const float lg = fmaf(lg2_fast(rcp), 0.6931471805599453f, fminf(s, 0.f));  // log(sigmoid(s))
+        out[e] = fmaf(1.f - gate, t, keep ? zv : zv * gate);        // (1 - m) z gate + (1 - gate) t + m z
+        ld += keep ? 0.f : lg;
+        zm = fmaxf(zm, fabsf(out[e]));
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
@@ -416,6 +419,7 @@ __global__ void __launch_bounds__(THREADS, 1) rnvp_f16_step(const __grid_constan
       }
     }
     ldp[(half + 2 * par) * BM + r] = ld;
+    if (!row_ok) zm = 0.f;  // rows beyond B hold zeros on input but not on output
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o));
@@ -438,37 +442,40 @@ __global__ void __launch_bounds__(THREADS, 1) rnvp_f16_step(const __grid_constan
   }
 }
 
-// ---- weights.  Column maxima -> exponents: esc[0:64) of W1's hidden columns, then [2][ncols] of Ws | Wt;
-// the inverse scales go where the step kernel reads them.
-__global__ void col_scales(int D, int H, int ncols, const float* __restrict__ w1, const float* __restrict__ ws,
-                           const float* __restrict__ wt, int64_t ld2, int* __restrict__ esc, float* __restrict__ s1inv,
-                           float* __restrict__ s2inv) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < HP) {
-    float m = 0.f;
-    if (i < H)
-      for (int k = 0; k < D; ++k) m = fmaxf(m, fabsf(w1[(int64_t)k * H + i]));
-    const int e = scale_exp(m);
-    esc[i] = e;
-    s1inv[i] = ldexpf(1.f, -e);
-  } else if (i < HP + 2 * ncols) {
-    const int j = i - HP, which = j / ncols, col = j - which * ncols;
-    float m = 0.f;
-    if (col < D) {
-      const float* w = which ? wt : ws;
-      for (int h = 0; h < H; ++h) m = fmaxf(m, fabsf(w[(int64_t)h * ld2 + col]));
+// ---- weights.  One power-of-two scale per matrix (max |W| * 2^e in [2^13, 2^14)): elements far below the
+// maximum lose relative precision in their lo plane (fp16 subnormals) but stay within 2^-38 of the maximum in
+// absolute terms.  Block 0: W1, block 1: Ws, block 2: Wt.
+__global__ void __launch_bounds__(1024) mat_scales(int D, int H, const float* __restrict__ w1, const float* __restrict__ ws,
+                                                   const float* __restrict__ wt, int64_t ld2, int* __restrict__ esc,
+                                                   float* __restrict__ sinv) {
+  __shared__ float red[32];
+  float m = 0.f;
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < D * H; i += 1024) m = fmaxf(m, fabsf(w1[i]));
+  } else {
+    const float* w = blockIdx.x == 1 ? ws : wt;
+    for (int i = threadIdx.x; i < D * H; i += 1024) {
+      const int h = i / D, c = i - h * D;
+      m = fmaxf(m, fabsf(w[(int64_t)h * ld2 + c]));
     }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 32; ++w) m = fmaxf(m, red[w]);
     const int e = scale_exp(m);
-    esc[i] = e;
-    s2inv[j] = ldexpf(1.f, -e);
+    esc[blockIdx.x] = e;
+    sinv[blockIdx.x] = ldexpf(1.f, -e);
   }
 }
 // one thread = one 16-byte chunk (8 consecutive k of one column), hi and lo
 __global__ void pack_weights(int D, int H, int kblocks, const float* __restrict__ w1, const float* __restrict__ ws,
                              const float* __restrict__ wt, int64_t ld2, const int* __restrict__ esc,
                              uint8_t* __restrict__ W1p, uint8_t* __restrict__ W2p) {
-  const int ncols = kblocks * TK;
   const int64_t n1 = (int64_t)kblocks * (TK / 8) * HP, n2 = (int64_t)kblocks * (HP / 8) * 64;
+  const int e1 = esc[0], es = esc[1], et = esc[2];
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n1 + n2; idx += (int64_t)gridDim.x * blockDim.x) {
     float w[8];
     uint8_t* dst;
@@ -477,7 +484,6 @@ __global__ void pack_weights(int D, int H, int kblocks, const float* __restrict_
       const int n = (int)(idx % HP);
       int64_t t = idx / HP;
       const int kc = (int)(t % (TK / 8)), kb = (int)(t / (TK / 8));
-      const int e1 = esc[n];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int k = kb * TK + kc * 8 + e;
@@ -492,7 +498,7 @@ __global__ void pack_weights(int D, int H, int kblocks, const float* __restrict_
       const int kc = (int)(t % (HP / 8)), c = (int)(t / (HP / 8));
       const int col = c * TK + (n & 31);
       const float* wsrc = n < 32 ? ws : wt;
-      const int e2 = esc[HP + (n < 32 ? 0 : ncols) + col];
+      const int e2 = n < 32 ? es : et;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int h = kc * 8 + e;
@@ -584,7 +590,7 @@ bool mnf_flow_f16_ok(const mnf_ctx* ctx, int64_t B, int64_t D, const mnf_flow_st
 }
 size_t mnf_flow_f16_pack_bytes(int D) {
   const size_t kb = (size_t)(D + f2::TK - 1) / f2::TK;
-  return kb * (f2::B1_STAGE + f2::B2_STAGE) + sizeof(float) * (f2::HP + 2 * kb * f2::TK) + sizeof(int) * (f2::HP + 2 * kb * f2::TK) + 256;
+  return kb * (f2::B1_STAGE + f2::B2_STAGE) + 256;
 }
 size_t mnf_flow_f16_tiles(int64_t B) { return (size_t)cdiv(B, f2::BM); }
 
@@ -638,7 +644,6 @@ int mnf_flow_f16_step(mnf_ctx* ctx, int64_t B, int D, const float* zin, float* z
   a.B = B; a.D = D; a.H = st.hidden; a.kblocks = (D + TK - 1) / TK;
   a.zin = zin; a.zout = zout; a.ld_in = ld_in; a.ld_out = ld_out; a.hid_save = hid_save;
   a.b1 = st.b1; a.bs = st.bs; a.bt = st.bt; a.bern = bern; a.tmax_in = tmax_in; a.tmax_out = tmax_out;
-  const int ncols = a.kblocks * TK;
   bool fresh = true;
   if (ctx->frozen) {
     pack_ws = (uint8_t*)mnf_packed(ctx, mnf_mix(0xF16F2ull, ((uint64_t)D << 32) | (uint32_t)st.hidden), (uint64_t)(uintptr_t)st.w1,
@@ -648,22 +653,21 @@ int mnf_flow_f16_step(mnf_ctx* ctx, int64_t B, int D, const float* zin, float* z
   }
   uint8_t* W1p = pack_ws;
   uint8_t* W2p = W1p + (size_t)a.kblocks * B1_STAGE;
-  float* s1inv = (float*)(W2p + (size_t)a.kblocks * B2_STAGE);
-  float* s2inv = s1inv + HP;
-  int* esc = (int*)(s2inv + 2 * ncols);
+  float* sinv = (float*)(W2p + (size_t)a.kblocks * B2_STAGE);
+  int* esc = (int*)(sinv + 4);
   if (fresh) {
-    col_scales<<<(unsigned)cdiv(HP + 2 * ncols, 128), 128, 0, ctx->stream>>>(D, st.hidden, ncols, st.w1, st.ws, st.wt, st.ld2, esc, s1inv, s2inv);
+    mat_scales<<<3, 1024, 0, ctx->stream>>>(D, st.hidden, st.w1, st.ws, st.wt, st.ld2, esc, sinv);
     MNF_LAUNCHED(ctx);
     const int64_t tot = (int64_t)a.kblocks * ((TK / 8) * HP + (HP / 8) * 64);
     pack_weights<<<(unsigned)cdiv(tot, 128), 128, 0, ctx->stream>>>(D, st.hidden, a.kblocks, st.w1, st.ws, st.wt, st.ld2, esc, W1p, W2p);
     MNF_LAUNCHED(ctx);
   }
-  a.W1p = W1p; a.W2p = W2p; a.s1inv = s1inv; a.s2inv = s2inv;
+  a.W1p = W1p; a.W2p = W2p; a.sinv = sinv;
   CUtensorMap tm_in, tm_out;
   if (int rc = make_tile_map(&tm_in, zin, B, D)) return rc;
   if (int rc = make_tile_map(&tm_out, zout, B, D)) return rc;
   const size_t smem = (size_t)REGION_X + NR * RAW_TILE + sizeof(uint32_t) * (size_t)a.kblocks * BM +
-                      sizeof(float) * (4 * (size_t)ncols + 2 * HP + 4 * BM + 32) + 8 * 32 + 16;
+                      sizeof(float) * (2 * (size_t)a.kblocks * TK + HP + 4 * BM + 32) + 8 * 32 + 16;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     MNF_CUDA(cudaFuncSetAttribute(rnvp_f16_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
