@@ -382,6 +382,25 @@ int mnf_conv2d_mc_maps(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, co
 int mnf_conv2d_mc_can_expand(mnf_ctx* ctx, int64_t Ho, int64_t Wo, int64_t F, int32_t fuse_relu_pool, int32_t* ok);
 int mnf_conv2d_mc_expand(mnf_ctx* ctx, int64_t B, int64_t n_rep, int64_t Ho, int64_t Wo, int64_t F, const float* mean,
                          const float* sd, const float* z, const mnf_noise* eps, int32_t fuse_relu_pool, float* y);
+
+/* The next MNFConv2D layer fed DIRECTLY from such a first layer (Monte-Carlo prediction, MNF-LeNet conv1 -> ReLU ->
+ * MaxPool2D -> conv2, mnf_lenet.py:23-26): its input x = MaxPool2x2(ReLU(mnf_conv2d_mc_expand(...))) is described by
+ * `src` instead of being materialised -- the tensor-core kernel's plane producers draw the first layer's noise
+ * themselves (same Philox counters), so the [B, Ho/2, Wo/2, F] activation is neither written nor read and the
+ * issue-bound noise generation runs beside the tensor-bound contraction on the same SMs.
+ * s: the shape of THIS layer's input (H = src->Ho / 2, W = src->Wo / 2, C = src->F), fuse_relu_pool as in
+ * mnf_conv2d_forward.  *used = 0: the shape / math mode is outside the fused kernel's domain (or src->eps is
+ * injected) and nothing was launched -- expand, then call mnf_conv2d_forward. */
+typedef struct {
+  int64_t n_rep, Ho, Wo, F;  /* the first layer's pre-pool output map and the number of samples per distinct row */
+  const float* mean;         /* [ceil(B / n_rep), Ho, Wo, F] from mnf_conv2d_mc_maps */
+  const float* sd;
+  const float* z;            /* [B, F] or NULL */
+  mnf_noise eps;             /* the first layer's output noise (not injected) */
+} mnf_mc_source;
+int mnf_conv2d_forward_mc(mnf_ctx* ctx, const mnf_conv_shape* s, const mnf_mc_source* src, const float* z, const float* mean_W,
+                          const float* log_std_W, const float* mean_b, const float* log_var_b, float max_std,
+                          const mnf_noise* eps, float* y, int32_t* used);
 /* ---- the data-parallel gradient all-reduce ---------------------------------------
  * The only collective of the design: where the reference applies its gradients
  * (notebooks/lenet_mnist.py:114-115, tape.gradient -> adam.apply_gradients), a data-parallel run sums

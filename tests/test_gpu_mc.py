@@ -104,3 +104,44 @@ def test_mc_predict_falls_back_when_unsupported():
     assert m1.mc_predict(x, 5).shape == (10, 6, 6, 6)
     m2 = MNFFeedForward(layer_sizes=(8, 4), flow_h_sizes=[8])
     assert m2.mc_predict(np.ones((3, 12), np.float32), 4).shape == (12, 4)
+
+
+def test_mc_predict_second_conv_generates_first_layer_rows():
+    """MNF-LeNet under mc_predict with enough rows for the CTA-pair conv kernel: the second MNFConv2D's plane
+    producers draw the first layer's noise themselves (mnf_conv2d_forward_mc, conv_raw_f16x2<gen>) instead of
+    reading the expanded, pooled activation.  Same Philox counters and the same arithmetic per element, so the
+    class probabilities equal those of the two-kernel path bit for bit; fresh noise on the second call."""
+    import tf_mnf_b200 as M
+    from tf_mnf_b200 import _lib as L
+    from tf_mnf_b200.models import MNFLeNet
+
+    ctx = M.default_context()
+    ctx.set_math("tf32x3")
+    x = np.random.RandomState(5).uniform(size=(4, 28, 28, 1)).astype(np.float32)
+    n = 301  # 1204 rows: 602 two-image tiles >= 2 per SM, ragged last pass
+    outs, paths = {}, {}
+    for fuse in (True, False):
+        M.set_seed(9)
+        model = MNFLeNet(flow_type="rnvp", flow_h_sizes=[50], std_init=10.0, max_std=1)
+        model.mc_fuse_second = fuse
+        model.presample_first = False
+        model.set_row_offset(77)
+        seen = []
+        conv2 = model.mnf_layers[1]
+        orig = conv2.call
+
+        def spy(*a, _o=orig, **k):
+            y = _o(*a, **k)
+            seen.append(L.last_path())
+            return y
+
+        conv2.call = spy
+        a = model.mc_predict(x, n).numpy()
+        b = model.mc_predict(x, n).numpy()
+        outs[fuse], paths[fuse] = (a, b), seen
+        assert not np.array_equal(a, b)
+    assert paths[True] == ["conv_raw_f16x2<gen>"] * 2, paths
+    assert paths[False] == ["conv_raw_f16x2"] * 2, paths
+    for k in (0, 1):
+        np.testing.assert_array_equal(outs[True][k], outs[False][k])
+        np.testing.assert_allclose(outs[True][k].sum(1), 1.0, rtol=1e-5)

@@ -31,6 +31,11 @@ class ConvShape(C.Structure):
                 ("same", C.c_int32), ("fuse_relu_pool", C.c_int32)]
 
 
+class McSource(C.Structure):
+    _fields_ = [("n_rep", C.c_int64), ("Ho", C.c_int64), ("Wo", C.c_int64), ("F", C.c_int64),
+                ("mean", vp), ("sd", vp), ("z", vp), ("eps", Noise)]
+
+
 class KlArgs(C.Structure):
     _fields_ = [("conv", C.c_int32), ("use_z", C.c_int32), ("r_all_states", C.c_int32), ("n_r_states", C.c_int32),
                 ("rows", C.c_int64), ("cols", C.c_int64),
@@ -129,6 +134,8 @@ SIGNATURES = {
     "mnf_conv2d_mc_maps": [vp, C.POINTER(ConvShape), vp, vp, vp, vp, vp, _f, vp, vp],
     "mnf_conv2d_mc_can_expand": [vp, _i64, _i64, _i64, _i32, C.POINTER(_i32)],
     "mnf_conv2d_mc_expand": [vp, _i64, _i64, _i64, _i64, _i64, vp, vp, vp, C.POINTER(Noise), _i32, vp],
+    "mnf_conv2d_forward_mc": [vp, C.POINTER(ConvShape), C.POINTER(McSource), vp, vp, vp, vp, vp, C.c_float, C.POINTER(Noise), vp,
+                              C.POINTER(_i32)],
     "mnf_u32_add": [vp, vp, C.c_uint32],
     "mnf_adam_step": [vp, _i64, vp, vp, vp, vp, _f, _f, _f, _f, _i32],
     "mnf_ctx_set_capturing": [vp, _i32],

@@ -83,7 +83,7 @@ int mnf_conv_raw_umma_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, co
 int mnf_conv_raw_f16_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, const float* x, const float* z,
                              const float* mean_W, const float* log_std_W, const float* mean_b,
                              const float* log_var_b, float max_std, const NoiseDev& eps, float* y, float* mean_out,
-                             float* sd_out, bool* used);
+                             float* sd_out, bool* used, const mnf_mc_source* gen = nullptr);
 // conv_win_umma.cu: single-channel stride-1 VALID convolutions (sliding-window planes)
 int mnf_conv_win_umma_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, const float* x, const float* z,
                               const float* mean_W, const float* log_std_W, const float* mean_b,

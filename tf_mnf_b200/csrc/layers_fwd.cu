@@ -900,4 +900,27 @@ int mnf_conv2d_forward(mnf_ctx* ctx, const mnf_conv_shape* s, const float* x, co
   return launch_paired<true>(ctx, a);
 }
 
+int mnf_conv2d_forward_mc(mnf_ctx* ctx, const mnf_conv_shape* s, const mnf_mc_source* src, const float* z, const float* mean_W,
+                          const float* log_std_W, const float* mean_b, const float* log_var_b, float max_std,
+                          const mnf_noise* eps, float* y, int32_t* used) {
+  MNF_CHECK_ARG(ctx && s && src && mean_W && log_std_W && mean_b && log_var_b && y && eps && used, "mnf_conv2d_forward_mc: NULL argument");
+  MNF_CHECK_ARG(src->mean && src->sd && src->n_rep >= 1 && src->Ho >= 2 && src->Wo >= 2 && src->F >= 1, "mnf_conv2d_forward_mc: bad source");
+  *used = 0;
+  int64_t Ho, Wo;
+  int rc = mnf_conv_out_hw(s, &Ho, &Wo);
+  if (rc) return rc;
+  if (s->B == 0 || ctx->math_mode == MNF_MATH_FP32 || s->same || !s->fuse_relu_pool || s->H * 2 != src->Ho || s->W * 2 != src->Wo ||
+      s->C != src->F || !mnf_tc_k_ok(ctx, s->kh * s->kw * s->C) || getenv("MNF_NO_F16") || getenv("MNF_NO_MC_FUSE"))
+    return MNF_OK;
+  int32_t ok = 0;
+  rc = mnf_conv2d_can_fuse_pool(ctx, s, &ok);
+  if (rc || !ok) return rc;
+  const int geo[11] = {(int)s->H, (int)s->W, (int)s->C, (int)s->kh, (int)s->kw, (int)Ho, (int)Wo, (int)s->stride, 0, 0, 1};
+  bool u = false;
+  rc = mnf_conv_raw_f16_forward(ctx, s->B, geo, (int)s->F, nullptr, z, mean_W, log_std_W, mean_b, log_var_b, max_std, make_noise(eps), y,
+                                nullptr, nullptr, &u, src);
+  *used = u ? 1 : 0;
+  return rc;
+}
+
 }  // extern "C"

@@ -314,8 +314,15 @@ int mnf_event_record(mnf_ctx* ctx, void* ev) {
 
 int mnf_event_elapsed_ms(void* start, void* stop, float* out) {
   MNF_CHECK_ARG(start && stop && out, "NULL argument");
-  MNF_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
-  MNF_CUDA(cudaEventElapsedTime(out, (cudaEvent_t)start, (cudaEvent_t)stop));
+  // a failure here (an event that was never recorded: a probe whose kernel family did not run) must not stay
+  // behind as the "last error" that the next launch check then reports as its own
+  cudaError_t e = cudaEventSynchronize((cudaEvent_t)stop);
+  if (e == cudaSuccess) e = cudaEventElapsedTime(out, (cudaEvent_t)start, (cudaEvent_t)stop);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    mnf_set_error("mnf_event_elapsed_ms: %s", cudaGetErrorString(e));
+    return MNF_ERR_CUDA;
+  }
   return MNF_OK;
 }
 

@@ -19,6 +19,32 @@ def conv_out_hw(H: int, W: int, kh: int, kw: int, stride: int, padding: str) -> 
     return (H - kh) // stride + 1, (W - kw) // stride + 1
 
 
+class McActivation:
+    """The output of a first MNFConv2D layer under Monte-Carlo prediction (call_mc(..., lazy=True)), NOT yet
+    expanded: per-image pre-noise maps + the per-row noise specification.  The next MNFConv2D consumes it
+    directly (mnf_conv2d_forward_mc: its tensor-core kernel generates the rows on the fly, so the [B, H, W, F]
+    activation never exists in memory); anything else calls materialize()."""
+
+    def __init__(self, ctx, B: int, n: int, Ho: int, Wo: int, F: int, mean, sd, z, eps, pooled: bool) -> None:
+        self.ctx, self.B, self.n, self.Ho, self.Wo, self.F = ctx, B, n, Ho, Wo, F
+        self.mean, self.sd, self.z, self.eps, self.pooled = mean, sd, z, eps, pooled
+        self.shape = (B, Ho // 2, Wo // 2, F) if pooled else (B, Ho, Wo, F)
+        self.ndim = 4
+
+    def source(self) -> L.McSource:
+        s = L.McSource()
+        s.n_rep, s.Ho, s.Wo, s.F = self.n, self.Ho, self.Wo, self.F
+        s.mean, s.sd, s.z, s.eps = self.mean.ptr, self.sd.ptr, (self.z.ptr if self.z is not None else None), self.eps
+        return s
+
+    def materialize(self) -> DeviceArray:
+        ctx = self.ctx
+        y = ctx.empty(self.shape)
+        L.check(ctx.lib.mnf_conv2d_mc_expand(ctx.handle, self.B, self.n, self.Ho, self.Wo, self.F, _p(self.mean), _p(self.sd),
+                                             _p(self.z), C.byref(self.eps), int(self.pooled), _p(y)))
+        return y
+
+
 class MNFConv2D(MNFLayerBase):
     """Bayesian conv2d layer, multiplicative noise on the OUTPUT filters (z scales conv+bias,
     mnf_conv.py:193).  `strides` / `padding` are the constructor arguments the reference's
@@ -68,7 +94,11 @@ class MNFConv2D(MNFLayerBase):
         layer in MNFLeNet (mnf_lenet.py:23-24); `self.last_fused` tells whether it did (it does
         not when training, or for shapes the fused epilogue does not cover)."""
         self.ctx = self.ctx or default_context()
-        x = as_device(x, self.ctx)
+        lazy = x if isinstance(x, McActivation) else None
+        if lazy is not None and (not lazy.pooled or self.training or noise or not fuse_relu_pool or lazy.ctx is not self.ctx):
+            x, lazy = lazy.materialize(), None
+        if lazy is None:
+            x = as_device(x, self.ctx)
         if x.ndim != 4:
             raise ValueError(f"MNFConv2D expects NHWC input, got shape {x.shape}")
         if not self.built:
@@ -79,6 +109,21 @@ class MNFConv2D(MNFLayerBase):
         Ho, Wo = conv_out_hw(x.shape[1], x.shape[2], *self.kernel_size, self.strides, self.padding)
         inj = noise or {}
         z, _, run = self._sample_z(B, nz.CALL_Z, nz.BERN_Q_CALL, inj, self.training, self.row_offset)
+        if lazy is not None:
+            # the first layer's rows are generated inside this layer's kernel (mnf_conv2d_forward_mc)
+            eps = nz.make(self.seed, self.call_index, self.uid, nz.CALL_OUT, self.row_offset, None)
+            s = self._shape(x)
+            s.fuse_relu_pool = 1
+            src, used = lazy.source(), C.c_int32(0)
+            y = ctx.empty((B, Ho // 2, Wo // 2, self.n_filters))
+            L.check(ctx.lib.mnf_conv2d_forward_mc(ctx.handle, C.byref(s), C.byref(src), _p(z), _p(self.mean_W), _p(self.log_std_W),
+                                                  _p(self.mean_b), _p(self.log_var_b), self.max_std, C.byref(eps), _p(y),
+                                                  C.byref(used)))
+            if used.value:
+                self.last_fused = True
+                self.call_index += 1
+                return y
+            x = lazy.materialize()  # outside the fused kernel's domain: expand, then the ordinary path
         oshape = (B, Ho, Wo, self.n_filters)
         eo = as_device(inj["eps_out"], ctx) if inj.get("eps_out") is not None else None
         if eo is not None and eo.shape != oshape:
@@ -115,12 +160,13 @@ class MNFConv2D(MNFLayerBase):
         L.check(ctx.lib.mnf_conv2d_mc_can_expand(ctx.handle, Ho, Wo, self.n_filters, int(fuse_relu_pool), C.byref(ok)))
         return bool(ok.value)
 
-    def call_mc(self, x: Any, n_samples: int, noise: dict | None = None, fuse_relu_pool: bool = False) -> DeviceArray:  # noqa: A002
+    def call_mc(self, x: Any, n_samples: int, noise: dict | None = None, fuse_relu_pool: bool = False,  # noqa: A002
+                lazy: bool = False) -> DeviceArray | McActivation:
         """call(np.repeat(x, n_samples, axis=0)) for a FIRST layer: z and eps enter
         after the contractions (mnf_conv.py:190-197), so the two convolutions are evaluated once per
         distinct input row and only the noise is drawn per (row, sample).  Same Philox counters as
         call() on the repeated batch; inference only.  noise: {eps_z [B,F], bern_q, eps_out [B,Ho,Wo,F]}
-        with B = len(x) * n_samples."""
+        with B = len(x) * n_samples.  lazy=True returns an McActivation (nothing expanded yet) for the next layer."""
         self.ctx = self.ctx or default_context()
         x = as_device(x, self.ctx)
         if x.ndim != 4:
@@ -147,11 +193,11 @@ class MNFConv2D(MNFLayerBase):
                                            _p(self.mean_b), _p(self.log_var_b), self.max_std, _p(mean), _p(sd)))
         eps = nz.make(self.seed, self.call_index, self.uid, nz.CALL_OUT, self.row_offset, eo)
         self.last_fused = bool(fuse_relu_pool)
-        y = ctx.empty((B, Ho // 2, Wo // 2, F) if fuse_relu_pool else (B, Ho, Wo, F))
-        L.check(ctx.lib.mnf_conv2d_mc_expand(ctx.handle, B, n, Ho, Wo, F, _p(mean), _p(sd), _p(z), C.byref(eps),
-                                             int(bool(fuse_relu_pool)), _p(y)))
         self.call_index += 1
-        return y
+        act = McActivation(ctx, B, n, Ho, Wo, F, mean, sd, z, eps, bool(fuse_relu_pool))
+        act._keep = eo
+        # lazy: leave the per-row expansion to the consumer (the next MNFConv2D's kernel draws this layer's noise)
+        return act if (lazy and eo is None) else act.materialize()
 
     def backward(self, dy: Any, need_dx: bool = True, fresh_grads: bool = False) -> DeviceArray | None:
         """Gradient of the most recent call() (made with `training=True`) given dL/dy:

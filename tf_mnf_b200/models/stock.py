@@ -165,6 +165,11 @@ class Sequential:
         self.presample_z = True   # draw the later layers' z on side streams beside the first layers
         self.presample_first = True  # ... and the first layer's z one call ahead (off inside captured graphs)
         self.mc_share_first = True   # mc_predict(): a first MNFConv2D convolves each distinct row once
+        # ... and a second MNFConv2D can generate the first one's rows inside its own kernel (mnf_conv2d_forward_mc).
+        # Off by default: bit-identical, but measured SLOWER on B200 (conv1 + conv2 470 us against 150 + 218 us) --
+        # the conv kernel's 10 producer warps per SM cannot hide the latency of the Philox chains and of the per-image
+        # map reads that 64 resident warps per SM hide in conv_mc_expand.
+        self.mc_fuse_second = False
         self._sides: list = []    # one forked context per later MNF layer: their flow chains
         #                           (80-CTA kernels at 10k rows) pack the SMs side by side
 
@@ -199,7 +204,13 @@ class Sequential:
                 nxt = self.layers[i + 1] if i + 1 < len(self.layers) else None
                 if n_mc and i == 0:
                     fuse = isinstance(nxt, ReLUMaxPool2D) and lyr.mc_supported(x.shape, True)
-                    x = lyr.call_mc(x, n_mc, noise=next(it, None), fuse_relu_pool=fuse)
+                    # conv -> ReLU/pool -> conv -> ReLU/pool (MNF-LeNet): the second conv's kernel generates the first
+                    # layer's rows itself (MNFConv2D.call on an McActivation)
+                    nn = self.layers[i + 2] if i + 2 < len(self.layers) else None
+                    nnn = self.layers[i + 3] if i + 3 < len(self.layers) else None
+                    lazy = (fuse and self.mc_fuse_second and not noise and hasattr(nn, "n_filters") and not nn.training
+                            and isinstance(nnn, ReLUMaxPool2D))
+                    x = lyr.call_mc(x, n_mc, noise=next(it, None), fuse_relu_pool=fuse, lazy=lazy)
                     skip = lyr.last_fused
                 elif isinstance(nxt, ReLUMaxPool2D) and hasattr(lyr, "n_filters") and not lyr.training:
                     x = lyr.call(x, noise=next(it, None), fuse_relu_pool=True)
@@ -214,7 +225,11 @@ class Sequential:
                     # for the NEXT call now, beside the rest of this call (same counters as in-line)
                     lyr.presample(self._first_rows, first[1])
             else:
+                if hasattr(x, "materialize"):
+                    x = x.materialize()
                 x = lyr(x)
+        if hasattr(x, "materialize"):
+            x = x.materialize()
         if first is not None:
             x.ctx.wait(first[1])  # a call is complete when its stream is: include the draw made for the next one
         return x
