@@ -50,7 +50,7 @@ STAGES = {
     "conv1+conv2 (conv_raw_f16x2<gen>: conv1's per-sample noise expansion inside conv2's CTA-pair tcgen05 kernel; 11520 + 3200 normals per row)":
         (20 * 4 + 4 * 4 * 50 * 4, 2 * 10 * 24 * 24 * 20 * 4 + CONV2_WEIGHT_BYTES, CONV2_FLOP_PER_ROW + 4 * 24 * 24 * 20),
     "d1 (row_pack + paired_f16x3, ReLU fused)": (2 * 800 * 4 + 500 * 4, 2 * 800 * 500 * 4, 2 * 2 * 800 * 500),
-    "d2 (dense_small, Softmax fused)": (2 * 500 * 4 + 10 * 4, 2 * 500 * 10 * 4, 2 * 2 * 500 * 10),
+    "d2 (dense_small_rows, Softmax fused)": (2 * 500 * 4 + 10 * 4, 2 * 500 * 10 * 4, 2 * 2 * 500 * 10),
 }
 LENET_BYTES_PER_ROW = 80776 + 5111520 / 10240   # SURVEY.md 8(d), layer-API boundary, B = 10240
 LENET_FLOP_PER_ROW = 9.994e6

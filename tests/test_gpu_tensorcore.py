@@ -27,7 +27,9 @@ def _f32(a):
 
 
 @pytest.mark.parametrize("K,N,B,use_z", [(800, 500, 300, True), (500, 10, 257, True), (136, 100, 64, True),
-                                         (25, 3, 1, True), (64, 64, 128, False), (130, 70, 129, True)])
+                                         (25, 3, 1, True), (64, 64, 128, False), (130, 70, 129, True),
+                                         (500, 10, 1029, True), (60, 3, 1100, False), (96, 14, 1024, True),
+                                         (1000, 10, 1040, True)])
 def test_dense_tensorcore(tc_ctx, K, N, B, use_z):
     rng = np.random.RandomState(K * 3 + N)
     P = O.make_layer_params(rng, (K, N), flow="iaf", std_init=10.0, dtype=np.float64)
@@ -40,7 +42,8 @@ def test_dense_tensorcore(tc_ctx, K, N, B, use_z):
     inj = dict(eps_out=_f32(eps))
     want_path = "paired_umma<128>" if N >= 256 else "paired_umma<64>"
     if N <= 16 and K % 4 == 0 and K * ((N + 3) // 4 * 4) <= 12288:
-        want_path = "dense_small"  # warp-per-row FFMA kernel of the classifier head
+        # FFMA kernels of the classifier head: warp per row; many rows: four rows per warp
+        want_path = "dense_small" if B < 1024 else "dense_small_rows"
     if use_z:
         inj["eps_z"] = _f32(eps_z)
     close(lyr(_f32(x), noise=inj).numpy(), ref, RTOL, "dense call (tf32x3)")

@@ -51,6 +51,10 @@ DENSE_CASES = [
     (130, 70, 1031, None, "paired_f16x3<128>"),      # ragged: K % 32, N % 4, M % 128 all non-zero
     (500, 10, 257, "softmax", "dense_small"),
     (500, 10, 33, None, "dense_small"),
+    (500, 10, 1301, "softmax", "dense_small_rows"),      # many rows: four rows per warp share the weight reads
+    (500, 10, 1027, None, "dense_small_rows"),
+    (100, 14, 1100, "relu", "dense_small_rows"),
+    (1000, 10, 1040, "softmax", "dense_small_rows"),
 ]
 
 

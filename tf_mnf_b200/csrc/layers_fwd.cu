@@ -602,6 +602,197 @@ __global__ void __launch_bounds__(256) dense_small_fwd(SmallDenseArgs a) {
   }
 }
 
+// The same layer for MANY rows (MNF-LeNet's 500 -> 10 head at 10240 rows).  The warp-per-row kernel above is bound
+// by its shared-memory WEIGHT reads: 2 NT float4 loads per k-quad and row, and a 128-bit warp-wide shared load
+// costs its four quarter-warp phases whether or not the lanes' addresses coincide (measured: sharing a load
+// between the lanes of different rows changed nothing, 41 us either way).  What helps is re-using a loaded weight
+// quad from REGISTERS: here a lane owns RPL rows (eight lanes split K per row group, four row groups per warp), so
+// every weight / variance float4 feeds RPL rows' FMAs; three shuffle steps finish the contraction and lane j < 4
+// of a group completes outputs 4j .. 4j+3 of its rows with one Philox call per row.
+// [2][NT][K + 4]: transposed mean weights, then clipped variances (zero rows for the padding outputs); packed once
+// per call -- or once per weight set when frozen -- so that a CTA's prologue is ONE bulk copy instead of ten
+// dependent rounds of scattered loads (which cost more than the contraction itself)
+__global__ void small_pack_weights(int K, int N, int NT, const float* __restrict__ Wm, const float* __restrict__ Ls, float max_std,
+                                   float* __restrict__ WV) {
+  const int Kp = K + 4, tot = NT * Kp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
+    const int n = i / Kp, k = i - n * Kp;
+    float w = 0.f, v = 0.f;
+    if (n < N && k < K) {
+      w = Wm[(int64_t)k * N + n];
+      const float sd = fminf(expf(Ls[(int64_t)k * N + n]), max_std);
+      v = sd * sd;
+    }
+    WV[i] = w;
+    WV[tot + i] = v;
+  }
+}
+template <int NT, int RPL>
+__global__ void __launch_bounds__(128) dense_small_rows_fwd(SmallDenseArgs a, const float* __restrict__ WV) {
+  extern __shared__ __align__(128) float sd_smem[];
+  const int K4 = a.K >> 2, Kp = a.K + 4;
+  float* Wt = sd_smem;
+  float* Vt = Wt + NT * Kp;
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(Vt + NT * Kp);
+  const uint32_t wbar_s = (uint32_t)__cvta_generic_to_shared(wbar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wbar_s));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = 2u * NT * Kp * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar_s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(Wt)),
+                 "l"(WV), "r"(bytes), "r"(wbar_s)
+                 : "memory");
+  }
+  __syncthreads();
+  {
+    uint32_t done = 0;
+    for (uint32_t polls = 0; !done; ++polls) {  // bounded: a copy that never lands ends as a launch failure
+      asm volatile(
+          "{\n\t.reg .pred P1;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, P1;\n\t}"
+          : "=r"(done)
+          : "r"(wbar_s)
+          : "memory");
+      if (!done && polls > (1u << 24)) __trap();
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int rg = lane >> 3, j8 = lane & 7, j = j8 & 3;  // (lanes 4-7 of a group end up with copies and do not store)
+  float bm4[4], vb4[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int n = 4 * j + e;
+    bm4[e] = n < a.N ? a.bm[n] : 0.f;
+    vb4[e] = n < a.N ? fminf(expf(a.lvb[n]), a.max_std * a.max_std) : 1.f;
+  }
+  constexpr int RW = 4 * RPL;  // rows per warp
+  const int64_t rstride = (int64_t)gridDim.x * wpb * RW;
+  for (int64_t rw0 = (blockIdx.x * (int64_t)wpb + warp) * RW; rw0 < a.B; rw0 += rstride) {
+    const int64_t row0 = rw0 + rg * RPL;  // this lane group's first row
+    float am[RPL][NT], av[RPL][NT];
+    const float4* xr[RPL];
+    const float4* zr[RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+#pragma unroll
+      for (int n = 0; n < NT; ++n) am[r][n] = av[r][n] = 0.f;
+      const int64_t rowc = row0 + r < a.B ? row0 + r : a.B - 1;
+      xr[r] = reinterpret_cast<const float4*>(a.x + rowc * a.K);
+      zr[r] = a.z ? reinterpret_cast<const float4*>(a.z + rowc * a.K) : nullptr;
+    }
+    constexpr int UI = 4;  // k-quads per lane whose loads are issued together
+    for (int kb = 0; kb < K4; kb += 8 * UI) {
+      float4 xv[UI][RPL], zv[UI][RPL];
+#pragma unroll
+      for (int u = 0; u < UI; ++u) {
+        const int k4 = kb + j8 + 8 * u;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+          xv[u][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          zv[u][r] = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (k4 < K4) {
+            xv[u][r] = __ldg(xr[r] + k4);
+            if (zr[r]) zv[u][r] = __ldg(zr[r] + k4);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UI; ++u) {
+        const int k4 = kb + j8 + 8 * u;
+        if (k4 < K4) {
+          float xz[RPL][4], x2[RPL][4];
+#pragma unroll
+          for (int r = 0; r < RPL; ++r) {
+            xz[r][0] = xv[u][r].x * zv[u][r].x; xz[r][1] = xv[u][r].y * zv[u][r].y;
+            xz[r][2] = xv[u][r].z * zv[u][r].z; xz[r][3] = xv[u][r].w * zv[u][r].w;
+            x2[r][0] = xv[u][r].x * xv[u][r].x; x2[r][1] = xv[u][r].y * xv[u][r].y;
+            x2[r][2] = xv[u][r].z * xv[u][r].z; x2[r][3] = xv[u][r].w * xv[u][r].w;
+          }
+          const float* wp = Wt + 4 * k4;
+          const float* vp = Vt + 4 * k4;
+#pragma unroll
+          for (int n = 0; n < NT; ++n) {
+            const float4 w = *reinterpret_cast<const float4*>(wp + n * Kp);
+            const float4 v = *reinterpret_cast<const float4*>(vp + n * Kp);
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+              am[r][n] = fmaf(xz[r][0], w.x, fmaf(xz[r][1], w.y, fmaf(xz[r][2], w.z, fmaf(xz[r][3], w.w, am[r][n]))));
+              av[r][n] = fmaf(x2[r][0], v.x, fmaf(x2[r][1], v.y, fmaf(x2[r][2], v.z, fmaf(x2[r][3], v.w, av[r][n]))));
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          am[r][n] += __shfl_xor_sync(0xffffffffu, am[r][n], o);
+          av[r][n] += __shfl_xor_sync(0xffffffffu, av[r][n], o);
+        }
+      }
+      const int64_t row = row0 + r;
+      const bool row_ok = row < a.B;
+      const int64_t rowc = row_ok ? row : a.B - 1;
+      // lane j of the group: outputs 4j .. 4j+3 of this row
+      float m4[4], v4[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        m4[e] = am[r][e]; v4[e] = av[r][e];
+        if (NT > 4 && j == 1) { m4[e] = am[r][(4 + e) % NT]; v4[e] = av[r][(4 + e) % NT]; }
+        if (NT > 8 && j == 2) { m4[e] = am[r][(8 + e) % NT]; v4[e] = av[r][(8 + e) % NT]; }
+        if (NT > 12 && j == 3) { m4[e] = am[r][(12 + e) % NT]; v4[e] = av[r][(12 + e) % NT]; }
+      }
+      float e4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (4 * j < a.N) {
+        if (a.eps.injected) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) e4[e] = 4 * j + e < a.N ? a.eps.injected[rowc * a.N + 4 * j + e] : 0.f;
+        } else {
+          philox_normal4(a.eps, a.eps.row_offset + (uint64_t)rowc, 0u, (uint32_t)j, e4);
+        }
+      }
+      float out[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = 4 * j + e;
+        const float sd = sqrtf(v4[e] + vb4[e]);
+        if (a.sd_out && row_ok && j8 < 4 && n < a.N) a.sd_out[row * a.N + n] = sd;
+        out[e] = fmaf(sd, e4[e], m4[e] + bm4[e]);
+        if (a.act == 1) out[e] = fmaxf(out[e], 0.f);
+      }
+      if (a.act == 2) {  // softmax over the row's N outputs (lanes 0-3 of the group; stock.cu:softmax_kernel arithmetic)
+        float mx = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (4 * j + e < a.N) mx = fmaxf(mx, out[e]);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float ssum = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          out[e] = 4 * j + e < a.N ? expf(out[e] - mx) : 0.f;
+          ssum += out[e];
+        }
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) out[e] = out[e] / ssum;
+      }
+      if (row_ok && j8 < 4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (4 * j + e < a.N) a.y[row * a.N + 4 * j + e] = out[e];
+      }
+    }
+  }
+}
+
 static bool small_dense_ok(int64_t K, int64_t N, const float* x, const float* z) {
   return N <= SD_NMAX && (K & 3) == 0 && K * ((N + 3) & ~3) <= 12288 && (((uintptr_t)x | (uintptr_t)z) & 15) == 0;
 }
@@ -770,6 +961,35 @@ int mnf_dense_forward_act(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const f
     if (smem > attr_smem[NT / 4 - 1]) {
       MNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_smem[NT / 4 - 1] = smem;
+    }
+    if (B >= 1024) {  // many rows: every weight quad read from shared memory feeds RPL rows
+      constexpr int RPL = 2;
+      auto k8 = NT == 4 ? dense_small_rows_fwd<4, RPL> : NT == 8 ? dense_small_rows_fwd<8, RPL> : NT == 12 ? dense_small_rows_fwd<12, RPL>
+                                                                                                  : dense_small_rows_fwd<16, RPL>;
+      static size_t attr8[4] = {0, 0, 0, 0};
+      if (smem > attr8[NT / 4 - 1]) {
+        MNF_CUDA(cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 16));
+        attr8[NT / 4 - 1] = smem;
+      }
+      int per_sm8 = 1;
+      MNF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm8, k8, 128, smem + 16));
+      per_sm8 = per_sm8 < 1 ? 1 : per_sm8;
+      const int64_t blocks8 = cdiv(B, 16 * RPL), cap8 = (int64_t)ctx->sm_count * per_sm8;
+      bool fresh = true;
+      float* WV = (float*)mnf_packed(ctx, mnf_mix(0x5DA11ull, ((uint64_t)K << 32) | (uint32_t)N), (uint64_t)(uintptr_t)mean_W,
+                                     (uint64_t)(uintptr_t)log_std_W, (uint64_t)__float_as_uint_host(max_std),
+                                     sizeof(float) * 2 * (size_t)NT * (K + 4), &fresh);
+      if (!WV) return MNF_ERR_CUDA;
+      if (fresh) {
+        small_pack_weights<<<(unsigned)cdiv((int64_t)NT * (K + 4), 256), 256, 0, ctx->stream>>>((int)K, (int)N, NT, mean_W, log_std_W, max_std, WV);
+        MNF_LAUNCHED(ctx);
+      }
+      mnf_note_path("dense_small_rows");
+      const bool probed8 = mnf_probe_begin(ctx, MNF_PROBE_DENSE_GEMM);
+      k8<<<(int)(blocks8 < cap8 ? blocks8 : cap8), 128, smem + 16, ctx->stream>>>(a, WV);
+      mnf_probe_end(ctx, probed8);
+      MNF_LAUNCHED(ctx);
+      return MNF_OK;
     }
     // latency-bound per warp (load -> FMAs -> shuffles -> Philox): fill the SMs with warps, as many
     // CTAs per SM as the transposed weights in shared memory allow
