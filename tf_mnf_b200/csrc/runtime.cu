@@ -107,6 +107,8 @@ int mnf_device_count(int* out) {
   return MNF_OK;
 }
 
+static bool g_fork_next = false;  // (contexts are created from one thread per process)
+
 int mnf_ctx_create(int device, void* stream, mnf_ctx** out) {
   MNF_CHECK_ARG(out, "mnf_ctx_create: out is NULL");
   int n = 0;
@@ -135,7 +137,12 @@ int mnf_ctx_create(int device, void* stream, mnf_ctx** out) {
     c->stream = (cudaStream_t)stream;
     c->owns_stream = false;
   } else {
-    MNF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // An owned stream of mnf_ctx_create runs at the device's greatest priority, a fork's (mnf_ctx_fork) at the
+    // least: the block scheduler then hands free SMs to the x-dependent main stream first and the side work
+    // (z chains, KL terms) fills in behind it -- the main stream's kernels run at their isolated durations.
+    int least = 0, greatest = 0;
+    MNF_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    MNF_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, g_fork_next ? least : greatest));
     c->owns_stream = true;
   }
   MNF_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -146,6 +153,16 @@ int mnf_ctx_create(int device, void* stream, mnf_ctx** out) {
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   *out = c;
+  return MNF_OK;
+}
+
+int mnf_ctx_fork(mnf_ctx* parent, mnf_ctx** out) {
+  MNF_CHECK_ARG(parent && out, "mnf_ctx_fork: NULL argument");
+  g_fork_next = true;
+  const int rc = mnf_ctx_create(parent->device, nullptr, out);
+  g_fork_next = false;
+  if (rc) return rc;
+  (*out)->math_mode = parent->math_mode;
   return MNF_OK;
 }
 

@@ -25,10 +25,13 @@ _ITEMSIZE = {k: np.dtype(v).itemsize for k, v in _DT.items()}
 class Context:
     """One (device, stream, workspace).  Not thread-safe: use one context per thread."""
 
-    def __init__(self, device: int = 0, stream: int | None = None) -> None:
+    def __init__(self, device: int = 0, stream: int | None = None, _fork_of: "Context | None" = None) -> None:
         self.lib = L.load()
         h = C.c_void_p()
-        L.check(self.lib.mnf_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        if _fork_of is not None:  # a low-priority sibling (mnf_ctx_fork)
+            L.check(self.lib.mnf_ctx_fork(_fork_of.handle, C.byref(h)))
+        else:
+            L.check(self.lib.mnf_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
         self.handle = h
         self.device = device
         self.math = "tf32x3"  # the library's default (mnf_b200.h): tcgen05 with hi/lo operand splitting
@@ -87,7 +90,7 @@ class Context:
     def fork(self) -> "Context":
         """A sibling context on the same device with its own stream and workspace (e.g. to run
         kl_div(), which does not depend on x, concurrently with a forward pass)."""
-        c = Context(self.device)
+        c = Context(self.device, _fork_of=self)
         if getattr(self, "math", None):
             c.set_math(self.math)
         if getattr(self, "frozen", False):
