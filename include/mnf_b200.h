@@ -428,6 +428,11 @@ int mnf_allreduce_grads(mnf_comm* comm, mnf_ctx* ctx, float* grads, int64_t n);
 /* Adam update on a flat parameter buffer (lenet_mnist.py:47,115). */
 int mnf_adam_step(mnf_ctx* ctx, int64_t n, float* param, const float* grad, float* m, float* v,
                   float lr, float beta1, float beta2, float eps, int32_t step);
+/* The same update with the step count kept on the device: d_state = {int32 step, float lr_t} (zero-initialised by
+ * the caller); every call increments step and derives the bias-corrected rate from it, so a training step
+ * captured into a CUDA graph (Trainer.capture) replays with the right rate. */
+int mnf_adam_step_dev(mnf_ctx* ctx, int64_t n, float* param, const float* grad, float* m, float* v, float lr, float beta1,
+                      float beta2, float eps, int32_t* d_state);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

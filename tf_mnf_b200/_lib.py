@@ -139,6 +139,7 @@ SIGNATURES = {
                               C.POINTER(_i32)],
     "mnf_u32_add": [vp, vp, C.c_uint32],
     "mnf_adam_step": [vp, _i64, vp, vp, vp, vp, _f, _f, _f, _f, _i32],
+    "mnf_adam_step_dev": [vp, _i64, vp, vp, vp, vp, _f, _f, _f, _f, vp],
     "mnf_ctx_set_capturing": [vp, _i32],
     "mnf_comm_nccl_version": [C.POINTER(C.c_int)],
     "mnf_comm_unique_id": [vp],

@@ -26,6 +26,10 @@ struct mnf_ctx {
   bool frozen;
   struct mnf_packed_entry* packed;
   int packed_n, packed_cap;
+  // geometry tables (mnf_geom_table): step offsets / k maps that depend on a layer's SHAPE only; uploaded once
+  // per context and kept whether or not the weights are frozen, so a captured training step holds no H2D copy
+  struct mnf_packed_entry* geom;
+  int geom_n, geom_cap;
 };
 struct mnf_packed_entry {
   uint64_t key[4];
@@ -113,6 +117,8 @@ void mnf_note_path(const char* name);              // which kernel family served
 // Where a call's packed weights go.  Not frozen: the transient workspace, *fresh = true (pack every
 // call).  Frozen: a persistent block per key; *fresh tells whether it still has to be filled.
 void* mnf_packed(mnf_ctx* ctx, uint64_t k0, uint64_t k1, uint64_t k2, uint64_t k3, size_t bytes, bool* fresh);
+// device copy of n host ints, cached by (key, a checksum of the data, n); nullptr on failure (error set)
+int* mnf_geom_table(mnf_ctx* ctx, uint64_t key, const int* h_data, size_t n);
 static inline uint32_t __float_as_uint_host(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);

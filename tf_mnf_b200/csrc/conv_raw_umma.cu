@@ -416,10 +416,9 @@ int mnf_conv_raw_umma_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, co
   if (!ws) return MNF_ERR_CUDA;
   float* Bp = (float*)ws;
   float* vb = Bp + bp_floats;
-  int* d_tab = (int*)(vb + ((N + 63) & ~63));
-  int* d_kmap = d_tab + ((tab.size() + 63) & ~(size_t)63);
-  MNF_CUDA(cudaMemcpyAsync(d_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, ctx->stream));
-  MNF_CUDA(cudaMemcpyAsync(d_kmap, kmap.data(), sizeof(int) * kmap.size(), cudaMemcpyHostToDevice, ctx->stream));
+  int* d_tab = mnf_geom_table(ctx, 0xC0A32A, tab.data(), tab.size());  // shape-only tables: uploaded once per context
+  int* d_kmap = mnf_geom_table(ctx, 0xC0A32B, kmap.data(), kmap.size());
+  if (!d_tab || !d_kmap) return MNF_ERR_CUDA;
   const int64_t tot = (int64_t)2 * a.steps * 2 * BN;
   int grid = (int)(cdiv(tot, 256) < ctx->sm_count * 4 ? cdiv(tot, 256) : ctx->sm_count * 4);
   pack_raw_weights<<<grid, 256, 0, ctx->stream>>>(N, a.steps, d_kmap, mean_W, log_std_W, max_std, Bp, log_var_b, vb);

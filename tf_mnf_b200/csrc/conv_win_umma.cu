@@ -407,11 +407,10 @@ int mnf_conv_win_umma_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, co
   if (!ws) return MNF_ERR_CUDA;
   float* Bp = (float*)ws;
   float* vb = Bp + bp_floats;
-  int* d_tab = (int*)(vb + ((N + 63) & ~63));
-  int* d_kmap = d_tab + ((tab.size() + 63) & ~(size_t)63);
+  int* d_tab = mnf_geom_table(ctx, 0xC017A, tab.data(), tab.size());  // shape-only tables: uploaded once per context
+  int* d_kmap = mnf_geom_table(ctx, 0xC017B, kmap.data(), kmap.size());
+  if (!d_tab || !d_kmap) return MNF_ERR_CUDA;
   if (fresh) {
-    MNF_CUDA(cudaMemcpyAsync(d_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, ctx->stream));
-    MNF_CUDA(cudaMemcpyAsync(d_kmap, kmap.data(), sizeof(int) * kmap.size(), cudaMemcpyHostToDevice, ctx->stream));
     const int tot = 2 * a.steps * 2 * BN * 4;
     pack_win_weights<<<cdiv(tot, 256), 256, 0, ctx->stream>>>(N, a.steps, d_kmap, mean_W, log_std_W, max_std, Bp, log_var_b, vb);
     MNF_LAUNCHED(ctx);

@@ -81,6 +81,41 @@ void* mnf_packed(mnf_ctx* ctx, uint64_t k0, uint64_t k1, uint64_t k2, uint64_t k
   return d;
 }
 
+int* mnf_geom_table(mnf_ctx* ctx, uint64_t key, const int* h_data, size_t n) {
+  uint64_t sum = 0xCBF29CE484222325ull;  // FNV-1a over the table: two shapes never share an entry by accident
+  for (size_t i = 0; i < n; ++i) sum = (sum ^ (uint32_t)h_data[i]) * 0x100000001B3ull;
+  for (int i = 0; i < ctx->geom_n; ++i) {
+    mnf_packed_entry& e = ctx->geom[i];
+    if (e.key[0] == key && e.key[1] == sum && e.bytes == n * sizeof(int)) return (int*)e.ptr;
+  }
+  if (ctx->capturing) {
+    mnf_set_error("geometry-table cache miss during CUDA-graph capture; run one eager step first");
+    return nullptr;
+  }
+  if (ctx->geom_n == ctx->geom_cap) {
+    const int cap = ctx->geom_cap ? ctx->geom_cap * 2 : 16;
+    mnf_packed_entry* p = (mnf_packed_entry*)realloc(ctx->geom, sizeof(mnf_packed_entry) * cap);
+    if (!p) {
+      mnf_set_error("geometry-table cache: out of host memory");
+      return nullptr;
+    }
+    ctx->geom = p;
+    ctx->geom_cap = cap;
+  }
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, n * sizeof(int) + 16);
+  if (e == cudaSuccess) e = cudaMemcpy(d, h_data, n * sizeof(int), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    mnf_set_error("geometry-table upload (%zu ints) failed: %s", n, cudaGetErrorString(e));
+    return nullptr;
+  }
+  mnf_packed_entry& ne = ctx->geom[ctx->geom_n++];
+  ne.key[0] = key; ne.key[1] = sum; ne.key[2] = ne.key[3] = 0;
+  ne.ptr = d;
+  ne.bytes = n * sizeof(int);
+  return (int*)d;
+}
+
 static void mnf_packed_clear(mnf_ctx* ctx) {
   if (ctx->packed_n) cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < ctx->packed_n; ++i) cudaFree(ctx->packed[i].ptr);
@@ -172,6 +207,8 @@ int mnf_ctx_destroy(mnf_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   mnf_packed_clear(ctx);
   free(ctx->packed);
+  for (int i = 0; i < ctx->geom_n; ++i) cudaFree(ctx->geom[i].ptr);
+  free(ctx->geom);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   free(ctx);

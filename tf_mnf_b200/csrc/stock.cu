@@ -143,6 +143,25 @@ __global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __res
 }
 
 
+// Adam with the step count on the DEVICE (a captured training step replays with a fresh bias correction):
+// state = {int32 step, float lr_t}; adam_dev_prepare bumps the step and derives lr_t as mnf_adam_step does.
+__global__ void adam_dev_prepare(int32_t* state, float lr, float b1, float b2) {
+  const int t = ++state[0];
+  reinterpret_cast<float*>(state)[1] = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+}
+__global__ void adam_dev_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, const int32_t* __restrict__ state, float b1, float b2, float eps) {
+  const float lr_t = reinterpret_cast<const float*>(state)[1];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
 // ---- tf.keras.layers.BatchNormalization over the last axis of [B, N] (mnf_feed_forward.py:20; Keras
 // defaults momentum 0.99, epsilon 1e-3).  Block = 32 columns x 8 row groups: lanes walk columns
 // (coalesced), row groups stride the batch; reductions over the batch through shared memory,
@@ -387,6 +406,17 @@ int mnf_adam_step(mnf_ctx* ctx, int64_t n, float* param, const float* grad, floa
   // Keras/TF Adam: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t); update = lr_t * m / (sqrt(v) + eps)
   double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step));
   adam_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(n, param, grad, m, v, (float)lr_t, beta1, beta2, eps);
+  MNF_LAUNCHED(ctx);
+  return MNF_OK;
+}
+
+int mnf_adam_step_dev(mnf_ctx* ctx, int64_t n, float* param, const float* grad, float* m, float* v, float lr, float beta1,
+                      float beta2, float eps, int32_t* d_state) {
+  MNF_CHECK_ARG(ctx && d_state && (n == 0 || (param && grad && m && v)) && n >= 0, "mnf_adam_step_dev: bad argument");
+  adam_dev_prepare<<<1, 1, 0, ctx->stream>>>(d_state, lr, beta1, beta2);
+  MNF_LAUNCHED(ctx);
+  if (n == 0) return MNF_OK;
+  adam_dev_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(n, param, grad, m, v, d_state, beta1, beta2, eps);
   MNF_LAUNCHED(ctx);
   return MNF_OK;
 }

@@ -37,6 +37,7 @@ class Trainer:
         self._z_sides: list = []  # one forked context per MNF layer: the z chains of a step run side by side
         self.flat_gk: DeviceArray | None = None
         self.kl_grads: list[dict] = []
+        self._dev_state: DeviceArray | None = None  # {int32 step, float lr_t} once a step has been captured
 
     def _forward_layers(self):
         layers = list(self.model.layers)
@@ -162,8 +163,12 @@ class Trainer:
     def apply(self) -> None:
         ctx = default_context()
         self.t += 1
-        L.check(ctx.lib.mnf_adam_step(ctx.handle, self.flat_p.size, _p(self.flat_p), _p(self.flat_g), _p(self.flat_m),
-                                      _p(self.flat_v), self.lr, self.beta1, self.beta2, self.eps, self.t))
+        if self._dev_state is not None:  # inside / after Trainer.capture: the step count lives on the device
+            L.check(ctx.lib.mnf_adam_step_dev(ctx.handle, self.flat_p.size, _p(self.flat_p), _p(self.flat_g), _p(self.flat_m),
+                                              _p(self.flat_v), self.lr, self.beta1, self.beta2, self.eps, _p(self._dev_state)))
+        else:
+            L.check(ctx.lib.mnf_adam_step(ctx.handle, self.flat_p.size, _p(self.flat_p), _p(self.flat_g), _p(self.flat_m),
+                                          _p(self.flat_v), self.lr, self.beta1, self.beta2, self.eps, self.t))
         bump_param_version()  # a z drawn ahead of the next call is stale now
 
     def step(self, x: Any, target: Any):
@@ -171,3 +176,84 @@ class Trainer:
         self.allreduce()
         self.apply()
         return loss, kl
+
+    def capture(self, x: Any, target: Any) -> "CapturedTrainStep":
+        """The whole step -- forward, loss, backward, the KL branch on its forked stream, Adam -- captured ONCE
+        into a CUDA graph (single process; the data-parallel all-reduce stays eager).  A LeNet step is ~170
+        small launches whose HOST enqueue (ctypes) costs more than the GPU work; a replay is one launch.
+        Noise stays fresh (device-side replay counter added to every Philox call index, graph.py), Adam's
+        bias correction follows a device-side step count (mnf_adam_step_dev), and unfrozen weights are
+        re-packed by kernels inside the graph (shape-only tables are uploaded once per context).  The warm-up
+        passes the capture needs run on a snapshot: parameters, moments, step and noise counters are restored,
+        so `cap.step(x, y)` k times equals `trainer.step(x, y)` k times."""
+        if self.world > 1:
+            raise NotImplementedError("Trainer.capture: single-process steps (the NCCL all-reduce is enqueued eagerly)")
+        return CapturedTrainStep(self, x, target)
+
+
+class CapturedTrainStep:
+    def __init__(self, tr: Trainer, x: Any, target: Any) -> None:
+        from .graph import CapturedStep
+
+        ctx = default_context()
+        self.tr = tr
+        self.x = ctx.to_device(np.asarray(x.numpy() if hasattr(x, "numpy") else x, np.float32))
+        self.y = ctx.to_device(np.asarray(target.numpy() if hasattr(target, "numpy") else target, np.float32))
+        tr._ensure_flat(self.x)
+        model = tr.model
+        # snapshot of everything the warm-up steps change
+        ctx.sync()
+        snap = [ctx.empty(b.shape) for b in (tr.flat_p, tr.flat_m, tr.flat_v)]
+        for dst, src in zip(snap, (tr.flat_p, tr.flat_m, tr.flat_v)):
+            L.check(ctx.lib.mnf_memcpy_d2d(ctx.handle, _p(dst), _p(src), src.nbytes))
+        idx = [(l.call_index, l.kl_index) for l in model.mnf_layers]
+        t0 = tr.t
+        state = np.zeros(2, np.uint32)
+        state[0] = t0
+        tr._dev_state = ctx.to_device(state, "u4")
+        ctx.sync()
+
+        def fn():
+            loss, kl = tr.loss_and_grads(self.x, self.y)
+            tr.apply()
+            return loss, kl
+
+        def restore():
+            for dst, src in zip((tr.flat_p, tr.flat_m, tr.flat_v), snap):
+                L.check(ctx.lib.mnf_memcpy_d2d(ctx.handle, _p(dst), _p(src), src.nbytes))
+            tr._dev_state.assign(state)
+            tr.t = t0
+            ctx.sync()
+
+        fn()  # the side contexts (z chains of wide layers) are created by the first step
+        ctx.sync()
+        forks = [c for c in [tr.kl_ctx, *tr._z_sides] if c is not None]
+        # CapturedStep runs fn eagerly three times (warm-up + stocking passes) and once under capture (nothing
+        # executes then); its launch() advances the layers' counters by one call / one kl_div per replay
+        self.cap = CapturedStep(ctx, fn, forks=forks, layers=model.mnf_layers, calls_per_step=1, kl_per_step=1)
+        ctx.sync()
+        restore()
+        # replay 0 must draw with the call indices of the step that was snapshotted: the device-side replay counter
+        # is added to the indices the CAPTURE pass used, so rewind the Python counters to those of the capture pass
+        # minus the three eager passes, and offset the counter accordingly
+        self._idx_capture = [(l.call_index - 1, l.kl_index - 1) for l in model.mnf_layers]  # indices baked into the graph
+        back = self._idx_capture[0][0] - idx[0][0] if idx else 0   # eager passes that ran before the capture
+        off = np.array([(0x100000000 - back) & 0xFFFFFFFF], np.uint32)  # counter = -back (mod 2^32): index + counter = snapshot index
+        self.cap.counter.assign(off)
+        for l, (ci, ki) in zip(model.mnf_layers, idx):
+            l.call_index, l.kl_index = ci, ki
+        self.cap.replays = 1  # launch() then advances the Python-side counters on every replay, the first included
+        ctx.sync()
+
+    def step(self, x: Any = None, target: Any = None):
+        """Copy the batch into the graph's input buffers (skipped for None) and replay the step; returns the
+        (re-used) loss and KL device arrays."""
+        ctx = default_context()
+        if x is not None:
+            self.x.assign(x)
+        if target is not None:
+            self.y.assign(target)
+        out = self.cap.launch()
+        self.tr.t += 1
+        bump_param_version()
+        return out

@@ -101,11 +101,22 @@ def train_config(args) -> None:
     for _ in range(max(args.warmup, 3)):
         tr.step(xd, yd)
     barrier()
+    cap = None
+    if args.graph and world == 1:
+        # the whole step replayed as ONE CUDA graph (Trainer.capture): a LeNet / MLP step is ~170 small launches and
+        # the host's enqueue through ctypes costs more than the GPU work
+        cap = tr.capture(xd, yd)
+        step = lambda: cap.step()
+    else:
+        step = lambda: tr.step(xd, yd)
+    for _ in range(3):
+        step()
+    barrier()
     def all_launches():  # the main context, the KL branch's forked context and the model's side contexts
         return ctx.launches + (tr.kl_ctx.launches if tr.kl_ctx else 0) + sum(c.launches for c in getattr(model, "_sides", []))
 
     n0 = all_launches()
-    tr.step(xd, yd)
+    tr.step(xd, yd)   # (eager: counts the kernels of one step; a replay launches the same ones)
     per_step = all_launches() - n0
     barrier()
     import time
@@ -113,7 +124,7 @@ def train_config(args) -> None:
     t0 = time.perf_counter()
     for i in range(args.steps):
         L.check(lib.mnf_event_record(ctx.handle, starts[i]))
-        tr.step(xd, yd)
+        step()
         L.check(lib.mnf_event_record(ctx.handle, stops[i]))
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
@@ -146,6 +157,7 @@ def train_config(args) -> None:
             "device_ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "global_batch": GB, "math": ctx.math, "n_params": int(n_params),
                        "allreduce_bytes": int(n_params) * 4 if world > 1 else 0,
+                       "launch": "one CUDA-graph replay per step (Trainer.capture)" if cap else "eager enqueue",
                        "timing": "wall clock barrier to barrier, max over ranks (steps contain host syncs)"},
             "gpu_launches": per_step * args.steps}))
     if dist is not None:
@@ -160,6 +172,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="c1: skip the CPU (NumPy restatement) train-step baseline")
+    ap.add_argument("--graph", action="store_true", help="c1 / c2 / c5 on one GPU: replay the train step as one CUDA graph")
     ap.add_argument("--rows", type=int, default=8192)
     ap.add_argument("--width", type=int, default=4096)
     args = ap.parse_args()
