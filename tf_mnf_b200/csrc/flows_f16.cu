@@ -524,12 +524,25 @@ __global__ void __launch_bounds__(256) sample_z0_tmax(int64_t B, int D, const fl
                                                       const float* __restrict__ q0_log_var, NoiseDev eps,
                                                       float* __restrict__ zout, float* __restrict__ tmax) {
   __shared__ float red[8];
+  extern __shared__ __align__(16) float zsm[];  // [2][D4 * 4]: q0_mean | exp(q0_log_var / 2), once per CTA (not per element)
   const int D4 = (D + 3) >> 2;
+  float* mean_s = zsm;
+  float* sd_s = zsm + 4 * D4;
+  for (int d = threadIdx.x; d < 4 * D4; d += 256) {
+    mean_s[d] = d < D ? __ldg(q0_mean + d) : 0.f;
+    sd_s[d] = d < D ? expf(0.5f * __ldg(q0_log_var + d)) : 0.f;
+  }
+  __syncthreads();
   const int64_t r0 = (int64_t)blockIdx.x * ZR;
+  const PhiloxKeys K = philox_keys(eps);
   float m = 0.f;
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(zout) & 15) == 0);
-  for (int i = threadIdx.x; i < ZR * D4; i += 256) {
-    const int rr = i / D4, g4 = i - rr * D4, d0 = g4 * 4;
+  // (row, quad) of this thread's items, advanced incrementally (no division per item)
+  const int step_r = 256 / D4, step_g = 256 - step_r * D4;
+  int rr = (int)threadIdx.x / D4, g4 = (int)threadIdx.x - rr * D4;
+  for (; rr < ZR; rr += step_r, g4 += step_g) {
+    if (g4 >= D4) { g4 -= D4; ++rr; if (rr >= ZR) break; }
+    const int d0 = g4 * 4;
     const int64_t r = r0 + rr;
     if (r >= B) break;
     float nrm[4];
@@ -537,15 +550,11 @@ __global__ void __launch_bounds__(256) sample_z0_tmax(int64_t B, int D, const fl
 #pragma unroll
       for (int e = 0; e < 4; ++e) nrm[e] = d0 + e < D ? eps.injected[r * D + d0 + e] : 0.f;
     } else {
-      philox_normal4(eps, eps.row_offset + (uint64_t)r, 0u, (uint32_t)g4, nrm);
+      philox_normal4_keys(eps, K, eps.row_offset + (uint64_t)r, 0u, (uint32_t)g4, nrm);
     }
-    float v[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int d = d0 + e;
-      v[e] = d < D ? fmaf(expf(0.5f * __ldg(q0_log_var + d)), nrm[e], __ldg(q0_mean + d)) : 0.f;
-      m = fmaxf(m, fabsf(v[e]));
-    }
+    const float4 mu = *reinterpret_cast<const float4*>(mean_s + d0), sd = *reinterpret_cast<const float4*>(sd_s + d0);
+    const float v[4] = {fmaf(sd.x, nrm[0], mu.x), fmaf(sd.y, nrm[1], mu.y), fmaf(sd.z, nrm[2], mu.z), fmaf(sd.w, nrm[3], mu.w)};
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));  // (padding elements are 0)
     if (vec) *reinterpret_cast<float4*>(zout + r * D + d0) = make_float4(v[0], v[1], v[2], v[3]);
     else
       for (int e = 0; e < 4; ++e)
@@ -598,7 +607,7 @@ size_t mnf_flow_f16_tiles(int64_t B) { return (size_t)cdiv(B, f2::BM); }
 int mnf_flow_f16_sample_z0(mnf_ctx* ctx, int64_t B, int D, const float* q0_mean, const float* q0_log_var, const NoiseDev& eps,
                            float* zout, float* tmax) {
   MNF_CUDA(cudaMemsetAsync(tmax, 0, sizeof(float) * mnf_flow_f16_tiles(B), ctx->stream));
-  f2::sample_z0_tmax<<<(unsigned)cdiv(B, f2::ZR), 256, 0, ctx->stream>>>(B, D, q0_mean, q0_log_var, eps, zout, tmax);
+  f2::sample_z0_tmax<<<(unsigned)cdiv(B, f2::ZR), 256, sizeof(float) * 8 * ((D + 3) / 4), ctx->stream>>>(B, D, q0_mean, q0_log_var, eps, zout, tmax);
   MNF_LAUNCHED(ctx);
   return MNF_OK;
 }
