@@ -269,11 +269,13 @@ def test_wide_iaf_chain_as_gemms(tc_ctx, math, D, B):
     close(nf.last_run.saved.numpy()[: B * 50].reshape(B, 50), caches[0]["acts"][1], RTOL, "saved hidden")
 
 
-@pytest.mark.parametrize("K,N,B,use_z,act", [(4096, 512, 256, True, None), (1500, 70, 33, True, "relu"), (2048, 24, 5, False, None)])
+@pytest.mark.parametrize("K,N,B,use_z,act", [(4096, 512, 256, True, None), (1500, 70, 33, True, "relu"), (2048, 24, 5, False, None),
+                                             (4096, 512, 1100, True, "relu"), (1504, 72, 1024, False, None)])
 def test_dense_long_contraction_keeps_fp32_parity(tc_ctx, K, N, B, use_z, act):
     """K > 1280 in the fp32-parity tensor-core mode: one TMEM accumulation chain of K terms would
     drift past 1e-5 (2.7e-5 measured at K = 4096), so the layer runs as split-K tcgen05 GEMMs with
-    chains of <= 1024 terms plus an epilogue kernel (`dense_long_gemm`)."""
+    chains of <= 1024 terms plus an epilogue kernel (`dense_long_gemm`) or, for many rows, as the packed
+    fp16 GEMM launched once per 1024-term segment with fp32 partial sums in between (`paired_f16x3<128>/segments`)."""
     from tf_mnf_b200 import _lib as L
 
     rng = np.random.RandomState(K + N)
@@ -290,7 +292,7 @@ def test_dense_long_contraction_keeps_fp32_parity(tc_ctx, K, N, B, use_z, act):
     if use_z:
         inj["eps_z"] = _f32(eps_z)
     y = lyr.call(_f32(x), noise=inj, activation=act)
-    assert L.last_path() == "dense_long_gemm", L.last_path()
+    assert L.last_path() == ("paired_f16x3<128>/segments" if B >= 1024 else "dense_long_gemm"), L.last_path()
     assert act is None or lyr.last_fused
     close(y.numpy(), ref, RTOL, "dense call (long K, tf32x3)")
 

@@ -57,6 +57,12 @@ struct Args {
   float* sd_out;
   NoiseDev eps;
   int act;
+  // K segments (contractions longer than MNF_TC_PARITY_KMAX in the fp32-parity mode): one launch covers k-blocks
+  // [kb0, kb1) -- a TMEM accumulation chain of <= 1024 terms -- and the un-scaled partial sums travel between the
+  // launches through `raw` ([2][M][N] fp32: mean, variance).  seg: 0 whole K in one launch, 1 first segment (raw =),
+  // 2 middle (raw +=), 3 last (raw + this segment, then the epilogue)
+  int kb0, kb1, seg;
+  float* raw;
 };
 
 __device__ __forceinline__ void split_f16x2(float a0, float a1, uint32_t& hi, uint32_t& lo) {
@@ -362,8 +368,9 @@ __global__ void __launch_bounds__(THREADS, 1) paired_f16x3(const __grid_constant
           for (int q = 0; q < 4; ++q) {
             const int nb = n0 + c0 + 4 * q;
             if (nb >= a.N) break;
-            float e[4];
-            if (a.eps.injected) {
+            float e[4] = {0.f, 0.f, 0.f, 0.f};
+            if (a.seg == 1 || a.seg == 2) {
+            } else if (a.eps.injected) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) e[j] = nb + j < a.N ? a.eps.injected[m * a.N + nb + j] : 0.f;
             } else {
@@ -374,14 +381,27 @@ __global__ void __launch_bounds__(THREADS, 1) paired_f16x3(const __grid_constant
             for (int j = 0; j < 4; ++j) {
               const int n = nb + j, cl = c0 + 4 * q + j;
               if (n < a.N) {
-                const float mean = fmaf(mv[4 * q + j], rs.x * __ldg(wm + cl), __ldg(a.bm + n));
-                const float sd = sqrt_fast(fmaf(vv[4 * q + j], rs.y * __ldg(wv + cl), __ldg(a.vb + n)));
+                float mean, var;
+                if (a.seg == 0) {
+                  mean = fmaf(mv[4 * q + j], rs.x * __ldg(wm + cl), __ldg(a.bm + n));
+                  var = fmaf(vv[4 * q + j], rs.y * __ldg(wv + cl), __ldg(a.vb + n));
+                } else {  // round-to-nearest fp32 sums of the segments' partial results
+                  float pm = mv[4 * q + j] * (rs.x * __ldg(wm + cl)), pv = vv[4 * q + j] * (rs.y * __ldg(wv + cl));
+                  float* rm = a.raw + m * a.N + n;
+                  float* rv = rm + a.M * a.N;
+                  if (a.seg >= 2) { pm += *rm; pv += *rv; }
+                  if (a.seg <= 2) { *rm = pm; *rv = pv; }
+                  mean = pm + __ldg(a.bm + n);
+                  var = pv + __ldg(a.vb + n);
+                }
+                const float sd = sqrt_fast(var);
                 s4[j] = sd;
                 const float out = fmaf(sd, e[j], mean);
                 o4[j] = a.act == 1 ? fmaxf(out, 0.f) : out;
               }
             }
             float* dstp = a.y + m * a.N + nb;
+            if (a.seg == 1 || a.seg == 2) continue;  // partial sums only: the last segment writes the layer's output
             if (nb + 3 < a.N && !(a.N & 3)) {
               *reinterpret_cast<float4*>(dstp) = make_float4(o4[0], o4[1], o4[2], o4[3]);
               if (a.sd_out) *reinterpret_cast<float4*>(a.sd_out + m * a.N + nb) = make_float4(s4[0], s4[1], s4[2], s4[3]);
@@ -408,7 +428,7 @@ __global__ void __launch_bounds__(THREADS, 1) paired_f16x3(const __grid_constant
       mbar_wait(&tempty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
       tc_fence_after();
       const uint32_t d_mean = tmem_base + (uint32_t)(buf * 2 * BN), d_var = d_mean + BN;
-      for (int kb = 0; kb < a.kblocks; ++kb) {
+      for (int kb = a.kb0; kb < a.kb1; ++kb) {
         mbar_wait(&full[stage], sph);
         tc_fence_after();
         const uint64_t ad = adesc0 + (uint64_t)((stage * A_STAGE) >> 4);
@@ -416,7 +436,7 @@ __global__ void __launch_bounds__(THREADS, 1) paired_f16x3(const __grid_constant
 #pragma unroll
         for (int j = 0; j < KS / 16; ++j) {  // one K = 16 instruction = two 16-byte chunks
           const uint64_t ao = ad + (uint64_t)((2 * j * BM * 16) >> 4), bo = bd + (uint64_t)((2 * j * BN * 16) >> 4);
-          const uint32_t acc = (kb == 0 && j == 0) ? 0u : 1u;
+          const uint32_t acc = (kb == a.kb0 && j == 0) ? 0u : 1u;
           constexpr uint64_t AV = A_VAR >> 4, BV = B_VAR >> 4;
           umma_f16_elect(d_mean, ao, bo, idesc, acc);            // xz_hi * W_hi
           umma_f16_elect(d_mean, ao + AV, bo, idesc, 1u);        // xz_lo * W_hi
@@ -426,7 +446,7 @@ __global__ void __launch_bounds__(THREADS, 1) paired_f16x3(const __grid_constant
           umma_f16_elect(d_var, ao + 2 * AV, bo + 3 * BV, idesc, 1u);    // s_hi * V_lo
         }
         umma_commit_elect(&empty[stage]);                         // smem stage free once these MMAs retire
-        if (kb == a.kblocks - 1) umma_commit_elect(&tfull[buf]);  // accumulators ready
+        if (kb == a.kb1 - 1) umma_commit_elect(&tfull[buf]);  // accumulators ready
         __syncwarp();
         if (++stage == STAGES) { stage = 0; sph ^= 1; }
       }
@@ -440,7 +460,7 @@ __global__ void __launch_bounds__(THREADS, 1) paired_f16x3(const __grid_constant
       const int nt = (int)(t - mt * a.ntiles);
       const uint8_t* asrc = a.Ap + mt * a.kblocks * (int64_t)A_STAGE;
       const uint8_t* bsrc = a.Bp + (int64_t)nt * a.kblocks * (int64_t)B_STAGE;
-      for (int kb = 0; kb < a.kblocks; ++kb) {
+      for (int kb = a.kb0; kb < a.kb1; ++kb) {
         mbar_wait(&empty[stage], sph ^ 1);
         if (lane == 0) {
           mbar_arrive_expect_tx(&full[stage], A_STAGE + B_STAGE);
@@ -463,8 +483,10 @@ __global__ void __launch_bounds__(THREADS, 1) paired_f16x3(const __grid_constant
 
 }  // namespace d3
 
+// K beyond MNF_TC_PARITY_KMAX: segments of SEG_KB k-blocks (1024 terms per TMEM accumulation chain), one GEMM launch each
+constexpr int SEG_KB = 1024 / d3::KS;
 bool mnf_dense_f16x3_ok(const mnf_ctx* ctx, int64_t M, int K, int N) {
-  return ctx->math_mode == MNF_MATH_TF32X3 && M >= 1024 && N > 16 && K >= 64 && K <= MNF_TC_PARITY_KMAX;
+  return ctx->math_mode == MNF_MATH_TF32X3 && M >= 1024 && N > 16 && K >= 64 && K <= 16384 && M * (int64_t)N < (1ll << 31);
 }
 
 // Entry used by layers_fwd.cu for many-row dense layers in the fp32-parity tensor-core mode.
@@ -483,6 +505,8 @@ int mnf_dense_f16x3_forward(mnf_ctx* ctx, int64_t M, int K, int N, const float* 
   const size_t r_bytes = sizeof(float2) * (size_t)a.mtiles * BM;
   const size_t bp_bytes = (size_t)a.ntiles * a.kblocks * B_STAGE;
   const size_t b_bytes = bp_bytes + sizeof(float) * (size_t)(2 * Npad + Npad) + sizeof(int) * (size_t)(2 * Npad);
+  const int nseg = K > MNF_TC_PARITY_KMAX ? (a.kblocks + SEG_KB - 1) / SEG_KB : 1;
+  const size_t raw_bytes = nseg > 1 ? (sizeof(float) * 2 * (size_t)M * N + 255) & ~(size_t)255 : 0;
   uint8_t *Ap, *Bp;
   bool fresh = true;
   if (ctx->frozen) {
@@ -491,12 +515,14 @@ int mnf_dense_f16x3_forward(mnf_ctx* ctx, int64_t M, int K, int N, const float* 
                               (uint64_t)(uintptr_t)log_std_W,
                               mnf_mix((uint64_t)(uintptr_t)log_var_b, (uint64_t)__float_as_uint_host(max_std)), b_bytes, &fresh);
     if (!Bp) return MNF_ERR_CUDA;
-    Ap = (uint8_t*)mnf_workspace(ctx, a_bytes + r_bytes);
+    Ap = (uint8_t*)mnf_workspace(ctx, a_bytes + r_bytes + raw_bytes);
     if (!Ap) return MNF_ERR_CUDA;
+    a.raw = (float*)(Ap + a_bytes + r_bytes);
   } else {
-    Ap = (uint8_t*)mnf_workspace(ctx, a_bytes + r_bytes + b_bytes);
+    Ap = (uint8_t*)mnf_workspace(ctx, a_bytes + r_bytes + raw_bytes + b_bytes);
     if (!Ap) return MNF_ERR_CUDA;
-    Bp = Ap + a_bytes + r_bytes;
+    a.raw = (float*)(Ap + a_bytes + r_bytes);
+    Bp = Ap + a_bytes + r_bytes + raw_bytes;
   }
   float2* rsc = (float2*)(Ap + a_bytes);
   float* wsc = (float*)(Bp + bp_bytes);
@@ -527,9 +553,14 @@ int mnf_dense_f16x3_forward(mnf_ctx* ctx, int64_t M, int K, int N, const float* 
   }
   const int64_t tiles = a.mtiles * a.ntiles;
   const int g = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-  mnf_note_path("paired_f16x3<128>");
-  paired_f16x3<<<g, THREADS, smem, ctx->stream>>>(a);
+  mnf_note_path(nseg > 1 ? "paired_f16x3<128>/segments" : "paired_f16x3<128>");
+  for (int sg = 0; sg < nseg; ++sg) {
+    a.kb0 = sg * (nseg > 1 ? SEG_KB : a.kblocks);
+    a.kb1 = nseg > 1 ? (a.kb0 + SEG_KB < a.kblocks ? a.kb0 + SEG_KB : a.kblocks) : a.kblocks;
+    a.seg = nseg == 1 ? 0 : sg == 0 ? 1 : sg == nseg - 1 ? 3 : 2;
+    paired_f16x3<<<g, THREADS, smem, ctx->stream>>>(a);
+    MNF_LAUNCHED(ctx);
+  }
   mnf_probe_end(ctx, probed);
-  MNF_LAUNCHED(ctx);
   return MNF_OK;
 }

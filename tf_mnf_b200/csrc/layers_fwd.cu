@@ -1009,6 +1009,10 @@ int mnf_dense_forward_act(mnf_ctx* ctx, int64_t B, int64_t K, int64_t N, const f
   if (ctx->math_mode == MNF_MATH_BF16)
     return mnf_dense_bf16_forward(ctx, B, (int)K, (int)N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std,
                                   make_noise(eps), y, sd_out, act);
+  // long contractions of MANY rows in the fp32-parity mode: the packed fp16 GEMM, one launch per 1024-term segment
+  if (!mnf_tc_k_ok(ctx, K) && mnf_dense_f16x3_ok(ctx, B, (int)K, (int)N) && !getenv("MNF_NO_F16X3"))
+    return mnf_dense_f16x3_forward(ctx, B, (int)K, (int)N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std,
+                                   make_noise(eps), y, sd_out, act);
   if (ctx->math_mode == MNF_MATH_TF32X3 && !mnf_tc_k_ok(ctx, K) && B < (1ll << 31))
     return dense_long_forward(ctx, B, K, N, x, z, mean_W, log_std_W, mean_b, log_var_b, max_std, make_noise(eps), act, y,
                               sd_out);
