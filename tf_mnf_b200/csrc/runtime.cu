@@ -401,7 +401,9 @@ int mnf_graph_end(mnf_ctx* ctx, void** graph_exec_out) {
   cudaGraph_t g;
   MNF_CUDA(cudaStreamEndCapture(ctx->stream, &g));
   cudaGraphExec_t ge;
-  cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+  // the kernel nodes carry the priority of the stream they were captured on (main stream: greatest, forks: least,
+  // mnf_ctx_fork); without this flag a replay runs every node at the launching stream's priority
+  cudaError_t e = cudaGraphInstantiate(&ge, g, cudaGraphInstantiateFlagUseNodePriority);
   cudaGraphDestroy(g);
   if (e != cudaSuccess) {
     mnf_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
