@@ -19,7 +19,7 @@
 //                    takes uniform-register operands, so per-lane addresses serialise: 8 k cycles per tile)
 //
 // fp16 lacks range: z is scaled by a power of two taken from the tile's max |z| (produced by whoever wrote z:
-// sample_z0_tmax, the previous step's epilogue, or tile_absmax), weight columns by their own maxima, h (in
+// sample_z0_tmax, the previous step's epilogue, or tile_absmax), each weight matrix by its own maximum, h (in
 // [-1, 1]) by 2^13; the epilogues multiply by the exact inverses.  flows_umma.cu (3xTF32) keeps IAF / MADE steps
 // and shapes this kernel does not take (D % 4 != 0).
 #include <cuda.h>
