@@ -142,9 +142,7 @@ int mnf_device_count(int* out) {
   return MNF_OK;
 }
 
-static bool g_fork_next = false;  // (contexts are created from one thread per process)
-
-int mnf_ctx_create(int device, void* stream, mnf_ctx** out) {
+static int ctx_create(int device, void* stream, bool low_priority, mnf_ctx** out) {
   MNF_CHECK_ARG(out, "mnf_ctx_create: out is NULL");
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -177,7 +175,7 @@ int mnf_ctx_create(int device, void* stream, mnf_ctx** out) {
     // (z chains, KL terms) fills in behind it -- the main stream's kernels run at their isolated durations.
     int least = 0, greatest = 0;
     MNF_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    MNF_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, g_fork_next ? least : greatest));
+    MNF_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, low_priority ? least : greatest));
     c->owns_stream = true;
   }
   MNF_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -191,11 +189,11 @@ int mnf_ctx_create(int device, void* stream, mnf_ctx** out) {
   return MNF_OK;
 }
 
+int mnf_ctx_create(int device, void* stream, mnf_ctx** out) { return ctx_create(device, stream, false, out); }
+
 int mnf_ctx_fork(mnf_ctx* parent, mnf_ctx** out) {
   MNF_CHECK_ARG(parent && out, "mnf_ctx_fork: NULL argument");
-  g_fork_next = true;
-  const int rc = mnf_ctx_create(parent->device, nullptr, out);
-  g_fork_next = false;
+  const int rc = ctx_create(parent->device, nullptr, true, out);
   if (rc) return rc;
   (*out)->math_mode = parent->math_mode;
   return MNF_OK;
