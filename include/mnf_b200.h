@@ -62,9 +62,10 @@ int mnf_device_count(int* out);
  * process is refused with MNF_ERR_UNSUPPORTED. */
 int mnf_ctx_create(int device, void* stream, mnf_ctx** out);
 /* A sibling context on the parent's device (own stream, own workspace, the parent's math mode) for work that does
- * not depend on the parent's data flow: z chains, kl_div.  Its stream has the device's LEAST priority, a stream
- * owned by mnf_ctx_create the greatest, so side work fills in behind the main stream instead of delaying it. */
-int mnf_ctx_fork(mnf_ctx* parent, mnf_ctx** out);
+ * not depend on the parent's data flow: z chains, kl_div.  Its stream runs `rank` levels above the device's LEAST
+ * priority and always below a stream owned by mnf_ctx_create (the greatest), so side work fills in behind the
+ * main stream instead of delaying it; rank the forks by how soon the main stream needs their results. */
+int mnf_ctx_fork(mnf_ctx* parent, int32_t rank, mnf_ctx** out);
 int mnf_ctx_destroy(mnf_ctx* ctx);
 int mnf_ctx_set_stream(mnf_ctx* ctx, void* stream);
 int mnf_ctx_get_stream(mnf_ctx* ctx, void** stream);

@@ -70,7 +70,7 @@ _i64, _i32, _f, _u64, _u32, _sz = C.c_int64, C.c_int32, C.c_float, C.c_uint64, C
 SIGNATURES = {
     "mnf_device_count": [C.POINTER(C.c_int)],
     "mnf_ctx_create": [C.c_int, vp, C.POINTER(vp)],
-    "mnf_ctx_fork": [vp, C.POINTER(vp)],
+    "mnf_ctx_fork": [vp, _i32, C.POINTER(vp)],
     "mnf_ctx_destroy": [vp],
     "mnf_ctx_set_stream": [vp, vp],
     "mnf_ctx_get_stream": [vp, C.POINTER(vp)],

@@ -142,7 +142,7 @@ int mnf_device_count(int* out) {
   return MNF_OK;
 }
 
-static int ctx_create(int device, void* stream, bool low_priority, mnf_ctx** out) {
+static int ctx_create(int device, void* stream, int rank, mnf_ctx** out) {  // rank < 0: the greatest priority; else `rank` levels above the least
   MNF_CHECK_ARG(out, "mnf_ctx_create: out is NULL");
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -170,12 +170,19 @@ static int ctx_create(int device, void* stream, bool low_priority, mnf_ctx** out
     c->stream = (cudaStream_t)stream;
     c->owns_stream = false;
   } else {
-    // An owned stream of mnf_ctx_create runs at the device's greatest priority, a fork's (mnf_ctx_fork) at the
-    // least: the block scheduler then hands free SMs to the x-dependent main stream first and the side work
-    // (z chains, KL terms) fills in behind it -- the main stream's kernels run at their isolated durations.
+    // An owned stream of mnf_ctx_create runs at the device's greatest priority, a fork's (mnf_ctx_fork) below it:
+    // the block scheduler then hands free SMs to the x-dependent main stream first and the side work (z chains,
+    // KL terms) fills in behind it -- the main stream's kernels run at their isolated durations.  Forks are
+    // ranked among themselves (`rank` levels above the least priority): the z chain the main stream needs NEXT
+    // must not queue behind the ones it needs later (a priority inversion otherwise: the main stream waits).
     int least = 0, greatest = 0;
     MNF_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    MNF_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, low_priority ? least : greatest));
+    int prio = greatest;
+    if (rank >= 0) {  // (numerically smaller = more urgent; a fork stays below the main streams)
+      prio = least - rank;
+      if (prio <= greatest) prio = greatest + (least > greatest ? 1 : 0);
+    }
+    MNF_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio));
     c->owns_stream = true;
   }
   MNF_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -189,11 +196,11 @@ static int ctx_create(int device, void* stream, bool low_priority, mnf_ctx** out
   return MNF_OK;
 }
 
-int mnf_ctx_create(int device, void* stream, mnf_ctx** out) { return ctx_create(device, stream, false, out); }
+int mnf_ctx_create(int device, void* stream, mnf_ctx** out) { return ctx_create(device, stream, -1, out); }
 
-int mnf_ctx_fork(mnf_ctx* parent, mnf_ctx** out) {
-  MNF_CHECK_ARG(parent && out, "mnf_ctx_fork: NULL argument");
-  const int rc = ctx_create(parent->device, nullptr, true, out);
+int mnf_ctx_fork(mnf_ctx* parent, int32_t rank, mnf_ctx** out) {
+  MNF_CHECK_ARG(parent && out && rank >= 0, "mnf_ctx_fork: bad argument");
+  const int rc = ctx_create(parent->device, nullptr, rank, out);
   if (rc) return rc;
   (*out)->math_mode = parent->math_mode;
   return MNF_OK;

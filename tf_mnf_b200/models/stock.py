@@ -189,7 +189,9 @@ class Sequential:
             mnf = [l for l in self.mnf_layers if l.built and l.use_z and l.ctx is x.ctx]
             if mnf:
                 if len(self._sides) < len(mnf) or self._sides[0].device != x.ctx.device:
-                    self._sides = [x.ctx.fork() for _ in mnf]
+                    # layer 0's side stream draws the z of the NEXT call (least priority); the later layers' chains are
+                    # needed in program order by THIS call: the earlier the consumer, the higher the rank
+                    self._sides = [x.ctx.fork(rank=0 if i == 0 else max(1, 5 - i)) for i in range(len(mnf))]
                 for lyr, side in zip(mnf, self._sides):
                     if lyr is self.mnf_layers[0]:
                         if self.presample_first:

@@ -25,11 +25,11 @@ _ITEMSIZE = {k: np.dtype(v).itemsize for k, v in _DT.items()}
 class Context:
     """One (device, stream, workspace).  Not thread-safe: use one context per thread."""
 
-    def __init__(self, device: int = 0, stream: int | None = None, _fork_of: "Context | None" = None) -> None:
+    def __init__(self, device: int = 0, stream: int | None = None, _fork_of: "Context | None" = None, _rank: int = 0) -> None:
         self.lib = L.load()
         h = C.c_void_p()
-        if _fork_of is not None:  # a low-priority sibling (mnf_ctx_fork)
-            L.check(self.lib.mnf_ctx_fork(_fork_of.handle, C.byref(h)))
+        if _fork_of is not None:  # a lower-priority sibling (mnf_ctx_fork)
+            L.check(self.lib.mnf_ctx_fork(_fork_of.handle, int(_rank), C.byref(h)))
         else:
             L.check(self.lib.mnf_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
         self.handle = h
@@ -87,10 +87,13 @@ class Context:
     def sync(self) -> None:
         L.check(self.lib.mnf_ctx_sync(self.handle))
 
-    def fork(self) -> "Context":
+    def fork(self, rank: int = 0) -> "Context":
         """A sibling context on the same device with its own stream and workspace (e.g. to run
-        kl_div(), which does not depend on x, concurrently with a forward pass)."""
-        c = Context(self.device, _fork_of=self)
+        kl_div(), which does not depend on x, concurrently with a forward pass).  Its stream runs below the
+        main streams' priority, `rank` levels above the device's least (mnf_ctx_fork): side work fills in
+        behind the main stream, and the side stream whose result the main stream needs first gets the
+        highest rank."""
+        c = Context(self.device, _fork_of=self, _rank=rank)
         if getattr(self, "math", None):
             c.set_math(self.math)
         if getattr(self, "frozen", False):
