@@ -31,10 +31,11 @@ __device__ __forceinline__ float4 ld4g(const float* p) { return __ldg(reinterpre
 
 // four outputs (one pixel, one filter quad) of a row; `off` = pix * F + 4 q indexes the row's injected
 // noise and the image's maps alike (32-bit: the per-quad 64-bit address arithmetic was 10 % of the kernel)
+template <bool INJ>
 __device__ __forceinline__ void mc_quad(const McArgs& a, const PhiloxKeys& K, const float* inj, uint64_t grow, const float* mimg,
                                         const float* simg, const float4& zq, int pix, int q, int off, float o[4]) {
   float e[4];
-  if (inj) {
+  if (INJ) {
     const float4 t = ld4g(inj + off);
     e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
   } else {
@@ -90,7 +91,9 @@ __global__ void __launch_bounds__(128) conv_mc_maps(MapArgs a) {
   }
 }
 
-template <bool POOL>
+// INJ: the noise is read from memory (tests); compiled apart so that the Philox path is branch-free and the four
+// independent Philox chains of a pooled item can be interleaved by the scheduler
+template <bool POOL, bool INJ>
 __global__ void __launch_bounds__(256) conv_mc_expand(McArgs a) {
   const int64_t brow = blockIdx.x;
   const int64_t img = brow / a.n_rep;
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(256) conv_mc_expand(McArgs a) {
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
         float o[4];
-        mc_quad(a, K, inj, grow, mimg, simg, zq, pix0 + dpix[d], q, off0 + doff[d], o);
+        mc_quad<INJ>(a, K, inj, grow, mimg, simg, zq, pix0 + dpix[d], q, off0 + doff[d], o);
 #pragma unroll
         for (int j = 0; j < 4; ++j) best[j] = fmaxf(best[j], o[j]);
       }
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(256) conv_mc_expand(McArgs a) {
       const int q = it % Q, pix = it / Q;
       const float4 zq = zrow ? ld4g(zrow + 4 * q) : make_float4(1.f, 1.f, 1.f, 1.f);
       float o[4];
-      mc_quad(a, K, inj, grow, mimg, simg, zq, pix, q, it * 4, o);
+      mc_quad<INJ>(a, K, inj, grow, mimg, simg, zq, pix, q, it * 4, o);
       *reinterpret_cast<float4*>(yrow + it * 4) = make_float4(o[0], o[1], o[2], o[3]);
     }
   }
@@ -193,8 +196,14 @@ int mnf_conv2d_mc_expand(mnf_ctx* ctx, int64_t B, int64_t n_rep, int64_t Ho, int
   a.mean = mean; a.sd = sd; a.z = z; a.eps = make_noise(eps); a.y = y;
   mnf_note_path(fuse_relu_pool ? "conv_mc_expand<pool>" : "conv_mc_expand");
   const bool probed = mnf_probe_begin(ctx, MNF_PROBE_MC_EXPAND);
-  if (fuse_relu_pool) conv_mc_expand<true><<<(unsigned)B, 256, 0, ctx->stream>>>(a);
-  else conv_mc_expand<false><<<(unsigned)B, 256, 0, ctx->stream>>>(a);
+  const bool inj = a.eps.injected != nullptr;
+  if (fuse_relu_pool) {
+    if (inj) conv_mc_expand<true, true><<<(unsigned)B, 256, 0, ctx->stream>>>(a);
+    else conv_mc_expand<true, false><<<(unsigned)B, 256, 0, ctx->stream>>>(a);
+  } else {
+    if (inj) conv_mc_expand<false, true><<<(unsigned)B, 256, 0, ctx->stream>>>(a);
+    else conv_mc_expand<false, false><<<(unsigned)B, 256, 0, ctx->stream>>>(a);
+  }
   mnf_probe_end(ctx, probed);
   MNF_LAUNCHED(ctx);
   return MNF_OK;
