@@ -298,6 +298,10 @@ __global__ void weight_pack(int K, int N, int Npad, int kblocks, int ntiles, con
   }
 }
 
+// INJ: the output noise is read from memory (tests); compiled apart so that the epilogue's Philox path is branch-free
+// SEG: one K segment of a long contraction (a.seg = 1 .. 3, partial sums through a.raw); the ordinary whole-K launch
+// is compiled without any of it
+template <bool INJ, bool SEG>
 __global__ void __launch_bounds__(THREADS, 1) paired_f16x3(const __grid_constant__ Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* As = smem;                    // [STAGES][4][CH][BM][16 B]
@@ -338,6 +342,7 @@ __global__ void __launch_bounds__(THREADS, 1) paired_f16x3(const __grid_constant
   if (warp < EPI_WARPS) {
     // ================================================================== epilogue warps
     const int r = warp * 32 + lane;  // tile row == TMEM lane
+    const PhiloxKeys EK = philox_keys(a.eps);  // round keys once per warp (warp-uniform: uniform registers)
     int it = 0;
     for (int64_t t = blockIdx.x; t < ntot; t += gridDim.x, ++it) {
       const int64_t mt = t / a.ntiles;
@@ -369,12 +374,12 @@ __global__ void __launch_bounds__(THREADS, 1) paired_f16x3(const __grid_constant
             const int nb = n0 + c0 + 4 * q;
             if (nb >= a.N) break;
             float e[4] = {0.f, 0.f, 0.f, 0.f};
-            if (a.seg == 1 || a.seg == 2) {
-            } else if (a.eps.injected) {
+            if (SEG && (a.seg == 1 || a.seg == 2)) {
+            } else if (INJ) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) e[j] = nb + j < a.N ? a.eps.injected[m * a.N + nb + j] : 0.f;
             } else {
-              philox_normal4(a.eps, a.eps.row_offset + (uint64_t)m, 0u, (uint32_t)(nb >> 2), e);
+              philox_normal4_keys(a.eps, EK, a.eps.row_offset + (uint64_t)m, 0u, (uint32_t)(nb >> 2), e);
             }
             float o4[4] = {0.f, 0.f, 0.f, 0.f}, s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -382,7 +387,7 @@ __global__ void __launch_bounds__(THREADS, 1) paired_f16x3(const __grid_constant
               const int n = nb + j, cl = c0 + 4 * q + j;
               if (n < a.N) {
                 float mean, var;
-                if (a.seg == 0) {
+                if (!SEG) {
                   mean = fmaf(mv[4 * q + j], rs.x * __ldg(wm + cl), __ldg(a.bm + n));
                   var = fmaf(vv[4 * q + j], rs.y * __ldg(wv + cl), __ldg(a.vb + n));
                 } else {  // round-to-nearest fp32 sums of the segments' partial results
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(THREADS, 1) paired_f16x3(const __grid_constant
               }
             }
             float* dstp = a.y + m * a.N + nb;
-            if (a.seg == 1 || a.seg == 2) continue;  // partial sums only: the last segment writes the layer's output
+            if (SEG && (a.seg == 1 || a.seg == 2)) continue;  // partial sums only: the last segment writes the layer's output
             if (nb + 3 < a.N && !(a.N & 3)) {
               *reinterpret_cast<float4*>(dstp) = make_float4(o4[0], o4[1], o4[2], o4[3]);
               if (a.sd_out) *reinterpret_cast<float4*>(a.sd_out + m * a.N + nb) = make_float4(s4[0], s4[1], s4[2], s4[3]);
@@ -548,7 +553,10 @@ int mnf_dense_f16x3_forward(mnf_ctx* ctx, int64_t M, int K, int N, const float* 
   const size_t smem = (size_t)STAGES * (A_STAGE + B_STAGE) + 256;
   static bool attr_set = false;  // one device per process (mnf_ctx_create)
   if (!attr_set) {
-    MNF_CUDA(cudaFuncSetAttribute(paired_f16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MNF_CUDA(cudaFuncSetAttribute(paired_f16x3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MNF_CUDA(cudaFuncSetAttribute(paired_f16x3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MNF_CUDA(cudaFuncSetAttribute(paired_f16x3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MNF_CUDA(cudaFuncSetAttribute(paired_f16x3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const int64_t tiles = a.mtiles * a.ntiles;
@@ -558,7 +566,13 @@ int mnf_dense_f16x3_forward(mnf_ctx* ctx, int64_t M, int K, int N, const float* 
     a.kb0 = sg * (nseg > 1 ? SEG_KB : a.kblocks);
     a.kb1 = nseg > 1 ? (a.kb0 + SEG_KB < a.kblocks ? a.kb0 + SEG_KB : a.kblocks) : a.kblocks;
     a.seg = nseg == 1 ? 0 : sg == 0 ? 1 : sg == nseg - 1 ? 3 : 2;
-    paired_f16x3<<<g, THREADS, smem, ctx->stream>>>(a);
+    if (nseg > 1) {
+      if (eps.injected) paired_f16x3<true, true><<<g, THREADS, smem, ctx->stream>>>(a);
+      else paired_f16x3<false, true><<<g, THREADS, smem, ctx->stream>>>(a);
+    } else {
+      if (eps.injected) paired_f16x3<true, false><<<g, THREADS, smem, ctx->stream>>>(a);
+      else paired_f16x3<false, false><<<g, THREADS, smem, ctx->stream>>>(a);
+    }
     MNF_LAUNCHED(ctx);
   }
   mnf_probe_end(ctx, probed);
