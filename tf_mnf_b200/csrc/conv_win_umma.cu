@@ -77,6 +77,8 @@ __device__ __forceinline__ void umma_tf32_nc(uint32_t d_tmem, uint64_t adesc, ui
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// INJ: the output noise is read from memory (tests); compiled apart so that the epilogue's Philox path is branch-free
+template <bool INJ>
 __global__ void __launch_bounds__(THREADS, 1) conv_win_umma(const __grid_constant__ Args a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_win_umma(const __grid_constan
     const int64_t my_sets = (nsets > blockIdx.x) ? (nsets - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t total_tiles = my_sets * ntile;
     uint32_t k = 0;  // this group's tile counter (parity of its accumulator barrier)
+    const PhiloxKeys EK = philox_keys(a.eps);  // round keys once per warp (warp-uniform: uniform registers)
     for (int64_t tc = grp; tc < total_tiles; tc += EPI_E, ++k) {
       const int64_t si = tc / ntile;
       const int tile = (int)(tc - si * ntile);
@@ -183,11 +186,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_win_umma(const __grid_constan
           if (lane == 0) mbar_arrive(&tempty[grp]);
         }
         float e[4];
-        if (inj) {
+        if (INJ) {
           const float4 t = *reinterpret_cast<const float4*>(inj + nb);
           e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
         } else {
-          philox_normal4(a.eps, grow, (uint32_t)outer, (uint32_t)q, e);
+          philox_normal4_keys(a.eps, EK, grow, (uint32_t)outer, (uint32_t)q, e);
         }
         float4 zq = make_float4(1.f, 1.f, 1.f, 1.f);
         if (zrow) zq = __ldg(reinterpret_cast<const float4*>(zrow + nb));
@@ -418,14 +421,16 @@ int mnf_conv_win_umma_forward(mnf_ctx* ctx, int64_t B, const int* geo, int N, co
   a.x = x; a.z = z; a.bm = mean_b; a.vb = vb; a.steptab = d_tab; a.Bp = Bp; a.y = y; a.eps = eps;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    MNF_CUDA(cudaFuncSetAttribute(conv_win_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MNF_CUDA(cudaFuncSetAttribute(conv_win_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MNF_CUDA(cudaFuncSetAttribute(conv_win_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
   const int64_t sets = cdiv(B, (int64_t)I);
   const int g = (int)(sets < ctx->sm_count ? sets : ctx->sm_count);
   const bool probed = mnf_probe_begin(ctx, MNF_PROBE_CONV_GEMM);
   mnf_note_path("conv_win_umma");
-  conv_win_umma<<<g, THREADS, smem, ctx->stream>>>(a);
+  if (eps.injected) conv_win_umma<true><<<g, THREADS, smem, ctx->stream>>>(a);
+  else conv_win_umma<false><<<g, THREADS, smem, ctx->stream>>>(a);
   mnf_probe_end(ctx, probed);
   MNF_LAUNCHED(ctx);
   *used = true;
