@@ -520,6 +520,7 @@ __global__ void pack_weights(int D, int H, int kblocks, const float* __restrict_
 // rows of one tile; a thread draws four consecutive elements per Philox call (same counters as every other
 // consumer of this draw: row, inner = d >> 2).
 constexpr int ZR = 8;
+template <bool INJ>  // INJ: eps read from memory (tests), compiled apart: the Philox path is branch-free
 __global__ void __launch_bounds__(256) sample_z0_tmax(int64_t B, int D, const float* __restrict__ q0_mean,
                                                       const float* __restrict__ q0_log_var, NoiseDev eps,
                                                       float* __restrict__ zout, float* __restrict__ tmax) {
@@ -546,7 +547,7 @@ __global__ void __launch_bounds__(256) sample_z0_tmax(int64_t B, int D, const fl
     const int64_t r = r0 + rr;
     if (r >= B) break;
     float nrm[4];
-    if (eps.injected) {
+    if (INJ) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) nrm[e] = d0 + e < D ? eps.injected[r * D + d0 + e] : 0.f;
     } else {
@@ -607,7 +608,9 @@ size_t mnf_flow_f16_tiles(int64_t B) { return (size_t)cdiv(B, f2::BM); }
 int mnf_flow_f16_sample_z0(mnf_ctx* ctx, int64_t B, int D, const float* q0_mean, const float* q0_log_var, const NoiseDev& eps,
                            float* zout, float* tmax) {
   MNF_CUDA(cudaMemsetAsync(tmax, 0, sizeof(float) * mnf_flow_f16_tiles(B), ctx->stream));
-  f2::sample_z0_tmax<<<(unsigned)cdiv(B, f2::ZR), 256, sizeof(float) * 8 * ((D + 3) / 4), ctx->stream>>>(B, D, q0_mean, q0_log_var, eps, zout, tmax);
+  const size_t zsm = sizeof(float) * 8 * ((D + 3) / 4);
+  if (eps.injected) f2::sample_z0_tmax<true><<<(unsigned)cdiv(B, f2::ZR), 256, zsm, ctx->stream>>>(B, D, q0_mean, q0_log_var, eps, zout, tmax);
+  else f2::sample_z0_tmax<false><<<(unsigned)cdiv(B, f2::ZR), 256, zsm, ctx->stream>>>(B, D, q0_mean, q0_log_var, eps, zout, tmax);
   MNF_LAUNCHED(ctx);
   return MNF_OK;
 }
