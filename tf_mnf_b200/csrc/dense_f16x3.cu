@@ -86,13 +86,15 @@ __device__ __forceinline__ int scale_exp(float m) {
   return e;
 }
 
-// ---- rows: one CTA = 32 rows of one 128-row tile, 8 warps x 4 rows.  Pass 1: a warp per row finds
+// ---- rows: one CTA = RP_ROWS rows of one 128-row tile, 8 warps x RP_ROWS / 8 rows.  The kernel is a chain of
+// dependent load phases per CTA, so more, smaller CTAs in flight win: 41 us with 32 rows per CTA, 33 us with 16,
+// 30 us with 8 (MNF-LeNet d1).  Pass 1: a warp per row finds
 // max |x z| and max x^2 (coalesced float4 reads) -> the row's two scales.  Pass 2, per slab of 256 k:
 // a lane converts ONE 16-byte chunk (8 consecutive k: 32 contiguous bytes of x and of z, the warp
 // reads 1 KB contiguous; second visit, L1 / L2 hits) of all four variants and parks it in shared
 // memory at [variant][chunk][row ^ chunk] (conflict-free both ways); then every (variant, chunk) line
 // of 32 rows x 16 B leaves as ONE 512-byte coalesced store.  x and z are read from HBM once.
-constexpr int RP_ROWS = 32, RP_THREADS = 256, RP_SLAB = 32;  // chunks per slab
+constexpr int RP_ROWS = 8, RP_THREADS = 256, RP_SLAB = 32;  // rows per CTA (8, 16 or 32), chunks per slab
 constexpr int RP_PARK_BYTES = 4 * RP_SLAB * RP_ROWS * 16;
 __global__ void __launch_bounds__(RP_THREADS) row_pack(int64_t M, int K, int kblocks, const float* __restrict__ x,
                                                        const float* __restrict__ z, uint8_t* __restrict__ Ap,
@@ -209,20 +211,23 @@ __global__ void __launch_bounds__(RP_THREADS) row_pack(int64_t M, int K, int kbl
         split_f16x2(xv[2 * e] * zv[2 * e] * fa, xv[2 * e + 1] * zv[2 * e + 1] * fa, ah[e], al[e]);
         split_f16x2(xv[2 * e] * xv[2 * e] * fs, xv[2 * e + 1] * xv[2 * e + 1] * fs, sh[e], sl[e]);
       }
-      const int slot = (rr ^ lane) & 31;
+      const int slot = (rr ^ lane) & (RP_ROWS - 1);
       park[0][lane][slot] = make_uint4(ah[0], ah[1], ah[2], ah[3]);
       park[1][lane][slot] = make_uint4(al[0], al[1], al[2], al[3]);
       park[2][lane][slot] = make_uint4(sh[0], sh[1], sh[2], sh[3]);
       park[3][lane][slot] = make_uint4(sl[0], sl[1], sl[2], sl[3]);
     }
     __syncthreads();
-    // copy-out: a warp per (variant, chunk) line; lane = destination row
-    for (int ln = warp; ln < 4 * RP_SLAB; ln += RP_THREADS / 32) {
+    // copy-out: 32 / RP_ROWS (variant, chunk) lines per warp pass; a lane = one destination row of its line
+    constexpr int LPW = 32 / RP_ROWS;
+    const int sub = lane / RP_ROWS, row = lane % RP_ROWS;
+    for (int lp = warp; lp < 4 * RP_SLAB / LPW; lp += RP_THREADS / 32) {
+      const int ln = lp * LPW + sub;
       const int v = ln / RP_SLAB, cl = ln - v * RP_SLAB, cg = c0 + cl;
       if (cg < nchunks) {
         const int kb = cg / CH, cc = cg - kb * CH;
-        uint8_t* dst = Ap + (mt * kblocks + kb) * (int64_t)A_STAGE + (int64_t)v * A_VAR + ((int64_t)cc * BM + r0 + lane) * 16;
-        *reinterpret_cast<uint4*>(dst) = park[v][cl][(lane ^ cl) & 31];
+        uint8_t* dst = Ap + (mt * kblocks + kb) * (int64_t)A_STAGE + (int64_t)v * A_VAR + ((int64_t)cc * BM + r0 + row) * 16;
+        *reinterpret_cast<uint4*>(dst) = park[v][cl][(row ^ cl) & (RP_ROWS - 1)];
       }
     }
     __syncthreads();
