@@ -5,7 +5,7 @@
 // reading its own row is conflict-free; out-of-range rows / columns are zero-filled on load and clipped on
 // store by the hardware):
 //
-//   loader warp      z[128 x 32] tiles -> raw ring (4 x 16 KB), pre-split weight blocks -> operand rings;
+//   loader warp      z[128 x 32] tiles -> raw ring (6 x 16 KB), pre-split weight blocks -> operand rings;
 //                    stage 1 and stage 2 walk the same ring
 //   mask warps 0-3   the step's Bernoulli(0.5) mask bits of the tile, once (one Philox call per 128 elements)
 //   stage 1          16 converter warps (thread = row): raw -> mask -> * 2^e -> fp16 hi/lo -> K-major A tiles;
@@ -33,14 +33,14 @@ using namespace um;
 
 constexpr int BM = 128, HP = 64, TK = 32;
 constexpr int RAW_TILE = BM * TK * 4;  // 16 KB: [128 rows][128 B], 16-byte chunk q of row r at chunk q ^ (r & 7)
-constexpr int NR = 4, S1 = 4, S2 = 3, NG = 4;
+constexpr int NR = 6, S1 = 4, S2 = 3, NG = 4;  // NR raw tiles in flight: four being converted + two on their way (TMA latency)
 constexpr int A1_VAR = (TK / 8) * BM * 16, A1_STAGE = 2 * A1_VAR;  // 8 KB / 16 KB
 constexpr int B1_VAR = (TK / 8) * HP * 16, B1_STAGE = 2 * B1_VAR;  // 4 KB / 8 KB
 constexpr int H_VAR = (HP / 8) * BM * 16;                          // 16 KB
 constexpr int B2_VAR = (HP / 8) * 64 * 16, B2_STAGE = 2 * B2_VAR;  // 8 KB / 16 KB
 constexpr int REGION_X = S1 * (A1_STAGE + B1_STAGE);               // 96 KB: stage-1 rings, then B2 ring + h
 static_assert(S2 * B2_STAGE + 2 * H_VAR <= REGION_X, "stage-2 buffers alias the stage-1 rings");
-static_assert(NR == NG && S1 == NG, "group g owns raw slot g and operand stage g");
+static_assert(S1 == NG && NR >= NG, "group g owns operand stage g; every group can hold a raw tile");
 constexpr int WARPS = 22, THREADS = WARPS * 32;  // 0-3 masks + epilogues, 4 MMA, 5-20 converters + epilogues, 21 loader
 constexpr int TMEM_COLS = 256;                   // acc_h 64 + 2 x 64
 constexpr float H_SCALE = 8192.f, H_INV = 1.f / 8192.f;
